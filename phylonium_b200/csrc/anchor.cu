@@ -1,0 +1,649 @@
+// Anchoring of all queries against the device ESA.  Replaces hot loop A of
+// /root/reference/src/process.cxx:433-458.  See walk.h for why the speculative,
+// chunk-parallel walk reproduces the reference's sequential walk exactly.
+//
+// Launch sequence for one batch of queries (all on one stream):
+//   k_walk_chunks     one thread per CH-base chunk: cold walk, events, dead bitmap, exit
+//   k_resolve_open    one warp per over-long match: link it to the next open match on the
+//                     same diagonal or scan on cooperatively to the mismatch
+//   k_open_jump       pointer jumping over those links
+//   k_apply_open      final lengths / exit states of open events
+//   k_bridge          one thread per chunk: from the exit state to the merge point
+//   k_resolve_path    one block per query: pointer doubling from walker 0 marks the true path
+//   (k_continue)      only if a give-up sits on a true path: exact serial continuation
+//   k_copy_events     true events, compacted per query
+//   assemble          right/left classification (max-scan for run heads) -> homologies
+//   sort + k_filter   radix sort by (query, projected start); chaining DP per query
+#include "anchor_device.h"
+#include "filter.h"
+#include "primitives.cuh"
+
+#include <algorithm>
+
+namespace phy
+{
+
+namespace
+{
+
+struct Timer {
+	cudaEvent_t a, b;
+	cudaStream_t s;
+	bool on;
+	Timer(cudaStream_t st, bool enabled) : s(st), on(enabled)
+	{
+		if (!on) return;
+		CUDA_CHECK(cudaEventCreate(&a));
+		CUDA_CHECK(cudaEventCreate(&b));
+		CUDA_CHECK(cudaEventRecord(a, s));
+	}
+	float lap()
+	{
+		if (!on) return 0.f;
+		CUDA_CHECK(cudaEventRecord(b, s));
+		CUDA_CHECK(cudaEventSynchronize(b));
+		float ms = 0;
+		CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+		CUDA_CHECK(cudaEventRecord(a, s));
+		return ms;
+	}
+	~Timer()
+	{
+		if (!on) return;
+		cudaEventDestroy(a);
+		cudaEventDestroy(b);
+	}
+};
+
+// ------------------------------------------------------------------ phase 1
+
+__global__ void __launch_bounds__(64) k_walk_chunks(WalkParams P, int *__restrict__ any_open)
+{
+	const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= P.total_chunks) return;
+	walk_chunk(P, g);
+	if (P.rec[g].open) *any_open = 1;
+}
+
+// ------------------------------------------------------------------ phase 2: open matches
+
+// first mismatch of Q[from, to) against S[from + diag, …), warp-cooperative; returns `to`
+// if there is none.  Positions at or beyond m in S count as mismatches.
+__device__ int32_t warp_first_mismatch(const uint8_t *__restrict__ q, const uint8_t *__restrict__ S, int64_t diag,
+                                       int32_t m, int32_t from, int32_t to)
+{
+	const int lane = threadIdx.x & 31;
+	for (int32_t base = from; base < to; base += 32) {
+		const int32_t x = base + lane;
+		bool miss = false;
+		if (x < to) {
+			const int64_t sp = (int64_t)x + diag;
+			miss = (sp >= m) || (q[x] != S[sp]);
+		}
+		const uint32_t b = __ballot_sync(0xffffffffu, miss);
+		if (b) return base + (__ffs(b) - 1);
+	}
+	return to;
+}
+
+// lnk[g]: chunk whose open event ends where ours does, or -1; endq[g]: end if known
+__global__ void k_resolve_open(WalkParams P, const int *__restrict__ any_open, int32_t *__restrict__ lnk,
+                               int32_t *__restrict__ endq)
+{
+	if (!*any_open) return;
+	const int32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (g >= P.total_chunks) return;
+	const ChunkRec &r = P.rec[g];
+	if (!r.open) {
+		if (lane == 0) {
+			lnk[g] = -1;
+			endq[g] = -1;
+		}
+		return;
+	}
+	int32_t link, end;
+	open_resolve_one(P, g, warp_first_mismatch, link, end);
+	if (lane == 0) {
+		lnk[g] = link;
+		endq[g] = end;
+	}
+}
+
+// resolves chains lnk -> lnk -> … -> end by pointer jumping; one block, ping-pong buffers
+__global__ void __launch_bounds__(1024)
+k_open_jump(int32_t total, const int *__restrict__ any_open, int32_t *lnk_a, int32_t *end_a, int32_t *lnk_b,
+            int32_t *end_b, int rounds)
+{
+	if (!*any_open) return;
+	int32_t *la = lnk_a, *ea = end_a, *lb = lnk_b, *eb = end_b;
+	for (int r = 0; r < rounds; r++) {
+		for (int32_t g = threadIdx.x; g < total; g += blockDim.x) {
+			int32_t l = la[g], e = ea[g];
+			if (l >= 0) {
+				const int32_t l2 = la[l];
+				if (l2 < 0) {
+					e = ea[l];
+					l = -1;
+				} else {
+					l = l2;
+				}
+			}
+			lb[g] = l;
+			eb[g] = e;
+		}
+		__syncthreads();
+		int32_t *t = la;
+		la = lb;
+		lb = t;
+		t = ea;
+		ea = eb;
+		eb = t;
+	}
+	// result must end up in the _a buffers
+	if (la != lnk_a) {
+		for (int32_t g = threadIdx.x; g < total; g += blockDim.x) {
+			lnk_a[g] = la[g];
+			end_a[g] = ea[g];
+		}
+	}
+}
+
+__global__ void k_apply_open(WalkParams P, const int *__restrict__ any_open, const int32_t *__restrict__ lnk,
+                             const int32_t *__restrict__ endq, int *__restrict__ err)
+{
+	if (!*any_open) return;
+	const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= P.total_chunks) return;
+	ChunkRec &r = P.rec[g];
+	if (!r.open) return;
+	if (lnk[g] >= 0 || endq[g] < 0) {
+		atomicExch(err, 1);
+		return;
+	}
+	Event &e = P.ev[(int64_t)g * P.cap_ev + r.n_events - 1];
+	e.len = endq[g] - e.pos;
+	r.exit.lastLen = e.len;
+	r.exit.pos = e.pos + e.len + 1;
+	r.open = 0;
+}
+
+// ------------------------------------------------------------------ phase 3
+
+__global__ void __launch_bounds__(64) k_bridge(WalkParams P)
+{
+	const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= P.total_chunks) return;
+	ChunkRec &r = P.rec[g];
+	r.link = bridge_walk(P, g, r.exit, 0, r.bridge_ev, P.cap_ev, P.CH, P.CAP);
+}
+
+// ------------------------------------------------------------------ phase 4
+
+// One block per query.  reach/from are per chunk; status[q] = -1 when the path reaches the
+// end of the query, else the (global) chunk whose bridge is unresolved.
+__global__ void __launch_bounds__(1024)
+k_resolve_path(WalkParams P, int32_t *__restrict__ jump_a, int32_t *__restrict__ jump_b, uint8_t *__restrict__ reach,
+               int32_t *__restrict__ from, int32_t *__restrict__ status)
+{
+	const int32_t qid = blockIdx.x;
+	const QueryInfo qi = P.qi[qid];
+	const int32_t base = qi.chunk_base, nc = qi.nchunks;
+	if (nc == 0) {
+		if (threadIdx.x == 0) status[qid] = -1;
+		return;
+	}
+	for (int32_t k = threadIdx.x; k < nc; k += blockDim.x) {
+		const ChunkRec &r = P.rec[base + k];
+		jump_a[base + k] = (r.link == LINK_MERGED) ? r.link_chunk : base + k; // terminal nodes point at themselves
+		reach[base + k] = (k == 0);
+		from[base + k] = 0;
+	}
+	__syncthreads();
+	int32_t *ja = jump_a, *jb = jump_b;
+	for (int32_t span = 1; span < nc; span <<= 1) {
+		for (int32_t k = threadIdx.x; k < nc; k += blockDim.x)
+			if (reach[base + k]) reach[ja[base + k]] = 1; // benign race: all writers store 1
+		__syncthreads();
+		for (int32_t k = threadIdx.x; k < nc; k += blockDim.x)
+			jb[base + k] = ja[ja[base + k]];
+		__syncthreads();
+		int32_t *t = ja;
+		ja = jb;
+		jb = t;
+	}
+	// one more marking step covers the last doubling
+	for (int32_t k = threadIdx.x; k < nc; k += blockDim.x)
+		if (reach[base + k]) reach[ja[base + k]] = 1;
+	__syncthreads();
+	for (int32_t k = threadIdx.x; k < nc; k += blockDim.x) {
+		if (!reach[base + k]) continue;
+		const ChunkRec &r = P.rec[base + k];
+		if (r.link == LINK_MERGED)
+			from[r.link_chunk] = r.link_from;
+		else
+			status[qid] = (r.link == LINK_END) ? -1 : base + k; // exactly one terminal node is reached
+	}
+}
+
+// exact, serial continuation of an unresolved bridge that lies on a true path
+__global__ void k_continue(WalkParams P, const int32_t *__restrict__ stuck, int32_t nstuck, Event *const *__restrict__ ovf,
+                           const int64_t *__restrict__ ovf_cap)
+{
+	const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= nstuck) return;
+	const int32_t g = stuck[t];
+	ChunkRec &r = P.rec[g];
+	Event *out = ovf[t];
+	for (int32_t k = 0; k < r.n_bridge; k++)
+		out[k] = r.bridge_ev[k];
+	r.bridge_ev = out;
+	r.link = bridge_walk(P, g, r.bstate, r.n_bridge, out, ovf_cap[t], -1, 0x7fffffff);
+}
+
+// ------------------------------------------------------------------ events -> homologies
+
+__global__ void k_copy_events(WalkParams P, const uint8_t *__restrict__ reach, const int32_t *__restrict__ from,
+                              const uint32_t *__restrict__ offs, Event *__restrict__ out, int32_t *__restrict__ out_q)
+{
+	const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= P.total_chunks || !reach[g]) return;
+	const ChunkRec &r = P.rec[g];
+	const int32_t qid = P.chunk_query[g];
+	const Event *ev = P.ev + (int64_t)g * P.cap_ev;
+	uint32_t w = offs[2 * (int64_t)g];
+	for (int32_t k = from[g]; k < r.n_events; k++, w++) {
+		out[w] = ev[k];
+		out_q[w] = qid;
+	}
+	w = offs[2 * (int64_t)g + 1];
+	for (int32_t k = 0; k < r.n_bridge; k++, w++) {
+		out[w] = r.bridge_ev[k];
+		out_q[w] = qid;
+	}
+}
+
+__device__ __forceinline__ bool ev_first_of_query(const int32_t *evq, int64_t t)
+{
+	return t == 0 || evq[t] != evq[t - 1];
+}
+
+__device__ __forceinline__ bool ev_is_right(const Event *ev, const int32_t *evq, int64_t t, int32_t border)
+{
+	const Event prev = ev_first_of_query(evq, t) ? Event{0, 0, 0} : ev[t - 1];
+	return event_is_right(prev, ev[t], border);
+}
+
+// offsets of each query's list inside an array sorted by query id
+__global__ void k_query_offsets(const int32_t *__restrict__ qids, int64_t n, int32_t nq, int64_t *__restrict__ offs)
+{
+	const int32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q > nq) return;
+	int64_t lo = 0, hi = n;
+	while (lo < hi) {
+		const int64_t mid = (lo + hi) >> 1;
+		if (qids[mid] < q)
+			lo = mid + 1;
+		else
+			hi = mid;
+	}
+	offs[q] = lo;
+}
+
+__global__ void k_filter(const int64_t *__restrict__ offs, int32_t nq, const int32_t *__restrict__ start,
+                         const int32_t *__restrict__ len, int64_t *__restrict__ score, int32_t *__restrict__ pred,
+                         uint8_t *__restrict__ keep)
+{
+	const int32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= nq) return;
+	const int64_t o = offs[q];
+	const int32_t h = (int32_t)(offs[q + 1] - o);
+	filter_overlaps_max(start + o, len + o, h, score + o, pred + o, keep + o);
+}
+
+int rounds_for(int64_t n)
+{
+	int r = 1;
+	while ((1ll << r) < n)
+		r++;
+	return r + 1;
+}
+
+} // namespace
+
+void host_sort_filter(std::vector<Hom> &list)
+{
+	// the very call of process.cxx:438-441: unstable, so equal starts keep libstdc++'s order
+	std::sort(list.begin(), list.end(), [](const Hom &a, const Hom &b) { return a.iproj < b.iproj; });
+	const int32_t h = (int32_t)list.size();
+	std::vector<int32_t> start(h), len(h), pred(h);
+	std::vector<int64_t> score(h);
+	std::vector<uint8_t> keep(h);
+	for (int32_t k = 0; k < h; k++) {
+		start[k] = list[k].iproj;
+		len[k] = list[k].len;
+	}
+	filter_overlaps_max(start.data(), len.data(), h, score.data(), pred.data(), keep.data());
+	size_t w = 0;
+	for (int32_t k = 0; k < h; k++)
+		if (keep[k]) list[w++] = list[k];
+	list.resize(w);
+}
+
+void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector<QueryInfo> &qi, int32_t thr,
+                           const AnchorOptions &opt, cudaStream_t s, AnchorResult &out, AnchorStats *stats)
+{
+	AnchorStats local;
+	AnchorStats &ST = stats ? *stats : local;
+	ST = AnchorStats();
+	const int32_t nq = (int32_t)qi.size();
+	if (thr < 1) throw std::invalid_argument("anchor threshold must be >= 1");
+	int32_t CH = opt.chunk > 0 ? opt.chunk : 4096;
+	CH = ((CH + 31) / 32) * 32;
+	if (CH <= thr + 1) CH = ((thr + 2 + 31) / 32) * 32;
+	int32_t CAP = opt.cap > 0 ? opt.cap : 2 * CH;
+	if (CAP < CH) CAP = CH; // an open match must cover the rest of its walker's chunk
+	if (CAP < thr + 1) CAP = thr + 1;
+
+	Timer total(s, opt.timings), lap(s, opt.timings);
+
+	// chunk geometry
+	int64_t total_chunks64 = 0;
+	for (auto &q : qi) {
+		q.chunk_base = (int32_t)total_chunks64;
+		q.nchunks = (q.qlen + CH - 1) / CH;
+		total_chunks64 += q.nchunks;
+	}
+	if (total_chunks64 > 0x3fffffff) throw std::invalid_argument("too many chunks in one batch");
+	const int32_t total_chunks = (int32_t)total_chunks64;
+	ST.chunks = total_chunks;
+	std::vector<int32_t> chunk_query((size_t)total_chunks);
+	for (int32_t k = 0; k < nq; k++)
+		std::fill(chunk_query.begin() + qi[k].chunk_base, chunk_query.begin() + qi[k].chunk_base + qi[k].nchunks, k);
+
+	out.offs.assign((size_t)nq + 1, 0);
+	out.raw_offs.assign((size_t)nq + 1, 0);
+	out.homs.release();
+	out.raw.release();
+	out.d_offs.alloc((size_t)nq + 1, s);
+	out.d_offs.zero();
+	if (total_chunks == 0) return;
+
+	const int32_t cap_ev = CH / (thr + 1) + 2;
+	DevBuf<QueryInfo> d_qi(nq, s);
+	DevBuf<int32_t> d_cq(total_chunks, s);
+	CUDA_CHECK(cudaMemcpyAsync(d_qi.get(), qi.data(), nq * sizeof(QueryInfo), cudaMemcpyHostToDevice, s));
+	CUDA_CHECK(cudaMemcpyAsync(d_cq.get(), chunk_query.data(), (size_t)total_chunks * sizeof(int32_t),
+	                           cudaMemcpyHostToDevice, s));
+	DevBuf<Event> ev((size_t)total_chunks * cap_ev, s), bev((size_t)total_chunks * cap_ev, s);
+	DevBuf<uint32_t> dead((size_t)total_chunks * (CH / 32), s);
+	dead.zero();
+	DevBuf<ChunkRec> rec(total_chunks, s);
+	DevBuf<int> flags(4, s); // [0] any_open, [1] error
+	flags.zero();
+
+	WalkParams P;
+	P.esa = esa.view();
+	P.Q = d_Q;
+	P.qi = d_qi.get();
+	P.nq = nq;
+	P.thr = thr;
+	P.CH = CH;
+	P.CAP = CAP;
+	P.cap_ev = cap_ev;
+	P.total_chunks = total_chunks;
+	P.ev = ev.get();
+	P.bev = bev.get();
+	P.dead = dead.get();
+	P.rec = rec.get();
+	P.chunk_query = d_cq.get();
+
+	// 1. cold walks
+	k_walk_chunks<<<div_up(total_chunks, 64), 64, 0, s>>>(P, flags.get());
+	KERNEL_CHECK();
+	ST.walk_ms = lap.lap();
+
+	// 2. open matches
+	{
+		DevBuf<int32_t> lnk_a(total_chunks, s), end_a(total_chunks, s), lnk_b(total_chunks, s), end_b(total_chunks, s);
+		k_resolve_open<<<div_up((int64_t)total_chunks * 32, 256), 256, 0, s>>>(P, flags.get(), lnk_a.get(), end_a.get());
+		KERNEL_CHECK();
+		k_open_jump<<<1, 1024, 0, s>>>(total_chunks, flags.get(), lnk_a.get(), end_a.get(), lnk_b.get(), end_b.get(),
+		                               rounds_for(total_chunks));
+		KERNEL_CHECK();
+		k_apply_open<<<div_up(total_chunks, 256), 256, 0, s>>>(P, flags.get(), lnk_a.get(), end_a.get(), flags.get() + 1);
+		KERNEL_CHECK();
+	}
+	ST.open_ms = lap.lap();
+
+	// 3. bridges
+	k_bridge<<<div_up(total_chunks, 64), 64, 0, s>>>(P);
+	KERNEL_CHECK();
+	ST.bridge_ms = lap.lap();
+
+	// 4. true path, with exact continuation of give-ups that lie on it
+	DevBuf<int32_t> jump_a(total_chunks, s), jump_b(total_chunks, s), from(total_chunks, s), status(nq, s);
+	DevBuf<uint8_t> reach(total_chunks, s);
+	std::vector<DevBuf<Event>> overflow;
+	std::vector<int32_t> h_status((size_t)nq);
+	for (int iter = 0;; iter++) {
+		k_resolve_path<<<nq, 1024, 0, s>>>(P, jump_a.get(), jump_b.get(), reach.get(), from.get(), status.get());
+		KERNEL_CHECK();
+		CUDA_CHECK(cudaMemcpyAsync(h_status.data(), status.get(), nq * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+		int h_flags[4];
+		CUDA_CHECK(cudaMemcpyAsync(h_flags, flags.get(), sizeof h_flags, cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaStreamSynchronize(s));
+		if (h_flags[1]) throw std::runtime_error("internal error: open match left unresolved");
+		ST.open_events += (iter == 0 && h_flags[0]) ? 1 : 0;
+		std::vector<int32_t> stuck;
+		for (int32_t q = 0; q < nq; q++)
+			if (h_status[q] >= 0) stuck.push_back(h_status[q]);
+		if (stuck.empty()) break;
+		if (iter > total_chunks + 2) throw std::runtime_error("internal error: path resolution does not terminate");
+		ST.unresolved += (int64_t)stuck.size();
+		std::vector<Event *> h_ptr;
+		std::vector<int64_t> h_cap;
+		for (int32_t g : stuck) {
+			const QueryInfo &q = qi[chunk_query[g]];
+			const int64_t capq = q.qlen / (thr + 1) + 2;
+			overflow.emplace_back((size_t)capq, s);
+			h_ptr.push_back(overflow.back().get());
+			h_cap.push_back(capq);
+		}
+		DevBuf<int32_t> d_stuck(stuck.size(), s);
+		DevBuf<Event *> d_ptr(stuck.size(), s);
+		DevBuf<int64_t> d_cap(stuck.size(), s);
+		CUDA_CHECK(cudaMemcpyAsync(d_stuck.get(), stuck.data(), stuck.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+		CUDA_CHECK(cudaMemcpyAsync(d_ptr.get(), h_ptr.data(), stuck.size() * sizeof(Event *), cudaMemcpyHostToDevice, s));
+		CUDA_CHECK(cudaMemcpyAsync(d_cap.get(), h_cap.data(), stuck.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+		k_continue<<<div_up((int64_t)stuck.size(), 32), 32, 0, s>>>(P, d_stuck.get(), (int32_t)stuck.size(), d_ptr.get(),
+		                                                            d_cap.get());
+		KERNEL_CHECK();
+		CUDA_CHECK(cudaStreamSynchronize(s)); // host vectors above go out of scope
+	}
+	ST.path_ms = lap.lap();
+
+	// 5. true events, compacted; then homologies
+	DevBuf<uint32_t> cnt((size_t)2 * total_chunks + 1, s);
+	{
+		uint32_t *c = cnt.get();
+		const ChunkRec *rc = rec.get();
+		const uint8_t *rh = reach.get();
+		const int32_t *fr = from.get();
+		const int64_t n2 = 2 * (int64_t)total_chunks;
+		device_scan<uint32_t>(
+			n2 + 1,
+			[rc, rh, fr, n2] __device__(int64_t i) -> uint32_t {
+				if (i >= n2) return 0u;
+				const int64_t g = i >> 1;
+				if (!rh[g]) return 0u;
+				return (i & 1) ? (uint32_t)rc[g].n_bridge : (uint32_t)(rc[g].n_events - fr[g]);
+			},
+			[c] __device__(int64_t i, uint32_t v) { c[i] = v; }, OpSum(), 0u, false, s);
+	}
+	const uint32_t n_events = d2h_scalar(cnt.get() + 2 * (int64_t)total_chunks, s);
+	ST.events = n_events;
+
+	DevBuf<Hom> raw;
+	DevBuf<int32_t> raw_q;
+	uint32_t n_raw = 0;
+	if (n_events) {
+		DevBuf<Event> tev(n_events, s);
+		DevBuf<int32_t> tevq(n_events, s);
+		k_copy_events<<<div_up(total_chunks, 128), 128, 0, s>>>(P, reach.get(), from.get(), cnt.get(), tev.get(), tevq.get());
+		KERNEL_CHECK();
+		// run heads by inclusive max-scan: 2(t+1)+1 for a left anchor, 2(t+1) for a query's
+		// first event that extends the virtual anchor (0,0,0), 0 otherwise
+		DevBuf<uint32_t> headcode(n_events, s);
+		const Event *E = tev.get();
+		const int32_t *EQ = tevq.get();
+		uint32_t *HC = headcode.get();
+		const int32_t border = esa.n;
+		device_scan<uint32_t>(
+			n_events,
+			[E, EQ, border] __device__(int64_t t) -> uint32_t {
+				const bool right = ev_is_right(E, EQ, t, border);
+				if (!right) return 2u * (uint32_t)(t + 1) + 1u;
+				return ev_first_of_query(EQ, t) ? 2u * (uint32_t)(t + 1) : 0u;
+			},
+			[HC] __device__(int64_t t, uint32_t v) { HC[t] = v; }, OpMax(), 0u, true, s);
+		// a run ends where the next event is a left anchor or belongs to another query
+		DevBuf<uint32_t> d_n(1, s);
+		const int64_t ne = n_events;
+		auto run_end_pushed = [E, EQ, HC, border, thr, ne] __device__(int64_t t, Hom *h) -> bool {
+			const bool last = (t + 1 == ne) || EQ[t + 1] != EQ[t] || !ev_is_right(E, EQ, t + 1, border);
+			if (!last) return false;
+			const uint32_t code = HC[t];
+			const int64_t first = (int64_t)(code >> 1) - 1;
+			const Event *base = E + first; // run_homology indexes relative to the run's first real event
+			const int32_t a = (code & 1) ? 0 : -1;
+			const int32_t b = (int32_t)(t - first);
+			Hom tmp;
+			const bool ok = run_homology(base, a, b, thr, border, tmp);
+			if (ok && h) *h = tmp;
+			return ok;
+		};
+		device_select(
+			n_events, [run_end_pushed] __device__(int64_t t) { return run_end_pushed(t, nullptr); },
+			[] __device__(int64_t, uint32_t) {}, d_n.get(), s);
+		n_raw = d2h_scalar(d_n.get(), s);
+		if (n_raw) {
+			raw.alloc(n_raw, s);
+			raw_q.alloc(n_raw, s);
+			Hom *R = raw.get();
+			int32_t *RQ = raw_q.get();
+			device_select(
+				n_events, [run_end_pushed] __device__(int64_t t) { return run_end_pushed(t, nullptr); },
+				[run_end_pushed, R, RQ, EQ] __device__(int64_t t, uint32_t w) {
+					Hom h;
+					run_end_pushed(t, &h);
+					R[w] = h;
+					RQ[w] = EQ[t];
+				},
+				d_n.get(), s);
+		}
+	}
+	ST.assemble_ms = lap.lap();
+
+	DevBuf<int64_t> d_raw_offs((size_t)nq + 1, s);
+	k_query_offsets<<<div_up(nq + 1, 128), 128, 0, s>>>(raw_q.get(), n_raw, nq, d_raw_offs.get());
+	KERNEL_CHECK();
+	CUDA_CHECK(cudaMemcpyAsync(out.raw_offs.data(), d_raw_offs.get(), ((size_t)nq + 1) * sizeof(int64_t),
+	                           cudaMemcpyDeviceToHost, s));
+	CUDA_CHECK(cudaStreamSynchronize(s));
+
+	// 6. sort by (query, projected start) and keep the heaviest chain per query
+	if (n_raw) {
+		DevBuf<uint64_t> keys(n_raw, s), keys_alt(n_raw, s);
+		DevBuf<uint32_t> idx(n_raw, s), idx_alt(n_raw, s);
+		{
+			uint64_t *K = keys.get();
+			const Hom *R = raw.get();
+			const int32_t *RQ = raw_q.get();
+			device_for(n_raw, [K, R, RQ] __device__(int64_t i) { K[i] = ((uint64_t)(uint32_t)RQ[i] << 32) | (uint32_t)R[i].iproj; }, s);
+		}
+		int qbits = 1;
+		while ((1ll << qbits) < nq)
+			qbits++;
+		const bool fl = radix_sort_pairs(keys.get(), idx.get(), keys_alt.get(), idx_alt.get(), n_raw, 0, 32 + qbits, true, s);
+		const uint64_t *KS = fl ? keys_alt.get() : keys.get();
+		const uint32_t *IS = fl ? idx_alt.get() : idx.get();
+		// equal (query, start) keys: the reference's std::sort is unstable there
+		DevBuf<uint32_t> d_ties(1, s);
+		device_select(
+			n_raw, [KS] __device__(int64_t i) { return i > 0 && KS[i] == KS[i - 1]; }, [] __device__(int64_t, uint32_t) {},
+			d_ties.get(), s);
+		const uint32_t ties = d2h_scalar(d_ties.get(), s);
+		if (!ties) {
+			DevBuf<int32_t> st(n_raw, s), ln(n_raw, s), pred(n_raw, s);
+			DevBuf<int64_t> score(n_raw, s);
+			DevBuf<uint8_t> keep(n_raw, s);
+			{
+				int32_t *ST_ = st.get(), *LN = ln.get();
+				const Hom *R = raw.get();
+				device_for(n_raw, [ST_, LN, R, IS] __device__(int64_t i) {
+					const Hom h = R[IS[i]];
+					ST_[i] = h.iproj;
+					LN[i] = h.len;
+				}, s);
+			}
+			k_filter<<<div_up(nq, 32), 32, 0, s>>>(d_raw_offs.get(), nq, st.get(), ln.get(), score.get(), pred.get(),
+			                                       keep.get());
+			KERNEL_CHECK();
+			DevBuf<uint32_t> d_n(1, s);
+			const uint8_t *KP = keep.get();
+			device_select(
+				n_raw, [KP] __device__(int64_t i) { return KP[i] != 0; }, [] __device__(int64_t, uint32_t) {}, d_n.get(), s);
+			const uint32_t n_final = d2h_scalar(d_n.get(), s);
+			out.homs.alloc(n_final, s);
+			DevBuf<int32_t> fq(n_final, s);
+			{
+				Hom *F = out.homs.get();
+				int32_t *FQ = fq.get();
+				const Hom *R = raw.get();
+				const int32_t *RQ = raw_q.get();
+				device_select(
+					n_raw, [KP] __device__(int64_t i) { return KP[i] != 0; },
+					[F, FQ, R, RQ, IS] __device__(int64_t i, uint32_t w) {
+						F[w] = R[IS[i]];
+						FQ[w] = RQ[IS[i]];
+					},
+					d_n.get(), s);
+			}
+			k_query_offsets<<<div_up(nq + 1, 128), 128, 0, s>>>(fq.get(), n_final, nq, out.d_offs.get());
+			KERNEL_CHECK();
+			CUDA_CHECK(cudaMemcpyAsync(out.offs.data(), out.d_offs.get(), ((size_t)nq + 1) * sizeof(int64_t),
+			                           cudaMemcpyDeviceToHost, s));
+			CUDA_CHECK(cudaStreamSynchronize(s));
+		} else {
+			// Rare: two homologies of one query start at the same reference position. Which one
+			// survives in the reference depends on libstdc++'s unstable std::sort, so run that
+			// very call on the push-order list (process.cxx:438-443) for the whole batch.
+			ST.tie_fallback++;
+			std::vector<Hom> h_raw(n_raw);
+			CUDA_CHECK(cudaMemcpyAsync(h_raw.data(), raw.get(), n_raw * sizeof(Hom), cudaMemcpyDeviceToHost, s));
+			CUDA_CHECK(cudaStreamSynchronize(s));
+			std::vector<Hom> fin;
+			for (int32_t q = 0; q < nq; q++) {
+				std::vector<Hom> list(h_raw.begin() + out.raw_offs[q], h_raw.begin() + out.raw_offs[q + 1]);
+				host_sort_filter(list);
+				out.offs[q] = (int64_t)fin.size();
+				fin.insert(fin.end(), list.begin(), list.end());
+			}
+			out.offs[nq] = (int64_t)fin.size();
+			out.homs.alloc(fin.size(), s);
+			if (!fin.empty())
+				CUDA_CHECK(cudaMemcpyAsync(out.homs.get(), fin.data(), fin.size() * sizeof(Hom), cudaMemcpyHostToDevice, s));
+			CUDA_CHECK(cudaMemcpyAsync(out.d_offs.get(), out.offs.data(), ((size_t)nq + 1) * sizeof(int64_t),
+			                           cudaMemcpyHostToDevice, s));
+			CUDA_CHECK(cudaStreamSynchronize(s));
+		}
+	}
+	ST.filter_ms = lap.lap();
+	if (opt.keep_raw) {
+		out.raw = std::move(raw);
+	}
+	ST.total_ms = total.lap();
+}
+
+} // namespace phy

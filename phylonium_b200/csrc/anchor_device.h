@@ -1,0 +1,47 @@
+// Per-query anchoring on the device (anchor.cu): replaces hot loop A of
+// /root/reference/src/process.cxx:433-458 — anchor_homologies() + std::sort +
+// filter_overlaps_max() for every query.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "esa_device.h"
+#include "walk.h"
+
+namespace phy
+{
+
+struct AnchorStats {
+	int64_t chunks = 0;
+	int64_t events = 0;        // accepted anchors on the true paths
+	int64_t open_events = 0;   // matches longer than the per-thread cap
+	int64_t unresolved = 0;    // bridges that gave up and were continued serially
+	int64_t tie_fallback = 0;  // batches whose sort went through std::sort on the host
+	float walk_ms = 0, open_ms = 0, bridge_ms = 0, path_ms = 0, assemble_ms = 0, filter_ms = 0, total_ms = 0;
+};
+
+struct AnchorOptions {
+	int32_t chunk = 4096; // CH, multiple of 32
+	int32_t cap = 0;      // comparison cap per thread; 0 = 2 * chunk
+	bool keep_raw = false; // also keep the unsorted, unfiltered lists (tests)
+	bool timings = false;
+};
+
+struct AnchorResult {
+	DevBuf<Hom> homs;          // filtered lists of all queries, concatenated
+	std::vector<int64_t> offs; // nq + 1 offsets into homs (host)
+	DevBuf<int64_t> d_offs;    // same on the device
+	DevBuf<Hom> raw;           // push-order lists before sort/filter (keep_raw)
+	std::vector<int64_t> raw_offs;
+};
+
+// d_Q: concatenated queries on the device, every query followed by at least one zero byte.
+// qi[k].chunk_base / nchunks are filled in here.
+void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector<QueryInfo> &qi, int32_t thr,
+                           const AnchorOptions &opt, cudaStream_t s, AnchorResult &out, AnchorStats *stats);
+
+// host std::sort + filter for one list; used when equal starts make the reference's
+// unstable sort implementation-defined (see anchor.cu)
+void host_sort_filter(std::vector<Hom> &list);
+
+} // namespace phy

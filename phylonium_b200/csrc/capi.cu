@@ -1,0 +1,684 @@
+// C ABI of include/phylonium_b200.h: context, argument checking, host<->device copies.
+// All numerical work is in esa_build.cu, anchor.cu and compare.cu.
+#include "../../include/phylonium_b200.h"
+
+#include "anchor_device.h"
+#include "compare_device.h"
+#include "esa_device.h"
+#include "esa_search.h"
+#include "primitives.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace phy;
+
+struct phylo_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	std::string err;
+
+	int64_t opt_chunk = 4096, opt_cap = 0, opt_kmer = -1;
+	bool keep_raw = false, timings = false;
+
+	EsaDevice esa;
+	bool esa_ready = false;
+
+	DevBuf<uint8_t> q_own;       // queries uploaded by phylo_map_queries
+	const uint8_t *dQ = nullptr; // q_own or the caller's device buffer
+	std::vector<QueryInfo> qi;
+	uint64_t N = 0; // sequences of the last map call
+	AnchorResult anchors;
+	bool mapped = false;
+
+	RowStore rows;
+	uint64_t rows_total = 0; // 0: follow N
+	uint64_t rows_first = 0;
+
+	DevBuf<unsigned long long> d_subst, d_hom;
+	uint64_t matN = 0;
+
+	std::map<std::string, double> stats;
+};
+
+namespace
+{
+
+thread_local std::string g_create_error;
+
+int fail(phylo_ctx *ctx, int code, const std::string &msg)
+{
+	if (ctx)
+		ctx->err = msg;
+	else
+		g_create_error = msg;
+	return code;
+}
+
+template <typename F> int guarded(phylo_ctx *ctx, F &&f)
+{
+	if (!ctx) return fail(nullptr, PHYLO_ERR_INVALID, "context is NULL");
+	try {
+		cudaError_t e = cudaSetDevice(ctx->device);
+		if (e != cudaSuccess) return fail(ctx, PHYLO_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+		f();
+		return PHYLO_OK;
+	} catch (const std::invalid_argument &e) {
+		return fail(ctx, PHYLO_ERR_INVALID, e.what());
+	} catch (const CudaError &e) {
+		cudaGetLastError();
+		return fail(ctx, PHYLO_ERR_CUDA, e.what());
+	} catch (const std::exception &e) {
+		return fail(ctx, PHYLO_ERR_INTERNAL, e.what());
+	}
+}
+
+struct WallTimer {
+	cudaEvent_t a, b;
+	cudaStream_t s;
+	explicit WallTimer(cudaStream_t st) : s(st)
+	{
+		CUDA_CHECK(cudaEventCreate(&a));
+		CUDA_CHECK(cudaEventCreate(&b));
+		CUDA_CHECK(cudaEventRecord(a, s));
+	}
+	float stop()
+	{
+		CUDA_CHECK(cudaEventRecord(b, s));
+		CUDA_CHECK(cudaEventSynchronize(b));
+		float ms = 0;
+		CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+		return ms;
+	}
+	~WallTimer()
+	{
+		cudaEventDestroy(a);
+		cudaEventDestroy(b);
+	}
+};
+
+void record_esa_stats(phylo_ctx *c, const EsaTimings &t)
+{
+	auto &s = c->stats;
+	s["esa.text_ms"] = t.text_ms;
+	s["esa.keys_ms"] = t.keys_ms;
+	s["esa.sort_ms"] = t.sort_ms;
+	s["esa.refine_ms"] = t.refine_ms;
+	s["esa.lcp_ms"] = t.lcp_ms;
+	s["esa.cld_ms"] = t.cld_ms;
+	s["esa.table_ms"] = t.table_ms;
+	s["esa.total_ms"] = t.total_ms;
+	s["esa.refine_rounds"] = t.refine_rounds;
+	s["esa.tied"] = (double)t.tied;
+	s["esa.kmer_k"] = c->esa.K;
+}
+
+void record_anchor_stats(phylo_ctx *c, const AnchorStats &t)
+{
+	auto &s = c->stats;
+	s["anchor.chunks"] = (double)t.chunks;
+	s["anchor.events"] = (double)t.events;
+	s["anchor.open"] = (double)t.open_events;
+	s["anchor.unresolved"] = (double)t.unresolved;
+	s["anchor.tie_fallback"] = (double)t.tie_fallback;
+	s["anchor.walk_ms"] = t.walk_ms;
+	s["anchor.open_ms"] = t.open_ms;
+	s["anchor.bridge_ms"] = t.bridge_ms;
+	s["anchor.path_ms"] = t.path_ms;
+	s["anchor.assemble_ms"] = t.assemble_ms;
+	s["anchor.filter_ms"] = t.filter_ms;
+	s["anchor.total_ms"] = t.total_ms;
+}
+
+__global__ void k_validate_queries(const uint8_t *__restrict__ Q, const QueryInfo *__restrict__ qi, int32_t nq,
+                                   int *__restrict__ bad)
+{
+	const int32_t k = blockIdx.y;
+	if (k >= nq) return;
+	const uint8_t *q = Q + qi[k].qoff;
+	const int32_t len = qi[k].qlen;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= len; i += (int64_t)gridDim.x * blockDim.x) {
+		const uint8_t c = q[i];
+		const bool ok = (i == len) ? (c == 0) : (c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == '!');
+		if (!ok) atomicExch(bad, (i == len) ? 2 : 1);
+	}
+}
+
+__global__ void k_get_matches(EsaView e, const uint8_t *__restrict__ text, const uint64_t *__restrict__ offs,
+                              const uint64_t *__restrict__ lens, uint64_t count, int use_table, int64_t *__restrict__ out)
+{
+	const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= count) return;
+	const uint8_t *q = text + offs[k];
+	const int32_t qlen = (int32_t)lens[k];
+	Match mt;
+	if (qlen <= 0) {
+		const Interval r = esa_root(e);
+		mt = Match{0, r.i, r.j, 0};
+	} else {
+		mt = use_table ? esa_match(e, q, qlen, 0x7fffffff) : esa_match_root(e, q, qlen, 0x7fffffff);
+	}
+	out[3 * k + 0] = mt.l;
+	out[3 * k + 1] = mt.i;
+	out[3 * k + 2] = mt.j;
+}
+
+void do_esa_build(phylo_ctx *c, const uint8_t *d_ref, uint64_t n)
+{
+	if (n < 1 || n > 0x3fffffffull) throw std::invalid_argument("reference length must be in [1, 2^30)");
+	c->esa_ready = false;
+	c->mapped = false;
+	EsaTimings t;
+	esa_build_device(c->esa, d_ref, (int32_t)n, (int)c->opt_kmer, c->stream, &t);
+	record_esa_stats(c, t);
+	c->esa_ready = true;
+}
+
+void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_t *lens, uint64_t N, uint64_t thr)
+{
+	if (!c->esa_ready) throw std::invalid_argument("phylo_esa_build has not been called");
+	if (thr < 1 || thr > 0x3fffffffull) throw std::invalid_argument("threshold out of range");
+	if (N > 0x7fff0000ull) throw std::invalid_argument("too many sequences");
+	c->mapped = false;
+	c->dQ = dQ;
+	c->N = N;
+	c->qi.assign((size_t)N, QueryInfo());
+	for (uint64_t k = 0; k < N; k++) {
+		if (lens[k] > 0x7fffff00ull) throw std::invalid_argument("sequence too long for 32-bit indices");
+		c->qi[k].qoff = (int64_t)offs[k];
+		c->qi[k].qlen = (int32_t)lens[k];
+	}
+	cudaStream_t s = c->stream;
+	AnchorOptions opt;
+	opt.chunk = (int32_t)c->opt_chunk;
+	opt.cap = (int32_t)c->opt_cap;
+	opt.keep_raw = c->keep_raw;
+	opt.timings = c->timings;
+	AnchorStats st;
+	DevBuf<QueryInfo> d_qi;
+	if (N) {
+		// the walk relies on the alphabet and on the zero byte behind every sequence
+		d_qi.alloc((size_t)N, s);
+		CUDA_CHECK(cudaMemcpyAsync(d_qi.get(), c->qi.data(), N * sizeof(QueryInfo), cudaMemcpyHostToDevice, s));
+		DevBuf<int> bad(1, s);
+		bad.zero();
+		for (uint64_t k0 = 0; k0 < N; k0 += 32768) {
+			const int32_t cnt = (int32_t)(N - k0 < 32768 ? N - k0 : 32768);
+			dim3 grid(64, cnt);
+			k_validate_queries<<<grid, 256, 0, s>>>(dQ, d_qi.get() + k0, cnt, bad.get());
+			KERNEL_CHECK();
+		}
+		const int b = d2h_scalar(bad.get(), s);
+		if (b == 1) throw std::invalid_argument("a sequence contains bytes outside {A,C,G,T,!}");
+		if (b == 2) throw std::invalid_argument("a sequence is not followed by a zero byte in the device buffer");
+	}
+	anchor_queries_device(c->esa, dQ, c->qi, (int32_t)thr, opt, s, c->anchors, &st);
+	record_anchor_stats(c, st);
+
+	// reference-coordinate rows for the all-pairs stage
+	WallTimer wt(s);
+	const uint64_t total = c->rows_total ? c->rows_total : N;
+	const uint64_t first = c->rows_total ? c->rows_first : 0;
+	if (first + N > total) throw std::invalid_argument("rows: first_row + N exceeds total_genomes");
+	if ((uint64_t)c->rows.genomes != total || c->rows.n != c->esa.n) rows_alloc(c->rows, (int64_t)total, c->esa.n, s);
+	if (N) {
+		CUDA_CHECK(cudaMemcpyAsync(d_qi.get(), c->qi.data(), N * sizeof(QueryInfo), cudaMemcpyHostToDevice, s));
+		rows_build(c->rows, (int64_t)first, dQ, d_qi.get(), (int32_t)N, c->anchors.homs.get(), c->anchors.d_offs.get(), s);
+	}
+	c->stats["rows.ms"] = wt.stop();
+	c->mapped = true;
+}
+
+void do_compare(phylo_ctx *c, int flags, int rank, int world, unsigned long long *d_subst,
+                unsigned long long *d_hom)
+{
+	if (!c->mapped) throw std::invalid_argument("phylo_map_queries has not been called");
+	if (world < 1 || rank < 0 || rank >= world) throw std::invalid_argument("bad tile rank/world");
+	const uint64_t total = c->rows_total ? c->rows_total : c->N;
+	WallTimer wt(c->stream);
+	compare_all_device(c->rows, (int64_t)total, (flags & PHYLO_FLAG_COMPLETE_DELETION) != 0, rank, world, d_subst, d_hom,
+	                   c->stream);
+	c->stats["compare.ms"] = wt.stop();
+	c->matN = total;
+}
+
+void ensure_matrix(phylo_ctx *c, uint64_t total)
+{
+	if (c->d_subst.size() != total * total) {
+		c->d_subst.alloc((size_t)(total * total), c->stream);
+		c->d_hom.alloc((size_t)(total * total), c->stream);
+	}
+}
+
+} // namespace
+
+extern "C" {
+
+const char *phylo_version(void)
+{
+	return "phylonium_b200 0.1 (pipeline of phylonium 1.7)";
+}
+
+int phylo_ctx_create(int device, phylo_ctx **out)
+{
+	if (!out) return fail(nullptr, PHYLO_ERR_INVALID, "out is NULL");
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0) {
+		cudaGetLastError();
+		return fail(nullptr, PHYLO_ERR_CUDA,
+		            std::string("no usable CUDA device (this library has no CPU path): ") +
+		                (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+	}
+	if (device < 0) {
+		e = cudaGetDevice(&device);
+		if (e != cudaSuccess) return fail(nullptr, PHYLO_ERR_CUDA, cudaGetErrorString(e));
+	}
+	if (device >= count) return fail(nullptr, PHYLO_ERR_INVALID, "device ordinal out of range");
+	e = cudaSetDevice(device);
+	if (e != cudaSuccess) return fail(nullptr, PHYLO_ERR_CUDA, cudaGetErrorString(e));
+	auto *c = new phylo_ctx;
+	c->device = device;
+	e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+	if (e != cudaSuccess) {
+		delete c;
+		return fail(nullptr, PHYLO_ERR_CUDA, cudaGetErrorString(e));
+	}
+	// keep freed temporaries in the pool instead of returning them to the driver
+	cudaMemPool_t pool;
+	if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+		uint64_t keep = ~0ull;
+		cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+	}
+	*out = c;
+	return PHYLO_OK;
+}
+
+void phylo_ctx_destroy(phylo_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	c->esa.release();
+	c->q_own.release();
+	c->anchors.homs.release();
+	c->anchors.raw.release();
+	c->anchors.d_offs.release();
+	c->rows.data.release();
+	c->d_subst.release();
+	c->d_hom.release();
+	cudaStreamSynchronize(c->stream);
+	cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+const char *phylo_last_error(const phylo_ctx *c)
+{
+	return c ? c->err.c_str() : g_create_error.c_str();
+}
+
+int phylo_set_option(phylo_ctx *c, const char *key, int64_t value)
+{
+	return guarded(c, [&] {
+		const std::string k = key ? key : "";
+		if (k == "chunk") {
+			if (value < 32 || value > (1 << 24)) throw std::invalid_argument("chunk must be in [32, 2^24]");
+			c->opt_chunk = value;
+		} else if (k == "cap") {
+			if (value < 0) throw std::invalid_argument("cap must be >= 0");
+			c->opt_cap = value;
+		} else if (k == "kmer_k") {
+			if (value < -1 || value > 12) throw std::invalid_argument("kmer_k must be in [-1, 12]");
+			c->opt_kmer = value;
+		} else if (k == "keep_raw") {
+			c->keep_raw = value != 0;
+		} else if (k == "timings") {
+			c->timings = value != 0;
+		} else {
+			throw std::invalid_argument("unknown option: " + k);
+		}
+	});
+}
+
+int phylo_get_stat(const phylo_ctx *c, const char *key, double *out)
+{
+	if (!c || !key || !out) return PHYLO_ERR_INVALID;
+	auto it = c->stats.find(key);
+	*out = it == c->stats.end() ? -1.0 : it->second;
+	return PHYLO_OK;
+}
+
+/* src/sequence.cxx:152-165: a byte counts as G or C iff it has both bits of 'G' & 'C' */
+double phylo_gc_content(const char *seq, uint64_t n)
+{
+	uint64_t gc = 0;
+	for (uint64_t i = 0; i < n; i++)
+		gc += ((seq[i] & 'G' & 'C') == ('G' & 'C'));
+	return (double)gc / (double)n;
+}
+
+namespace
+{
+/* src/process.cxx:103-125 */
+uint64_t binomial(uint64_t n, uint64_t k)
+{
+	if (n == 0 || k > n) return 0;
+	if (k == 0 || k == n) return 1;
+	if (k > n - k) k = n - k;
+	uint64_t r = 1;
+	for (uint64_t i = 1; i <= k; i++) {
+		r *= n - k + i;
+		r /= i;
+	}
+	return r;
+}
+
+/* src/process.cxx:140-161, same operation order so the doubles agree bit for bit */
+double shuprop(uint64_t x, double p, uint64_t l)
+{
+	const double xx = (double)x, ll = (double)l;
+	double s = 0.0;
+	for (uint64_t k = 0; k <= x; k++) {
+		const double kk = (double)k;
+		const double t = pow(p, kk) * pow(0.5 - p, xx - kk);
+		s += pow(2, xx) * (t * pow(1 - t, ll)) * (double)binomial(x, k);
+		if (s >= 1.0) {
+			s = 1.0;
+			break;
+		}
+	}
+	return s;
+}
+} // namespace
+
+uint64_t phylo_min_anchor_length(double p, double gc, uint64_t l)
+{
+	uint64_t x = 1;
+	while (shuprop(x, gc / 2, l) < 1 - p)
+		x++;
+	return x;
+}
+
+int phylo_esa_build(phylo_ctx *c, const char *ref, uint64_t n)
+{
+	return guarded(c, [&] {
+		if (!ref) throw std::invalid_argument("ref is NULL");
+		if (n < 1 || n > 0x3fffffffull) throw std::invalid_argument("reference length must be in [1, 2^30)");
+		DevBuf<uint8_t> d(n, c->stream);
+		CUDA_CHECK(cudaMemcpyAsync(d.get(), ref, n, cudaMemcpyHostToDevice, c->stream));
+		do_esa_build(c, d.get(), n);
+	});
+}
+
+int phylo_esa_build_dev(phylo_ctx *c, const void *d_ref, uint64_t n)
+{
+	return guarded(c, [&] {
+		if (!d_ref) throw std::invalid_argument("d_ref is NULL");
+		do_esa_build(c, (const uint8_t *)d_ref, n);
+	});
+}
+
+int phylo_esa_size(const phylo_ctx *c, uint64_t *m)
+{
+	if (!c || !m) return PHYLO_ERR_INVALID;
+	*m = (uint64_t)c->esa.m;
+	return PHYLO_OK;
+}
+
+int phylo_esa_get_arrays(const phylo_ctx *cc, int64_t *SA, int64_t *LCP, int64_t *CLD, char *FVC, char *S)
+{
+	auto *c = const_cast<phylo_ctx *>(cc);
+	return guarded(c, [&] {
+		if (!c->esa_ready) throw std::invalid_argument("no index");
+		const size_t m = (size_t)c->esa.m;
+		cudaStream_t s = c->stream;
+		std::vector<int32_t> tmp(m + 1);
+		auto fetch = [&](const int32_t *d, size_t cnt, int64_t *dst) {
+			CUDA_CHECK(cudaMemcpyAsync(tmp.data(), d, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+			CUDA_CHECK(cudaStreamSynchronize(s));
+			for (size_t i = 0; i < cnt; i++)
+				dst[i] = tmp[i];
+		};
+		if (SA) fetch(c->esa.SA.get(), m, SA);
+		if (LCP) fetch(c->esa.LCP.get(), m + 1, LCP);
+		if (CLD) fetch(c->esa.CLD.get(), m + 1, CLD);
+		if (FVC) CUDA_CHECK(cudaMemcpyAsync(FVC, c->esa.FVC.get(), m, cudaMemcpyDeviceToHost, s));
+		if (S) CUDA_CHECK(cudaMemcpyAsync(S, c->esa.S.get(), m, cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaStreamSynchronize(s));
+	});
+}
+
+int phylo_esa_get_matches(phylo_ctx *c, const char *text, const uint64_t *offs, const uint64_t *lens, uint64_t count,
+                          int use_table, int64_t *out)
+{
+	return guarded(c, [&] {
+		if (!c->esa_ready) throw std::invalid_argument("no index");
+		if (!count) return;
+		if (!text || !offs || !lens || !out) throw std::invalid_argument("NULL argument");
+		uint64_t extent = 0;
+		for (uint64_t k = 0; k < count; k++) {
+			if (lens[k] > 0x7fffff00ull) throw std::invalid_argument("string too long");
+			extent = std::max(extent, offs[k] + lens[k]);
+		}
+		cudaStream_t s = c->stream;
+		DevBuf<uint8_t> d_text(extent + 64, s);
+		d_text.zero();
+		DevBuf<uint64_t> d_offs(count, s), d_lens(count, s);
+		DevBuf<int64_t> d_out(3 * count, s);
+		CUDA_CHECK(cudaMemcpyAsync(d_text.get(), text, extent, cudaMemcpyHostToDevice, s));
+		CUDA_CHECK(cudaMemcpyAsync(d_offs.get(), offs, count * 8, cudaMemcpyHostToDevice, s));
+		CUDA_CHECK(cudaMemcpyAsync(d_lens.get(), lens, count * 8, cudaMemcpyHostToDevice, s));
+		k_get_matches<<<div_up((int64_t)count, 64), 64, 0, s>>>(c->esa.view(), d_text.get(), d_offs.get(), d_lens.get(),
+		                                                       count, use_table, d_out.get());
+		KERNEL_CHECK();
+		CUDA_CHECK(cudaMemcpyAsync(out, d_out.get(), 3 * count * 8, cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaStreamSynchronize(s));
+	});
+}
+
+int phylo_map_queries(phylo_ctx *c, const char *const *queries, const uint64_t *lens, uint64_t N, uint64_t threshold)
+{
+	return guarded(c, [&] {
+		if (N && (!queries || !lens)) throw std::invalid_argument("NULL argument");
+		std::vector<uint64_t> offs((size_t)N);
+		uint64_t total = 0;
+		for (uint64_t k = 0; k < N; k++) {
+			if (!queries[k] && lens[k]) throw std::invalid_argument("NULL sequence");
+			offs[k] = total;
+			total = (total + lens[k] + 1 + 15) / 16 * 16; // >= 1 zero byte, 16-byte aligned starts
+		}
+		cudaStream_t s = c->stream;
+		c->q_own.alloc(total + 64, s);
+		c->q_own.zero();
+		for (uint64_t k = 0; k < N; k++)
+			if (lens[k])
+				CUDA_CHECK(cudaMemcpyAsync(c->q_own.get() + offs[k], queries[k], lens[k], cudaMemcpyHostToDevice, s));
+		do_map(c, c->q_own.get(), offs.data(), lens, N, threshold);
+	});
+}
+
+int phylo_map_queries_dev(phylo_ctx *c, const void *d_queries, const uint64_t *offs, const uint64_t *lens, uint64_t N,
+                          uint64_t threshold)
+{
+	return guarded(c, [&] {
+		if (N && (!d_queries || !offs || !lens)) throw std::invalid_argument("NULL argument");
+		c->q_own.release();
+		do_map(c, (const uint8_t *)d_queries, offs, lens, N, threshold);
+	});
+}
+
+int phylo_homology_counts(const phylo_ctx *c, uint64_t *counts, int raw)
+{
+	if (!c || !counts) return PHYLO_ERR_INVALID;
+	if (!c->mapped) return PHYLO_ERR_INVALID;
+	const auto &o = raw ? c->anchors.raw_offs : c->anchors.offs;
+	for (uint64_t k = 0; k < c->N; k++)
+		counts[k] = (uint64_t)(o[k + 1] - o[k]);
+	return PHYLO_OK;
+}
+
+int phylo_get_homologies(const phylo_ctx *cc, uint64_t index, int raw, phylo_homology *out, uint64_t cap,
+                         uint64_t *written)
+{
+	auto *c = const_cast<phylo_ctx *>(cc);
+	return guarded(c, [&] {
+		if (!c->mapped) throw std::invalid_argument("phylo_map_queries has not been called");
+		if (index >= c->N) throw std::invalid_argument("sequence index out of range");
+		if (raw && !c->keep_raw) throw std::invalid_argument("raw lists need option keep_raw");
+		const auto &o = raw ? c->anchors.raw_offs : c->anchors.offs;
+		const Hom *src = raw ? c->anchors.raw.get() : c->anchors.homs.get();
+		const uint64_t cnt = (uint64_t)(o[index + 1] - o[index]);
+		if (written) *written = cnt;
+		const uint64_t take = cnt < cap ? cnt : cap;
+		if (!take) return;
+		if (!out) throw std::invalid_argument("out is NULL");
+		std::vector<Hom> h(take);
+		CUDA_CHECK(cudaMemcpyAsync(h.data(), src + o[index], take * sizeof(Hom), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_CHECK(cudaStreamSynchronize(c->stream));
+		for (uint64_t k = 0; k < take; k++) {
+			out[k].direction = h[k].dir;
+			out[k].index_reference = h[k].iref;
+			out[k].index_reference_projected = h[k].iproj;
+			out[k].index_query = h[k].iq;
+			out[k].length = h[k].len;
+		}
+	});
+}
+
+int phylo_compare_all(phylo_ctx *c, int flags, uint64_t *subst, uint64_t *homologs)
+{
+	return guarded(c, [&] {
+		if (!subst || !homologs) throw std::invalid_argument("NULL argument");
+		if (!c->mapped) throw std::invalid_argument("phylo_map_queries has not been called");
+		const uint64_t total = c->rows_total ? c->rows_total : c->N;
+		ensure_matrix(c, total);
+		do_compare(c, flags, 0, 1, c->d_subst.get(), c->d_hom.get());
+		const size_t bytes = (size_t)(total * total) * sizeof(uint64_t);
+		CUDA_CHECK(cudaMemcpyAsync(subst, c->d_subst.get(), bytes, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_CHECK(cudaMemcpyAsync(homologs, c->d_hom.get(), bytes, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_CHECK(cudaStreamSynchronize(c->stream));
+	});
+}
+
+int phylo_compare_all_dev(phylo_ctx *c, int flags, void *d_subst, void *d_homologs)
+{
+	return phylo_compare_tiles_dev(c, flags, 0, 1, d_subst, d_homologs);
+}
+
+int phylo_compare_tiles_dev(phylo_ctx *c, int flags, int rank, int world, void *d_subst, void *d_homologs)
+{
+	return guarded(c, [&] {
+		if (!d_subst || !d_homologs) throw std::invalid_argument("NULL argument");
+		do_compare(c, flags, rank, world, (unsigned long long *)d_subst, (unsigned long long *)d_homologs);
+		const uint64_t total = c->matN;
+		ensure_matrix(c, total);
+		const size_t bytes = (size_t)(total * total) * sizeof(uint64_t);
+		CUDA_CHECK(cudaMemcpyAsync(c->d_subst.get(), d_subst, bytes, cudaMemcpyDeviceToDevice, c->stream));
+		CUDA_CHECK(cudaMemcpyAsync(c->d_hom.get(), d_homologs, bytes, cudaMemcpyDeviceToDevice, c->stream));
+		CUDA_CHECK(cudaStreamSynchronize(c->stream));
+	});
+}
+
+int phylo_estimate(phylo_ctx *c, int kind, double *dist)
+{
+	return guarded(c, [&] {
+		if (!dist) throw std::invalid_argument("dist is NULL");
+		if (!c->matN) throw std::invalid_argument("no matrix yet");
+		if (kind < 0 || kind > 2) throw std::invalid_argument("unknown estimator");
+		const uint64_t n2 = c->matN * c->matN;
+		DevBuf<double> d(n2, c->stream);
+		estimate_device(c->d_subst.get(), c->d_hom.get(), (int64_t)c->matN, kind, d.get(), c->stream);
+		CUDA_CHECK(cudaMemcpyAsync(dist, d.get(), n2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_CHECK(cudaStreamSynchronize(c->stream));
+	});
+}
+
+int phylo_process(phylo_ctx *c, const char *const *seqs, const uint64_t *lens, uint64_t N, uint64_t ref_index, int flags,
+                  uint64_t *subst, uint64_t *homologs)
+{
+	if (!c) return fail(nullptr, PHYLO_ERR_INVALID, "context is NULL");
+	if (!seqs || !lens || ref_index >= N) return fail(c, PHYLO_ERR_INVALID, "bad arguments to phylo_process");
+	int rc = phylo_esa_build(c, seqs[ref_index], lens[ref_index]);
+	if (rc) return rc;
+	// process.cxx:416-417
+	const double gc = phylo_gc_content(seqs[ref_index], lens[ref_index]);
+	const uint64_t thr = phylo_min_anchor_length(0.025, gc, 2 * lens[ref_index] + 1);
+	c->stats["threshold"] = (double)thr;
+	rc = phylo_map_queries(c, seqs, lens, N, thr);
+	if (rc) return rc;
+	return phylo_compare_all(c, flags, subst, homologs);
+}
+
+int phylo_esa_alloc(phylo_ctx *c, uint64_t n)
+{
+	return guarded(c, [&] {
+		if (n < 1 || n > 0x3fffffffull) throw std::invalid_argument("reference length must be in [1, 2^30)");
+		cudaStream_t s = c->stream;
+		c->esa_ready = false;
+		c->mapped = false;
+		c->esa.release();
+		const int32_t m = (int32_t)(2 * n + 1);
+		const int32_t padded = ((m + 64 + 255) / 256) * 256;
+		c->esa.n = (int32_t)n;
+		c->esa.m = m;
+		c->esa.S.alloc(padded, s);
+		c->esa.S.zero();
+		c->esa.SA.alloc(m, s);
+		c->esa.LCP.alloc((size_t)m + 1, s);
+		c->esa.CLD.alloc((size_t)m + 1, s);
+		c->esa.FVC.alloc(m, s);
+		CUDA_CHECK(cudaStreamSynchronize(s));
+	});
+}
+
+int phylo_esa_device_arrays(const phylo_ctx *c, void **S, uint64_t *S_bytes, void **SA, void **LCP, void **CLD,
+                            void **FVC)
+{
+	if (!c || !c->esa.m) return PHYLO_ERR_INVALID;
+	if (S) *S = c->esa.S.get();
+	if (S_bytes) *S_bytes = c->esa.S.size();
+	if (SA) *SA = c->esa.SA.get();
+	if (LCP) *LCP = c->esa.LCP.get();
+	if (CLD) *CLD = c->esa.CLD.get();
+	if (FVC) *FVC = c->esa.FVC.get();
+	return PHYLO_OK;
+}
+
+int phylo_esa_finish_import(phylo_ctx *c)
+{
+	return guarded(c, [&] {
+		if (!c->esa.m) throw std::invalid_argument("phylo_esa_alloc has not been called");
+		esa_build_table(c->esa, (int)c->opt_kmer, c->stream);
+		CUDA_CHECK(cudaStreamSynchronize(c->stream));
+		c->stats["esa.kmer_k"] = c->esa.K;
+		c->esa_ready = true;
+	});
+}
+
+int phylo_rows_configure(phylo_ctx *c, uint64_t total_genomes, uint64_t first_row)
+{
+	return guarded(c, [&] {
+		if (total_genomes && first_row >= total_genomes) throw std::invalid_argument("first_row out of range");
+		c->rows_total = total_genomes;
+		c->rows_first = first_row;
+		if (total_genomes && c->esa.m && ((uint64_t)c->rows.genomes != total_genomes || c->rows.n != c->esa.n)) {
+			rows_alloc(c->rows, (int64_t)total_genomes, c->esa.n, c->stream);
+			CUDA_CHECK(cudaStreamSynchronize(c->stream));
+		}
+	});
+}
+
+int phylo_rows_device(const phylo_ctx *c, void **rows, uint64_t *bytes_per_genome, uint64_t *total_genomes)
+{
+	if (!c || !c->rows.data.get()) return PHYLO_ERR_INVALID;
+	if (rows) *rows = c->rows.data.get();
+	if (bytes_per_genome) *bytes_per_genome = (uint64_t)c->rows.genome_words() * sizeof(uint32_t);
+	if (total_genomes) *total_genomes = (uint64_t)c->rows.genomes;
+	return PHYLO_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,48 @@
+// All-pairs comparison on the device (compare.cu): replaces hot loop B of
+// /root/reference/src/process.cxx:524-549 (compare() over all pairs, :566-658, with
+// evo_model::account/account_rev -> seqcmp/revseqcmp) and evo_model's estimators.
+#pragma once
+#include "common.cuh"
+#include "walk.h"
+
+namespace phy
+{
+
+// Reference-coordinate rows, bit-sliced.  For every genome five planes of W 32-bit words
+// (bit b of word w <-> reference column 32 w + b):
+//   V   column covered by one of the genome's (filtered, disjoint) homologies
+//   C0  low  bit of the nucleotide code  (byte & 6) >> 1: A=0 C=1 T=2 G=3, '!'=0;
+//   C1  high bit;  a reverse-strand homology stores code ^ 2, i.e. the complement
+//   D   the covering homology is on the reverse strand
+//   B   the query byte is the contig separator '!'
+// Two genomes differ in a column iff the codes differ, or — same strand only — the '!'
+// flags differ (seqcmp compares bytes, revseqcmp only bits 1-2).
+constexpr int ROW_PLANES = 5;
+enum : int { PL_V = 0, PL_C0 = 1, PL_C1 = 2, PL_D = 3, PL_B = 4 };
+
+struct RowStore {
+	DevBuf<uint32_t> data; // genomes * ROW_PLANES * W
+	int64_t genomes = 0;   // capacity in genomes
+	int64_t W = 0;         // words per plane, multiple of 4
+	int32_t n = 0;         // reference length (columns)
+	uint32_t *row(int64_t g) const { return data.get() + g * ROW_PLANES * W; }
+	int64_t genome_words() const { return ROW_PLANES * W; }
+};
+
+void rows_alloc(RowStore &rs, int64_t genomes, int32_t n, cudaStream_t s);
+
+// rows of `count` genomes (their homology lists in d_homs / d_offs, bases in d_Q / d_qi)
+// written to rs.row(first_row + k)
+void rows_build(RowStore &rs, int64_t first_row, const uint8_t *d_Q, const QueryInfo *d_qi, int32_t count,
+                const Hom *d_homs, const int64_t *d_offs, cudaStream_t s);
+
+// substitutions / homologs (N*N, row-major, symmetric, zero diagonal) for the tile pairs
+// tile_rank, tile_rank + tile_world, … ; the rest of the matrix is left zero.
+void compare_all_device(const RowStore &rs, int64_t N, bool complete_deletion, int tile_rank, int tile_world,
+                        unsigned long long *d_subst, unsigned long long *d_homologs, cudaStream_t s);
+
+// kind 0 raw, 1 Jukes-Cantor, 2 ANI (evo_model.cxx:100-131); diagonal 0
+void estimate_device(const unsigned long long *d_subst, const unsigned long long *d_homologs, int64_t N, int kind,
+                     double *d_out, cudaStream_t s);
+
+} // namespace phy

@@ -1,0 +1,438 @@
+// Enhanced suffix array construction on the GPU.
+//
+// Replaces the single-threaded esa::esa of /root/reference/src/esa.cxx:69-81:
+//   S = R '#' revcomp(R)                                   (esa.cxx:72, sequence.cxx:73-103)
+//   SA   divsufsort64                                      (esa.cxx:73-75, external library)
+//   LCP  PHI/Kasai                                         (esa.cxx:305-347)
+//   CLD  stack child table                                 (esa.cxx:256-298)
+//   FVC  S[SA[i] + LCP[i]]                                 (esa.cxx:239-250)
+//   6-mer interval cache                                   (esa.cxx:90-228)
+//
+// GPU formulation (all streaming except where noted):
+//   1. k_build_text      S and its zero padding.
+//   2. k_make_keys       63-bit key per suffix = its first 21 characters in 3-bit codes
+//                        (end < '!' < '#' < A < C < G < T, i.e. unsigned byte order).
+//   3. radix sort        (key, index) pairs, 8 passes of 8 bits (primitives.cuh).
+//   4. k_keys_to_lcp     neighbours with different keys give LCP (count of equal leading
+//                        codes) and FVC (the next code of the right neighbour) straight
+//                        from the sorted keys — no random access.  Equal keys mark a tie.
+//   5. refinement        only suffixes inside tie groups: prefix doubling on the compacted
+//                        set — key = (group rank, rank of suffix + h), h = 21, 42, 84, … —
+//                        until every group is a singleton; ranks live in an ISA array.
+//                        Random access, but over the tied fraction only.
+//   6. k_tie_lcp         LCP/FVC of the tied neighbours by direct comparison from offset 21.
+//   7. min-pyramid + k_cld   child table from its closed form (cld_search.h).
+//   8. k_table           K-mer table for the descents (esa_search.h).
+#include "cld_search.h"
+#include "esa_device.h"
+#include "esa_search.h"
+#include "primitives.cuh"
+
+#include <vector>
+
+namespace phy
+{
+
+namespace
+{
+
+constexpr int KEY_CHARS = 21;
+constexpr uint64_t KEY_MASK = (1ull << 63) - 1;
+
+// ---------------------------------------------------------------- text
+
+__global__ void k_build_text(const uint8_t *__restrict__ ref, int32_t n, uint8_t *__restrict__ S, int32_t padded,
+                             int *__restrict__ bad)
+{
+	const int32_t m = 2 * n + 1;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += (int64_t)gridDim.x * blockDim.x) {
+		uint8_t c = 0;
+		if (i < n) {
+			c = ref[i];
+			if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == '!')) atomicExch(bad, 1);
+		} else if (i == n) {
+			c = '#';
+		} else if (i < m) {
+			c = ref[2 * (int64_t)n - i]; // S[n+1+k] = comp(R[n-1-k])
+			if (c >= 'A') c ^= (c & 2) ? 4 : 21;
+		}
+		S[i] = c;
+	}
+}
+
+// ---------------------------------------------------------------- keys
+
+constexpr int KEY_THREADS = 256;
+constexpr int KEY_ITEMS = 8;
+constexpr int KEY_TILE = KEY_THREADS * KEY_ITEMS;
+
+__global__ void __launch_bounds__(KEY_THREADS)
+k_make_keys(const uint8_t *__restrict__ S, int32_t m, int32_t padded, uint64_t *__restrict__ keys)
+{
+	__shared__ __align__(16) uint8_t sm[KEY_TILE + 32];
+	const int64_t base = (int64_t)blockIdx.x * KEY_TILE;
+	for (int o = threadIdx.x * 4; o < KEY_TILE + 32; o += KEY_THREADS * 4) {
+		uint32_t w = 0;
+		if (base + o + 3 < padded) w = *reinterpret_cast<const uint32_t *>(S + base + o);
+		*reinterpret_cast<uint32_t *>(sm + o) = w;
+	}
+	__syncthreads();
+	const int p = threadIdx.x * KEY_ITEMS;
+	uint64_t key = 0;
+#pragma unroll
+	for (int t = 0; t < KEY_CHARS; t++)
+		key = (key << 3) | text_code(sm[p + t]);
+	uint64_t out[KEY_ITEMS];
+	out[0] = key;
+#pragma unroll
+	for (int k = 1; k < KEY_ITEMS; k++) {
+		key = ((key << 3) & KEY_MASK) | text_code(sm[p + k + KEY_CHARS - 1]);
+		out[k] = key;
+	}
+	const int64_t i0 = base + p;
+	if (i0 + KEY_ITEMS <= m) {
+		ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(keys + i0);
+#pragma unroll
+		for (int k = 0; k < KEY_ITEMS; k += 2)
+			dst[k / 2] = make_ulonglong2(out[k], out[k + 1]);
+	} else {
+		for (int k = 0; k < KEY_ITEMS; k++)
+			if (i0 + k < m) keys[i0 + k] = out[k];
+	}
+}
+
+// ---------------------------------------------------------------- LCP / FVC from sorted keys
+
+constexpr int32_t LCP_TIE = -2;
+
+__global__ void k_keys_to_lcp(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ sa,
+                              const uint8_t *__restrict__ S, int32_t m, int32_t *__restrict__ SA,
+                              int32_t *__restrict__ LCP, uint8_t *__restrict__ FVC)
+{
+	const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= m) return;
+	const uint64_t key = keys[j];
+	const uint32_t pos = sa[j];
+	SA[j] = (int32_t)pos;
+	if (j == 0) {
+		LCP[0] = -1; // esa.cxx:313-314
+		LCP[m] = -1;
+		FVC[0] = pos > 0 ? S[pos - 1] : 0; // esa.cxx:247-248 reads S[SA[0] + LCP[0]] with LCP[0] = -1
+		return;
+	}
+	const uint64_t x = key ^ keys[j - 1];
+	if (x == 0) {
+		LCP[j] = LCP_TIE;
+		return;
+	}
+	const int l = (__clzll((long long)x) - 1) / 3; // equal leading 3-bit codes
+	LCP[j] = l;
+	FVC[j] = text_char((uint32_t)(key >> (3 * (KEY_CHARS - 1 - l))) & 7u);
+}
+
+// ---------------------------------------------------------------- refinement helpers
+
+__global__ void k_gather_refine_keys(const uint32_t *__restrict__ sa_c, const uint32_t *__restrict__ grank_c,
+                                     const int32_t *__restrict__ ISA, int32_t m, int32_t h, int shift, uint32_t count,
+                                     uint64_t *__restrict__ keys_c)
+{
+	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= count) return;
+	const int64_t nxt = (int64_t)sa_c[r] + h;
+	const uint64_t k2 = nxt < m ? (uint64_t)ISA[nxt] + 1 : 0; // a suffix that ends sorts first
+	keys_c[r] = ((uint64_t)grank_c[r] << shift) | k2;
+}
+
+__global__ void k_tie_lcp(const uint32_t *__restrict__ slots, uint32_t count, const int32_t *__restrict__ SA,
+                          const uint8_t *__restrict__ S, int32_t *__restrict__ LCP, uint8_t *__restrict__ FVC)
+{
+	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= count) return;
+	const uint32_t j = slots[r];
+	if (LCP[j] != LCP_TIE) return; // group head: its LCP came from the keys
+	const uint8_t *a = S + SA[j - 1];
+	const uint8_t *b = S + SA[j];
+	int32_t l = KEY_CHARS;
+	// S is followed by zeros; two different suffixes never reach them at the same offset
+	while (a[l] == b[l])
+		l++;
+	LCP[j] = l;
+	FVC[j] = b[l];
+}
+
+// ---------------------------------------------------------------- CLD
+
+__global__ void k_pyramid_level(const int32_t *__restrict__ in, int32_t n_in, int32_t *__restrict__ out, int32_t n_out)
+{
+	const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (o >= n_out) return;
+	const int64_t b = o * 32;
+	int32_t mn = 0x7fffffff;
+	const int32_t e = (int32_t)((b + 32 < n_in) ? b + 32 : n_in);
+	for (int32_t t = (int32_t)b; t < e; t++)
+		mn = min(mn, in[t]);
+	out[o] = mn;
+}
+
+__global__ void k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > m) return;
+	CLD[i] = (i == m) ? 0 : cld_entry(py, (int32_t)i);
+}
+
+// ---------------------------------------------------------------- table
+
+__global__ void k_table(EsaView e, int32_t K, Interval *__restrict__ table)
+{
+	const uint32_t code = blockIdx.x * blockDim.x + threadIdx.x;
+	if (code >= (1u << (2 * K))) return;
+	table[code] = esa_table_entry(e, code, K);
+}
+
+int bits_for(uint64_t v)
+{
+	int b = 0;
+	while ((1ull << b) <= v && b < 63)
+		b++;
+	return b;
+}
+
+struct Timer {
+	cudaEvent_t a, b;
+	cudaStream_t s;
+	explicit Timer(cudaStream_t st) : s(st)
+	{
+		CUDA_CHECK(cudaEventCreate(&a));
+		CUDA_CHECK(cudaEventCreate(&b));
+		CUDA_CHECK(cudaEventRecord(a, s));
+	}
+	float lap()
+	{
+		CUDA_CHECK(cudaEventRecord(b, s));
+		CUDA_CHECK(cudaEventSynchronize(b));
+		float ms = 0;
+		CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+		CUDA_CHECK(cudaEventRecord(a, s));
+		return ms;
+	}
+	~Timer()
+	{
+		cudaEventDestroy(a);
+		cudaEventDestroy(b);
+	}
+};
+
+} // namespace
+
+int esa_default_k(int32_t m)
+{
+	// about one table record per 4..16 suffixes; 4^K records of 16 bytes
+	int k = 1;
+	while (k < 12 && (1ll << (2 * (k + 1))) * 4 <= (int64_t)m)
+		k++;
+	return k;
+}
+
+void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t s)
+{
+	int K = kmer_k < 0 ? esa_default_k(esa.m) : kmer_k;
+	if (K > 12) K = 12;
+	esa.K = 0;
+	esa.table.release();
+	if (K <= 0) return;
+	const uint32_t entries = 1u << (2 * K);
+	esa.table.alloc(entries, s);
+	EsaView v = esa.view();
+	v.K = 0;
+	k_table<<<div_up(entries, 128), 128, 0, s>>>(v, K, esa.table.get());
+	KERNEL_CHECK();
+	esa.K = K;
+}
+
+void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k, cudaStream_t s, EsaTimings *tm)
+{
+	if (n < 1) throw std::invalid_argument("reference is empty");
+	if ((int64_t)n * 2 + 1 > 0x7fffffffll - 128) throw std::invalid_argument("reference too long for 32-bit indices");
+	const int32_t m = 2 * n + 1;
+	const int32_t padded = ((m + 64 + 255) / 256) * 256;
+	EsaTimings local;
+	EsaTimings &T = tm ? *tm : local;
+	T = EsaTimings();
+	Timer total(s);
+	Timer lap(s);
+
+	esa.release();
+	esa.n = n;
+	esa.m = m;
+	esa.S.alloc(padded, s);
+	esa.SA.alloc(m, s);
+	esa.LCP.alloc((size_t)m + 1, s);
+	esa.CLD.alloc((size_t)m + 1, s);
+	esa.FVC.alloc(m, s);
+
+	// 1. text
+	DevBuf<int> bad(1, s);
+	bad.zero();
+	k_build_text<<<NUM_SMS_B200 * 8, 256, 0, s>>>(d_ref, n, esa.S.get(), padded, bad.get());
+	KERNEL_CHECK();
+	if (d2h_scalar(bad.get(), s)) throw std::invalid_argument("reference contains bytes outside {A,C,G,T,!}");
+	T.text_ms = lap.lap();
+
+	{
+		// 2. keys, 3. sort
+		DevBuf<uint64_t> keys(m, s), keys_alt(m, s);
+		DevBuf<uint32_t> vals(m, s), vals_alt(m, s);
+		k_make_keys<<<div_up(m, KEY_TILE), KEY_THREADS, 0, s>>>(esa.S.get(), m, padded, keys.get());
+		KERNEL_CHECK();
+		T.keys_ms = lap.lap();
+		const bool flipped =
+			radix_sort_pairs(keys.get(), vals.get(), keys_alt.get(), vals_alt.get(), m, 0, 63, true, s);
+		const uint64_t *K1 = flipped ? keys_alt.get() : keys.get();
+		const uint32_t *V1 = flipped ? vals_alt.get() : vals.get();
+		T.sort_ms = lap.lap();
+
+		// 4. LCP/FVC from neighbouring keys; SA in its final place for all untied suffixes
+		k_keys_to_lcp<<<div_up(m, 256), 256, 0, s>>>(K1, V1, esa.S.get(), m, esa.SA.get(), esa.LCP.get(),
+		                                             esa.FVC.get());
+		KERNEL_CHECK();
+
+		// 5. refinement of tie groups
+		const int32_t *LCP = esa.LCP.get();
+		DevBuf<uint32_t> d_count(1, s);
+		DevBuf<uint32_t> slots0, slots, sa_c, grank_c;
+		uint32_t count = 0;
+		{
+			// first a count, then buffers of the right size
+			auto tied = [LCP, m] __device__(int64_t j) {
+				return LCP[j] == LCP_TIE || (j + 1 < m && LCP[j + 1] == LCP_TIE);
+			};
+			device_select(m, tied, [] __device__(int64_t, uint32_t) {}, d_count.get(), s);
+			count = d2h_scalar(d_count.get(), s);
+			T.tied = count;
+			if (count) {
+				slots0.alloc(count, s);
+				sa_c.alloc(count, s);
+				uint32_t *sl = slots0.get(), *sc = sa_c.get();
+				device_select(
+					m, tied,
+					[sl, sc, V1] __device__(int64_t j, uint32_t r) {
+						sl[r] = (uint32_t)j;
+						sc[r] = V1[j];
+					},
+					d_count.get(), s);
+			}
+		}
+		T.lcp_ms = lap.lap();
+		if (count) {
+			// ISA[SA[j]] = index of the first member of j's group (ties share a rank)
+			DevBuf<int32_t> ISA(m, s);
+			{
+				int32_t *isa = ISA.get();
+				device_scan<int32_t>(
+					m, [LCP] __device__(int64_t j) { return LCP[j] == LCP_TIE ? 0 : (int32_t)j; },
+					[isa, V1] __device__(int64_t j, int32_t head) { isa[V1[j]] = head; }, OpMax(), 0, true, s);
+			}
+			grank_c.alloc(count, s);
+			{
+				uint32_t *gr = grank_c.get();
+				const uint32_t *sc = sa_c.get();
+				const int32_t *isa = ISA.get();
+				device_for(count, [gr, sc, isa] __device__(int64_t r) { gr[r] = (uint32_t)isa[sc[r]]; }, s);
+			}
+			slots.alloc(count, s);
+			CUDA_CHECK(cudaMemcpyAsync(slots.get(), slots0.get(), count * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+			const uint32_t count0 = count;
+			const int shift = bits_for((uint64_t)m + 1);
+			const int key_bits = shift + bits_for((uint64_t)m);
+			int64_t h = KEY_CHARS;
+			while (count) {
+				T.refine_rounds++;
+				DevBuf<uint64_t> kc(count, s), kc_alt(count, s);
+				DevBuf<uint32_t> sa_alt(count, s);
+				k_gather_refine_keys<<<div_up(count, 256), 256, 0, s>>>(
+					sa_c.get(), grank_c.get(), ISA.get(), m, (int32_t)(h > 0x7fffffff ? 0x7fffffff : h), shift, count,
+					kc.get());
+				KERNEL_CHECK();
+				const bool fl =
+					radix_sort_pairs(kc.get(), sa_c.get(), kc_alt.get(), sa_alt.get(), count, 0, key_bits, false, s);
+				const uint64_t *ks = fl ? kc_alt.get() : kc.get();
+				const uint32_t *ss = fl ? sa_alt.get() : sa_c.get();
+				// new ranks: slot of the first member of each (group, key2) run
+				int32_t *isa = ISA.get();
+				int32_t *SAo = esa.SA.get();
+				const uint32_t *sl = slots.get();
+				DevBuf<uint32_t> newrank(count, s);
+				uint32_t *nr = newrank.get();
+				device_scan<uint32_t>(
+					count,
+					[ks, sl] __device__(int64_t r) { return (r == 0 || ks[r] != ks[r - 1]) ? sl[r] : 0u; },
+					[isa, SAo, ss, sl, nr] __device__(int64_t r, uint32_t rank) {
+						const uint32_t suf = ss[r];
+						SAo[sl[r]] = (int32_t)suf;
+						isa[suf] = (int32_t)rank;
+						nr[r] = rank;
+					},
+					OpMax(), 0u, true, s);
+				// keep the members of runs that are still longer than one
+				DevBuf<uint32_t> slots_n(count, s), sa_n(count, s), gr_n(count, s);
+				uint32_t *sln = slots_n.get(), *san = sa_n.get(), *grn = gr_n.get();
+				const uint32_t cnt = count;
+				device_select(
+					count,
+					[ks, cnt] __device__(int64_t r) {
+						const bool head = (r == 0 || ks[r] != ks[r - 1]);
+						const bool next_head = (r + 1 == cnt || ks[r + 1] != ks[r]);
+						return !(head && next_head);
+					},
+					[sln, san, grn, sl, ss, nr] __device__(int64_t r, uint32_t w) {
+						sln[w] = sl[r];
+						san[w] = ss[r];
+						grn[w] = nr[r];
+					},
+					d_count.get(), s);
+				count = d2h_scalar(d_count.get(), s);
+				slots.swap(slots_n);
+				sa_c.swap(sa_n);
+				grank_c.swap(gr_n);
+				h *= 2;
+			}
+			T.refine_ms = lap.lap();
+			// 6. LCP/FVC of tied neighbours
+			k_tie_lcp<<<div_up(count0, 128), 128, 0, s>>>(slots0.get(), count0, esa.SA.get(), esa.S.get(),
+			                                              esa.LCP.get(), esa.FVC.get());
+			KERNEL_CHECK();
+			T.lcp_ms += lap.lap();
+		}
+	}
+
+	// 7. child table
+	{
+		Pyramid py;
+		std::vector<DevBuf<int32_t>> levels;
+		py.level[0] = esa.LCP.get();
+		py.size[0] = m + 1;
+		py.levels = 1;
+		while (py.size[py.levels - 1] > 1) {
+			if (py.levels >= PYR_MAX_LEVELS) throw std::runtime_error("pyramid too deep");
+			const int32_t n_in = py.size[py.levels - 1];
+			const int32_t n_out = (n_in + 31) / 32;
+			levels.emplace_back((size_t)n_out, s);
+			k_pyramid_level<<<div_up(n_out, 256), 256, 0, s>>>(py.level[py.levels - 1], n_in, levels.back().get(), n_out);
+			KERNEL_CHECK();
+			py.level[py.levels] = levels.back().get();
+			py.size[py.levels] = n_out;
+			py.levels++;
+		}
+		k_cld<<<div_up((int64_t)m + 1, 256), 256, 0, s>>>(py, m, esa.CLD.get());
+		KERNEL_CHECK();
+		T.cld_ms = lap.lap();
+	}
+
+	// 8. K-mer table
+	esa_build_table(esa, kmer_k, s);
+	T.table_ms = lap.lap();
+	T.total_ms = total.lap();
+}
+
+} // namespace phy

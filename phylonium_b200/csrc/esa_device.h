@@ -1,0 +1,61 @@
+// Device-resident enhanced suffix array and its construction (esa_build.cu).
+// Replaces esa::esa of /root/reference/src/esa.cxx:69-81 (divsufsort64 + init_LCP +
+// init_CLD + init_FVC + init_cache).
+#pragma once
+#include "common.cuh"
+#include "esa_types.h"
+
+namespace phy
+{
+
+struct EsaTimings {
+	float text_ms = 0, keys_ms = 0, sort_ms = 0, refine_ms = 0, lcp_ms = 0, cld_ms = 0, table_ms = 0, total_ms = 0;
+	int refine_rounds = 0;
+	int64_t tied = 0; // suffixes whose first 21 characters were not unique
+};
+
+struct EsaDevice {
+	int32_t n = 0, m = 0, K = 0;
+	DevBuf<uint8_t> S;   // m + 64 bytes, zero padded
+	DevBuf<uint8_t> FVC; // m
+	DevBuf<int32_t> SA;  // m
+	DevBuf<int32_t> LCP; // m + 1
+	DevBuf<int32_t> CLD; // m + 1
+	DevBuf<Interval> table; // 4^K
+	EsaView view() const
+	{
+		EsaView v;
+		v.S = S.get();
+		v.SA = SA.get();
+		v.LCP = LCP.get();
+		v.CLD = CLD.get();
+		v.FVC = FVC.get();
+		v.table = table.get();
+		v.K = K;
+		v.m = m;
+		v.n = n;
+		return v;
+	}
+	void release()
+	{
+		S.release();
+		FVC.release();
+		SA.release();
+		LCP.release();
+		CLD.release();
+		table.release();
+		n = m = K = 0;
+	}
+};
+
+// d_ref: n reference bytes over {A,C,G,T,!} already on the device. Throws CudaError /
+// std::invalid_argument. kmer_k < 0 picks K from m.
+void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k, cudaStream_t stream,
+                      EsaTimings *timings);
+
+// builds only the table (used after importing S/SA/LCP/CLD/FVC from another GPU)
+void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t stream);
+
+int esa_default_k(int32_t m);
+
+} // namespace phy

@@ -1,0 +1,177 @@
+// Longest-match search on the device-resident ESA: the interval descent of
+// /root/reference/src/esa.cxx:361-563 restated for int32 arrays, usable from CUDA
+// kernels and (for the CPU emulation tests) from plain C++.
+//
+// Differences from the reference that do not change results:
+//  * the 6-mer interval cache (src/esa.cxx:90-228) is replaced by a K-mer table,
+//    K chosen from the text length (esa_build.cu), holding for every K-mer the
+//    deepest descent state that needs no character beyond the K-mer. SURVEY.md A.4:
+//    the cache is a pure accelerator; only (l, i == j, SA[i]) are consumed.
+//  * the byte-by-byte extension of a singleton interval can be capped so that very long
+//    matches are finished cooperatively (anchor.cu); the Match then has open != 0.
+#pragma once
+#include "esa_types.h"
+
+namespace phy
+{
+
+PHY_HD Interval esa_root(const EsaView &e)
+{
+	// src/esa.cxx:527-528: m = left_child(m_size) = CLD[m_size - 1]
+	int32_t mr = e.CLD[e.m - 1];
+	return Interval{e.LCP[mr], 0, e.m - 1, mr};
+}
+
+PHY_HD bool interval_empty(const Interval &ij)
+{
+	return ij.i == -1 && ij.j == -1;
+}
+
+// src/esa.cxx:361-427 — child interval of ij whose suffixes continue with character a.
+PHY_HD Interval esa_get_interval(const EsaView &e, Interval ij, uint8_t a)
+{
+	int32_t i = ij.i;
+	const int32_t j = ij.j;
+	if (i == j) {
+		if (e.S[e.SA[i] + ij.l] != a) ij.i = ij.j = -1;
+		return ij;
+	}
+	int32_t m = ij.m;
+	const int32_t l = ij.l;
+	uint8_t c = e.S[e.SA[i] + l];
+	for (;;) {
+		if (c == a) {
+			if (i != m - 1) {
+				int32_t nm = e.CLD[m - 1]; // left_child(m)
+				return Interval{e.LCP[nm], i, m - 1, nm};
+			}
+			return Interval{e.LCP[i], i, i, -1};
+		}
+		if (c > a) break;
+		i = m;
+		if (i == j) break;
+		m = e.CLD[m]; // right_child(m)
+		if (e.LCP[m] != l) break;
+		c = e.FVC[i];
+	}
+	const bool hit = (i != ij.i) ? (e.FVC[i] == a) : (e.S[e.SA[i] + l] == a);
+	if (!hit) {
+		ij.i = ij.j = -1;
+		return ij;
+	}
+	ij.i = i;
+	ij.l = e.LCP[m];
+	ij.m = m;
+	return ij;
+}
+
+// Extension of a singleton: characters [k, …) of the query against S[p + k …).
+// Stops at the first mismatch (the NUL after S counts as one), at qlen, or — still
+// matching — once `cap` characters are verified (open).
+PHY_HD Match esa_extend_singleton(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t k,
+                                  int32_t idx, int32_t cap)
+{
+	const uint8_t *s = e.S + e.SA[idx];
+	const int32_t lim = qlen < cap ? qlen : cap;
+	while (k < lim && s[k] == q[k])
+		k++;
+	Match r;
+	r.l = k;
+	r.i = r.j = idx;
+	r.open = (k >= lim && lim < qlen) ? 1 : 0;
+	return r;
+}
+
+// src/esa.cxx:446-513 — continue a match of q[0..k) that sits in interval ij (k == ij.l
+// for a proper interval, k == number of verified characters for a singleton).
+PHY_HD Match esa_match_from(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t k,
+                            Interval ij, int32_t cap)
+{
+	if (ij.i == ij.j) return esa_extend_singleton(e, q, qlen, k, ij.i, cap);
+	Match res;
+	res.i = ij.i;
+	res.j = ij.j;
+	res.open = 0;
+	do {
+		ij = esa_get_interval(e, ij, q[k]);
+		if (interval_empty(ij)) {
+			res.l = k;
+			return res;
+		}
+		res.i = ij.i;
+		res.j = ij.j;
+		k++; // by definition the k-th letter matched
+		if (ij.i == ij.j) return esa_extend_singleton(e, q, qlen, k, ij.i, cap);
+		const int32_t l = ij.l < qlen ? ij.l : qlen;
+		const uint8_t *s = e.S + e.SA[ij.i];
+		for (; k < l; k++) {
+			if (s[k] != q[k]) {
+				res.l = k;
+				return res;
+			}
+		}
+	} while (k < qlen);
+	res.l = qlen;
+	return res;
+}
+
+// src/esa.cxx:525-531
+PHY_HD Match esa_match_root(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t cap)
+{
+	return esa_match_from(e, q, qlen, 0, esa_root(e), cap);
+}
+
+// src/esa.cxx:542-563 with the K-mer table in the role of the cache
+PHY_HD Match esa_match(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t cap)
+{
+	const int32_t K = e.K;
+	if (K <= 0 || qlen <= K) return esa_match_root(e, q, qlen, cap);
+	uint32_t code = 0;
+	for (int32_t t = 0; t < K; t++) {
+		int c = kmer_code(q[t]);
+		if (c < 0) return esa_match_root(e, q, qlen, cap);
+		code = (code << 2) | (uint32_t)c;
+	}
+	Interval ij = e.table[code];
+	if (ij.i == ij.j) return esa_extend_singleton(e, q, qlen, ij.l, ij.i, cap);
+	int32_t k = ij.l;
+	if (k > K) {
+		// the table verified K characters of this deep interval; finish its label
+		const int32_t l = ij.l < qlen ? ij.l : qlen;
+		const uint8_t *s = e.S + e.SA[ij.i];
+		for (k = K; k < l; k++) {
+			if (s[k] != q[k]) return Match{k, ij.i, ij.j, 0};
+		}
+		if (k >= qlen) return Match{qlen, ij.i, ij.j, 0};
+	}
+	return esa_match_from(e, q, qlen, k, ij, cap);
+}
+
+// One record of the K-mer table: descend on the K characters of `code`, stop before a
+// character beyond the K-mer would be needed. See the header comment.
+PHY_HD Interval esa_table_entry(const EsaView &e, uint32_t code, int32_t K)
+{
+	uint8_t w[16];
+	for (int32_t t = 0; t < K; t++)
+		w[t] = (uint8_t)(0x54474341u >> (8 * ((code >> (2 * (K - 1 - t))) & 3))); // "ACGT"
+	Interval ij = esa_root(e);
+	while (ij.l < K) {
+		Interval nx = esa_get_interval(e, ij, w[ij.l]);
+		if (interval_empty(nx)) break; // resuming repeats the failing step
+		const uint8_t *s = e.S + e.SA[nx.i];
+		int32_t k = ij.l + 1;
+		if (nx.i == nx.j) {
+			while (k < K && s[k] == w[k])
+				k++;
+			return Interval{k, nx.i, nx.i, -1};
+		}
+		const int32_t upto = nx.l < K ? nx.l : K;
+		while (k < upto && s[k] == w[k])
+			k++;
+		if (k < upto) break; // mismatch inside the edge label: resume from the parent
+		ij = nx;             // min(K, nx.l) characters verified
+	}
+	return ij;
+}
+
+} // namespace phy

@@ -1,0 +1,330 @@
+// Device-wide building blocks written for this library: scan, stream compaction and a
+// stable LSD radix sort of (64-bit key, 32-bit value) pairs.  No CUB/Thrust on the path.
+//
+// Radix sort: 8-bit digits.  Each pass is three launches
+//   1. rs_histogram   per-tile digit counts            reads  8 B/element
+//   2. scan           exclusive sum over (digit, tile)  tiny
+//   3. rs_scatter     stable rank inside the tile (warp match_any + per-warp counters),
+//                     exchange through shared memory so that every digit's run leaves the
+//                     SM as one contiguous, coalesced store   reads 12 B, writes 12 B/element
+// HBM-bound: 32 B of traffic per element and pass.
+#pragma once
+#include "common.cuh"
+
+namespace phy
+{
+
+// ----------------------------------------------------------------------------- scan
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_scan_exclusive(T v, Op op, T identity, T *total, T *smem /* 32 */)
+{
+	// exclusive scan of one value per thread over a 256-thread block
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	T inc = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		T o = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= d) inc = op(o, inc);
+	}
+	if (lane == 31) smem[warp] = inc;
+	__syncthreads();
+	if (warp == 0) {
+		T w = lane < (SCAN_THREADS / 32) ? smem[lane] : identity;
+		T winc = w;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			T o = __shfl_up_sync(0xffffffffu, winc, d);
+			if (lane >= d) winc = op(o, winc);
+		}
+		T wexc = __shfl_up_sync(0xffffffffu, winc, 1);
+		if (lane == 0) wexc = identity;
+		if (lane < (SCAN_THREADS / 32)) smem[lane] = wexc;
+		if (lane == (SCAN_THREADS / 32) - 1) smem[16] = winc; // block total
+	}
+	__syncthreads();
+	T exc = __shfl_up_sync(0xffffffffu, inc, 1);
+	if (lane == 0) exc = identity;
+	exc = op(smem[warp], exc);
+	if (total) *total = smem[16];
+	__syncthreads();
+	return exc;
+}
+
+template <typename T, typename InF, typename Op>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(int64_t n, InF in, Op op, T identity, T *block_sums)
+{
+	__shared__ T smem[32];
+	const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+	T acc = identity;
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; k++) {
+		int64_t i = base + k;
+		if (i < n) acc = op(acc, in(i));
+	}
+	T total;
+	block_scan_exclusive(acc, op, identity, &total, smem);
+	if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+template <typename T, typename InF, typename OutF, typename Op>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_apply_kernel(int64_t n, InF in, OutF out, Op op, T identity, const T *block_prefix, bool inclusive)
+{
+	__shared__ T smem[32];
+	const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+	T v[SCAN_ITEMS];
+	T acc = identity;
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; k++) {
+		int64_t i = base + k;
+		v[k] = i < n ? in(i) : identity;
+		acc = op(acc, v[k]);
+	}
+	T exc = block_scan_exclusive(acc, op, identity, (T *)nullptr, smem);
+	T run = op(block_prefix ? block_prefix[blockIdx.x] : identity, exc);
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; k++) {
+		int64_t i = base + k;
+		T incl = op(run, v[k]);
+		if (i < n) out(i, inclusive ? incl : run);
+		run = incl;
+	}
+}
+
+template <typename T> struct ScanPtrIn {
+	const T *p;
+	__device__ __forceinline__ T operator()(int64_t i) const { return p[i]; }
+};
+template <typename T> struct ScanPtrOut {
+	T *p;
+	__device__ __forceinline__ void operator()(int64_t i, T v) const { p[i] = v; }
+};
+
+// out(i, scan value); exclusive: value before element i, inclusive: including it.
+template <typename T, typename InF, typename OutF, typename Op>
+void device_scan(int64_t n, InF in, OutF out, Op op, T identity, bool inclusive, cudaStream_t s)
+{
+	if (n <= 0) return;
+	const int nblocks = div_up(n, SCAN_TILE);
+	if (nblocks == 1) {
+		scan_apply_kernel<T><<<1, SCAN_THREADS, 0, s>>>(n, in, out, op, identity, (const T *)nullptr, inclusive);
+		KERNEL_CHECK();
+		return;
+	}
+	DevBuf<T> sums(nblocks, s);
+	scan_reduce_kernel<T><<<nblocks, SCAN_THREADS, 0, s>>>(n, in, op, identity, sums.get());
+	KERNEL_CHECK();
+	// plain functors here: a lambda would make every recursion level a new instantiation
+	device_scan<T>(nblocks, ScanPtrIn<T>{sums.get()}, ScanPtrOut<T>{sums.get()}, op, identity, false, s);
+	scan_apply_kernel<T><<<nblocks, SCAN_THREADS, 0, s>>>(n, in, out, op, identity, sums.get(), inclusive);
+	KERNEL_CHECK();
+}
+
+struct OpSum {
+	template <typename T> __device__ __forceinline__ T operator()(T a, T b) const { return a + b; }
+};
+struct OpMax {
+	template <typename T> __device__ __forceinline__ T operator()(T a, T b) const { return a > b ? a : b; }
+};
+
+inline void exclusive_sum_u32(const uint32_t *in, uint32_t *out, int64_t n, cudaStream_t s)
+{
+	device_scan<uint32_t>(n, ScanPtrIn<uint32_t>{in}, ScanPtrOut<uint32_t>{out}, OpSum(), 0u, false, s);
+}
+
+template <typename F> __global__ void for_kernel(int64_t n, F f)
+{
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+		f(i);
+}
+
+// f(i) for every i in [0, n)
+template <typename F> void device_for(int64_t n, F f, cudaStream_t s)
+{
+	if (n <= 0) return;
+	int64_t blocks = (n + 255) / 256;
+	if (blocks > NUM_SMS_B200 * 16) blocks = NUM_SMS_B200 * 16;
+	for_kernel<<<(int)blocks, 256, 0, s>>>(n, f);
+	KERNEL_CHECK();
+}
+
+// Stream compaction: for every i with pred(i), call emit(i, rank) with rank = number of
+// selected elements before i.  *d_count receives the total (device pointer).
+template <typename PredF, typename EmitF>
+void device_select(int64_t n, PredF pred, EmitF emit, uint32_t *d_count, cudaStream_t s)
+{
+	if (n <= 0) {
+		CUDA_CHECK(cudaMemsetAsync(d_count, 0, sizeof(uint32_t), s));
+		return;
+	}
+	device_scan<uint32_t>(
+		n, [pred] __device__(int64_t i) { return pred(i) ? 1u : 0u; },
+		[pred, emit, d_count, n] __device__(int64_t i, uint32_t before) {
+			const bool p = pred(i);
+			if (p) emit(i, before);
+			if (i == n - 1) *d_count = before + (p ? 1u : 0u);
+		},
+		OpSum(), 0u, false, s);
+}
+
+// ----------------------------------------------------------------------------- radix sort
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS; // 4096 pairs per tile
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_BINS = 256;
+
+__device__ __forceinline__ uint32_t rs_digit(uint64_t key, int shift)
+{
+	return (uint32_t)(key >> shift) & (RS_BINS - 1);
+}
+
+// counts[d * ntiles + tile]
+static __global__ void __launch_bounds__(RS_THREADS)
+rs_histogram(const uint64_t *__restrict__ keys, int64_t n, int shift, int ntiles, uint32_t *__restrict__ counts)
+{
+	__shared__ uint32_t h[RS_BINS];
+	h[threadIdx.x] = 0;
+	__syncthreads();
+	const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+	const int lane = threadIdx.x & 31;
+#pragma unroll
+	for (int r = 0; r < RS_ITEMS; r++) {
+		const int64_t i = base + r * RS_THREADS + threadIdx.x;
+		const bool valid = i < n;
+		const uint32_t d = valid ? rs_digit(keys[i], shift) : RS_BINS; // invalid lanes group together
+		const uint32_t peers = __match_any_sync(0xffffffffu, d);
+		if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&h[d], (uint32_t)__popc(peers));
+	}
+	__syncthreads();
+	counts[(int64_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+}
+
+struct RsSmem {
+	uint64_t keys[RS_TILE];
+	uint32_t vals[RS_TILE];
+	uint32_t warp_cnt[RS_WARPS][RS_BINS]; // per-warp digit counts, then per-warp offsets
+	uint32_t tile_start[RS_BINS];         // exclusive scan of the tile's digit counts
+	uint32_t gbase[RS_BINS];              // global output offset of (digit, this tile)
+	uint32_t scan_tmp[32];
+};
+
+// offsets[d * ntiles + tile] = exclusive scan of counts. vals_in == nullptr: value = index.
+static __global__ void __launch_bounds__(RS_THREADS)
+rs_scatter(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint64_t *__restrict__ keys_out,
+           uint32_t *__restrict__ vals_out, int64_t n, int shift, int ntiles, const uint32_t *__restrict__ offsets)
+{
+	extern __shared__ __align__(16) unsigned char rs_smem_raw[];
+	RsSmem &sm = *reinterpret_cast<RsSmem *>(rs_smem_raw);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int64_t tile_base = (int64_t)blockIdx.x * RS_TILE;
+	const int64_t remaining = n - tile_base;
+	const int nvalid = remaining < RS_TILE ? (int)remaining : RS_TILE;
+
+	for (int b = threadIdx.x; b < RS_WARPS * RS_BINS; b += RS_THREADS)
+		(&sm.warp_cnt[0][0])[b] = 0;
+	sm.gbase[threadIdx.x] = offsets[(int64_t)threadIdx.x * ntiles + blockIdx.x];
+	__syncthreads();
+
+	// warp-striped load: item r of lane l sits at warp_base + r*32 + l (tile order)
+	uint64_t key[RS_ITEMS];
+	uint32_t val[RS_ITEMS];
+	uint32_t rank[RS_ITEMS];
+	const int warp_base = warp * (32 * RS_ITEMS);
+#pragma unroll
+	for (int r = 0; r < RS_ITEMS; r++) {
+		const int t = warp_base + r * 32 + lane;
+		const int64_t i = tile_base + t;
+		if (t < nvalid) {
+			key[r] = keys_in[i];
+			val[r] = vals_in ? vals_in[i] : (uint32_t)i;
+		} else {
+			key[r] = ~0ull; // sorts last inside the tile, never written out
+			val[r] = 0;
+		}
+	}
+	// stable rank of every item among the items of its warp with the same digit
+#pragma unroll
+	for (int r = 0; r < RS_ITEMS; r++) {
+		const uint32_t d = rs_digit(key[r], shift);
+		const uint32_t peers = __match_any_sync(0xffffffffu, d);
+		const uint32_t before = sm.warp_cnt[warp][d];
+		__syncwarp();
+		if (lane == (__ffs(peers) - 1)) sm.warp_cnt[warp][d] = before + __popc(peers);
+		__syncwarp();
+		rank[r] = before + __popc(peers & ((1u << lane) - 1));
+	}
+	__syncthreads();
+	// thread d: turn per-warp counts of digit d into exclusive offsets, get the tile count
+	{
+		const int d = threadIdx.x;
+		uint32_t run = 0;
+#pragma unroll
+		for (int w = 0; w < RS_WARPS; w++) {
+			uint32_t c = sm.warp_cnt[w][d];
+			sm.warp_cnt[w][d] = run;
+			run += c;
+		}
+		uint32_t start = block_scan_exclusive<uint32_t>(run, OpSum(), 0u, (uint32_t *)nullptr, sm.scan_tmp);
+		sm.tile_start[d] = start;
+	}
+	__syncthreads();
+	// exchange: place every pair at its position in the tile's digit-sorted order
+#pragma unroll
+	for (int r = 0; r < RS_ITEMS; r++) {
+		const uint32_t d = rs_digit(key[r], shift);
+		const uint32_t p = sm.tile_start[d] + sm.warp_cnt[warp][d] + rank[r];
+		sm.keys[p] = key[r];
+		sm.vals[p] = val[r];
+	}
+	__syncthreads();
+#pragma unroll
+	for (int r = 0; r < RS_ITEMS; r++) {
+		const int p = r * RS_THREADS + threadIdx.x;
+		if (p < nvalid) {
+			const uint64_t k = sm.keys[p];
+			const uint32_t d = rs_digit(k, shift);
+			const int64_t o = (int64_t)sm.gbase[d] + (p - sm.tile_start[d]);
+			keys_out[o] = k;
+			vals_out[o] = sm.vals[p];
+		}
+	}
+}
+
+// Sorts n pairs by bits [bit_lo, bit_hi) of the key, stable.  Ping-pongs between
+// (keys, vals) and (keys_alt, vals_alt); returns true if the result ended up in the
+// alternate buffers.  vals may be nullptr on input: values start as 0..n-1 and are written
+// to vals_alt/vals from the first pass on (vals must still be a valid buffer then).
+inline bool radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_alt, uint32_t *vals_alt, int64_t n,
+                             int bit_lo, int bit_hi, bool iota_values, cudaStream_t s)
+{
+	if (n <= 0 || bit_hi <= bit_lo) return false;
+	CUDA_CHECK(cudaFuncSetAttribute(rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+	const int ntiles = div_up(n, RS_TILE);
+	DevBuf<uint32_t> counts((size_t)ntiles * RS_BINS, s);
+	bool flipped = false;
+	bool first = true;
+	for (int shift = bit_lo; shift < bit_hi; shift += 8) {
+		const uint64_t *kin = flipped ? keys_alt : keys;
+		const uint32_t *vin = flipped ? vals_alt : vals;
+		uint64_t *kout = flipped ? keys : keys_alt;
+		uint32_t *vout = flipped ? vals : vals_alt;
+		rs_histogram<<<ntiles, RS_THREADS, 0, s>>>(kin, n, shift, ntiles, counts.get());
+		KERNEL_CHECK();
+		exclusive_sum_u32(counts.get(), counts.get(), (int64_t)ntiles * RS_BINS, s);
+		rs_scatter<<<ntiles, RS_THREADS, sizeof(RsSmem), s>>>(kin, (first && iota_values) ? nullptr : vin, kout, vout,
+		                                                      n, shift, ntiles, counts.get());
+		KERNEL_CHECK();
+		flipped = !flipped;
+		first = false;
+	}
+	return flipped;
+}
+
+} // namespace phy

@@ -1,0 +1,233 @@
+"""Parity of the CUDA path with the oracle, through the C ABI (needs a B200).
+
+Bar: bit-exact for SA, LCP, CLD, FVC, longest matches, homology lists (before and after
+sort/filter) and per-pair counts; distances evaluated on the device within 1e-12
+relative (BASELINE.json north_star); PHYLIP text identical."""
+import numpy as np
+import pytest
+
+import datasets
+import oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import phylonium_b200
+
+    return phylonium_b200
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return oracle_lib.best()
+
+
+@pytest.fixture()
+def ctx(pb):
+    c = pb.Context(keep_raw=1)
+    yield c
+    c.close()
+
+
+SETS = sorted(datasets.ALL_SETS)
+
+
+@pytest.mark.parametrize("name", SETS)
+def test_esa_arrays(ctx, oracle, name):
+    ref = datasets.ALL_SETS[name]()[0]
+    ctx.esa_build(ref)
+    got = ctx.esa_arrays()
+    want = oracle.esa(ref).arrays()
+    for k in ("S", "SA", "LCP", "CLD", "FVC"):
+        assert np.array_equal(got[k], want[k]), k
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 1023, 1024, 2047, 2048, 2049, 4095, 4096, 4097, 70001])
+def test_esa_sizes_across_tile_boundaries(ctx, oracle, n):
+    rng = np.random.default_rng(n)
+    ref = datasets.random_dna(rng, n)
+    ctx.esa_build(ref)
+    got = ctx.esa_arrays()
+    want = oracle.esa(ref).arrays()
+    for k in ("SA", "LCP", "CLD", "FVC"):
+        assert np.array_equal(got[k], want[k]), k
+
+
+@pytest.mark.parametrize("ref", [b"A" * 3000, b"AC" * 2500, b"ACGTTGCA" * 700, (b"ACGGTCA" * 50 + b"!") * 9 + b"AC"])
+def test_esa_degenerate_repeats(ctx, oracle, ref):
+    """every suffix ties on its first 21 characters: all work goes through the refinement"""
+    ctx.esa_build(ref)
+    got = ctx.esa_arrays()
+    want = oracle.esa(ref).arrays()
+    for k in ("SA", "LCP", "CLD", "FVC"):
+        assert np.array_equal(got[k], want[k]), k
+    assert ctx.stat("esa.tied") > 0 and ctx.stat("esa.refine_rounds") >= 1
+
+
+@pytest.mark.parametrize("name", ["multi_contig", "repeats", "tiny", "bang_vs_base", "divergent"])
+@pytest.mark.parametrize("K", [-1, 0, 1, 4, 9])
+def test_longest_matches(pb, oracle, name, K):
+    genomes = datasets.ALL_SETS[name]()
+    ref = genomes[0]
+    esa = oracle.esa(ref)
+    with pb.Context(kmer_k=K) as ctx:
+        ctx.esa_build(ref)
+        rng = np.random.default_rng(7)
+        text = b"".join(genomes[1:4]) + b"ACGTAC!GT"
+        pos = np.unique(np.concatenate([rng.integers(0, len(text), size=400), np.arange(max(0, len(text) - 14), len(text))]))
+        lens = np.minimum(rng.integers(1, 4000, size=len(pos)), len(text) - pos)
+        for use_table in (True, False):
+            got = ctx.get_matches(text, pos, lens, use_table)
+            for k in range(len(pos)):
+                want = esa.get_match(text[pos[k] : pos[k] + lens[k]], cached=True)
+                assert tuple(got[k]) == want, (k, pos[k], lens[k])
+
+
+@pytest.mark.parametrize("name", SETS)
+@pytest.mark.parametrize("chunk,cap", [(32, 0), (64, 64), (256, 300), (4096, 0)])
+def test_homologies(pb, oracle, name, chunk, cap):
+    genomes = [g for g in datasets.ALL_SETS[name]() if len(g)]
+    ref = genomes[0]
+    thr = oracle.threshold(ref)
+    assert thr == pb.threshold_for(ref)
+    esa = oracle.esa(ref)
+    with pb.Context(keep_raw=1, chunk=chunk, cap=cap) as ctx:
+        ctx.esa_build(ref)
+        ctx.map_queries(genomes, thr)
+        for k, q in enumerate(genomes):
+            raw = esa.anchor_homologies(thr, q)
+            assert np.array_equal(ctx.homologies(k, raw=True), raw), (k, "raw")
+            assert np.array_equal(ctx.homologies(k), oracle.sort_filter(raw)), (k, "filtered")
+
+
+@pytest.mark.parametrize("thr", [1, 3, 6])
+def test_homologies_low_threshold(pb, oracle, thr):
+    genomes = datasets.divergent_set(seed=21, n=6000, rates=(0.05, 0.15, 0.3))
+    ref = genomes[0]
+    esa = oracle.esa(ref)
+    with pb.Context(keep_raw=1, chunk=64) as ctx:
+        ctx.esa_build(ref)
+        ctx.map_queries(genomes, thr)
+        for k, q in enumerate(genomes):
+            raw = esa.anchor_homologies(thr, q)
+            assert np.array_equal(ctx.homologies(k, raw=True), raw)
+            assert np.array_equal(ctx.homologies(k), oracle.sort_filter(raw))
+
+
+@pytest.mark.parametrize("name", SETS)
+@pytest.mark.parametrize("flags", [0, 4])
+def test_pair_counts_and_matrix(pb, oracle, ctx, name, flags):
+    genomes = [g for g in datasets.ALL_SETS[name]() if len(g)]
+    if flags == 4 and name in ("tiny", "identical_unrelated"):
+        pytest.skip("complete deletion dereferences empty lists in the reference")
+    want = oracle.process(genomes, 0, flags, threads=4)
+    subst, homol = ctx.process(genomes, 0, flags)
+    assert np.array_equal(homol, want["homologs"])
+    assert np.array_equal(subst, want["subst"])
+    names = [f"g{i}" for i in range(len(genomes))]
+    mat = [pb.EvoModel(int(subst[i, j]), int(homol[i, j])) for i in range(len(genomes)) for j in range(len(genomes))]
+    for kind in (0, 1, 2):
+        assert pb.format_matrix(names, mat, kind) == oracle.format_matrix(names, want["subst"], want["homologs"], kind)
+        dev = ctx.estimate(kind)
+        for i in range(len(genomes)):
+            for j in range(len(genomes)):
+                ref_val = 0.0 if i == j else oracle.estimate(want["subst"][i, j], want["homologs"][i, j], kind)
+                if np.isnan(ref_val):
+                    assert np.isnan(dev[i, j])
+                else:
+                    assert abs(dev[i, j] - ref_val) <= 1e-12 * max(1.0, abs(ref_val))  # tolerance of the north star
+
+
+def test_reference_need_not_be_first(pb, oracle, ctx):
+    genomes = datasets.multi_contig_set()
+    for ref_index in (2, 5):
+        want = oracle.process(genomes, ref_index, 0, threads=4)
+        subst, homol = ctx.process(genomes, ref_index, 0)
+        assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
+
+
+def test_many_genomes_tiles(pb, oracle, ctx):
+    """more genomes than one 4x4 tile, odd count: diagonal and ragged tiles"""
+    rng = np.random.default_rng(17)
+    r = datasets.random_dna(rng, 4000)
+    genomes = [r] + [datasets.mutate(rng, r, 0.002 * (k + 1)) for k in range(12)]
+    genomes[5] = datasets.revcomp(genomes[5])
+    genomes[9] = genomes[9][:2000]
+    want = oracle.process(genomes, 0, 0, threads=4)
+    subst, homol = ctx.process(genomes, 0, 0)
+    assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
+    want = oracle.process(genomes, 0, 4, threads=4)
+    subst, homol = ctx.process(genomes, 0, 4)
+    assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
+
+
+def test_config1_simf(pb, oracle, ctx):
+    """BASELINE.json configs[0]: 2 x 100 kbp, d = 0.01, the reference's own CPU-runnable case"""
+    genomes = oracle_lib.port().simf_set(1, 100000, [0.01])
+    want = oracle.process(genomes, 0, 0, threads=2)
+    subst, homol = ctx.process(genomes, 0, 0)
+    assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
+    mat = [pb.EvoModel(int(subst[i, j]), int(homol[i, j])) for i in range(2) for j in range(2)]
+    assert pb.format_matrix(["g0", "g1"], mat) == "2\ng0  0.0000e+00  9.9410e-03\ng1  9.9410e-03  0.0000e+00\n"
+
+
+def test_index_arrays_1mbp(pb, oracle, ctx):
+    genomes = oracle_lib.port().simf_set(5, 1000000, [0.02])
+    ctx.esa_build(genomes[0])
+    got = ctx.esa_arrays()
+    want = oracle.esa(genomes[0]).arrays()
+    for k in ("SA", "LCP", "CLD", "FVC"):
+        assert np.array_equal(got[k], want[k]), k
+
+
+@pytest.mark.slow
+def test_config2_full_size(pb, oracle, ctx):
+    """BASELINE.json configs[1]: 8 x 5 Mbp (simf -s 2, d up to 0.05), full size, every count"""
+    dists = [0.001, 0.002, 0.005, 0.01, 0.02, 0.03, 0.05]
+    genomes = oracle_lib.port().simf_set(2, 5000000, dists)
+    want = oracle.process(genomes, 0, 0, threads=16, timed=True)
+    subst, homol = ctx.process(genomes, 0, 0)
+    assert np.array_equal(homol, want["homologs"])
+    assert np.array_equal(subst, want["subst"])
+    assert np.array_equal(ctx.homology_counts(), want["hom_counts"].astype(np.uint64))
+
+
+def test_properties_without_oracle(pb, ctx):
+    """size-independent properties: symmetric matrix, zero diagonal, identical genomes have
+    distance zero and full coverage, subst <= homologs <= min(lengths)"""
+    rng = np.random.default_rng(3)
+    r = datasets.random_dna(rng, 300000)
+    genomes = [r, r, datasets.mutate(rng, r, 0.01), datasets.revcomp(datasets.mutate(rng, r, 0.03))]
+    subst, homol = ctx.process(genomes, 0, 0)
+    assert np.array_equal(subst, subst.T) and np.array_equal(homol, homol.T)
+    assert not subst.diagonal().any() and not homol.diagonal().any()
+    assert subst[0, 1] == 0 and homol[0, 1] == len(r)
+    assert (subst <= homol).all() and (homol <= len(r)).all()
+    # sortedness / disjointness of every filtered list
+    for k in range(len(genomes)):
+        h = ctx.homologies(k)
+        ends = h["index_reference_projected"] + h["length"]
+        assert (h["index_reference_projected"][1:] >= ends[:-1]).all()
+
+
+def test_error_behaviour(pb):
+    with pb.Context() as ctx:
+        with pytest.raises(pb.PhyloError):
+            ctx.map_queries([b"ACGT"], 5)  # no index yet
+        with pytest.raises(pb.PhyloError):
+            ctx.esa_build(b"")
+        with pytest.raises(pb.PhyloError):
+            ctx.esa_build(b"ACGTNNACGT")
+        ctx.esa_build(b"ACGTACGTTTGACCA")
+        with pytest.raises(pb.PhyloError):
+            ctx.map_queries([b"ACGTXACGT"], 5)
+        with pytest.raises(pb.PhyloError):
+            ctx.map_queries([b"ACGTACGT"], 0)
+        with pytest.raises(pb.PhyloError):
+            ctx.set_option("nonsense", 1)
+        # still usable afterwards
+        ctx.map_queries([b"ACGTACGTTTGACCA", b""], 5)
+        subst, homol = ctx.compare_all()
+        assert homol[0, 1] == 0
