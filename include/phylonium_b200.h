@@ -69,6 +69,11 @@ void phylo_ctx_destroy(phylo_ctx *ctx);
 const char *phylo_last_error(const phylo_ctx *ctx);
 const char *phylo_version(void);
 
+/* Issue all further work of ctx on `stream` (a cudaStream_t of ctx's device, e.g. the
+ * framework's current stream); NULL restores the context's own stream.  The stream must
+ * outlive the buffers allocated while it was set. */
+int phylo_set_stream(phylo_ctx *ctx, void *stream);
+
 /* tuning knobs; results never depend on them (tests sweep them):
  *   "chunk"    bases per speculative walker (default 4096)
  *   "cap"      per-thread comparison cap (default 2 * chunk)

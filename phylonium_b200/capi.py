@@ -35,6 +35,7 @@ SIGNATURES = {
     "phylo_ctx_destroy": (None, [C.c_void_p]),
     "phylo_last_error": (C.c_char_p, [C.c_void_p]),
     "phylo_version": (C.c_char_p, []),
+    "phylo_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "phylo_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "phylo_get_stat": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double)]),
     "phylo_gc_content": (C.c_double, [C.c_char_p, C.c_uint64]),
@@ -149,6 +150,9 @@ class Context:
     def set_option(self, key: str, value: int):
         self._check(self.lib.phylo_set_option(self.h, key.encode(), int(value)))
 
+    def set_stream(self, stream_ptr):
+        self._check(self.lib.phylo_set_stream(self.h, stream_ptr))
+
     def stat(self, key: str) -> float:
         out = C.c_double()
         self._check(self.lib.phylo_get_stat(self.h, key.encode(), C.byref(out)))
@@ -244,6 +248,18 @@ class Context:
         self._check(self.lib.phylo_process(self.h, arr, lens.ctypes.data, N, ref_index, flags, subst.ctypes.data, homol.ctypes.data))
         self.N = N
         return subst, homol
+
+    def process_ptrs(self, ptrs, lens, ref_index: int = 0, flags: int = 0, out=None):
+        """phylo_process on caller-owned host memory (e.g. pinned buffers): ptrs are
+        addresses, out = (subst, homologs) numpy uint64 N x N arrays to fill."""
+        N = len(ptrs)
+        arr = (C.c_char_p * N)(*[C.c_char_p(int(p)) for p in ptrs])
+        lens = np.ascontiguousarray(lens, dtype=np.uint64)
+        if out is None:
+            out = (np.zeros((N, N), np.uint64), np.zeros((N, N), np.uint64))
+        self._check(self.lib.phylo_process(self.h, arr, lens.ctypes.data, N, ref_index, flags, out[0].ctypes.data, out[1].ctypes.data))
+        self.N = N
+        return out
 
     # ---- multi-GPU plumbing ---------------------------------------------------
     def esa_alloc(self, n: int):

@@ -18,7 +18,8 @@ using namespace phy;
 
 struct phylo_ctx {
 	int device = 0;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr;     // the stream all work is issued on
+	cudaStream_t own_stream = nullptr; // created with the context
 	std::string err;
 
 	int64_t opt_chunk = 4096, opt_cap = 0, opt_kmer = -1;
@@ -111,9 +112,14 @@ void record_esa_stats(phylo_ctx *c, const EsaTimings &t)
 	s["esa.cld_ms"] = t.cld_ms;
 	s["esa.table_ms"] = t.table_ms;
 	s["esa.total_ms"] = t.total_ms;
+	s["esa.hist_ms_avg"] = t.hist_ms_avg;
+	s["esa.scan_ms_avg"] = t.scan_ms_avg;
+	s["esa.scatter_ms_avg"] = t.scatter_ms_avg;
+	s["esa.scatter_launches"] = t.sort_passes;
 	s["esa.refine_rounds"] = t.refine_rounds;
 	s["esa.tied"] = (double)t.tied;
 	s["esa.kmer_k"] = c->esa.K;
+	s["esa.gc_count"] = (double)c->esa.gc_count;
 }
 
 void record_anchor_stats(phylo_ctx *c, const AnchorStats &t)
@@ -172,7 +178,7 @@ void do_esa_build(phylo_ctx *c, const uint8_t *d_ref, uint64_t n)
 	c->esa_ready = false;
 	c->mapped = false;
 	EsaTimings t;
-	esa_build_device(c->esa, d_ref, (int32_t)n, (int)c->opt_kmer, c->stream, &t);
+	esa_build_device(c->esa, d_ref, (int32_t)n, (int)c->opt_kmer, c->stream, c->timings ? &t : nullptr);
 	record_esa_stats(c, t);
 	c->esa_ready = true;
 }
@@ -283,11 +289,12 @@ int phylo_ctx_create(int device, phylo_ctx **out)
 	if (e != cudaSuccess) return fail(nullptr, PHYLO_ERR_CUDA, cudaGetErrorString(e));
 	auto *c = new phylo_ctx;
 	c->device = device;
-	e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+	e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
 	if (e != cudaSuccess) {
 		delete c;
 		return fail(nullptr, PHYLO_ERR_CUDA, cudaGetErrorString(e));
 	}
+	c->stream = c->own_stream;
 	// keep freed temporaries in the pool instead of returning them to the driver
 	cudaMemPool_t pool;
 	if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -312,8 +319,16 @@ void phylo_ctx_destroy(phylo_ctx *c)
 	c->d_subst.release();
 	c->d_hom.release();
 	cudaStreamSynchronize(c->stream);
-	cudaStreamDestroy(c->stream);
+	cudaStreamDestroy(c->own_stream);
 	delete c;
+}
+
+int phylo_set_stream(phylo_ctx *c, void *stream)
+{
+	return guarded(c, [&] {
+		CUDA_CHECK(cudaStreamSynchronize(c->stream));
+		c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+	});
 }
 
 const char *phylo_last_error(const phylo_ctx *c)
@@ -347,6 +362,10 @@ int phylo_set_option(phylo_ctx *c, const char *key, int64_t value)
 int phylo_get_stat(const phylo_ctx *c, const char *key, double *out)
 {
 	if (!c || !key || !out) return PHYLO_ERR_INVALID;
+	if (std::string(key) == "launches") {
+		*out = (double)g_kernel_launches; // process-wide count of kernel launches so far
+		return PHYLO_OK;
+	}
 	auto it = c->stats.find(key);
 	*out = it == c->stats.end() ? -1.0 : it->second;
 	return PHYLO_OK;
@@ -604,8 +623,9 @@ int phylo_process(phylo_ctx *c, const char *const *seqs, const uint64_t *lens, u
 	if (!seqs || !lens || ref_index >= N) return fail(c, PHYLO_ERR_INVALID, "bad arguments to phylo_process");
 	int rc = phylo_esa_build(c, seqs[ref_index], lens[ref_index]);
 	if (rc) return rc;
-	// process.cxx:416-417
-	const double gc = phylo_gc_content(seqs[ref_index], lens[ref_index]);
+	// process.cxx:416-417; the G/C count comes out of the text kernel, the division and the
+	// threshold search are the reference's double arithmetic on the host
+	const double gc = (double)c->esa.gc_count / (double)lens[ref_index];
 	const uint64_t thr = phylo_min_anchor_length(0.025, gc, 2 * lens[ref_index] + 1);
 	c->stats["threshold"] = (double)thr;
 	rc = phylo_map_queries(c, seqs, lens, N, thr);

@@ -24,7 +24,14 @@ inline void cuda_check(cudaError_t e, const char *what, const char *file, int li
 }
 
 #define CUDA_CHECK(x) ::phy::cuda_check((x), #x, __FILE__, __LINE__)
-#define KERNEL_CHECK() ::phy::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)
+// every kernel launch of the library goes through KERNEL_CHECK; the count is reported as
+// the "launches" statistic
+inline uint64_t g_kernel_launches = 0;
+#define KERNEL_CHECK()                                                                              \
+	do {                                                                                            \
+		::phy::g_kernel_launches++;                                                                 \
+		::phy::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__);                 \
+	} while (0)
 
 constexpr int NUM_SMS_B200 = 148;
 

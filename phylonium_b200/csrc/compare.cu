@@ -217,6 +217,7 @@ void rows_alloc(RowStore &rs, int64_t genomes, int32_t n, cudaStream_t s)
 	rs.W = (((int64_t)n + 31) / 32 + 3) / 4 * 4;
 	rs.genomes = genomes;
 	rs.data.alloc((size_t)(genomes * ROW_PLANES * rs.W), s);
+	rs.data.zero(); // rows never written (padding genomes of a sharded run) are all-invalid
 }
 
 void rows_build(RowStore &rs, int64_t first_row, const uint8_t *d_Q, const QueryInfo *d_qi, int32_t count,

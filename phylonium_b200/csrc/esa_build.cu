@@ -41,15 +41,18 @@ constexpr uint64_t KEY_MASK = (1ull << 63) - 1;
 
 // ---------------------------------------------------------------- text
 
+// flags[0]: bad byte seen; flags[1]: number of G/C bytes (gc_content, sequence.cxx:152-165)
 __global__ void k_build_text(const uint8_t *__restrict__ ref, int32_t n, uint8_t *__restrict__ S, int32_t padded,
-                             int *__restrict__ bad)
+                             int *__restrict__ flags)
 {
 	const int32_t m = 2 * n + 1;
+	int gc = 0;
 	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += (int64_t)gridDim.x * blockDim.x) {
 		uint8_t c = 0;
 		if (i < n) {
 			c = ref[i];
-			if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == '!')) atomicExch(bad, 1);
+			if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == '!')) atomicExch(flags, 1);
+			gc += ((c & 'G' & 'C') == ('G' & 'C'));
 		} else if (i == n) {
 			c = '#';
 		} else if (i < m) {
@@ -58,6 +61,10 @@ __global__ void k_build_text(const uint8_t *__restrict__ ref, int32_t n, uint8_t
 		}
 		S[i] = c;
 	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1)
+		gc += __shfl_xor_sync(0xffffffffu, gc, d);
+	if ((threadIdx.x & 31) == 0 && gc) atomicAdd(flags + 1, gc);
 }
 
 // ---------------------------------------------------------------- keys
@@ -201,14 +208,17 @@ int bits_for(uint64_t v)
 struct Timer {
 	cudaEvent_t a, b;
 	cudaStream_t s;
-	explicit Timer(cudaStream_t st) : s(st)
+	bool on;
+	Timer(cudaStream_t st, bool enabled) : s(st), on(enabled)
 	{
+		if (!on) return;
 		CUDA_CHECK(cudaEventCreate(&a));
 		CUDA_CHECK(cudaEventCreate(&b));
 		CUDA_CHECK(cudaEventRecord(a, s));
 	}
 	float lap()
 	{
+		if (!on) return 0.f;
 		CUDA_CHECK(cudaEventRecord(b, s));
 		CUDA_CHECK(cudaEventSynchronize(b));
 		float ms = 0;
@@ -218,6 +228,7 @@ struct Timer {
 	}
 	~Timer()
 	{
+		if (!on) return;
 		cudaEventDestroy(a);
 		cudaEventDestroy(b);
 	}
@@ -259,8 +270,8 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 	EsaTimings local;
 	EsaTimings &T = tm ? *tm : local;
 	T = EsaTimings();
-	Timer total(s);
-	Timer lap(s);
+	Timer total(s, tm != nullptr);
+	Timer lap(s, tm != nullptr);
 
 	esa.release();
 	esa.n = n;
@@ -272,11 +283,17 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 	esa.FVC.alloc(m, s);
 
 	// 1. text
-	DevBuf<int> bad(1, s);
+	DevBuf<int> bad(2, s);
 	bad.zero();
 	k_build_text<<<NUM_SMS_B200 * 8, 256, 0, s>>>(d_ref, n, esa.S.get(), padded, bad.get());
 	KERNEL_CHECK();
-	if (d2h_scalar(bad.get(), s)) throw std::invalid_argument("reference contains bytes outside {A,C,G,T,!}");
+	{
+		int h_flags[2];
+		CUDA_CHECK(cudaMemcpyAsync(h_flags, bad.get(), sizeof h_flags, cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaStreamSynchronize(s));
+		if (h_flags[0]) throw std::invalid_argument("reference contains bytes outside {A,C,G,T,!}");
+		esa.gc_count = h_flags[1];
+	}
 	T.text_ms = lap.lap();
 
 	{
@@ -286,8 +303,15 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 		k_make_keys<<<div_up(m, KEY_TILE), KEY_THREADS, 0, s>>>(esa.S.get(), m, padded, keys.get());
 		KERNEL_CHECK();
 		T.keys_ms = lap.lap();
-		const bool flipped =
-			radix_sort_pairs(keys.get(), vals.get(), keys_alt.get(), vals_alt.get(), m, 0, 63, true, s);
+		RsProfile prof;
+		const bool flipped = radix_sort_pairs(keys.get(), vals.get(), keys_alt.get(), vals_alt.get(), m, 0, 63, true, s,
+		                                      tm ? &prof : nullptr);
+		if (tm && prof.passes) {
+			T.sort_passes = prof.passes;
+			T.hist_ms_avg = prof.hist_ms / prof.passes;
+			T.scan_ms_avg = prof.scan_ms / prof.passes;
+			T.scatter_ms_avg = prof.scatter_ms / prof.passes;
+		}
 		const uint64_t *K1 = flipped ? keys_alt.get() : keys.get();
 		const uint32_t *V1 = flipped ? vals_alt.get() : vals.get();
 		T.sort_ms = lap.lap();

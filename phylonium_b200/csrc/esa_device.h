@@ -10,12 +10,15 @@ namespace phy
 
 struct EsaTimings {
 	float text_ms = 0, keys_ms = 0, sort_ms = 0, refine_ms = 0, lcp_ms = 0, cld_ms = 0, table_ms = 0, total_ms = 0;
+	float hist_ms_avg = 0, scan_ms_avg = 0, scatter_ms_avg = 0; // per radix pass of the main sort
+	int sort_passes = 0;
 	int refine_rounds = 0;
 	int64_t tied = 0; // suffixes whose first 21 characters were not unique
 };
 
 struct EsaDevice {
 	int32_t n = 0, m = 0, K = 0;
+	int64_t gc_count = 0; // G/C bytes in the reference (for the anchor threshold)
 	DevBuf<uint8_t> S;   // m + 64 bytes, zero padded
 	DevBuf<uint8_t> FVC; // m
 	DevBuf<int32_t> SA;  // m

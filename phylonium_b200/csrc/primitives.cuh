@@ -11,6 +11,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <vector>
+
 namespace phy
 {
 
@@ -301,8 +303,14 @@ rs_scatter(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ va
 // (keys, vals) and (keys_alt, vals_alt); returns true if the result ended up in the
 // alternate buffers.  vals may be nullptr on input: values start as 0..n-1 and are written
 // to vals_alt/vals from the first pass on (vals must still be a valid buffer then).
+// optional per-kernel timing of a sort (CUDA events on the launching stream)
+struct RsProfile {
+	float hist_ms = 0, scan_ms = 0, scatter_ms = 0;
+	int passes = 0;
+};
+
 inline bool radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_alt, uint32_t *vals_alt, int64_t n,
-                             int bit_lo, int bit_hi, bool iota_values, cudaStream_t s)
+                             int bit_lo, int bit_hi, bool iota_values, cudaStream_t s, RsProfile *prof = nullptr)
 {
 	if (n <= 0 || bit_hi <= bit_lo) return false;
 	CUDA_CHECK(cudaFuncSetAttribute(rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
@@ -310,19 +318,46 @@ inline bool radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_alt,
 	DevBuf<uint32_t> counts((size_t)ntiles * RS_BINS, s);
 	bool flipped = false;
 	bool first = true;
+	std::vector<cudaEvent_t> evs;
+	auto mark = [&] {
+		if (!prof) return;
+		cudaEvent_t e;
+		CUDA_CHECK(cudaEventCreate(&e));
+		CUDA_CHECK(cudaEventRecord(e, s));
+		evs.push_back(e);
+	};
 	for (int shift = bit_lo; shift < bit_hi; shift += 8) {
 		const uint64_t *kin = flipped ? keys_alt : keys;
 		const uint32_t *vin = flipped ? vals_alt : vals;
 		uint64_t *kout = flipped ? keys : keys_alt;
 		uint32_t *vout = flipped ? vals : vals_alt;
+		mark();
 		rs_histogram<<<ntiles, RS_THREADS, 0, s>>>(kin, n, shift, ntiles, counts.get());
 		KERNEL_CHECK();
+		mark();
 		exclusive_sum_u32(counts.get(), counts.get(), (int64_t)ntiles * RS_BINS, s);
+		mark();
 		rs_scatter<<<ntiles, RS_THREADS, sizeof(RsSmem), s>>>(kin, (first && iota_values) ? nullptr : vin, kout, vout,
 		                                                      n, shift, ntiles, counts.get());
 		KERNEL_CHECK();
+		mark();
 		flipped = !flipped;
 		first = false;
+	}
+	if (prof) {
+		CUDA_CHECK(cudaStreamSynchronize(s));
+		for (size_t k = 0; k + 3 < evs.size(); k += 4) {
+			float a = 0, b = 0, c = 0;
+			CUDA_CHECK(cudaEventElapsedTime(&a, evs[k], evs[k + 1]));
+			CUDA_CHECK(cudaEventElapsedTime(&b, evs[k + 1], evs[k + 2]));
+			CUDA_CHECK(cudaEventElapsedTime(&c, evs[k + 2], evs[k + 3]));
+			prof->hist_ms += a;
+			prof->scan_ms += b;
+			prof->scatter_ms += c;
+			prof->passes++;
+		}
+		for (auto e : evs)
+			cudaEventDestroy(e);
 	}
 	return flipped;
 }

@@ -1,0 +1,99 @@
+"""One-process-per-GPU sharding of the pipeline.
+
+  index    built on rank 0, broadcast in place (S, SA, LCP, CLD, FVC = 14 B per suffix);
+           each receiver then builds its descent table locally
+  queries  genome g belongs to rank g // per_rank (contiguous blocks, so that a rank's
+           reference-coordinate rows are one contiguous slice of the row store)
+  rows     all-gather of the bit-plane rows: afterwards every GPU holds all rows
+  matrix   4x4 tile pairs dealt round-robin to ranks; partial N x N count matrices are
+           summed with one all-reduce (every cell is written by exactly one rank)
+
+torch.distributed is plumbing only; the collectives move buffers that live inside the
+phylo contexts (wrapped without copying).  The same helpers run under the gloo backend
+with CPU tensors in the tests.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class ShardPlan:
+    world: int
+    rank: int
+    total: int      # genomes over all ranks
+    per_rank: int   # genomes per rank (the last ranks may hold padding rows)
+    first: int      # global index of this rank's first genome
+    count: int      # genomes this rank really owns
+
+    @property
+    def padded_total(self) -> int:
+        return self.per_rank * self.world
+
+
+def make_plan(total: int, world: int, rank: int) -> ShardPlan:
+    per_rank = (total + world - 1) // world
+    first = min(rank * per_rank, total)
+    count = max(0, min(per_rank, total - first))
+    return ShardPlan(world, rank, total, per_rank, rank * per_rank, count)
+
+
+def owner_of(plan: ShardPlan, genome: int) -> int:
+    return genome // plan.per_rank
+
+
+def tile_pairs_of_rank(n_genomes: int, rank: int, world: int, tile: int = 4) -> List[tuple]:
+    """the (ti, tj) tile pairs rank `rank` computes — same enumeration as k_compare_pairs"""
+    side = (n_genomes + tile - 1) // tile
+    pairs = [(ti, tj) for ti in range(side) for tj in range(ti, side)]
+    return pairs[rank::world]
+
+
+class DeviceBuffer:
+    """A region of device memory owned by a phylo context, viewable as a torch tensor."""
+
+    def __init__(self, ptr: int, nbytes: int, device_index: int):
+        self.ptr, self.nbytes, self.device_index = ptr, nbytes, device_index
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes,),
+            "typestr": "|u1",
+            "data": (ptr, False),
+            "version": 2,
+        }
+
+    def tensor(self) -> torch.Tensor:
+        return torch.as_tensor(self, device=torch.device("cuda", self.device_index))
+
+
+def broadcast_index(ctx, n: int, src: int, rank: int, device_index: int) -> int:
+    """In-place broadcast of the five ESA arrays from `src`; returns the bytes moved."""
+    if rank != src:
+        ctx.esa_alloc(n)
+    moved = 0
+    for name, (ptr, nbytes) in ctx.esa_device_arrays().items():
+        t = DeviceBuffer(ptr, nbytes, device_index).tensor()
+        dist.broadcast(t, src=src)
+        moved += nbytes
+    if rank != src:
+        ctx.esa_finish_import()
+    return moved
+
+
+def allgather_rows(ctx, plan: ShardPlan, device_index: int) -> int:
+    """All-gather of the row store (each rank contributed rows [first, first + per_rank))."""
+    ptr, bytes_per_genome, total = ctx.rows_device()
+    assert total == plan.padded_total
+    store = DeviceBuffer(ptr, bytes_per_genome * total, device_index).tensor()
+    mine = store[plan.first * bytes_per_genome : (plan.first + plan.per_rank) * bytes_per_genome]
+    dist.all_gather_into_tensor(store, mine)
+    return bytes_per_genome * total
+
+
+def reduce_matrix(subst: torch.Tensor, homol: torch.Tensor) -> None:
+    """Sum of the per-rank partial count matrices (int64 views of the uint64 counts)."""
+    dist.all_reduce(subst, op=dist.ReduceOp.SUM)
+    dist.all_reduce(homol, op=dist.ReduceOp.SUM)
