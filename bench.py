@@ -38,11 +38,12 @@ SIMF_SEED = 2
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--length", type=int, default=5_000_000, help="genome length (configs[1]: 5 Mbp)")
     ap.add_argument("--genomes", type=int, default=8, help="genomes per GPU (configs[1]: 8)")
+    ap.add_argument("--chunk", type=int, default=0, help="walker chunk length (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile-pass", action="store_true")
     return ap.parse_args()
@@ -76,8 +77,13 @@ class ClockSampler:
 
     def start(self):
         try:
+            fields = self.FIELDS
+            probe = subprocess.run(["nvidia-smi", f"--query-gpu={fields}", "--format=csv,noheader,nounits", "-i",
+                                    str(self.gpu_index)], capture_output=True, text=True, timeout=20)
+            if probe.returncode != 0 or "not a valid field" in (probe.stdout + probe.stderr).lower():
+                fields = fields.replace("clocks_event_reasons", "clocks_throttle_reasons")
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={fields}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu_index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
@@ -210,6 +216,8 @@ def run_b200(args):
     stream = torch.cuda.current_stream()
     ctx = pb.Context(local_rank)
     ctx.set_stream(stream.cuda_stream)
+    if args.chunk:
+        ctx.set_option("chunk", args.chunk)
     d_subst = torch.zeros(total * total, dtype=torch.int64, device=dev)
     d_homol = torch.zeros(total * total, dtype=torch.int64, device=dev)
     if world > 1:
@@ -245,12 +253,12 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    launches0 = ctx.stat("launches")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    launches0 = ctx.stat("launches")
     step_ms = []
     barrier()
     for _ in range(args.steps):

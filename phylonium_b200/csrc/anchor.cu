@@ -57,11 +57,19 @@ struct Timer {
 
 // ------------------------------------------------------------------ phase 1
 
-__global__ void __launch_bounds__(64) k_walk_chunks(WalkParams P, int *__restrict__ any_open)
+// Walkers are latency-bound pointer chasers that diverge from the first step on.  Threads
+// of one warp that sit at different PCs are serialised (their memory latencies add up),
+// so each walker gets a warp of its own: every walker is then an independent instruction
+// stream and the SM overlaps their latencies (64 walkers per SM).  All 32 lanes execute the
+// walker's scalar logic redundantly (same addresses: broadcast loads, merged stores) and
+// share the byte comparisons, 32 bases per step (match_run<true>).
+constexpr int WALK_WARPS_PER_BLOCK = 4;
+
+__global__ void __launch_bounds__(32 * WALK_WARPS_PER_BLOCK) k_walk_chunks(WalkParams P, int *__restrict__ any_open)
 {
-	const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	const int32_t g = blockIdx.x * WALK_WARPS_PER_BLOCK + (threadIdx.x >> 5);
 	if (g >= P.total_chunks) return;
-	walk_chunk(P, g);
+	walk_chunk<true>(P, g);
 	if (P.rec[g].open) *any_open = 1;
 }
 
@@ -170,12 +178,14 @@ __global__ void k_apply_open(WalkParams P, const int *__restrict__ any_open, con
 
 // ------------------------------------------------------------------ phase 3
 
-__global__ void __launch_bounds__(64) k_bridge(WalkParams P)
+__global__ void __launch_bounds__(32 * WALK_WARPS_PER_BLOCK) k_bridge(WalkParams P)
 {
-	const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	const int32_t g = blockIdx.x * WALK_WARPS_PER_BLOCK + (threadIdx.x >> 5); // one walker per warp
 	if (g >= P.total_chunks) return;
 	ChunkRec &r = P.rec[g];
-	r.link = bridge_walk(P, g, r.exit, 0, r.bridge_ev, P.cap_ev, P.CH, P.CAP);
+	const int32_t link = bridge_walk<true>(P, g, r.exit, 0, r.bridge_ev, P.cap_ev, P.CH, P.CAP);
+	__syncwarp();
+	r.link = link;
 }
 
 // ------------------------------------------------------------------ phase 4
@@ -290,12 +300,14 @@ __global__ void k_query_offsets(const int32_t *__restrict__ qids, int64_t n, int
 	offs[q] = lo;
 }
 
+// overlap[q] == 0: no two neighbours of query q's sorted list overlap, hence no two
+// elements at all — every homology is kept (keep[] is preset to 1) and the DP is skipped.
 __global__ void k_filter(const int64_t *__restrict__ offs, int32_t nq, const int32_t *__restrict__ start,
                          const int32_t *__restrict__ len, int64_t *__restrict__ score, int32_t *__restrict__ pred,
-                         uint8_t *__restrict__ keep)
+                         uint8_t *__restrict__ keep, const int32_t *__restrict__ overlap)
 {
 	const int32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-	if (q >= nq) return;
+	if (q >= nq || !overlap[q]) return;
 	const int64_t o = offs[q];
 	const int32_t h = (int32_t)(offs[q + 1] - o);
 	filter_overlaps_max(start + o, len + o, h, score + o, pred + o, keep + o);
@@ -399,7 +411,7 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	P.chunk_query = d_cq.get();
 
 	// 1. cold walks
-	k_walk_chunks<<<div_up(total_chunks, 64), 64, 0, s>>>(P, flags.get());
+	k_walk_chunks<<<div_up(total_chunks, WALK_WARPS_PER_BLOCK), 32 * WALK_WARPS_PER_BLOCK, 0, s>>>(P, flags.get());
 	KERNEL_CHECK();
 	ST.walk_ms = lap.lap();
 
@@ -417,7 +429,7 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	ST.open_ms = lap.lap();
 
 	// 3. bridges
-	k_bridge<<<div_up(total_chunks, 64), 64, 0, s>>>(P);
+	k_bridge<<<div_up(total_chunks, WALK_WARPS_PER_BLOCK), 32 * WALK_WARPS_PER_BLOCK, 0, s>>>(P);
 	KERNEL_CHECK();
 	ST.bridge_ms = lap.lap();
 
@@ -578,17 +590,25 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 			DevBuf<int32_t> st(n_raw, s), ln(n_raw, s), pred(n_raw, s);
 			DevBuf<int64_t> score(n_raw, s);
 			DevBuf<uint8_t> keep(n_raw, s);
+			DevBuf<int32_t> overlap(nq, s);
+			overlap.zero();
 			{
-				int32_t *ST_ = st.get(), *LN = ln.get();
+				int32_t *ST_ = st.get(), *LN = ln.get(), *OV = overlap.get();
+				uint8_t *KP_ = keep.get();
 				const Hom *R = raw.get();
-				device_for(n_raw, [ST_, LN, R, IS] __device__(int64_t i) {
+				device_for(n_raw, [ST_, LN, KP_, OV, R, IS, KS] __device__(int64_t i) {
 					const Hom h = R[IS[i]];
 					ST_[i] = h.iproj;
 					LN[i] = h.len;
+					KP_[i] = 1;
+					if (i > 0 && (KS[i] >> 32) == (KS[i - 1] >> 32)) {
+						const Hom p = R[IS[i - 1]];
+						if ((int64_t)p.iproj + p.len > h.iproj) OV[KS[i] >> 32] = 1;
+					}
 				}, s);
 			}
 			k_filter<<<div_up(nq, 32), 32, 0, s>>>(d_raw_offs.get(), nq, st.get(), ln.get(), score.get(), pred.get(),
-			                                       keep.get());
+			                                       keep.get(), overlap.get());
 			KERNEL_CHECK();
 			DevBuf<uint32_t> d_n(1, s);
 			const uint8_t *KP = keep.get();

@@ -22,7 +22,7 @@ struct phylo_ctx {
 	cudaStream_t own_stream = nullptr; // created with the context
 	std::string err;
 
-	int64_t opt_chunk = 4096, opt_cap = 0, opt_kmer = -1;
+	int64_t opt_chunk = 4096, opt_cap = 0, opt_kmer = -1, opt_key_chars = 0;
 	bool keep_raw = false, timings = false;
 
 	EsaDevice esa;
@@ -116,6 +116,7 @@ void record_esa_stats(phylo_ctx *c, const EsaTimings &t)
 	s["esa.scan_ms_avg"] = t.scan_ms_avg;
 	s["esa.scatter_ms_avg"] = t.scatter_ms_avg;
 	s["esa.scatter_launches"] = t.sort_passes;
+	s["esa.key_chars"] = t.key_chars;
 	s["esa.refine_rounds"] = t.refine_rounds;
 	s["esa.tied"] = (double)t.tied;
 	s["esa.kmer_k"] = c->esa.K;
@@ -178,7 +179,8 @@ void do_esa_build(phylo_ctx *c, const uint8_t *d_ref, uint64_t n)
 	c->esa_ready = false;
 	c->mapped = false;
 	EsaTimings t;
-	esa_build_device(c->esa, d_ref, (int32_t)n, (int)c->opt_kmer, c->stream, c->timings ? &t : nullptr);
+	t.enabled = c->timings;
+	esa_build_device(c->esa, d_ref, (int32_t)n, (int)c->opt_kmer, (int)c->opt_key_chars, c->stream, &t);
 	record_esa_stats(c, t);
 	c->esa_ready = true;
 }
@@ -349,6 +351,9 @@ int phylo_set_option(phylo_ctx *c, const char *key, int64_t value)
 		} else if (k == "kmer_k") {
 			if (value < -1 || value > 12) throw std::invalid_argument("kmer_k must be in [-1, 12]");
 			c->opt_kmer = value;
+		} else if (k == "key_chars") {
+			if (value < 0 || value > 21) throw std::invalid_argument("key_chars must be in [0, 21]");
+			c->opt_key_chars = value;
 		} else if (k == "keep_raw") {
 			c->keep_raw = value != 0;
 		} else if (k == "timings") {

@@ -36,8 +36,7 @@ namespace phy
 namespace
 {
 
-constexpr int KEY_CHARS = 21;
-constexpr uint64_t KEY_MASK = (1ull << 63) - 1;
+constexpr int KEY_CHARS = 21; // most characters a 63-bit key can hold
 
 // ---------------------------------------------------------------- text
 
@@ -74,8 +73,9 @@ constexpr int KEY_ITEMS = 8;
 constexpr int KEY_TILE = KEY_THREADS * KEY_ITEMS;
 
 __global__ void __launch_bounds__(KEY_THREADS)
-k_make_keys(const uint8_t *__restrict__ S, int32_t m, int32_t padded, uint64_t *__restrict__ keys)
+k_make_keys(const uint8_t *__restrict__ S, int32_t m, int32_t padded, uint64_t *__restrict__ keys, int kc)
 {
+	const uint64_t key_mask = (1ull << (3 * kc)) - 1; // kc <= 21 characters, 3 bits each
 	__shared__ __align__(16) uint8_t sm[KEY_TILE + 32];
 	const int64_t base = (int64_t)blockIdx.x * KEY_TILE;
 	for (int o = threadIdx.x * 4; o < KEY_TILE + 32; o += KEY_THREADS * 4) {
@@ -88,12 +88,12 @@ k_make_keys(const uint8_t *__restrict__ S, int32_t m, int32_t padded, uint64_t *
 	uint64_t key = 0;
 #pragma unroll
 	for (int t = 0; t < KEY_CHARS; t++)
-		key = (key << 3) | text_code(sm[p + t]);
+		if (t < kc) key = (key << 3) | text_code(sm[p + t]);
 	uint64_t out[KEY_ITEMS];
 	out[0] = key;
 #pragma unroll
 	for (int k = 1; k < KEY_ITEMS; k++) {
-		key = ((key << 3) & KEY_MASK) | text_code(sm[p + k + KEY_CHARS - 1]);
+		key = ((key << 3) & key_mask) | text_code(sm[p + k + kc - 1]);
 		out[k] = key;
 	}
 	const int64_t i0 = base + p;
@@ -114,7 +114,7 @@ constexpr int32_t LCP_TIE = -2;
 
 __global__ void k_keys_to_lcp(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ sa,
                               const uint8_t *__restrict__ S, int32_t m, int32_t *__restrict__ SA,
-                              int32_t *__restrict__ LCP, uint8_t *__restrict__ FVC)
+                              int32_t *__restrict__ LCP, uint8_t *__restrict__ FVC, int kc)
 {
 	const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= m) return;
@@ -132,9 +132,10 @@ __global__ void k_keys_to_lcp(const uint64_t *__restrict__ keys, const uint32_t 
 		LCP[j] = LCP_TIE;
 		return;
 	}
-	const int l = (__clzll((long long)x) - 1) / 3; // equal leading 3-bit codes
+	// equal leading 3-bit codes: the key occupies bits [0, 3 kc)
+	const int l = (__clzll((long long)x) - (64 - 3 * kc)) / 3;
 	LCP[j] = l;
-	FVC[j] = text_char((uint32_t)(key >> (3 * (KEY_CHARS - 1 - l))) & 7u);
+	FVC[j] = text_char((uint32_t)(key >> (3 * (kc - 1 - l))) & 7u);
 }
 
 // ---------------------------------------------------------------- refinement helpers
@@ -151,7 +152,7 @@ __global__ void k_gather_refine_keys(const uint32_t *__restrict__ sa_c, const ui
 }
 
 __global__ void k_tie_lcp(const uint32_t *__restrict__ slots, uint32_t count, const int32_t *__restrict__ SA,
-                          const uint8_t *__restrict__ S, int32_t *__restrict__ LCP, uint8_t *__restrict__ FVC)
+                          const uint8_t *__restrict__ S, int32_t *__restrict__ LCP, uint8_t *__restrict__ FVC, int kc)
 {
 	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= count) return;
@@ -159,7 +160,7 @@ __global__ void k_tie_lcp(const uint32_t *__restrict__ slots, uint32_t count, co
 	if (LCP[j] != LCP_TIE) return; // group head: its LCP came from the keys
 	const uint8_t *a = S + SA[j - 1];
 	const uint8_t *b = S + SA[j];
-	int32_t l = KEY_CHARS;
+	int32_t l = kc;
 	// S is followed by zeros; two different suffixes never reach them at the same offset
 	while (a[l] == b[l])
 		l++;
@@ -261,7 +262,20 @@ void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t s)
 	esa.K = K;
 }
 
-void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k, cudaStream_t s, EsaTimings *tm)
+int esa_default_key_chars(int32_t m)
+{
+	// enough characters that ties are rare (4^c >= 16 m), rounded up to whole radix passes
+	int need = 2;
+	while (need < KEY_CHARS && (1ll << (2 * need)) < (int64_t)m)
+		need++;
+	need += 2;
+	const int passes = (3 * need + 7) / 8;
+	const int c = (8 * passes) / 3;
+	return c > KEY_CHARS ? KEY_CHARS : c;
+}
+
+void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k, int key_chars, cudaStream_t s,
+                      EsaTimings *tm)
 {
 	if (n < 1) throw std::invalid_argument("reference is empty");
 	if ((int64_t)n * 2 + 1 > 0x7fffffffll - 128) throw std::invalid_argument("reference too long for 32-bit indices");
@@ -269,9 +283,15 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 	const int32_t padded = ((m + 64 + 255) / 256) * 256;
 	EsaTimings local;
 	EsaTimings &T = tm ? *tm : local;
+	const bool timed = tm && tm->enabled; // event timers synchronise; off unless asked for
 	T = EsaTimings();
-	Timer total(s, tm != nullptr);
-	Timer lap(s, tm != nullptr);
+	T.enabled = timed;
+	Timer total(s, timed);
+	Timer lap(s, timed);
+
+	int kc = key_chars > 0 ? key_chars : esa_default_key_chars(m);
+	if (kc > KEY_CHARS) kc = KEY_CHARS;
+	T.key_chars = kc;
 
 	esa.release();
 	esa.n = n;
@@ -300,13 +320,13 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 		// 2. keys, 3. sort
 		DevBuf<uint64_t> keys(m, s), keys_alt(m, s);
 		DevBuf<uint32_t> vals(m, s), vals_alt(m, s);
-		k_make_keys<<<div_up(m, KEY_TILE), KEY_THREADS, 0, s>>>(esa.S.get(), m, padded, keys.get());
+		k_make_keys<<<div_up(m, KEY_TILE), KEY_THREADS, 0, s>>>(esa.S.get(), m, padded, keys.get(), kc);
 		KERNEL_CHECK();
 		T.keys_ms = lap.lap();
 		RsProfile prof;
-		const bool flipped = radix_sort_pairs(keys.get(), vals.get(), keys_alt.get(), vals_alt.get(), m, 0, 63, true, s,
-		                                      tm ? &prof : nullptr);
-		if (tm && prof.passes) {
+		const bool flipped = radix_sort_pairs(keys.get(), vals.get(), keys_alt.get(), vals_alt.get(), m, 0, 3 * kc, true, s,
+		                                      timed ? &prof : nullptr);
+		if (timed && prof.passes) {
 			T.sort_passes = prof.passes;
 			T.hist_ms_avg = prof.hist_ms / prof.passes;
 			T.scan_ms_avg = prof.scan_ms / prof.passes;
@@ -318,7 +338,7 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 
 		// 4. LCP/FVC from neighbouring keys; SA in its final place for all untied suffixes
 		k_keys_to_lcp<<<div_up(m, 256), 256, 0, s>>>(K1, V1, esa.S.get(), m, esa.SA.get(), esa.LCP.get(),
-		                                             esa.FVC.get());
+		                                             esa.FVC.get(), kc);
 		KERNEL_CHECK();
 
 		// 5. refinement of tie groups
@@ -369,7 +389,7 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 			const uint32_t count0 = count;
 			const int shift = bits_for((uint64_t)m + 1);
 			const int key_bits = shift + bits_for((uint64_t)m);
-			int64_t h = KEY_CHARS;
+			int64_t h = kc;
 			while (count) {
 				T.refine_rounds++;
 				DevBuf<uint64_t> kc(count, s), kc_alt(count, s);
@@ -424,7 +444,7 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 			T.refine_ms = lap.lap();
 			// 6. LCP/FVC of tied neighbours
 			k_tie_lcp<<<div_up(count0, 128), 128, 0, s>>>(slots0.get(), count0, esa.SA.get(), esa.S.get(),
-			                                              esa.LCP.get(), esa.FVC.get());
+			                                              esa.LCP.get(), esa.FVC.get(), kc);
 			KERNEL_CHECK();
 			T.lcp_ms += lap.lap();
 		}

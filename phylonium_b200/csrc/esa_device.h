@@ -9,9 +9,11 @@ namespace phy
 {
 
 struct EsaTimings {
+	bool enabled = false; // in: record per-phase device times (adds synchronisation)
 	float text_ms = 0, keys_ms = 0, sort_ms = 0, refine_ms = 0, lcp_ms = 0, cld_ms = 0, table_ms = 0, total_ms = 0;
 	float hist_ms_avg = 0, scan_ms_avg = 0, scatter_ms_avg = 0; // per radix pass of the main sort
 	int sort_passes = 0;
+	int key_chars = 0; // characters per sort key actually used
 	int refine_rounds = 0;
 	int64_t tied = 0; // suffixes whose first 21 characters were not unique
 };
@@ -53,7 +55,8 @@ struct EsaDevice {
 
 // d_ref: n reference bytes over {A,C,G,T,!} already on the device. Throws CudaError /
 // std::invalid_argument. kmer_k < 0 picks K from m.
-void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k, cudaStream_t stream,
+// key_chars <= 0 picks the number of characters per sort key from m.
+void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k, int key_chars, cudaStream_t stream,
                       EsaTimings *timings);
 
 // builds only the table (used after importing S/SA/LCP/CLD/FVC from another GPU)

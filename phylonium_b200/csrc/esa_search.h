@@ -65,16 +65,39 @@ PHY_HD Interval esa_get_interval(const EsaView &e, Interval ij, uint8_t a)
 	return ij;
 }
 
+// First k in [from, to) with a[k] != b[k], or `to`.
+// COOP = true: called by all 32 lanes of a warp with identical arguments (the walkers of
+// anchor.cu run their scalar logic redundantly on every lane); the lanes then compare 32
+// bytes per step and agree on the result through a ballot.  COOP = false: plain loop.
+template <bool COOP> PHY_HD int32_t match_run(const uint8_t *a, const uint8_t *b, int32_t from, int32_t to)
+{
+#if defined(__CUDA_ARCH__)
+	if (COOP) {
+		const int lane = threadIdx.x & 31;
+		for (int32_t base = from; base < to; base += 32) {
+			const int32_t x = base + lane;
+			const bool miss = x < to && a[x] != b[x];
+			const uint32_t bal = __ballot_sync(0xffffffffu, miss);
+			if (bal) return base + (__ffs(bal) - 1);
+		}
+		return to;
+	}
+#endif
+	int32_t k = from;
+	while (k < to && a[k] == b[k])
+		k++;
+	return k;
+}
+
 // Extension of a singleton: characters [k, …) of the query against S[p + k …).
 // Stops at the first mismatch (the NUL after S counts as one), at qlen, or — still
 // matching — once `cap` characters are verified (open).
-PHY_HD Match esa_extend_singleton(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t k,
-                                  int32_t idx, int32_t cap)
+template <bool COOP = false>
+PHY_HD Match esa_extend_singleton(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t k, int32_t idx, int32_t cap)
 {
 	const uint8_t *s = e.S + e.SA[idx];
 	const int32_t lim = qlen < cap ? qlen : cap;
-	while (k < lim && s[k] == q[k])
-		k++;
+	if (k < lim) k = match_run<COOP>(s, q, k, lim);
 	Match r;
 	r.l = k;
 	r.i = r.j = idx;
@@ -84,10 +107,10 @@ PHY_HD Match esa_extend_singleton(const EsaView &e, const uint8_t *q, int32_t ql
 
 // src/esa.cxx:446-513 — continue a match of q[0..k) that sits in interval ij (k == ij.l
 // for a proper interval, k == number of verified characters for a singleton).
-PHY_HD Match esa_match_from(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t k,
-                            Interval ij, int32_t cap)
+template <bool COOP = false>
+PHY_HD Match esa_match_from(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t k, Interval ij, int32_t cap)
 {
-	if (ij.i == ij.j) return esa_extend_singleton(e, q, qlen, k, ij.i, cap);
+	if (ij.i == ij.j) return esa_extend_singleton<COOP>(e, q, qlen, k, ij.i, cap);
 	Match res;
 	res.i = ij.i;
 	res.j = ij.j;
@@ -101,11 +124,11 @@ PHY_HD Match esa_match_from(const EsaView &e, const uint8_t *q, int32_t qlen, in
 		res.i = ij.i;
 		res.j = ij.j;
 		k++; // by definition the k-th letter matched
-		if (ij.i == ij.j) return esa_extend_singleton(e, q, qlen, k, ij.i, cap);
+		if (ij.i == ij.j) return esa_extend_singleton<COOP>(e, q, qlen, k, ij.i, cap);
 		const int32_t l = ij.l < qlen ? ij.l : qlen;
-		const uint8_t *s = e.S + e.SA[ij.i];
-		for (; k < l; k++) {
-			if (s[k] != q[k]) {
+		if (k < l) {
+			k = match_run<COOP>(e.S + e.SA[ij.i], q, k, l);
+			if (k < l) {
 				res.l = k;
 				return res;
 			}
@@ -116,35 +139,33 @@ PHY_HD Match esa_match_from(const EsaView &e, const uint8_t *q, int32_t qlen, in
 }
 
 // src/esa.cxx:525-531
-PHY_HD Match esa_match_root(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t cap)
+template <bool COOP = false> PHY_HD Match esa_match_root(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t cap)
 {
-	return esa_match_from(e, q, qlen, 0, esa_root(e), cap);
+	return esa_match_from<COOP>(e, q, qlen, 0, esa_root(e), cap);
 }
 
 // src/esa.cxx:542-563 with the K-mer table in the role of the cache
-PHY_HD Match esa_match(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t cap)
+template <bool COOP = false> PHY_HD Match esa_match(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t cap)
 {
 	const int32_t K = e.K;
-	if (K <= 0 || qlen <= K) return esa_match_root(e, q, qlen, cap);
+	if (K <= 0 || qlen <= K) return esa_match_root<COOP>(e, q, qlen, cap);
 	uint32_t code = 0;
 	for (int32_t t = 0; t < K; t++) {
 		int c = kmer_code(q[t]);
-		if (c < 0) return esa_match_root(e, q, qlen, cap);
+		if (c < 0) return esa_match_root<COOP>(e, q, qlen, cap);
 		code = (code << 2) | (uint32_t)c;
 	}
 	Interval ij = e.table[code];
-	if (ij.i == ij.j) return esa_extend_singleton(e, q, qlen, ij.l, ij.i, cap);
+	if (ij.i == ij.j) return esa_extend_singleton<COOP>(e, q, qlen, ij.l, ij.i, cap);
 	int32_t k = ij.l;
 	if (k > K) {
 		// the table verified K characters of this deep interval; finish its label
 		const int32_t l = ij.l < qlen ? ij.l : qlen;
-		const uint8_t *s = e.S + e.SA[ij.i];
-		for (k = K; k < l; k++) {
-			if (s[k] != q[k]) return Match{k, ij.i, ij.j, 0};
-		}
+		k = match_run<COOP>(e.S + e.SA[ij.i], q, K, l);
+		if (k < l) return Match{k, ij.i, ij.j, 0};
 		if (k >= qlen) return Match{qlen, ij.i, ij.j, 0};
 	}
-	return esa_match_from(e, q, qlen, k, ij, cap);
+	return esa_match_from<COOP>(e, q, qlen, k, ij, cap);
 }
 
 // One record of the K-mer table: descend on the K characters of `code`, stop before a

@@ -55,6 +55,8 @@ PHY_HD bool walk_is_dead(const WalkState &st, int32_t thr)
 
 // One iteration of the while loop at process.cxx:245-282, without the homology
 // bookkeeping.  q points at the query's first base.
+// COOP: see match_run in esa_search.h.
+template <bool COOP = false>
 PHY_HD StepOut walk_step(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t thr, int32_t cap,
                          const WalkState &st)
 {
@@ -71,11 +73,7 @@ PHY_HD StepOut walk_step(const EsaView &e, const uint8_t *q, int32_t qlen, int32
 		if (tr < (int64_t)e.m && gap <= thr) {
 			const int32_t limit = qlen - pos;
 			const int32_t lim = limit < cap ? limit : cap;
-			const uint8_t *a = q + pos;
-			const uint8_t *b = e.S + tr;
-			int32_t k = 0;
-			while (k < lim && a[k] == b[k])
-				k++;
+			const int32_t k = match_run<COOP>(q + pos, e.S + tr, 0, lim);
 			o.posS = (int32_t)tr;
 			o.len = k;
 			o.accepted = k >= thr;
@@ -83,7 +81,7 @@ PHY_HD StepOut walk_step(const EsaView &e, const uint8_t *q, int32_t qlen, int32
 		}
 	}
 	if (!o.accepted) { // anchor, process.cxx:219-225
-		Match mt = esa_match(e, q + pos, qlen - pos, cap);
+		Match mt = esa_match<COOP>(e, q + pos, qlen - pos, cap);
 		o.len = mt.l > 0 ? mt.l : 0;
 		o.posS = e.SA[mt.i];
 		o.accepted = (mt.i == mt.j && o.len >= thr);
@@ -151,7 +149,7 @@ struct WalkParams {
 // ---------------------------------------------------------------------------------
 // Phase 1: cold walk of one chunk
 
-PHY_HD void walk_chunk(const WalkParams &P, int32_t g)
+template <bool COOP = false> PHY_HD void walk_chunk(const WalkParams &P, int32_t g)
 {
 	const int32_t qid = P.chunk_query[g];
 	const QueryInfo qi = P.qi[qid];
@@ -180,7 +178,7 @@ PHY_HD void walk_chunk(const WalkParams &P, int32_t g)
 			}
 			cur_bits |= 1u << (rel & 31);
 		}
-		StepOut o = walk_step(P.esa, q, qi.qlen, P.thr, P.CAP, st);
+		StepOut o = walk_step<COOP>(P.esa, q, qi.qlen, P.thr, P.CAP, st);
 		if (o.accepted) {
 			ev[nev].pos = st.pos;
 			ev[nev].posS = o.posS;
@@ -299,6 +297,7 @@ PHY_HD bool dead_visited(const WalkParams &P, int32_t g, int32_t rel)
 // (in query bases); budget < 0 means until merged or the query ends.  `out` receives
 // the accepted anchors (at most out_cap); cap is the comparison cap for this walk.
 // Returns LINK_*; fills r.link_chunk / r.link_from / r.n_bridge / r.bstate.
+template <bool COOP = false>
 PHY_HD int32_t bridge_walk(const WalkParams &P, int32_t g, WalkState st, int32_t nb, Event *out,
                            int64_t out_cap, int32_t budget, int32_t cap)
 {
@@ -340,7 +339,7 @@ PHY_HD int32_t bridge_walk(const WalkParams &P, int32_t g, WalkState st, int32_t
 			result = LINK_MERGED;
 			break;
 		}
-		StepOut o = walk_step(P.esa, q, qi.qlen, P.thr, cap, st);
+		StepOut o = walk_step<COOP>(P.esa, q, qi.qlen, P.thr, cap, st);
 		if (o.accepted) {
 			int32_t idx = (c > g) ? match_event(P, c, st.pos, o.posS, o.len) : -1;
 			if (idx >= 0) {

@@ -55,7 +55,11 @@ def test_esa_sizes_across_tile_boundaries(ctx, oracle, n):
         assert np.array_equal(got[k], want[k]), k
 
 
-@pytest.mark.parametrize("ref", [b"A" * 3000, b"AC" * 2500, b"ACGTTGCA" * 700, (b"ACGGTCA" * 50 + b"!") * 9 + b"AC"])
+@pytest.mark.parametrize(
+    "ref",
+    [b"A" * 3000, b"AC" * 2500, b"ACGTTGCA" * 700, (b"ACGGTCA" * 50 + b"!") * 9 + b"AC"],
+    ids=["polyA", "AC-repeat", "palindromic-8mer", "tandem-with-separators"],
+)
 def test_esa_degenerate_repeats(ctx, oracle, ref):
     """every suffix ties on its first 21 characters: all work goes through the refinement"""
     ctx.esa_build(ref)
@@ -64,6 +68,20 @@ def test_esa_degenerate_repeats(ctx, oracle, ref):
     for k in ("SA", "LCP", "CLD", "FVC"):
         assert np.array_equal(got[k], want[k]), k
     assert ctx.stat("esa.tied") > 0 and ctx.stat("esa.refine_rounds") >= 1
+
+
+@pytest.mark.parametrize("name", ["multi_contig", "repeats", "rearranged", "tiny"])
+@pytest.mark.parametrize("key_chars", [1, 2, 5, 11, 21])
+def test_esa_any_sort_key_length(pb, oracle, name, key_chars):
+    """short sort keys leave most suffixes tied: the refinement rounds must finish the order"""
+    ref = datasets.ALL_SETS[name]()[0]
+    want = oracle.esa(ref).arrays()
+    with pb.Context(key_chars=key_chars) as ctx:
+        ctx.esa_build(ref)
+        got = ctx.esa_arrays()
+        for k in ("SA", "LCP", "CLD", "FVC"):
+            assert np.array_equal(got[k], want[k]), k
+        assert ctx.stat("esa.key_chars") == key_chars
 
 
 @pytest.mark.parametrize("name", ["multi_contig", "repeats", "tiny", "bang_vs_base", "divergent"])
