@@ -75,7 +75,7 @@ const char *phylo_version(void);
 int phylo_set_stream(phylo_ctx *ctx, void *stream);
 
 /* tuning knobs; results never depend on them (tests sweep them):
- *   "chunk"    bases per speculative walker (default 4096)
+ *   "chunk"    bases per speculative walker (default 2048)
  *   "cap"      per-thread comparison cap (default 2 * chunk)
  *   "kmer_k"   K of the descent table, 0 = none, -1 = from the text length (default)
  *   "key_chars" characters per suffix-sort key (1..21), 0 = from the text length (default)

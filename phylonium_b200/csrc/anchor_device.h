@@ -21,7 +21,7 @@ struct AnchorStats {
 };
 
 struct AnchorOptions {
-	int32_t chunk = 4096; // CH, multiple of 32
+	int32_t chunk = 2048; // CH, multiple of 32
 	int32_t cap = 0;      // comparison cap per thread; 0 = 2 * chunk
 	bool keep_raw = false; // also keep the unsorted, unfiltered lists (tests)
 	bool timings = false;

@@ -8,6 +8,7 @@
 #include "esa_search.h"
 #include "primitives.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -22,7 +23,7 @@ struct phylo_ctx {
 	cudaStream_t own_stream = nullptr; // created with the context
 	std::string err;
 
-	int64_t opt_chunk = 4096, opt_cap = 0, opt_kmer = -1, opt_key_chars = 0;
+	int64_t opt_chunk = 2048, opt_cap = 0, opt_kmer = -1, opt_key_chars = 0;
 	bool keep_raw = false, timings = false;
 
 	EsaDevice esa;
@@ -119,6 +120,7 @@ void record_esa_stats(phylo_ctx *c, const EsaTimings &t)
 	s["esa.key_chars"] = t.key_chars;
 	s["esa.refine_rounds"] = t.refine_rounds;
 	s["esa.tied"] = (double)t.tied;
+	s["esa.tie_groups"] = (double)t.tie_groups;
 	s["esa.kmer_k"] = c->esa.K;
 	s["esa.gc_count"] = (double)c->esa.gc_count;
 }
@@ -140,17 +142,36 @@ void record_anchor_stats(phylo_ctx *c, const AnchorStats &t)
 	s["anchor.total_ms"] = t.total_ms;
 }
 
-__global__ void k_validate_queries(const uint8_t *__restrict__ Q, const QueryInfo *__restrict__ qi, int32_t nq,
-                                   int *__restrict__ bad)
+// Alphabet check of every sequence plus the zero byte that must follow it (the walk and the
+// cooperative comparisons rely on both).  16 bases per thread, one 128-bit load when the
+// sequence start is 16-byte aligned (phylo_map_queries lays them out that way).
+__global__ void __launch_bounds__(256)
+k_validate_queries(const uint8_t *__restrict__ Q, const QueryInfo *__restrict__ qi, int32_t nq, int *__restrict__ bad)
 {
 	const int32_t k = blockIdx.y;
 	if (k >= nq) return;
 	const uint8_t *q = Q + qi[k].qoff;
-	const int32_t len = qi[k].qlen;
-	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= len; i += (int64_t)gridDim.x * blockDim.x) {
-		const uint8_t c = q[i];
-		const bool ok = (i == len) ? (c == 0) : (c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == '!');
-		if (!ok) atomicExch(bad, (i == len) ? 2 : 1);
+	const int64_t len = qi[k].qlen;
+	const bool aligned = (reinterpret_cast<uintptr_t>(q) & 15) == 0;
+	for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; i <= len; i += (int64_t)gridDim.x * blockDim.x * 16) {
+		uint8_t c[16];
+		if (aligned && i + 16 <= len + 1) {
+			*reinterpret_cast<uint4 *>(c) = *reinterpret_cast<const uint4 *>(q + i);
+		} else {
+			for (int t = 0; t < 16; t++)
+				c[t] = (i + t <= len) ? q[i + t] : (uint8_t)'A';
+		}
+		int flag = 0;
+#pragma unroll
+		for (int t = 0; t < 16; t++) {
+			const uint8_t x = c[t];
+			const bool letter = (x == 'A' || x == 'C' || x == 'G' || x == 'T' || x == '!');
+			if (i + t == len)
+				flag |= (x == 0) ? 0 : 2;
+			else if (i + t < len)
+				flag |= letter ? 0 : 1;
+		}
+		if (flag) atomicOr(bad, flag);
 	}
 }
 
@@ -215,13 +236,16 @@ void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_
 		bad.zero();
 		for (uint64_t k0 = 0; k0 < N; k0 += 32768) {
 			const int32_t cnt = (int32_t)(N - k0 < 32768 ? N - k0 : 32768);
-			dim3 grid(64, cnt);
+			uint64_t longest = 0;
+			for (uint64_t k = k0; k < k0 + (uint64_t)cnt; k++)
+				longest = std::max<uint64_t>(longest, lens[k]);
+			dim3 grid((unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (longest / 16 + 256) / 256), 4096), cnt);
 			k_validate_queries<<<grid, 256, 0, s>>>(dQ, d_qi.get() + k0, cnt, bad.get());
 			KERNEL_CHECK();
 		}
 		const int b = d2h_scalar(bad.get(), s);
-		if (b == 1) throw std::invalid_argument("a sequence contains bytes outside {A,C,G,T,!}");
-		if (b == 2) throw std::invalid_argument("a sequence is not followed by a zero byte in the device buffer");
+		if (b & 1) throw std::invalid_argument("a sequence contains bytes outside {A,C,G,T,!}");
+		if (b & 2) throw std::invalid_argument("a sequence is not followed by a zero byte in the device buffer");
 	}
 	anchor_queries_device(c->esa, dQ, c->qi, (int32_t)thr, opt, s, c->anchors, &st);
 	record_anchor_stats(c, st);

@@ -138,6 +138,93 @@ __global__ void k_keys_to_lcp(const uint64_t *__restrict__ keys, const uint32_t 
 	FVC[j] = text_char((uint32_t)(key >> (3 * (kc - 1 - l))) & 7u);
 }
 
+// ---------------------------------------------------------------- small tie groups
+//
+// On non-repetitive text the few suffixes that tie on their sort key come in groups of
+// two or three whose order is decided a handful of characters later.  Those are finished
+// right here — one thread per group, insertion sort by direct comparison, with their LCP
+// and FVC — so that the rank array and the doubling rounds are only needed when something
+// harder (a real repeat) is left over.
+
+constexpr int SMALL_GROUP = 8;    // largest group handled by direct comparison
+constexpr int SMALL_COMPARE = 256; // characters beyond the key a comparison may look at
+
+// heads[] receives the first SA index of every tie group
+__global__ void k_tie_heads(const uint64_t *__restrict__ keys, int32_t m, int32_t *__restrict__ heads,
+                            uint32_t *__restrict__ counters)
+{
+	const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j + 1 >= m) return;
+	const uint64_t k = keys[j];
+	if (k != keys[j + 1]) return;
+	if (j > 0 && keys[j - 1] == k) return;
+	heads[atomicAdd(&counters[0], 1u)] = (int32_t)j;
+}
+
+// returns the number of equal characters beyond offset `from`, or -1 when the cap is hit;
+// less = suffix a sorts before suffix b (the zeros behind S make the shorter one smaller)
+__device__ __forceinline__ int32_t suffix_compare(const uint8_t *__restrict__ S, int32_t a, int32_t b, int32_t from,
+                                                  bool &less)
+{
+	const uint8_t *pa = S + a + from, *pb = S + b + from;
+	for (int32_t t = 0; t < SMALL_COMPARE; t++) {
+		const uint8_t ca = pa[t], cb = pb[t];
+		if (ca != cb) {
+			less = ca < cb;
+			return t;
+		}
+	}
+	return -1;
+}
+
+// counters[0] = number of groups, counters[1] = groups left for the doubling rounds
+__global__ void k_small_groups(const int32_t *__restrict__ heads, uint32_t *__restrict__ counters,
+                               const uint64_t *__restrict__ keys, const uint8_t *__restrict__ S, int32_t m,
+                               int32_t *__restrict__ SA, int32_t *__restrict__ LCP, uint8_t *__restrict__ FVC, int kc)
+{
+	const uint32_t groups = counters[0];
+	for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+		const int32_t j0 = heads[g];
+		const uint64_t key = keys[j0];
+		int32_t size = 1;
+		while (size <= SMALL_GROUP && j0 + size < m && keys[j0 + size] == key)
+			size++;
+		bool hard = size > SMALL_GROUP;
+		int32_t sa[SMALL_GROUP];
+		if (!hard) {
+			for (int32_t t = 0; t < size; t++)
+				sa[t] = SA[j0 + t];
+			for (int32_t t = 1; t < size && !hard; t++) { // insertion sort
+				const int32_t x = sa[t];
+				int32_t u = t;
+				while (u > 0) {
+					bool less;
+					if (suffix_compare(S, x, sa[u - 1], kc, less) < 0) {
+						hard = true;
+						break;
+					}
+					if (!less) break;
+					sa[u] = sa[u - 1];
+					u--;
+				}
+				sa[u] = x;
+			}
+		}
+		if (hard) {
+			atomicAdd(&counters[1], 1u); // its LCP markers stay: the doubling path picks it up
+			continue;
+		}
+		SA[j0] = sa[0];
+		for (int32_t t = 1; t < size; t++) {
+			bool less;
+			const int32_t l = kc + suffix_compare(S, sa[t - 1], sa[t], kc, less);
+			SA[j0 + t] = sa[t];
+			LCP[j0 + t] = l;
+			FVC[j0 + t] = S[sa[t] + l];
+		}
+	}
+}
+
 // ---------------------------------------------------------------- refinement helpers
 
 __global__ void k_gather_refine_keys(const uint32_t *__restrict__ sa_c, const uint32_t *__restrict__ grank_c,
@@ -182,11 +269,187 @@ __global__ void k_pyramid_level(const int32_t *__restrict__ in, int32_t n_in, in
 	out[o] = mn;
 }
 
-__global__ void k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD)
+// Child table, one entry per thread (closed form of cld_search.h).  Nearly every entry is
+// decided within a few positions of i, so the block stages its stretch of LCP plus a halo
+// in shared memory and scans there; only a scan that runs off the staged window falls back
+// to the min-pyramid in global memory.
+constexpr int CLD_THREADS = 256;
+constexpr int CLD_ITEMS = 4;
+constexpr int CLD_TILE = CLD_THREADS * CLD_ITEMS; // entries per block
+constexpr int CLD_HALO = 64; // also the longest scan tried in shared memory: longer ones are
+                             // better served by the pyramid than by a lane the warp waits for
+
+__global__ void __launch_bounds__(CLD_THREADS)
+k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ long_list, uint32_t *__restrict__ long_count)
 {
-	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i > m) return;
-	CLD[i] = (i == m) ? 0 : cld_entry(py, (int32_t)i);
+	__shared__ int32_t W[CLD_TILE + 2 * CLD_HALO + 1];
+	const int32_t *__restrict__ LCP = py.level[0];
+	const int64_t tile0 = (int64_t)blockIdx.x * CLD_TILE;
+	const int64_t lo = tile0 - CLD_HALO;                // global index of W[0]
+	const int64_t span = CLD_TILE + 2 * CLD_HALO + 1;   // staged entries
+	for (int t = threadIdx.x; t < span; t += CLD_THREADS) {
+		const int64_t g = lo + t;
+		W[t] = (g >= 0 && g <= m) ? LCP[g] : 0x7fffffff;
+	}
+	__syncthreads();
+	const int64_t w_first = lo < 0 ? 0 : lo;            // valid window, global indices
+	const int64_t w_last = (lo + span - 1 > m) ? m : lo + span - 1;
+#pragma unroll
+	for (int r = 0; r < CLD_ITEMS; r++) {
+		const int64_t i = tile0 + r * CLD_THREADS + threadIdx.x;
+		if (i > m) continue;
+		if (i == m) {
+			CLD[i] = 0;
+			continue;
+		}
+		const int t = (int)(i - lo);
+		const int32_t a = W[t], b = W[t + 1];
+		int32_t res = -1;
+		if (b < a) { // up: leftmost minimum of (p, i], p = last position left of i with LCP <= b
+			int32_t minv = a, minpos = t;
+			int q = t - 1;
+			int qmin = (int)(w_first - lo);
+			if (qmin < t - CLD_HALO) qmin = t - CLD_HALO;
+			while (q >= qmin && W[q] > b) {
+				if (W[q] <= minv) {
+					minv = W[q];
+					minpos = q;
+				}
+				q--;
+			}
+			if (q >= qmin) res = (int32_t)(lo + minpos);
+		} else { // next l-index, or leftmost minimum of (i, s) with s = first position right of i with LCP <= a
+			int32_t minv = 0x7fffffff, minpos = -1;
+			int q = t + 1;
+			int qmax = (int)(w_last - lo);
+			if (qmax > t + CLD_HALO) qmax = t + CLD_HALO;
+			while (q <= qmax && W[q] > a) {
+				if (W[q] < minv) {
+					minv = W[q];
+					minpos = q;
+				}
+				q++;
+			}
+			if (q <= qmax) res = (int32_t)(lo + (W[q] == a ? q : minpos));
+		}
+		if (res >= 0) {
+			CLD[i] = res;
+		} else {
+			// long scan: queue the entry for the warp-cooperative kernel
+			const uint32_t at = atomicAdd(long_count, 1u);
+			long_list[at] = (int32_t)i;
+		}
+	}
+}
+
+// ---- warp-cooperative pyramid searches (all 32 lanes call with identical arguments) ----
+
+__device__ __forceinline__ int32_t coop_first_le_right(const Pyramid &py, int32_t from, int32_t v)
+{
+	const int lane = threadIdx.x & 31;
+	int32_t lvl = 0, idx = from;
+	for (;;) {
+		const int32_t base = idx & ~31;
+		const int32_t pos = base + lane;
+		const int32_t val = (pos >= idx && pos < py.size[lvl]) ? py.level[lvl][pos] : 0x7fffffff;
+		const uint32_t bal = __ballot_sync(0xffffffffu, val <= v);
+		if (bal) {
+			idx = base + (__ffs(bal) - 1);
+			break;
+		}
+		idx = (base + 32) >> 5;
+		lvl++;
+	}
+	while (lvl > 0) {
+		lvl--;
+		const int32_t base = idx << 5;
+		const int32_t pos = base + lane;
+		const int32_t val = pos < py.size[lvl] ? py.level[lvl][pos] : 0x7fffffff;
+		const uint32_t bal = __ballot_sync(0xffffffffu, val <= v);
+		idx = base + (__ffs(bal) - 1);
+	}
+	return idx;
+}
+
+__device__ __forceinline__ int32_t coop_last_le_left(const Pyramid &py, int32_t from, int32_t v)
+{
+	const int lane = threadIdx.x & 31;
+	int32_t lvl = 0, idx = from;
+	for (;;) {
+		const int32_t base = idx & ~31;
+		const int32_t pos = base + lane;
+		const int32_t val = (pos <= idx) ? py.level[lvl][pos] : 0x7fffffff;
+		const uint32_t bal = __ballot_sync(0xffffffffu, val <= v);
+		if (bal) {
+			idx = base + (31 - __clz(bal));
+			break;
+		}
+		idx = (base >> 5) - 1;
+		lvl++;
+	}
+	while (lvl > 0) {
+		lvl--;
+		const int32_t base = idx << 5;
+		const int32_t pos = base + lane;
+		const int32_t val = pos < py.size[lvl] ? py.level[lvl][pos] : 0x7fffffff;
+		const uint32_t bal = __ballot_sync(0xffffffffu, val <= v);
+		idx = base + (31 - __clz(bal));
+	}
+	return idx;
+}
+
+__device__ __forceinline__ int32_t coop_range_min(const Pyramid &py, int32_t a, int32_t b)
+{
+	const int lane = threadIdx.x & 31;
+	int32_t mn = 0x7fffffff;
+	int32_t lo = a, hi = b + 1, lvl = 0;
+	while (lo < hi) {
+		const int32_t *L = py.level[lvl];
+		int32_t lend = (lo + 31) & ~31;
+		if (lend > hi) lend = hi;
+		if (lo + lane < lend) mn = min(mn, L[lo + lane]); // fewer than 32 entries
+		lo = lend;
+		int32_t hbeg = hi & ~31;
+		if (hbeg < lo) hbeg = lo;
+		if (hbeg + lane < hi) mn = min(mn, L[hbeg + lane]);
+		hi = hbeg;
+		lo >>= 5;
+		hi >>= 5;
+		lvl++;
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1)
+		mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+	return mn;
+}
+
+// entries whose scans are long: one warp each, 32 positions per step
+__global__ void __launch_bounds__(256)
+k_cld_long(Pyramid py, const int32_t *__restrict__ long_list, const uint32_t *__restrict__ long_count,
+           int32_t *__restrict__ CLD)
+{
+	const uint32_t count = *long_count;
+	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+	const int32_t *__restrict__ LCP = py.level[0];
+	for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < count; k += nwarps) {
+		const int32_t i = long_list[k];
+		const int32_t a = LCP[i], b = LCP[i + 1];
+		int32_t res;
+		if (b < a) {
+			const int32_t p = coop_last_le_left(py, i, b);
+			const int32_t mv = coop_range_min(py, p + 1, i);
+			res = coop_first_le_right(py, p + 1, mv);
+		} else {
+			const int32_t s = coop_first_le_right(py, i + 1, a);
+			if (LCP[s] == a) {
+				res = s;
+			} else {
+				const int32_t mv = coop_range_min(py, i + 1, s - 1);
+				res = coop_first_le_right(py, i + 1, mv);
+			}
+		}
+		if ((threadIdx.x & 31) == 0) CLD[i] = res;
+	}
 }
 
 // ---------------------------------------------------------------- table
@@ -341,12 +604,29 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 		                                             esa.FVC.get(), kc);
 		KERNEL_CHECK();
 
-		// 5. refinement of tie groups
+		// 5a. small tie groups by direct comparison
+		uint32_t h_counters[2] = {0, 0};
+		{
+			DevBuf<int32_t> heads((size_t)m / 2 + 1, s);
+			DevBuf<uint32_t> counters(2, s);
+			counters.zero();
+			k_tie_heads<<<div_up(m, 256), 256, 0, s>>>(K1, m, heads.get(), counters.get());
+			KERNEL_CHECK();
+			k_small_groups<<<NUM_SMS_B200 * 4, 128, 0, s>>>(heads.get(), counters.get(), K1, esa.S.get(), m, esa.SA.get(),
+			                                               esa.LCP.get(), esa.FVC.get(), kc);
+			KERNEL_CHECK();
+			CUDA_CHECK(cudaMemcpyAsync(h_counters, counters.get(), sizeof h_counters, cudaMemcpyDeviceToHost, s));
+			CUDA_CHECK(cudaStreamSynchronize(s));
+			T.tie_groups = h_counters[0];
+		}
+
+		// 5b. refinement of the tie groups that are left (repeats): prefix doubling
 		const int32_t *LCP = esa.LCP.get();
+		const int32_t *SAcur = esa.SA.get();
 		DevBuf<uint32_t> d_count(1, s);
 		DevBuf<uint32_t> slots0, slots, sa_c, grank_c;
 		uint32_t count = 0;
-		{
+		if (h_counters[1]) {
 			// first a count, then buffers of the right size
 			auto tied = [LCP, m] __device__(int64_t j) {
 				return LCP[j] == LCP_TIE || (j + 1 < m && LCP[j + 1] == LCP_TIE);
@@ -360,9 +640,9 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 				uint32_t *sl = slots0.get(), *sc = sa_c.get();
 				device_select(
 					m, tied,
-					[sl, sc, V1] __device__(int64_t j, uint32_t r) {
+					[sl, sc, SAcur] __device__(int64_t j, uint32_t r) {
 						sl[r] = (uint32_t)j;
-						sc[r] = V1[j];
+						sc[r] = (uint32_t)SAcur[j];
 					},
 					d_count.get(), s);
 			}
@@ -375,7 +655,7 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 				int32_t *isa = ISA.get();
 				device_scan<int32_t>(
 					m, [LCP] __device__(int64_t j) { return LCP[j] == LCP_TIE ? 0 : (int32_t)j; },
-					[isa, V1] __device__(int64_t j, int32_t head) { isa[V1[j]] = head; }, OpMax(), 0, true, s);
+					[isa, SAcur] __device__(int64_t j, int32_t head) { isa[SAcur[j]] = head; }, OpMax(), 0, true, s);
 			}
 			grank_c.alloc(count, s);
 			{
@@ -468,7 +748,13 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 			py.size[py.levels] = n_out;
 			py.levels++;
 		}
-		k_cld<<<div_up((int64_t)m + 1, 256), 256, 0, s>>>(py, m, esa.CLD.get());
+		DevBuf<int32_t> long_list((size_t)m + 1, s);
+		DevBuf<uint32_t> long_count(1, s);
+		long_count.zero();
+		k_cld<<<div_up((int64_t)m + 1, CLD_TILE), CLD_THREADS, 0, s>>>(py, m, esa.CLD.get(), long_list.get(),
+		                                                               long_count.get());
+		KERNEL_CHECK();
+		k_cld_long<<<NUM_SMS_B200 * 8, 256, 0, s>>>(py, long_list.get(), long_count.get(), esa.CLD.get());
 		KERNEL_CHECK();
 		T.cld_ms = lap.lap();
 	}

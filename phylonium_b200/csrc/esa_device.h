@@ -15,7 +15,8 @@ struct EsaTimings {
 	int sort_passes = 0;
 	int key_chars = 0; // characters per sort key actually used
 	int refine_rounds = 0;
-	int64_t tied = 0; // suffixes whose first 21 characters were not unique
+	int64_t tie_groups = 0; // groups of suffixes with equal sort keys
+	int64_t tied = 0;       // suffixes left to the doubling rounds (groups too large or too similar)
 };
 
 struct EsaDevice {

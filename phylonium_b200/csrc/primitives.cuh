@@ -187,6 +187,20 @@ __device__ __forceinline__ uint32_t rs_digit(uint64_t key, int shift)
 	return (uint32_t)(key >> shift) & (RS_BINS - 1);
 }
 
+// lanes of the warp that hold the same 8-bit digit: one ballot per bit (cheaper than
+// match.any, which the hardware executes as a long micro-coded loop)
+__device__ __forceinline__ uint32_t warp_peers8(uint32_t d)
+{
+	uint32_t peers = 0xffffffffu;
+#pragma unroll
+	for (int b = 0; b < 8; b++) {
+		const bool bit = (d >> b) & 1u;
+		const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+		peers &= bit ? bal : ~bal;
+	}
+	return peers;
+}
+
 // counts[d * ntiles + tile]
 static __global__ void __launch_bounds__(RS_THREADS)
 rs_histogram(const uint64_t *__restrict__ keys, int64_t n, int shift, int ntiles, uint32_t *__restrict__ counts)
@@ -200,8 +214,8 @@ rs_histogram(const uint64_t *__restrict__ keys, int64_t n, int shift, int ntiles
 	for (int r = 0; r < RS_ITEMS; r++) {
 		const int64_t i = base + r * RS_THREADS + threadIdx.x;
 		const bool valid = i < n;
-		const uint32_t d = valid ? rs_digit(keys[i], shift) : RS_BINS; // invalid lanes group together
-		const uint32_t peers = __match_any_sync(0xffffffffu, d);
+		const uint32_t d = valid ? rs_digit(keys[i], shift) : 0;
+		const uint32_t peers = warp_peers8(d) & __ballot_sync(0xffffffffu, valid);
 		if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&h[d], (uint32_t)__popc(peers));
 	}
 	__syncthreads();
@@ -255,7 +269,7 @@ rs_scatter(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ va
 #pragma unroll
 	for (int r = 0; r < RS_ITEMS; r++) {
 		const uint32_t d = rs_digit(key[r], shift);
-		const uint32_t peers = __match_any_sync(0xffffffffu, d);
+		const uint32_t peers = warp_peers8(d);
 		const uint32_t before = sm.warp_cnt[warp][d];
 		__syncwarp();
 		if (lane == (__ffs(peers) - 1)) sm.warp_cnt[warp][d] = before + __popc(peers);
