@@ -256,20 +256,23 @@ __global__ void k_continue(WalkParams P, const int32_t *__restrict__ stuck, int3
 __global__ void k_copy_events(WalkParams P, const uint8_t *__restrict__ reach, const int32_t *__restrict__ from,
                               const uint32_t *__restrict__ offs, Event *__restrict__ out, int32_t *__restrict__ out_q)
 {
-	const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	// one warp per chunk, lanes stride over its events
+	const int32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
 	if (g >= P.total_chunks || !reach[g]) return;
 	const ChunkRec &r = P.rec[g];
 	const int32_t qid = P.chunk_query[g];
 	const Event *ev = P.ev + (int64_t)g * P.cap_ev;
+	const int32_t f = from[g];
 	uint32_t w = offs[2 * (int64_t)g];
-	for (int32_t k = from[g]; k < r.n_events; k++, w++) {
-		out[w] = ev[k];
-		out_q[w] = qid;
+	for (int32_t k = f + lane; k < r.n_events; k += 32) {
+		out[w + (k - f)] = ev[k];
+		out_q[w + (k - f)] = qid;
 	}
 	w = offs[2 * (int64_t)g + 1];
-	for (int32_t k = 0; k < r.n_bridge; k++, w++) {
-		out[w] = r.bridge_ev[k];
-		out_q[w] = qid;
+	for (int32_t k = lane; k < r.n_bridge; k += 32) {
+		out[w + k] = r.bridge_ev[k];
+		out_q[w + k] = qid;
 	}
 }
 
@@ -502,7 +505,8 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	if (n_events) {
 		DevBuf<Event> tev(n_events, s);
 		DevBuf<int32_t> tevq(n_events, s);
-		k_copy_events<<<div_up(total_chunks, 128), 128, 0, s>>>(P, reach.get(), from.get(), cnt.get(), tev.get(), tevq.get());
+		k_copy_events<<<div_up((int64_t)total_chunks * 32, 256), 256, 0, s>>>(P, reach.get(), from.get(), cnt.get(),
+		                                                                      tev.get(), tevq.get());
 		KERNEL_CHECK();
 		// run heads by inclusive max-scan: 2(t+1)+1 for a left anchor, 2(t+1) for a query's
 		// first event that extends the virtual anchor (0,0,0), 0 otherwise

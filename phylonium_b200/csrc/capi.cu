@@ -375,6 +375,9 @@ int phylo_set_option(phylo_ctx *c, const char *key, int64_t value)
 		} else if (k == "kmer_k") {
 			if (value < -1 || value > 12) throw std::invalid_argument("kmer_k must be in [-1, 12]");
 			c->opt_kmer = value;
+		} else if (k == "sort_mode") {
+			if (value < 0 || value > 2) throw std::invalid_argument("sort_mode must be 0, 1 or 2");
+			g_rs_mode = (int)value; // process-wide
 		} else if (k == "key_chars") {
 			if (value < 0 || value > 21) throw std::invalid_argument("key_chars must be in [0, 21]");
 			c->opt_key_chars = value;

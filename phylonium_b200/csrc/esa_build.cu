@@ -259,14 +259,14 @@ __global__ void k_tie_lcp(const uint32_t *__restrict__ slots, uint32_t count, co
 
 __global__ void k_pyramid_level(const int32_t *__restrict__ in, int32_t n_in, int32_t *__restrict__ out, int32_t n_out)
 {
-	const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (o >= n_out) return;
-	const int64_t b = o * 32;
-	int32_t mn = 0x7fffffff;
-	const int32_t e = (int32_t)((b + 32 < n_in) ? b + 32 : n_in);
-	for (int32_t t = (int32_t)b; t < e; t++)
-		mn = min(mn, in[t]);
-	out[o] = mn;
+	// one element per thread (coalesced), one output per warp
+	const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	int32_t mn = t < n_in ? in[t] : 0x7fffffff;
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1)
+		mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+	const int64_t o = t >> 5;
+	if ((threadIdx.x & 31) == 0 && o < n_out) out[o] = mn;
 }
 
 // Child table, one entry per thread (closed form of cld_search.h).  Nearly every entry is
@@ -742,7 +742,8 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 			const int32_t n_in = py.size[py.levels - 1];
 			const int32_t n_out = (n_in + 31) / 32;
 			levels.emplace_back((size_t)n_out, s);
-			k_pyramid_level<<<div_up(n_out, 256), 256, 0, s>>>(py.level[py.levels - 1], n_in, levels.back().get(), n_out);
+			k_pyramid_level<<<div_up((int64_t)n_out * 32, 256), 256, 0, s>>>(py.level[py.levels - 1], n_in,
+			                                                                 levels.back().get(), n_out);
 			KERNEL_CHECK();
 			py.level[py.levels] = levels.back().get();
 			py.size[py.levels] = n_out;

@@ -209,14 +209,16 @@ rs_histogram(const uint64_t *__restrict__ keys, int64_t n, int shift, int ntiles
 	h[threadIdx.x] = 0;
 	__syncthreads();
 	const int64_t base = (int64_t)blockIdx.x * RS_TILE;
-	const int lane = threadIdx.x & 31;
+	uint64_t key[RS_ITEMS];
+#pragma unroll
+	for (int r = 0; r < RS_ITEMS; r++) { // all loads first, then the shared-memory atomics
+		const int64_t i = base + r * RS_THREADS + threadIdx.x;
+		key[r] = i < n ? keys[i] : 0;
+	}
 #pragma unroll
 	for (int r = 0; r < RS_ITEMS; r++) {
 		const int64_t i = base + r * RS_THREADS + threadIdx.x;
-		const bool valid = i < n;
-		const uint32_t d = valid ? rs_digit(keys[i], shift) : 0;
-		const uint32_t peers = warp_peers8(d) & __ballot_sync(0xffffffffu, valid);
-		if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&h[d], (uint32_t)__popc(peers));
+		if (i < n) atomicAdd(&h[rs_digit(key[r], shift)], 1u);
 	}
 	__syncthreads();
 	counts[(int64_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
@@ -231,21 +233,71 @@ struct RsSmem {
 	uint32_t scan_tmp[32];
 };
 
-// offsets[d * ntiles + tile] = exclusive scan of counts. vals_in == nullptr: value = index.
+// All digit histograms of a sort in one read of the keys: ghist[pass * 256 + digit].
+constexpr int RS_MAX_PASSES = 8;
+
+static __global__ void __launch_bounds__(RS_THREADS)
+rs_global_hist(const uint64_t *__restrict__ keys, int64_t n, int bit_lo, int passes, uint32_t *__restrict__ ghist)
+{
+	__shared__ uint32_t h[RS_MAX_PASSES][RS_BINS];
+	for (int p = 0; p < passes; p++)
+		h[p][threadIdx.x] = 0;
+	__syncthreads();
+	for (int64_t i = (int64_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RS_THREADS) {
+		const uint64_t key = keys[i];
+		for (int p = 0; p < passes; p++)
+			atomicAdd(&h[p][rs_digit(key, bit_lo + 8 * p)], 1u);
+	}
+	__syncthreads();
+	for (int p = 0; p < passes; p++) {
+		const uint32_t v = h[p][threadIdx.x];
+		if (v) atomicAdd(&ghist[p * RS_BINS + threadIdx.x], v);
+	}
+}
+
+// ghist -> exclusive prefix per pass (one block per pass)
+static __global__ void __launch_bounds__(RS_THREADS) rs_digit_bases(uint32_t *__restrict__ ghist)
+{
+	__shared__ uint32_t tmp[32];
+	uint32_t *g = ghist + blockIdx.x * RS_BINS;
+	const uint32_t v = g[threadIdx.x];
+	const uint32_t e = block_scan_exclusive<uint32_t>(v, OpSum(), 0u, (uint32_t *)nullptr, tmp);
+	g[threadIdx.x] = e;
+}
+
+// tile status word of the decoupled look-back: flag in the top two bits, count below
+constexpr unsigned long long RS_FLAG_LOCAL = 1ull << 62;     // count of this tile only
+constexpr unsigned long long RS_FLAG_INCLUSIVE = 2ull << 62; // count of this tile and all before it
+constexpr unsigned long long RS_VALUE_MASK = (1ull << 62) - 1;
+
+// One radix pass.  LOOKBACK = false: offsets[d * ntiles + tile] holds the exclusive scan of
+// per-tile digit counts made by rs_histogram + scan.  LOOKBACK = true ("onesweep"): offsets
+// holds the 256 global digit bases of this pass; tiles are handed out in launch order by an
+// atomic counter and every tile gets the number of equal digits in the tiles before it by
+// looking back through the status words of its predecessors (which are already running, so
+// the wait is bounded).  vals_in == nullptr: value = index.
+template <bool LOOKBACK>
 static __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint64_t *__restrict__ keys_out,
-           uint32_t *__restrict__ vals_out, int64_t n, int shift, int ntiles, const uint32_t *__restrict__ offsets)
+           uint32_t *__restrict__ vals_out, int64_t n, int shift, int ntiles, const uint32_t *__restrict__ offsets,
+           unsigned long long *status, uint32_t *tile_counter, int *err)
 {
 	extern __shared__ __align__(16) unsigned char rs_smem_raw[];
 	RsSmem &sm = *reinterpret_cast<RsSmem *>(rs_smem_raw);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int64_t tile_base = (int64_t)blockIdx.x * RS_TILE;
+	int tile = blockIdx.x;
+	if (LOOKBACK) {
+		if (threadIdx.x == 0) sm.scan_tmp[31] = atomicAdd(tile_counter, 1u);
+		__syncthreads();
+		tile = (int)sm.scan_tmp[31];
+	}
+	const int64_t tile_base = (int64_t)tile * RS_TILE;
 	const int64_t remaining = n - tile_base;
 	const int nvalid = remaining < RS_TILE ? (int)remaining : RS_TILE;
 
 	for (int b = threadIdx.x; b < RS_WARPS * RS_BINS; b += RS_THREADS)
 		(&sm.warp_cnt[0][0])[b] = 0;
-	sm.gbase[threadIdx.x] = offsets[(int64_t)threadIdx.x * ntiles + blockIdx.x];
+	if (!LOOKBACK) sm.gbase[threadIdx.x] = offsets[(int64_t)threadIdx.x * ntiles + tile];
 	__syncthreads();
 
 	// warp-striped load: item r of lane l sits at warp_base + r*32 + l (tile order)
@@ -287,6 +339,34 @@ rs_scatter(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ va
 			sm.warp_cnt[w][d] = run;
 			run += c;
 		}
+		if (LOOKBACK) {
+			// publish this tile's count of digit d, then add up the predecessors' counts
+			unsigned long long *mine = status + (int64_t)tile * RS_BINS + d;
+			if (tile == 0) {
+				atomicExch(mine, RS_FLAG_INCLUSIVE | run);
+				sm.gbase[d] = offsets[d];
+			} else {
+				atomicExch(mine, RS_FLAG_LOCAL | run);
+				unsigned long long before = 0;
+				int t = tile - 1;
+				long long spins = 0;
+				for (;;) {
+					const unsigned long long v = *(volatile unsigned long long *)(status + (int64_t)t * RS_BINS + d);
+					if ((v >> 62) == 0) {
+						if (++spins > (1ll << 28)) { // a bug, not a wait: bail out instead of hanging the GPU
+							atomicExch(err, 1);
+							break;
+						}
+						continue;
+					}
+					before += v & RS_VALUE_MASK;
+					if (v & RS_FLAG_INCLUSIVE) break;
+					t--;
+				}
+				atomicExch(mine, RS_FLAG_INCLUSIVE | (before + run));
+				sm.gbase[d] = offsets[d] + (uint32_t)before;
+			}
+		}
 		uint32_t start = block_scan_exclusive<uint32_t>(run, OpSum(), 0u, (uint32_t *)nullptr, sm.scan_tmp);
 		sm.tile_start[d] = start;
 	}
@@ -317,6 +397,10 @@ rs_scatter(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ va
 // (keys, vals) and (keys_alt, vals_alt); returns true if the result ended up in the
 // alternate buffers.  vals may be nullptr on input: values start as 0..n-1 and are written
 // to vals_alt/vals from the first pass on (vals must still be a valid buffer then).
+// 0: pick by size, 1: histogram + scan + scatter per pass, 2: onesweep (option "sort_mode")
+inline int g_rs_mode = 0;
+constexpr int RS_ONESWEEP_MIN_TILES = 16384; // ~67 M pairs
+
 // optional per-kernel timing of a sort (CUDA events on the launching stream)
 struct RsProfile {
 	float hist_ms = 0, scan_ms = 0, scatter_ms = 0;
@@ -327,11 +411,68 @@ inline bool radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_alt,
                              int bit_lo, int bit_hi, bool iota_values, cudaStream_t s, RsProfile *prof = nullptr)
 {
 	if (n <= 0 || bit_hi <= bit_lo) return false;
-	CUDA_CHECK(cudaFuncSetAttribute(rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+	CUDA_CHECK(cudaFuncSetAttribute(rs_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+	CUDA_CHECK(cudaFuncSetAttribute(rs_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
 	const int ntiles = div_up(n, RS_TILE);
-	DevBuf<uint32_t> counts((size_t)ntiles * RS_BINS, s);
-	bool flipped = false;
-	bool first = true;
+	const int passes = (bit_hi - bit_lo + 7) / 8;
+	if (passes > RS_MAX_PASSES) throw std::invalid_argument("radix sort: more than 8 passes");
+	// Two schemes.  Look-back ("onesweep") moves 24 B per element and pass instead of 32, but
+	// the first wave of resident tiles pays a serial look-back of ~0.1 ms per pass (measured
+	// on B200), so it only wins once there are many waves of tiles.
+	const bool onesweep = g_rs_mode == 2 || (g_rs_mode == 0 && ntiles >= RS_ONESWEEP_MIN_TILES);
+	if (!onesweep) {
+		DevBuf<uint32_t> counts((size_t)ntiles * RS_BINS, s);
+		std::vector<cudaEvent_t> evs;
+		auto mark = [&] {
+			if (!prof) return;
+			cudaEvent_t e;
+			CUDA_CHECK(cudaEventCreate(&e));
+			CUDA_CHECK(cudaEventRecord(e, s));
+			evs.push_back(e);
+		};
+		bool flipped = false, first = true;
+		for (int p = 0; p < passes; p++) {
+			const int shift = bit_lo + 8 * p;
+			const uint64_t *kin = flipped ? keys_alt : keys;
+			const uint32_t *vin = flipped ? vals_alt : vals;
+			uint64_t *kout = flipped ? keys : keys_alt;
+			uint32_t *vout = flipped ? vals : vals_alt;
+			mark();
+			rs_histogram<<<ntiles, RS_THREADS, 0, s>>>(kin, n, shift, ntiles, counts.get());
+			KERNEL_CHECK();
+			mark();
+			exclusive_sum_u32(counts.get(), counts.get(), (int64_t)ntiles * RS_BINS, s);
+			mark();
+			rs_scatter<false><<<ntiles, RS_THREADS, sizeof(RsSmem), s>>>(kin, (first && iota_values) ? nullptr : vin, kout,
+			                                                             vout, n, shift, ntiles, counts.get(), nullptr,
+			                                                             nullptr, nullptr);
+			KERNEL_CHECK();
+			mark();
+			flipped = !flipped;
+			first = false;
+		}
+		if (prof) {
+			CUDA_CHECK(cudaStreamSynchronize(s));
+			for (size_t k = 0; k + 3 < evs.size(); k += 4) {
+				float a = 0, b = 0, c = 0;
+				CUDA_CHECK(cudaEventElapsedTime(&a, evs[k], evs[k + 1]));
+				CUDA_CHECK(cudaEventElapsedTime(&b, evs[k + 1], evs[k + 2]));
+				CUDA_CHECK(cudaEventElapsedTime(&c, evs[k + 2], evs[k + 3]));
+				prof->hist_ms += a;
+				prof->scan_ms += b;
+				prof->scatter_ms += c;
+				prof->passes++;
+			}
+			for (auto e : evs)
+				cudaEventDestroy(e);
+		}
+		return flipped;
+	}
+	// digit bases of every pass from one read of the keys ("onesweep")
+	DevBuf<uint32_t> ghist((size_t)passes * RS_BINS, s);
+	DevBuf<unsigned long long> status((size_t)ntiles * RS_BINS, s);
+	DevBuf<uint32_t> ctl(2, s); // [0] tile counter, [1] error flag
+	ghist.zero();
 	std::vector<cudaEvent_t> evs;
 	auto mark = [&] {
 		if (!prof) return;
@@ -340,19 +481,29 @@ inline bool radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_alt,
 		CUDA_CHECK(cudaEventRecord(e, s));
 		evs.push_back(e);
 	};
-	for (int shift = bit_lo; shift < bit_hi; shift += 8) {
+	mark();
+	{
+		int blocks = ntiles < NUM_SMS_B200 * 8 ? ntiles : NUM_SMS_B200 * 8;
+		rs_global_hist<<<blocks, RS_THREADS, 0, s>>>(keys, n, bit_lo, passes, ghist.get());
+		KERNEL_CHECK();
+		rs_digit_bases<<<passes, RS_THREADS, 0, s>>>(ghist.get());
+		KERNEL_CHECK();
+	}
+	mark();
+	bool flipped = false;
+	bool first = true;
+	for (int p = 0; p < passes; p++) {
+		const int shift = bit_lo + 8 * p;
 		const uint64_t *kin = flipped ? keys_alt : keys;
 		const uint32_t *vin = flipped ? vals_alt : vals;
 		uint64_t *kout = flipped ? keys : keys_alt;
 		uint32_t *vout = flipped ? vals : vals_alt;
+		status.zero();
+		ctl.zero();
 		mark();
-		rs_histogram<<<ntiles, RS_THREADS, 0, s>>>(kin, n, shift, ntiles, counts.get());
-		KERNEL_CHECK();
-		mark();
-		exclusive_sum_u32(counts.get(), counts.get(), (int64_t)ntiles * RS_BINS, s);
-		mark();
-		rs_scatter<<<ntiles, RS_THREADS, sizeof(RsSmem), s>>>(kin, (first && iota_values) ? nullptr : vin, kout, vout,
-		                                                      n, shift, ntiles, counts.get());
+		rs_scatter<true><<<ntiles, RS_THREADS, sizeof(RsSmem), s>>>(
+			kin, (first && iota_values) ? nullptr : vin, kout, vout, n, shift, ntiles, ghist.get() + (size_t)p * RS_BINS,
+			status.get(), ctl.get(), (int *)(ctl.get() + 1));
 		KERNEL_CHECK();
 		mark();
 		flipped = !flipped;
@@ -360,13 +511,12 @@ inline bool radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_alt,
 	}
 	if (prof) {
 		CUDA_CHECK(cudaStreamSynchronize(s));
-		for (size_t k = 0; k + 3 < evs.size(); k += 4) {
-			float a = 0, b = 0, c = 0;
-			CUDA_CHECK(cudaEventElapsedTime(&a, evs[k], evs[k + 1]));
-			CUDA_CHECK(cudaEventElapsedTime(&b, evs[k + 1], evs[k + 2]));
-			CUDA_CHECK(cudaEventElapsedTime(&c, evs[k + 2], evs[k + 3]));
-			prof->hist_ms += a;
-			prof->scan_ms += b;
+		float a = 0;
+		CUDA_CHECK(cudaEventElapsedTime(&a, evs[0], evs[1]));
+		prof->hist_ms += a;
+		for (size_t k = 2; k + 1 < evs.size(); k += 2) {
+			float c = 0;
+			CUDA_CHECK(cudaEventElapsedTime(&c, evs[k], evs[k + 1]));
 			prof->scatter_ms += c;
 			prof->passes++;
 		}

@@ -84,6 +84,27 @@ def test_esa_any_sort_key_length(pb, oracle, name, key_chars):
         assert ctx.stat("esa.key_chars") == key_chars
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_both_radix_sort_schemes(pb, oracle, mode):
+    """the look-back ("onesweep") passes are normally used only for very large inputs"""
+    try:
+        with pb.Context(sort_mode=mode, keep_raw=1) as ctx:
+            for name in ("repeats", "rearranged"):
+                genomes = datasets.ALL_SETS[name]()
+                ref = genomes[0]
+                ctx.esa_build(ref)
+                got, want = ctx.esa_arrays(), oracle.esa(ref).arrays()
+                for k in ("SA", "LCP", "CLD", "FVC"):
+                    assert np.array_equal(got[k], want[k]), (name, k)
+            genomes = oracle_lib.port().simf_set(9, 300000, [0.03])
+            want = oracle.process(genomes, 0, 0, threads=2)
+            subst, homol = ctx.process(genomes, 0, 0)
+            assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
+    finally:
+        with pb.Context(sort_mode=0):
+            pass
+
+
 @pytest.mark.parametrize("name", ["multi_contig", "repeats", "tiny", "bang_vs_base", "divergent"])
 @pytest.mark.parametrize("K", [-1, 0, 1, 4, 9])
 def test_longest_matches(pb, oracle, name, K):
