@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--length", type=int, default=5_000_000, help="genome length (configs[1]: 5 Mbp)")
     ap.add_argument("--genomes", type=int, default=8, help="genomes per GPU (configs[1]: 8)")
     ap.add_argument("--chunk", type=int, default=0, help="walker chunk length (0 = library default)")
+    ap.add_argument("--index", default="replicate", choices=["replicate", "broadcast"],
+                    help="multi-GPU: every rank builds the index, or rank 0 builds and broadcasts it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile-pass", action="store_true")
     return ap.parse_args()
@@ -218,8 +220,14 @@ def run_b200(args):
     ctx.set_stream(stream.cuda_stream)
     if args.chunk:
         ctx.set_option("chunk", args.chunk)
-    d_subst = torch.zeros(total * total, dtype=torch.int64, device=dev)
-    d_homol = torch.zeros(total * total, dtype=torch.int64, device=dev)
+    d_counts = torch.zeros(2, total * total, dtype=torch.int64, device=dev)
+    d_subst, d_homol = d_counts[0], d_counts[1]
+    if rank == 0:
+        d_ref = dQ[:L]
+    else:
+        ref_host = torch.zeros(L, dtype=torch.uint8).pin_memory()
+        simgen.simf(SIMF_SEED, SIMF_SEED, L, 0.0, out=ref_host.data_ptr())
+        d_ref = ref_host.to(dev)
     if world > 1:
         ctx.rows_configure(plan.padded_total, plan.first)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -232,19 +240,20 @@ def run_b200(args):
 
     def step():
         """one pass of the hot path, inputs resident on the device"""
-        if rank == 0:
-            ctx.esa_build_dev(dQ.data_ptr(), L)
-            thr_box[0] = threshold()
-        if world > 1:
+        if world == 1 or args.index == "replicate":
+            # every rank indexes the (shared) reference itself: no rank waits for another
+            ctx.esa_build_dev(d_ref.data_ptr(), L)
+        else:
+            # north-star layout: built once on rank 0, broadcast over NVLink
+            if rank == 0:
+                ctx.esa_build_dev(d_ref.data_ptr(), L)
             sharding.broadcast_index(ctx, L, 0, rank, local_rank)
-            t = torch.tensor([thr_box[0] or 0], dtype=torch.int64, device=dev)
-            dist.broadcast(t, src=0)
-            thr_box[0] = int(t.item())
+        thr_box[0] = threshold()
         ctx.map_queries_dev(dQ.data_ptr(), offs, lens, thr_box[0])
         if world > 1:
             sharding.allgather_rows(ctx, plan, local_rank)
-            ctx.compare_tiles_dev(d_subst.data_ptr(), d_homol.data_ptr(), rank, world)
-            sharding.reduce_matrix(d_subst, d_homol)
+            ctx.compare_tiles_dev(d_counts[0].data_ptr(), d_counts[1].data_ptr(), rank, world)
+            dist.all_reduce(d_counts, op=dist.ReduceOp.SUM)  # every cell is written by one rank
         else:
             ctx.compare_all_dev(d_subst.data_ptr(), d_homol.data_ptr())
 
@@ -366,7 +375,8 @@ def run_b200(args):
             "config": {"workload": workload_name(args, world), "genomes_per_gpu": G, "genome_length": L,
                        "l2": "flushed between timed steps (512 MiB memset)",
                        "step": "ESA build + anchoring of all genomes + all-pairs counts (process())",
-                       "parallelism": f"query-sharded x{world}" if world > 1 else "single GPU"},
+                       "parallelism": (f"queries sharded x{world}, index {args.index}d, rows all-gathered, "
+                                       f"matrix tiles dealt to ranks + all-reduce") if world > 1 else "single GPU"},
             "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
             "phases": phases,
         }

@@ -175,6 +175,18 @@ k_validate_queries(const uint8_t *__restrict__ Q, const QueryInfo *__restrict__ 
 	}
 }
 
+// G/C bytes of the reference (first n bytes of S), for ranks that received the index
+__global__ void k_count_gc(const uint8_t *__restrict__ S, int32_t n, unsigned long long *__restrict__ out)
+{
+	unsigned int gc = 0;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+		gc += ((S[i] & 'G' & 'C') == ('G' & 'C'));
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1)
+		gc += __shfl_xor_sync(0xffffffffu, gc, d);
+	if ((threadIdx.x & 31) == 0 && gc) atomicAdd(out, (unsigned long long)gc);
+}
+
 __global__ void k_get_matches(EsaView e, const uint8_t *__restrict__ text, const uint64_t *__restrict__ offs,
                               const uint64_t *__restrict__ lens, uint64_t count, int use_table, int64_t *__restrict__ out)
 {
@@ -705,7 +717,12 @@ int phylo_esa_finish_import(phylo_ctx *c)
 	return guarded(c, [&] {
 		if (!c->esa.m) throw std::invalid_argument("phylo_esa_alloc has not been called");
 		esa_build_table(c->esa, (int)c->opt_kmer, c->stream);
-		CUDA_CHECK(cudaStreamSynchronize(c->stream));
+		DevBuf<unsigned long long> gc(1, c->stream);
+		gc.zero();
+		k_count_gc<<<NUM_SMS_B200 * 4, 256, 0, c->stream>>>(c->esa.S.get(), c->esa.n, gc.get());
+		KERNEL_CHECK();
+		c->esa.gc_count = (int64_t)d2h_scalar(gc.get(), c->stream);
+		c->stats["esa.gc_count"] = (double)c->esa.gc_count;
 		c->stats["esa.kmer_k"] = c->esa.K;
 		c->esa_ready = true;
 	});

@@ -83,13 +83,25 @@ def broadcast_index(ctx, n: int, src: int, rank: int, device_index: int) -> int:
     return moved
 
 
+def allgather_store(store: torch.Tensor, plan: ShardPlan, bytes_per_genome: int) -> None:
+    """In-place all-gather of a genome-major byte store: rank r owns rows
+    [r * per_rank, (r + 1) * per_rank)."""
+    mine = store[plan.first * bytes_per_genome : (plan.first + plan.per_rank) * bytes_per_genome]
+    if dist.get_backend() == "gloo":
+        parts = [torch.empty_like(mine) for _ in range(plan.world)]
+        dist.all_gather(parts, mine.clone())
+        for r, part in enumerate(parts):
+            store[r * plan.per_rank * bytes_per_genome : (r + 1) * plan.per_rank * bytes_per_genome] = part
+    else:
+        dist.all_gather_into_tensor(store, mine)
+
+
 def allgather_rows(ctx, plan: ShardPlan, device_index: int) -> int:
     """All-gather of the row store (each rank contributed rows [first, first + per_rank))."""
     ptr, bytes_per_genome, total = ctx.rows_device()
     assert total == plan.padded_total
     store = DeviceBuffer(ptr, bytes_per_genome * total, device_index).tensor()
-    mine = store[plan.first * bytes_per_genome : (plan.first + plan.per_rank) * bytes_per_genome]
-    dist.all_gather_into_tensor(store, mine)
+    allgather_store(store, plan, bytes_per_genome)
     return bytes_per_genome * total
 
 

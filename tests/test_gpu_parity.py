@@ -233,6 +233,61 @@ def test_config2_full_size(pb, oracle, ctx):
     assert np.array_equal(ctx.homology_counts(), want["hom_counts"].astype(np.uint64))
 
 
+def test_sharded_plumbing_on_one_gpu(pb, oracle):
+    """the multi-GPU C ABI (index export/import, row store slices, matrix tiles) with two
+    contexts on one device and plain copies in place of the NCCL collectives"""
+    import torch
+
+    from phylonium_b200 import sharding
+
+    rng = np.random.default_rng(23)
+    r = datasets.random_dna(rng, 30000)
+    genomes = [r] + [datasets.mutate(rng, r, 0.004 * (k + 1)) for k in range(6)]
+    genomes[3] = datasets.revcomp(genomes[3])
+    total, world = len(genomes), 2
+    want = oracle.process(genomes, 0, 0, threads=4)
+    thr = pb.threshold_for(r)
+    ctxs = [pb.Context(), pb.Context()]
+    try:
+        plans = [sharding.make_plan(total, world, k) for k in range(world)]
+        ctxs[0].esa_build(r)
+        ctxs[1].esa_alloc(len(r))
+        a0, a1 = ctxs[0].esa_device_arrays(), ctxs[1].esa_device_arrays()
+        for name in a0:  # stands in for the broadcast
+            src = sharding.DeviceBuffer(a0[name][0], a0[name][1], 0).tensor()
+            dst = sharding.DeviceBuffer(a1[name][0], a1[name][1], 0).tensor()
+            dst.copy_(src)
+        torch.cuda.synchronize()
+        ctxs[1].esa_finish_import()
+        assert ctxs[1].stat("esa.gc_count") == ctxs[0].stat("esa.gc_count")
+        stores = []
+        for k in range(world):
+            p = plans[k]
+            ctxs[k].rows_configure(p.padded_total, p.first)
+            ctxs[k].map_queries(genomes[p.first : p.first + p.count], thr)
+            ptr, bpg, tot = ctxs[k].rows_device()
+            assert tot == p.padded_total
+            stores.append((sharding.DeviceBuffer(ptr, bpg * tot, 0).tensor(), bpg))
+        for k in range(world):  # stands in for the all-gather
+            p, (st, bpg) = plans[k], stores[k]
+            lo, hi = p.first * bpg, (p.first + p.per_rank) * bpg
+            stores[1 - k][0][lo:hi].copy_(st[lo:hi])
+        torch.cuda.synchronize()
+        n = plans[0].padded_total
+        acc = torch.zeros(2, n * n, dtype=torch.int64, device="cuda")
+        for k in range(world):  # stands in for the all-reduce
+            part = torch.zeros(2, n * n, dtype=torch.int64, device="cuda")
+            ctxs[k].compare_tiles_dev(part[0].data_ptr(), part[1].data_ptr(), k, world)
+            acc += part
+        subst = acc[0].cpu().numpy().reshape(n, n)[:total, :total].astype(np.uint64)
+        homol = acc[1].cpu().numpy().reshape(n, n)[:total, :total].astype(np.uint64)
+        assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
+        assert not acc[1].cpu().numpy().reshape(n, n)[total:, :].any()  # padding rows stay empty
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def test_properties_without_oracle(pb, ctx):
     """size-independent properties: symmetric matrix, zero diagonal, identical genomes have
     distance zero and full coverage, subst <= homologs <= min(lengths)"""
