@@ -1,0 +1,64 @@
+"""The phylonium-b200 command line against the unmodified reference binary
+(oracle/_ref/phylonium) on the same FASTA files: stdout must be byte-identical."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import datasets
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "phylonium_b200", "bin", "phylonium-b200")
+THEIRS = os.path.join(ROOT, "oracle", "_ref", "phylonium")
+
+
+def write_fasta(path, contigs, width=70, lower=False, junk=False):
+    with open(path, "w") as f:
+        for k, c in enumerate(contigs):
+            s = c.decode()
+            if lower:
+                s = s.lower()
+            if junk:
+                s = s[:50] + "NNNNnn-" + s[50:]
+            f.write(f">contig{k} some description\n")
+            for i in range(0, len(s), width):
+                f.write(s[i : i + width] + "\n")
+
+
+@pytest.fixture(scope="module")
+def fasta_dir(tmp_path_factory):
+    if not (os.path.exists(OURS) and os.path.exists(THEIRS)):
+        pytest.skip("needs the host binary and the compiled reference")
+    d = tmp_path_factory.mktemp("fasta")
+    rng = np.random.default_rng(31)
+    base = [datasets.random_dna(rng, 20000), datasets.random_dna(rng, 15000), datasets.random_dna(rng, 9000)]
+    write_fasta(d / "alpha.fasta", base)
+    write_fasta(d / "beta.fa", [datasets.mutate(rng, c, 0.01) for c in base], width=60, lower=True)
+    write_fasta(d / "gamma.fas", [datasets.revcomp(datasets.mutate(rng, base[1], 0.03)), datasets.mutate(rng, base[0], 0.03)], junk=True)
+    write_fasta(d / "delta.fasta", [datasets.mutate(rng, b"".join(base), 0.05)])
+    write_fasta(d / "epsilon.fasta", [datasets.mutate(rng, base[2], 0.02), datasets.mutate(rng, base[0][:12000], 0.02)])
+    return d
+
+
+CASES = [
+    ["-r", "alpha.fasta"],
+    ["-r", "delta.fasta", "--distance=raw"],
+    ["-r", "beta.fa", "--distance=ani"],
+    ["-r", "alpha.fasta", "--complete-deletion"],
+    ["-r", "gamma.fas", "--2pass"],
+    [],
+    ["-2"],
+]
+
+
+@pytest.mark.parametrize("opts", CASES, ids=[" ".join(c) or "defaults" for c in CASES])
+def test_same_stdout(fasta_dir, opts):
+    files = ["alpha.fasta", "beta.fa", "gamma.fas", "delta.fasta", "epsilon.fasta"]
+    a = subprocess.run([OURS] + opts + files, cwd=fasta_dir, capture_output=True)
+    b = subprocess.run([THEIRS, "-t", "2"] + opts + files, cwd=fasta_dir, capture_output=True)
+    assert b.stdout, b.stderr
+    assert a.stdout == b.stdout, (a.stderr, b.stderr)
+    assert a.returncode == b.returncode
