@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--length", type=int, default=5_000_000, help="genome length (configs[1]: 5 Mbp)")
     ap.add_argument("--genomes", type=int, default=8, help="genomes per GPU (configs[1]: 8)")
     ap.add_argument("--chunk", type=int, default=0, help="walker chunk length (0 = library default)")
+    ap.add_argument("--kmer-k", type=int, default=None, help="K of the descent table (library default: from m)")
     ap.add_argument("--index", default="replicate", choices=["replicate", "broadcast"],
                     help="multi-GPU: every rank builds the index, or rank 0 builds and broadcasts it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -220,6 +221,8 @@ def run_b200(args):
     ctx.set_stream(stream.cuda_stream)
     if args.chunk:
         ctx.set_option("chunk", args.chunk)
+    if args.kmer_k is not None:
+        ctx.set_option("kmer_k", args.kmer_k)
     d_counts = torch.zeros(2, total * total, dtype=torch.int64, device=dev)
     d_subst, d_homol = d_counts[0], d_counts[1]
     if rank == 0:

@@ -67,8 +67,12 @@ constexpr int WALK_WARPS_PER_BLOCK = 4;
 
 __global__ void __launch_bounds__(32 * WALK_WARPS_PER_BLOCK) k_walk_chunks(WalkParams P, int *__restrict__ any_open)
 {
-	const int32_t g = blockIdx.x * WALK_WARPS_PER_BLOCK + (threadIdx.x >> 5);
-	if (g >= P.total_chunks) return;
+	const int32_t w = blockIdx.x * WALK_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+	if (w >= P.total_chunks) return;
+	// walkers of divergent genomes take several times longer than those of close ones and a
+	// genome's chunks are numbered consecutively: spread them over the launch order so that
+	// the last wave is not made of the slow ones only
+	const int32_t g = (int32_t)(((int64_t)w * P.perm_mul) % P.total_chunks);
 	walk_chunk<true>(P, g);
 	if (P.rec[g].open) *any_open = 1;
 }
@@ -180,8 +184,9 @@ __global__ void k_apply_open(WalkParams P, const int *__restrict__ any_open, con
 
 __global__ void __launch_bounds__(32 * WALK_WARPS_PER_BLOCK) k_bridge(WalkParams P)
 {
-	const int32_t g = blockIdx.x * WALK_WARPS_PER_BLOCK + (threadIdx.x >> 5); // one walker per warp
-	if (g >= P.total_chunks) return;
+	const int32_t w = blockIdx.x * WALK_WARPS_PER_BLOCK + (threadIdx.x >> 5); // one walker per warp
+	if (w >= P.total_chunks) return;
+	const int32_t g = (int32_t)(((int64_t)w * P.perm_mul) % P.total_chunks);
 	ChunkRec &r = P.rec[g];
 	const int32_t link = bridge_walk<true>(P, g, r.exit, 0, r.bridge_ev, P.cap_ev, P.CH, P.CAP);
 	__syncwarp();
@@ -407,6 +412,21 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	P.CAP = CAP;
 	P.cap_ev = cap_ev;
 	P.total_chunks = total_chunks;
+	{
+		// multiplier of the launch-order permutation: near the golden ratio, coprime to the count
+		auto gcd = [](int64_t a, int64_t b) {
+			while (b) {
+				const int64_t t = a % b;
+				a = b;
+				b = t;
+			}
+			return a;
+		};
+		int64_t mul = (int64_t)(0.6180339887 * total_chunks) | 1;
+		while (mul > 1 && gcd(mul, total_chunks) != 1)
+			mul -= 2;
+		P.perm_mul = (int32_t)(mul < 1 ? 1 : mul);
+	}
 	P.ev = ev.get();
 	P.bev = bev.get();
 	P.dead = dead.get();

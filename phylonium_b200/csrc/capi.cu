@@ -197,7 +197,7 @@ __global__ void k_get_matches(EsaView e, const uint8_t *__restrict__ text, const
 	Match mt;
 	if (qlen <= 0) {
 		const Interval r = esa_root(e);
-		mt = Match{0, r.i, r.j, 0};
+		mt = Match{0, r.i, r.j, 0, -1};
 	} else {
 		mt = use_table ? esa_match(e, q, qlen, 0x7fffffff) : esa_match_root(e, q, qlen, 0x7fffffff);
 	}

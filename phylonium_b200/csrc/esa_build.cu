@@ -269,31 +269,67 @@ __global__ void k_pyramid_level(const int32_t *__restrict__ in, int32_t n_in, in
 	if ((threadIdx.x & 31) == 0 && o < n_out) out[o] = mn;
 }
 
-// Child table, one entry per thread (closed form of cld_search.h).  Nearly every entry is
-// decided within a few positions of i, so the block stages its stretch of LCP plus a halo
-// in shared memory and scans there; only a scan that runs off the staged window falls back
-// to the min-pyramid in global memory.
+// Child table, one entry per thread (closed form of cld_search.h).  The block stages its
+// stretch of LCP plus a halo in shared memory and builds a small sparse table over it
+// (ST[k][t] = min of 2^k entries from t).  "First entry to the right / last entry to the left
+// that is <= v" then takes 8 galloping steps, the same for every lane, and a range minimum
+// two loads; entries whose answer lies more than 255 positions away (about 1 in 100) are
+// queued for k_cld_long.
 constexpr int CLD_THREADS = 256;
 constexpr int CLD_ITEMS = 4;
 constexpr int CLD_TILE = CLD_THREADS * CLD_ITEMS; // entries per block
-constexpr int CLD_HALO = 64; // also the longest scan tried in shared memory: longer ones are
-                             // better served by the pyramid than by a lane the warp waits for
+constexpr int CLD_HALO = 128;
+constexpr int CLD_LEVELS = 8;                     // windows of 1 .. 128 entries
+constexpr int CLD_SPAN = CLD_TILE + 2 * CLD_HALO + 1;
+
+struct CldTable {
+	int32_t st[CLD_LEVELS][CLD_SPAN];
+
+	// first position >= from with value <= v, or -1 if it is not within reach
+	__device__ __forceinline__ int first_le_right(int from, int32_t v) const
+	{
+		int pos = from;
+#pragma unroll
+		for (int k = CLD_LEVELS - 1; k >= 0; k--)
+			if (pos + (1 << k) <= CLD_SPAN && st[k][pos] > v) pos += 1 << k;
+		return (pos < CLD_SPAN && st[0][pos] <= v) ? pos : -1;
+	}
+	// last position <= from with value <= v, or -1
+	__device__ __forceinline__ int last_le_left(int from, int32_t v) const
+	{
+		int pos = from;
+#pragma unroll
+		for (int k = CLD_LEVELS - 1; k >= 0; k--)
+			if (pos - (1 << k) + 1 >= 0 && st[k][pos - (1 << k) + 1] > v) pos -= 1 << k;
+		return (pos >= 0 && st[0][pos] <= v) ? pos : -1;
+	}
+	// minimum over [a, b], 1 <= b - a + 1 <= 256 (two windows of 128 still cover 256)
+	__device__ __forceinline__ int32_t range_min(int a, int b) const
+	{
+		int k = 31 - __clz(b - a + 1);
+		if (k > CLD_LEVELS - 1) k = CLD_LEVELS - 1;
+		return min(st[k][a], st[k][b - (1 << k) + 1]);
+	}
+};
 
 __global__ void __launch_bounds__(CLD_THREADS)
 k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ long_list, uint32_t *__restrict__ long_count)
 {
-	__shared__ int32_t W[CLD_TILE + 2 * CLD_HALO + 1];
+	__shared__ CldTable T;
 	const int32_t *__restrict__ LCP = py.level[0];
 	const int64_t tile0 = (int64_t)blockIdx.x * CLD_TILE;
-	const int64_t lo = tile0 - CLD_HALO;                // global index of W[0]
-	const int64_t span = CLD_TILE + 2 * CLD_HALO + 1;   // staged entries
-	for (int t = threadIdx.x; t < span; t += CLD_THREADS) {
+	const int64_t lo = tile0 - CLD_HALO; // global index of window position 0
+	for (int t = threadIdx.x; t < CLD_SPAN; t += CLD_THREADS) {
 		const int64_t g = lo + t;
-		W[t] = (g >= 0 && g <= m) ? LCP[g] : 0x7fffffff;
+		T.st[0][t] = (g >= 0 && g <= m) ? LCP[g] : 0x7fffffff;
+	}
+	for (int k = 1; k < CLD_LEVELS; k++) {
+		__syncthreads();
+		const int half = 1 << (k - 1);
+		for (int t = threadIdx.x; t < CLD_SPAN; t += CLD_THREADS)
+			T.st[k][t] = (t + 2 * half <= CLD_SPAN) ? min(T.st[k - 1][t], T.st[k - 1][t + half]) : 0x7fffffff;
 	}
 	__syncthreads();
-	const int64_t w_first = lo < 0 ? 0 : lo;            // valid window, global indices
-	const int64_t w_last = (lo + span - 1 > m) ? m : lo + span - 1;
 #pragma unroll
 	for (int r = 0; r < CLD_ITEMS; r++) {
 		const int64_t i = tile0 + r * CLD_THREADS + threadIdx.x;
@@ -303,39 +339,19 @@ k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ lo
 			continue;
 		}
 		const int t = (int)(i - lo);
-		const int32_t a = W[t], b = W[t + 1];
-		int32_t res = -1;
+		const int32_t a = T.st[0][t], b = T.st[0][t + 1];
+		int res = -1;
 		if (b < a) { // up: leftmost minimum of (p, i], p = last position left of i with LCP <= b
-			int32_t minv = a, minpos = t;
-			int q = t - 1;
-			int qmin = (int)(w_first - lo);
-			if (qmin < t - CLD_HALO) qmin = t - CLD_HALO;
-			while (q >= qmin && W[q] > b) {
-				if (W[q] <= minv) {
-					minv = W[q];
-					minpos = q;
-				}
-				q--;
-			}
-			if (q >= qmin) res = (int32_t)(lo + minpos);
-		} else { // next l-index, or leftmost minimum of (i, s) with s = first position right of i with LCP <= a
-			int32_t minv = 0x7fffffff, minpos = -1;
-			int q = t + 1;
-			int qmax = (int)(w_last - lo);
-			if (qmax > t + CLD_HALO) qmax = t + CLD_HALO;
-			while (q <= qmax && W[q] > a) {
-				if (W[q] < minv) {
-					minv = W[q];
-					minpos = q;
-				}
-				q++;
-			}
-			if (q <= qmax) res = (int32_t)(lo + (W[q] == a ? q : minpos));
+			const int p = T.last_le_left(t - 1, b);
+			if (p >= 0) res = T.first_le_right(p + 1, T.range_min(p + 1, t));
+		} else { // next l-index, or leftmost minimum of (i, s), s = first position right of i with LCP <= a
+			const int s = T.first_le_right(t + 1, a);
+			if (s >= 0) res = (T.st[0][s] == a) ? s : T.first_le_right(t + 1, T.range_min(t + 1, s - 1));
 		}
 		if (res >= 0) {
-			CLD[i] = res;
+			CLD[i] = (int32_t)(lo + res);
 		} else {
-			// long scan: queue the entry for the warp-cooperative kernel
+			// far away: queue the entry for the warp-cooperative kernel
 			const uint32_t at = atomicAdd(long_count, 1u);
 			long_list[at] = (int32_t)i;
 		}
@@ -509,8 +525,30 @@ int esa_default_k(int32_t m)
 	return k;
 }
 
+namespace
+{
+__global__ void k_pack_nodes(const int32_t *__restrict__ SA, const int32_t *__restrict__ LCP,
+                             const int32_t *__restrict__ CLD, const uint8_t *__restrict__ FVC, int32_t m,
+                             EsaNode *__restrict__ node)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > m) return;
+	int4 v;
+	v.x = i < m ? SA[i] : 0;
+	v.y = LCP[i];
+	v.z = CLD[i];
+	v.w = i < m ? FVC[i] : 0;
+	reinterpret_cast<int4 *>(node)[i] = v;
+}
+} // namespace
+
 void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t s)
 {
+	// the descent reads interleaved records: pack them first (13 B read, 16 B written per suffix)
+	esa.node.alloc((size_t)esa.m + 1, s);
+	k_pack_nodes<<<div_up((int64_t)esa.m + 1, 256), 256, 0, s>>>(esa.SA.get(), esa.LCP.get(), esa.CLD.get(),
+	                                                            esa.FVC.get(), esa.m, esa.node.get());
+	KERNEL_CHECK();
 	int K = kmer_k < 0 ? esa_default_k(esa.m) : kmer_k;
 	if (K > 12) K = 12;
 	esa.K = 0;

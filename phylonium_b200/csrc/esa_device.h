@@ -27,6 +27,7 @@ struct EsaDevice {
 	DevBuf<int32_t> SA;  // m
 	DevBuf<int32_t> LCP; // m + 1
 	DevBuf<int32_t> CLD; // m + 1
+	DevBuf<EsaNode> node;   // m + 1: SA/LCP/CLD/FVC interleaved for the descent (esa_search.h)
 	DevBuf<Interval> table; // 4^K
 	EsaView view() const
 	{
@@ -36,6 +37,7 @@ struct EsaDevice {
 		v.LCP = LCP.get();
 		v.CLD = CLD.get();
 		v.FVC = FVC.get();
+		v.node = node.get();
 		v.table = table.get();
 		v.K = K;
 		v.m = m;
@@ -49,6 +51,7 @@ struct EsaDevice {
 		SA.release();
 		LCP.release();
 		CLD.release();
+		node.release();
 		table.release();
 		n = m = K = 0;
 	}

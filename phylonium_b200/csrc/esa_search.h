@@ -3,10 +3,13 @@
 // kernels and (for the CPU emulation tests) from plain C++.
 //
 // Differences from the reference that do not change results:
+//  * the descent reads one 16-byte record per suffix-array index (EsaNode = SA, LCP, CLD,
+//    FVC side by side) instead of four arrays: every step of the sibling walk is then ONE
+//    dependent load instead of three — the descent is bound by memory latency, not bandwidth;
 //  * the 6-mer interval cache (src/esa.cxx:90-228) is replaced by a K-mer table,
 //    K chosen from the text length (esa_build.cu), holding for every K-mer the
 //    deepest descent state that needs no character beyond the K-mer. SURVEY.md A.4:
-//    the cache is a pure accelerator; only (l, i == j, SA[i]) are consumed.
+//    the cache is a pure accelerator; only (l, i == j, SA[i]) are consumed;
 //  * the byte-by-byte extension of a singleton interval can be capped so that very long
 //    matches are finished cooperatively (anchor.cu); the Match then has open != 0.
 #pragma once
@@ -15,11 +18,21 @@
 namespace phy
 {
 
+PHY_HD EsaNode esa_node(const EsaView &e, int32_t idx)
+{
+#if defined(__CUDA_ARCH__)
+	const int4 v = __ldg(reinterpret_cast<const int4 *>(e.node) + idx);
+	return EsaNode{v.x, v.y, v.z, v.w};
+#else
+	return e.node[idx];
+#endif
+}
+
 PHY_HD Interval esa_root(const EsaView &e)
 {
 	// src/esa.cxx:527-528: m = left_child(m_size) = CLD[m_size - 1]
-	int32_t mr = e.CLD[e.m - 1];
-	return Interval{e.LCP[mr], 0, e.m - 1, mr};
+	const int32_t mr = esa_node(e, e.m - 1).cld;
+	return Interval{esa_node(e, mr).lcp, 0, e.m - 1, mr};
 }
 
 PHY_HD bool interval_empty(const Interval &ij)
@@ -28,39 +41,47 @@ PHY_HD bool interval_empty(const Interval &ij)
 }
 
 // src/esa.cxx:361-427 — child interval of ij whose suffixes continue with character a.
-PHY_HD Interval esa_get_interval(const EsaView &e, Interval ij, uint8_t a)
+// sa receives SA[result.i] (undefined for an empty result).
+PHY_HD Interval esa_get_interval(const EsaView &e, Interval ij, uint8_t a, int32_t &sa)
 {
 	int32_t i = ij.i;
 	const int32_t j = ij.j;
+	EsaNode ni = esa_node(e, i);
+	sa = ni.sa;
 	if (i == j) {
-		if (e.S[e.SA[i] + ij.l] != a) ij.i = ij.j = -1;
+		if (e.S[ni.sa + ij.l] != a) ij.i = ij.j = -1;
 		return ij;
 	}
 	int32_t m = ij.m;
 	const int32_t l = ij.l;
-	uint8_t c = e.S[e.SA[i] + l];
+	EsaNode nm = esa_node(e, m); // independent of the text load below
+	const uint8_t c0 = e.S[ni.sa + l];
+	uint8_t c = c0;
 	for (;;) {
 		if (c == a) {
 			if (i != m - 1) {
-				int32_t nm = e.CLD[m - 1]; // left_child(m)
-				return Interval{e.LCP[nm], i, m - 1, nm};
+				const int32_t up = esa_node(e, m - 1).cld; // left_child(m)
+				return Interval{esa_node(e, up).lcp, i, m - 1, up};
 			}
-			return Interval{e.LCP[i], i, i, -1};
+			return Interval{ni.lcp, i, i, -1};
 		}
 		if (c > a) break;
 		i = m;
+		ni = nm;
+		sa = ni.sa;
 		if (i == j) break;
-		m = e.CLD[m]; // right_child(m)
-		if (e.LCP[m] != l) break;
-		c = e.FVC[i];
+		m = nm.cld; // right_child(m)
+		nm = esa_node(e, m);
+		if (nm.lcp != l) break;
+		c = (uint8_t)ni.fvc;
 	}
-	const bool hit = (i != ij.i) ? (e.FVC[i] == a) : (e.S[e.SA[i] + l] == a);
+	const bool hit = (i != ij.i) ? ((uint8_t)ni.fvc == a) : (c0 == a);
 	if (!hit) {
 		ij.i = ij.j = -1;
 		return ij;
 	}
 	ij.i = i;
-	ij.l = e.LCP[m];
+	ij.l = nm.lcp; // LCP[m]; for i == j == m this is LCP[i] like in the reference
 	ij.m = m;
 	return ij;
 }
@@ -74,11 +95,28 @@ template <bool COOP> PHY_HD int32_t match_run(const uint8_t *a, const uint8_t *b
 #if defined(__CUDA_ARCH__)
 	if (COOP) {
 		const int lane = threadIdx.x & 31;
-		for (int32_t base = from; base < to; base += 32) {
-			const int32_t x = base + lane;
+		// first 32 bytes alone: most comparisons at high divergence end here
+		{
+			const int32_t x = from + lane;
 			const bool miss = x < to && a[x] != b[x];
 			const uint32_t bal = __ballot_sync(0xffffffffu, miss);
-			if (bal) return base + (__ffs(bal) - 1);
+			if (bal) return from + (__ffs(bal) - 1);
+		}
+		// then 128 bytes per round, all eight loads in flight before the first ballot:
+		// the loop is bound by the latency of a round trip to L2/HBM, not by bandwidth
+		for (int32_t base = from + 32; base < to; base += 128) {
+			uint8_t va[4], vb[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const int32_t x = base + 32 * u + lane;
+				va[u] = x < to ? a[x] : 0;
+				vb[u] = x < to ? b[x] : 0;
+			}
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const uint32_t bal = __ballot_sync(0xffffffffu, va[u] != vb[u]);
+				if (bal) return base + 32 * u + (__ffs(bal) - 1);
+			}
 		}
 		return to;
 	}
@@ -89,34 +127,37 @@ template <bool COOP> PHY_HD int32_t match_run(const uint8_t *a, const uint8_t *b
 	return k;
 }
 
-// Extension of a singleton: characters [k, …) of the query against S[p + k …).
+// Extension of a singleton: characters [k, …) of the query against S[sa + k …).
 // Stops at the first mismatch (the NUL after S counts as one), at qlen, or — still
 // matching — once `cap` characters are verified (open).
 template <bool COOP = false>
-PHY_HD Match esa_extend_singleton(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t k, int32_t idx, int32_t cap)
+PHY_HD Match esa_extend_singleton(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t k, int32_t idx, int32_t sa,
+                                  int32_t cap)
 {
-	const uint8_t *s = e.S + e.SA[idx];
+	const uint8_t *s = e.S + sa;
 	const int32_t lim = qlen < cap ? qlen : cap;
 	if (k < lim) k = match_run<COOP>(s, q, k, lim);
 	Match r;
 	r.l = k;
 	r.i = r.j = idx;
 	r.open = (k >= lim && lim < qlen) ? 1 : 0;
+	r.sa = sa;
 	return r;
 }
 
-// src/esa.cxx:446-513 — continue a match of q[0..k) that sits in interval ij (k == ij.l
-// for a proper interval, k == number of verified characters for a singleton).
+// src/esa.cxx:446-513 — continue a match of q[0..k) that sits in the proper interval ij
+// (i < j, k == ij.l).
 template <bool COOP = false>
 PHY_HD Match esa_match_from(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t k, Interval ij, int32_t cap)
 {
-	if (ij.i == ij.j) return esa_extend_singleton<COOP>(e, q, qlen, k, ij.i, cap);
 	Match res;
 	res.i = ij.i;
 	res.j = ij.j;
 	res.open = 0;
+	res.sa = -1;
 	do {
-		ij = esa_get_interval(e, ij, q[k]);
+		int32_t sa;
+		ij = esa_get_interval(e, ij, q[k], sa);
 		if (interval_empty(ij)) {
 			res.l = k;
 			return res;
@@ -124,10 +165,10 @@ PHY_HD Match esa_match_from(const EsaView &e, const uint8_t *q, int32_t qlen, in
 		res.i = ij.i;
 		res.j = ij.j;
 		k++; // by definition the k-th letter matched
-		if (ij.i == ij.j) return esa_extend_singleton<COOP>(e, q, qlen, k, ij.i, cap);
+		if (ij.i == ij.j) return esa_extend_singleton<COOP>(e, q, qlen, k, ij.i, sa, cap);
 		const int32_t l = ij.l < qlen ? ij.l : qlen;
 		if (k < l) {
-			k = match_run<COOP>(e.S + e.SA[ij.i], q, k, l);
+			k = match_run<COOP>(e.S + sa, q, k, l);
 			if (k < l) {
 				res.l = k;
 				return res;
@@ -144,26 +185,44 @@ template <bool COOP = false> PHY_HD Match esa_match_root(const EsaView &e, const
 	return esa_match_from<COOP>(e, q, qlen, 0, esa_root(e), cap);
 }
 
-// src/esa.cxx:542-563 with the K-mer table in the role of the cache
+// src/esa.cxx:542-563 with the K-mer table in the role of the cache.
+// Table records: i == j: singleton with l verified characters and m = SA[i];
+//                i <  j: interval with lcp value l (min(K, l) characters verified).
 template <bool COOP = false> PHY_HD Match esa_match(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t cap)
 {
 	const int32_t K = e.K;
 	if (K <= 0 || qlen <= K) return esa_match_root<COOP>(e, q, qlen, cap);
 	uint32_t code = 0;
-	for (int32_t t = 0; t < K; t++) {
-		int c = kmer_code(q[t]);
-		if (c < 0) return esa_match_root<COOP>(e, q, qlen, cap);
-		code = (code << 2) | (uint32_t)c;
+#if defined(__CUDA_ARCH__)
+	if (COOP) {
+		// lane t reads character t; the 2-bit codes are OR-ed together across the warp
+		const int lane = threadIdx.x & 31;
+		const int c = lane < K ? kmer_code(q[lane]) : 0;
+		if (__any_sync(0xffffffffu, c < 0)) return esa_match_root<COOP>(e, q, qlen, cap);
+		code = __reduce_or_sync(0xffffffffu, lane < K ? ((uint32_t)c << (2 * (K - 1 - lane))) : 0u);
+	} else
+#endif
+	{
+		for (int32_t t = 0; t < K; t++) {
+			int c = kmer_code(q[t]);
+			if (c < 0) return esa_match_root<COOP>(e, q, qlen, cap);
+			code = (code << 2) | (uint32_t)c;
+		}
 	}
+#if defined(__CUDA_ARCH__)
+	const int4 tv = __ldg(reinterpret_cast<const int4 *>(e.table) + code);
+	Interval ij{tv.x, tv.y, tv.z, tv.w};
+#else
 	Interval ij = e.table[code];
-	if (ij.i == ij.j) return esa_extend_singleton<COOP>(e, q, qlen, ij.l, ij.i, cap);
+#endif
+	if (ij.i == ij.j) return esa_extend_singleton<COOP>(e, q, qlen, ij.l, ij.i, ij.m, cap);
 	int32_t k = ij.l;
 	if (k > K) {
 		// the table verified K characters of this deep interval; finish its label
 		const int32_t l = ij.l < qlen ? ij.l : qlen;
-		k = match_run<COOP>(e.S + e.SA[ij.i], q, K, l);
-		if (k < l) return Match{k, ij.i, ij.j, 0};
-		if (k >= qlen) return Match{qlen, ij.i, ij.j, 0};
+		k = match_run<COOP>(e.S + esa_node(e, ij.i).sa, q, K, l);
+		if (k < l) return Match{k, ij.i, ij.j, 0, -1};
+		if (k >= qlen) return Match{qlen, ij.i, ij.j, 0, -1};
 	}
 	return esa_match_from<COOP>(e, q, qlen, k, ij, cap);
 }
@@ -177,14 +236,15 @@ PHY_HD Interval esa_table_entry(const EsaView &e, uint32_t code, int32_t K)
 		w[t] = (uint8_t)(0x54474341u >> (8 * ((code >> (2 * (K - 1 - t))) & 3))); // "ACGT"
 	Interval ij = esa_root(e);
 	while (ij.l < K) {
-		Interval nx = esa_get_interval(e, ij, w[ij.l]);
+		int32_t sa;
+		Interval nx = esa_get_interval(e, ij, w[ij.l], sa);
 		if (interval_empty(nx)) break; // resuming repeats the failing step
-		const uint8_t *s = e.S + e.SA[nx.i];
+		const uint8_t *s = e.S + sa;
 		int32_t k = ij.l + 1;
 		if (nx.i == nx.j) {
 			while (k < K && s[k] == w[k])
 				k++;
-			return Interval{k, nx.i, nx.i, -1};
+			return Interval{k, nx.i, nx.i, sa};
 		}
 		const int32_t upto = nx.l < K ? nx.l : K;
 		while (k < upto && s[k] == w[k])

@@ -24,12 +24,18 @@ struct Interval {
 	int32_t l, i, j, m;
 };
 
+// everything the descent needs to know about one suffix-array index, in one 16-byte load
+struct alignas(16) EsaNode {
+	int32_t sa, lcp, cld, fvc;
+};
+
 struct EsaView {
 	const uint8_t *S;   // m bytes, followed by >= 64 zero bytes
 	const int32_t *SA;  // m
 	const int32_t *LCP; // m + 1, LCP[0] = LCP[m] = -1
 	const int32_t *CLD; // m + 1
 	const uint8_t *FVC; // m
+	const EsaNode *node; // m + 1: the four arrays above interleaved (used by the descent)
 	const Interval *table; // 4^K records, the GPU counterpart of the 6-mer cache (src/esa.cxx:90-228)
 	int32_t K;
 	int32_t m; // 2n + 1
@@ -40,6 +46,7 @@ struct EsaView {
 struct Match {
 	int32_t l, i, j;
 	int32_t open; // != 0: comparison stopped at the cap while still matching (singletons only)
+	int32_t sa;   // SA[i] when i == j (the only case in which the walk uses it), else -1
 };
 
 // 3-bit text codes used by the suffix sorter. Order == unsigned byte order of the

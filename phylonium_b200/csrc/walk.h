@@ -83,7 +83,7 @@ PHY_HD StepOut walk_step(const EsaView &e, const uint8_t *q, int32_t qlen, int32
 	if (!o.accepted) { // anchor, process.cxx:219-225
 		Match mt = esa_match<COOP>(e, q + pos, qlen - pos, cap);
 		o.len = mt.l > 0 ? mt.l : 0;
-		o.posS = e.SA[mt.i];
+		o.posS = mt.sa; // SA[i] of a unique match; unused otherwise
 		o.accepted = (mt.i == mt.j && o.len >= thr);
 		o.open = o.accepted ? mt.open : 0;
 	}
@@ -139,6 +139,7 @@ struct WalkParams {
 	int32_t CAP;     // per-thread comparison cap (>= thr + 1)
 	int32_t cap_ev;  // event slots per chunk: CH / (thr + 1) + 2
 	int32_t total_chunks;
+	int32_t perm_mul; // launch-order permutation of the walkers: walker w takes chunk w * perm_mul mod total
 	Event *ev;          // total_chunks * cap_ev
 	Event *bev;         // total_chunks * cap_ev (bridge events)
 	uint32_t *dead;     // total_chunks * CH / 32 bitmap words, zero-initialised

@@ -26,6 +26,7 @@ struct HostEsa {
 	std::vector<uint8_t> S, FVC;
 	std::vector<int32_t> SA, LCP, CLD;
 	std::vector<Interval> table;
+	std::vector<EsaNode> node;
 	EsaView view;
 };
 
@@ -45,6 +46,10 @@ HostEsa make_esa(const uint8_t *S, const int64_t *SA, const int64_t *LCP, const 
 		e.LCP[i] = (int32_t)LCP[i];
 		e.CLD[i] = (int32_t)CLD[i];
 	}
+	e.node.resize((size_t)m + 1);
+	for (int32_t i = 0; i <= m; i++)
+		e.node[i] = EsaNode{i < m ? e.SA[i] : 0, e.LCP[i], e.CLD[i], i < m ? (int32_t)e.FVC[i] : 0};
+	e.view.node = e.node.data();
 	e.view.S = e.S.data();
 	e.view.SA = e.SA.data();
 	e.view.LCP = e.LCP.data();
