@@ -311,7 +311,7 @@ def run_b200(args):
         same = bool((torch.from_numpy(out[0].astype(np.int64)).reshape(-1) == subst_ref.cpu()).all()
                     and (torch.from_numpy(out[1].astype(np.int64)).reshape(-1) == homol_ref.cpu()).all())
         e2e = {"value": bases_total / 1e6 / (e_ms / 1e3), "unit": "Mbp/s", "ms_per_step": e_ms,
-               "h2d_bytes_per_step": int(bases_local + L), "d2h_bytes_per_step": int(2 * G * G * 8),
+               "h2d_bytes_per_step": int(bases_local), "d2h_bytes_per_step": int(2 * G * G * 8),
                "same_counts_as_device_path": same}
 
     # ---- profile pass: per-phase device times and the roofline of the dominant kernel -------

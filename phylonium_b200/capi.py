@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphylonium_b200.so")
+# PHYLONIUM_B200_LIB: another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("PHYLONIUM_B200_LIB") or os.path.join(_HERE, "libphylonium_b200.so")
 
 PHYLO_FLAG_COMPLETE_DELETION = 4
 DIST_RAW, DIST_JC, DIST_ANI = 0, 1, 2

@@ -98,39 +98,39 @@ __device__ int32_t warp_first_mismatch(const uint8_t *__restrict__ q, const uint
 	return to;
 }
 
-// lnk[g]: chunk whose open event ends where ours does, or -1; endq[g]: end if known
-__global__ void k_resolve_open(WalkParams P, const int *__restrict__ any_open, int32_t *__restrict__ lnk,
-                               int32_t *__restrict__ endq)
+// lnk[g]: chunk whose open event ends where ours does, or -1; endq[g]: end if known.
+// open chunks are also appended to open_list (count in ctl[2]) for the jumping kernel.
+__global__ void k_resolve_open(WalkParams P, int *__restrict__ ctl, int32_t *__restrict__ lnk,
+                               int32_t *__restrict__ endq, int32_t *__restrict__ open_list)
 {
-	if (!*any_open) return;
+	if (!ctl[0]) return;
 	const int32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31;
 	if (g >= P.total_chunks) return;
 	const ChunkRec &r = P.rec[g];
-	if (!r.open) {
-		if (lane == 0) {
-			lnk[g] = -1;
-			endq[g] = -1;
-		}
-		return;
-	}
+	if (!r.open) return;
 	int32_t link, end;
 	open_resolve_one(P, g, warp_first_mismatch, link, end);
 	if (lane == 0) {
 		lnk[g] = link;
 		endq[g] = end;
+		open_list[atomicAdd(&ctl[2], 1)] = g;
 	}
 }
 
-// resolves chains lnk -> lnk -> … -> end by pointer jumping; one block, ping-pong buffers
+// resolves chains lnk -> lnk -> … -> end by pointer jumping over the open chunks only;
+// one block, ping-pong buffers (indexed by chunk, touched only at open chunks)
 __global__ void __launch_bounds__(1024)
-k_open_jump(int32_t total, const int *__restrict__ any_open, int32_t *lnk_a, int32_t *end_a, int32_t *lnk_b,
-            int32_t *end_b, int rounds)
+k_open_jump(const int *__restrict__ ctl, const int32_t *__restrict__ open_list, int32_t *lnk_a, int32_t *end_a,
+            int32_t *lnk_b, int32_t *end_b, int rounds)
 {
-	if (!*any_open) return;
+	if (!ctl[0]) return;
+	const int32_t count = ctl[2];
 	int32_t *la = lnk_a, *ea = end_a, *lb = lnk_b, *eb = end_b;
 	for (int r = 0; r < rounds; r++) {
-		for (int32_t g = threadIdx.x; g < total; g += blockDim.x) {
+		bool any = false;
+		for (int32_t k = threadIdx.x; k < count; k += blockDim.x) {
+			const int32_t g = open_list[k];
 			int32_t l = la[g], e = ea[g];
 			if (l >= 0) {
 				const int32_t l2 = la[l];
@@ -139,22 +139,25 @@ k_open_jump(int32_t total, const int *__restrict__ any_open, int32_t *lnk_a, int
 					l = -1;
 				} else {
 					l = l2;
+					any = true;
 				}
 			}
 			lb[g] = l;
 			eb[g] = e;
 		}
-		__syncthreads();
+		const int more = __syncthreads_or(any);
 		int32_t *t = la;
 		la = lb;
 		lb = t;
 		t = ea;
 		ea = eb;
 		eb = t;
+		if (!more) break;
 	}
 	// result must end up in the _a buffers
 	if (la != lnk_a) {
-		for (int32_t g = threadIdx.x; g < total; g += blockDim.x) {
+		for (int32_t k = threadIdx.x; k < count; k += blockDim.x) {
+			const int32_t g = open_list[k];
 			lnk_a[g] = la[g];
 			end_a[g] = ea[g];
 		}
@@ -441,9 +444,11 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	// 2. open matches
 	{
 		DevBuf<int32_t> lnk_a(total_chunks, s), end_a(total_chunks, s), lnk_b(total_chunks, s), end_b(total_chunks, s);
-		k_resolve_open<<<div_up((int64_t)total_chunks * 32, 256), 256, 0, s>>>(P, flags.get(), lnk_a.get(), end_a.get());
+		DevBuf<int32_t> open_list(total_chunks, s);
+		k_resolve_open<<<div_up((int64_t)total_chunks * 32, 256), 256, 0, s>>>(P, flags.get(), lnk_a.get(), end_a.get(),
+		                                                                       open_list.get());
 		KERNEL_CHECK();
-		k_open_jump<<<1, 1024, 0, s>>>(total_chunks, flags.get(), lnk_a.get(), end_a.get(), lnk_b.get(), end_b.get(),
+		k_open_jump<<<1, 1024, 0, s>>>(flags.get(), open_list.get(), lnk_a.get(), end_a.get(), lnk_b.get(), end_b.get(),
 		                               rounds_for(total_chunks));
 		KERNEL_CHECK();
 		k_apply_open<<<div_up(total_chunks, 256), 256, 0, s>>>(P, flags.get(), lnk_a.get(), end_a.get(), flags.get() + 1);

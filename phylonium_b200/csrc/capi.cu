@@ -21,6 +21,8 @@ struct phylo_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;     // the stream all work is issued on
 	cudaStream_t own_stream = nullptr; // created with the context
+	cudaStream_t copy_stream = nullptr; // host-to-device copies that overlap the index build
+	cudaEvent_t ev_main = nullptr, ev_copy = nullptr;
 	std::string err;
 
 	int64_t opt_chunk = 2048, opt_cap = 0, opt_kmer = -1, opt_key_chars = 0;
@@ -333,6 +335,13 @@ int phylo_ctx_create(int device, phylo_ctx **out)
 		return fail(nullptr, PHYLO_ERR_CUDA, cudaGetErrorString(e));
 	}
 	c->stream = c->own_stream;
+	if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess) {
+		cudaStreamDestroy(c->own_stream);
+		delete c;
+		return fail(nullptr, PHYLO_ERR_CUDA, "could not create the copy stream");
+	}
 	// keep freed temporaries in the pool instead of returning them to the driver
 	cudaMemPool_t pool;
 	if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -357,6 +366,10 @@ void phylo_ctx_destroy(phylo_ctx *c)
 	c->d_subst.release();
 	c->d_hom.release();
 	cudaStreamSynchronize(c->stream);
+	cudaStreamSynchronize(c->copy_stream);
+	cudaStreamDestroy(c->copy_stream);
+	cudaEventDestroy(c->ev_main);
+	cudaEventDestroy(c->ev_copy);
 	cudaStreamDestroy(c->own_stream);
 	delete c;
 }
@@ -555,6 +568,7 @@ int phylo_map_queries(phylo_ctx *c, const char *const *queries, const uint64_t *
 			total = (total + lens[k] + 1 + 15) / 16 * 16; // >= 1 zero byte, 16-byte aligned starts
 		}
 		cudaStream_t s = c->stream;
+		CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
 		c->q_own.alloc(total + 64, s);
 		c->q_own.zero();
 		for (uint64_t k = 0; k < N; k++)
@@ -664,17 +678,50 @@ int phylo_process(phylo_ctx *c, const char *const *seqs, const uint64_t *lens, u
                   uint64_t *subst, uint64_t *homologs)
 {
 	if (!c) return fail(nullptr, PHYLO_ERR_INVALID, "context is NULL");
-	if (!seqs || !lens || ref_index >= N) return fail(c, PHYLO_ERR_INVALID, "bad arguments to phylo_process");
-	int rc = phylo_esa_build(c, seqs[ref_index], lens[ref_index]);
-	if (rc) return rc;
-	// process.cxx:416-417; the G/C count comes out of the text kernel, the division and the
-	// threshold search are the reference's double arithmetic on the host
-	const double gc = (double)c->esa.gc_count / (double)lens[ref_index];
-	const uint64_t thr = phylo_min_anchor_length(0.025, gc, 2 * lens[ref_index] + 1);
-	c->stats["threshold"] = (double)thr;
-	rc = phylo_map_queries(c, seqs, lens, N, thr);
-	if (rc) return rc;
-	return phylo_compare_all(c, flags, subst, homologs);
+	if (!seqs || !lens || !subst || !homologs || ref_index >= N)
+		return fail(c, PHYLO_ERR_INVALID, "bad arguments to phylo_process");
+	return guarded(c, [&] {
+		// one device buffer for all sequences; the reference goes first on the main stream,
+		// the other sequences follow on the copy stream while the index is being built
+		std::vector<uint64_t> offs((size_t)N);
+		uint64_t total = 0;
+		for (uint64_t k = 0; k < N; k++) {
+			if (!seqs[k] && lens[k]) throw std::invalid_argument("NULL sequence");
+			offs[k] = total;
+			total = (total + lens[k] + 1 + 15) / 16 * 16;
+		}
+		cudaStream_t s = c->stream;
+		CUDA_CHECK(cudaStreamSynchronize(c->copy_stream)); // nothing may still write into the old buffer
+		c->q_own.alloc(total + 64, s);
+		c->q_own.zero();
+		uint8_t *dq = c->q_own.get();
+		if (lens[ref_index])
+			CUDA_CHECK(cudaMemcpyAsync(dq + offs[ref_index], seqs[ref_index], lens[ref_index], cudaMemcpyHostToDevice, s));
+		CUDA_CHECK(cudaEventRecord(c->ev_main, s));
+		CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+		for (uint64_t k = 0; k < N; k++)
+			if (k != ref_index && lens[k])
+				CUDA_CHECK(cudaMemcpyAsync(dq + offs[k], seqs[k], lens[k], cudaMemcpyHostToDevice, c->copy_stream));
+		CUDA_CHECK(cudaEventRecord(c->ev_copy, c->copy_stream));
+
+		do_esa_build(c, dq + offs[ref_index], lens[ref_index]);
+		// process.cxx:416-417; the G/C count comes out of the text kernel, the division and the
+		// threshold search are the reference's double arithmetic on the host
+		const double gc = (double)c->esa.gc_count / (double)lens[ref_index];
+		const uint64_t thr = phylo_min_anchor_length(0.025, gc, 2 * lens[ref_index] + 1);
+		c->stats["threshold"] = (double)thr;
+
+		CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_copy, 0));
+		do_map(c, dq, offs.data(), lens, N, thr);
+
+		const uint64_t tot = c->rows_total ? c->rows_total : c->N;
+		ensure_matrix(c, tot);
+		do_compare(c, flags, 0, 1, c->d_subst.get(), c->d_hom.get());
+		const size_t bytes = (size_t)(tot * tot) * sizeof(uint64_t);
+		CUDA_CHECK(cudaMemcpyAsync(subst, c->d_subst.get(), bytes, cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaMemcpyAsync(homologs, c->d_hom.get(), bytes, cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaStreamSynchronize(s));
+	});
 }
 
 int phylo_esa_alloc(phylo_ctx *c, uint64_t n)

@@ -154,11 +154,19 @@ __global__ void k_tie_heads(const uint64_t *__restrict__ keys, int32_t m, int32_
                             uint32_t *__restrict__ counters)
 {
 	const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (j + 1 >= m) return;
-	const uint64_t k = keys[j];
-	if (k != keys[j + 1]) return;
-	if (j > 0 && keys[j - 1] == k) return;
-	heads[atomicAdd(&counters[0], 1u)] = (int32_t)j;
+	bool head = false;
+	if (j + 1 < m) {
+		const uint64_t k = keys[j];
+		head = (k == keys[j + 1]) && !(j > 0 && keys[j - 1] == k);
+	}
+	// one atomic per warp: with short keys hundreds of thousands of groups get appended
+	const uint32_t bal = __ballot_sync(0xffffffffu, head);
+	if (!bal) return;
+	const int lane = threadIdx.x & 31;
+	uint32_t base = 0;
+	if (lane == __ffs(bal) - 1) base = atomicAdd(&counters[0], (uint32_t)__popc(bal));
+	base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+	if (head) heads[base + __popc(bal & ((1u << lane) - 1))] = (int32_t)j;
 }
 
 // returns the number of equal characters beyond offset `from`, or -1 when the cap is hit;
@@ -333,27 +341,30 @@ k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ lo
 #pragma unroll
 	for (int r = 0; r < CLD_ITEMS; r++) {
 		const int64_t i = tile0 + r * CLD_THREADS + threadIdx.x;
-		if (i > m) continue;
-		if (i == m) {
-			CLD[i] = 0;
-			continue;
-		}
-		const int t = (int)(i - lo);
-		const int32_t a = T.st[0][t], b = T.st[0][t + 1];
 		int res = -1;
-		if (b < a) { // up: leftmost minimum of (p, i], p = last position left of i with LCP <= b
-			const int p = T.last_le_left(t - 1, b);
-			if (p >= 0) res = T.first_le_right(p + 1, T.range_min(p + 1, t));
-		} else { // next l-index, or leftmost minimum of (i, s), s = first position right of i with LCP <= a
-			const int s = T.first_le_right(t + 1, a);
-			if (s >= 0) res = (T.st[0][s] == a) ? s : T.first_le_right(t + 1, T.range_min(t + 1, s - 1));
+		if (i < m) {
+			const int t = (int)(i - lo);
+			const int32_t a = T.st[0][t], b = T.st[0][t + 1];
+			if (b < a) { // up: leftmost minimum of (p, i], p = last position left of i with LCP <= b
+				const int p = T.last_le_left(t - 1, b);
+				if (p >= 0) res = T.first_le_right(p + 1, T.range_min(p + 1, t));
+			} else { // next l-index, or leftmost minimum of (i, s), s = first position right of i with LCP <= a
+				const int s = T.first_le_right(t + 1, a);
+				if (s >= 0) res = (T.st[0][s] == a) ? s : T.first_le_right(t + 1, T.range_min(t + 1, s - 1));
+			}
+			if (res >= 0) CLD[i] = (int32_t)(lo + res);
+		} else if (i == m) {
+			CLD[i] = 0;
 		}
-		if (res >= 0) {
-			CLD[i] = (int32_t)(lo + res);
-		} else {
-			// far away: queue the entry for the warp-cooperative kernel
-			const uint32_t at = atomicAdd(long_count, 1u);
-			long_list[at] = (int32_t)i;
+		// far away: queue the entry for the warp-cooperative kernel (one atomic per warp)
+		const bool far = i < m && res < 0;
+		const uint32_t bal = __ballot_sync(0xffffffffu, far);
+		if (bal) {
+			const int lane = threadIdx.x & 31;
+			uint32_t base = 0;
+			if (lane == __ffs(bal) - 1) base = atomicAdd(long_count, (uint32_t)__popc(bal));
+			base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+			if (far) long_list[base + __popc(bal & ((1u << lane) - 1))] = (int32_t)i;
 		}
 	}
 }
@@ -569,7 +580,8 @@ int esa_default_key_chars(int32_t m)
 	int need = 2;
 	while (need < KEY_CHARS && (1ll << (2 * need)) < (int64_t)m)
 		need++;
-	need += 2;
+	need += 2; // with one character less a pass is saved at 5 Mbp, but the ~14 % of suffixes that
+	           // then tie cost more in k_small_groups than the pass (measured on B200)
 	const int passes = (3 * need + 7) / 8;
 	const int c = (8 * passes) / 3;
 	return c > KEY_CHARS ? KEY_CHARS : c;
