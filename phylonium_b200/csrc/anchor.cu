@@ -296,11 +296,12 @@ __device__ __forceinline__ bool ev_is_right(const Event *ev, const int32_t *evq,
 }
 
 // offsets of each query's list inside an array sorted by query id
-__global__ void k_query_offsets(const int32_t *__restrict__ qids, int64_t n, int32_t nq, int64_t *__restrict__ offs)
+__global__ void k_query_offsets(const int32_t *__restrict__ qids, const uint32_t *__restrict__ n_ptr, int32_t nq,
+                                int64_t *__restrict__ offs)
 {
 	const int32_t q = blockIdx.x * blockDim.x + threadIdx.x;
 	if (q > nq) return;
-	int64_t lo = 0, hi = n;
+	int64_t lo = 0, hi = *n_ptr;
 	while (lo < hi) {
 		const int64_t mid = (lo + hi) >> 1;
 		if (qids[mid] < q)
@@ -322,6 +323,108 @@ __global__ void k_filter(const int64_t *__restrict__ offs, int32_t nq, const int
 	const int64_t o = offs[q];
 	const int32_t h = (int32_t)(offs[q + 1] - o);
 	filter_overlaps_max(start + o, len + o, h, score + o, pred + o, keep + o);
+}
+
+// ------------------------------------------------------------------ sort + filter, one block per query
+//
+// The usual case — a few thousand homologies per query at most — needs no global sort:
+// the block sorts (projected start, push index) in shared memory (bitonic), checks for
+// equal starts (ties: the reference's unstable std::sort decides, see below) and for
+// overlaps, runs the chaining DP only if something overlaps, and writes the survivors.
+// Queries with more than FIN_CAP homologies, or ties, are flagged; the caller then takes
+// the general path (global radix sort / host std::sort) for the batch.
+constexpr int FIN_THREADS = 256;
+constexpr int FIN_CAP = 2048;
+constexpr int FIN_FLAG_TIES = 1, FIN_FLAG_BIG = 2;
+
+struct FinSmem {
+	uint64_t key[FIN_CAP]; // (start << 32) | push index; padding keys are all ones
+	int64_t score[FIN_CAP];
+	int32_t start[FIN_CAP], len[FIN_CAP], pred[FIN_CAP];
+	uint8_t keep[FIN_CAP];
+	uint32_t scan_tmp[32];
+	int flags;
+};
+
+__global__ void __launch_bounds__(FIN_THREADS)
+k_sort_filter(const int64_t *__restrict__ raw_offs, const Hom *__restrict__ raw, Hom *__restrict__ fin,
+              int32_t *__restrict__ fin_count, int32_t *__restrict__ fin_flags)
+{
+	extern __shared__ __align__(16) unsigned char fin_smem_raw[];
+	FinSmem &sm = *reinterpret_cast<FinSmem *>(fin_smem_raw);
+	const int32_t q = blockIdx.x;
+	const int64_t lo = raw_offs[q];
+	const int32_t h = (int32_t)(raw_offs[q + 1] - lo);
+	if (h > FIN_CAP) {
+		if (threadIdx.x == 0) {
+			fin_count[q] = 0;
+			fin_flags[q] = FIN_FLAG_BIG;
+		}
+		return;
+	}
+	if (threadIdx.x == 0) sm.flags = 0;
+	// power of two >= h
+	int32_t npow = 1;
+	while (npow < h)
+		npow <<= 1;
+	for (int32_t k = threadIdx.x; k < npow; k += FIN_THREADS)
+		sm.key[k] = k < h ? (((uint64_t)(uint32_t)raw[lo + k].iproj << 32) | (uint32_t)k) : ~0ull;
+	__syncthreads();
+	for (int32_t size = 2; size <= npow; size <<= 1) {
+		for (int32_t stride = size >> 1; stride > 0; stride >>= 1) {
+			for (int32_t t = threadIdx.x; t < (npow >> 1); t += FIN_THREADS) {
+				const int32_t i = 2 * t - (t & (stride - 1)); // lower index of the pair
+				const int32_t j = i + stride;
+				const bool up = (i & size) == 0;
+				const uint64_t a = sm.key[i], b = sm.key[j];
+				if ((a > b) == up) {
+					sm.key[i] = b;
+					sm.key[j] = a;
+				}
+			}
+			__syncthreads();
+		}
+	}
+	// sorted order -> start/len; ties and overlaps between neighbours
+	int my_flags = 0, overlap = 0;
+	for (int32_t k = threadIdx.x; k < h; k += FIN_THREADS) {
+		const Hom x = raw[lo + (uint32_t)sm.key[k]];
+		sm.start[k] = x.iproj;
+		sm.len[k] = x.len;
+		sm.keep[k] = 1;
+		if (k > 0) {
+			const Hom p = raw[lo + (uint32_t)sm.key[k - 1]];
+			if (p.iproj == x.iproj) my_flags |= FIN_FLAG_TIES;
+			if ((int64_t)p.iproj + p.len > x.iproj) overlap = 1;
+		}
+	}
+	overlap = __syncthreads_or(overlap);
+	my_flags = __syncthreads_or(my_flags);
+	if (my_flags) {
+		if (threadIdx.x == 0) {
+			fin_count[q] = 0;
+			fin_flags[q] = FIN_FLAG_TIES;
+		}
+		return;
+	}
+	if (overlap) {
+		if (threadIdx.x == 0) filter_overlaps_max(sm.start, sm.len, h, sm.score, sm.pred, sm.keep);
+		__syncthreads();
+	}
+	// survivors, in sorted order, to fin[lo ...]
+	uint32_t carry = 0;
+	for (int32_t base = 0; base < h; base += FIN_THREADS) {
+		const int32_t k = base + threadIdx.x;
+		const uint32_t kept = (k < h && sm.keep[k]) ? 1u : 0u;
+		uint32_t total;
+		const uint32_t before = block_scan_exclusive<uint32_t>(kept, OpSum(), 0u, &total, sm.scan_tmp);
+		if (kept) fin[lo + carry + before] = raw[lo + (uint32_t)sm.key[k]];
+		carry += total;
+	}
+	if (threadIdx.x == 0) {
+		fin_count[q] = (int32_t)carry;
+		fin_flags[q] = 0;
+	}
 }
 
 int rounds_for(int64_t n)
@@ -390,6 +493,12 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	out.raw.release();
 	out.d_offs.alloc((size_t)nq + 1, s);
 	out.d_offs.zero();
+	out.begin.assign((size_t)nq, 0);
+	out.count.assign((size_t)nq, 0);
+	out.d_begin.alloc((size_t)nq, s);
+	out.d_count.alloc((size_t)nq, s);
+	out.d_begin.zero();
+	out.d_count.zero();
 	if (total_chunks == 0) return;
 
 	const int32_t cap_ev = CH / (thr + 1) + 2;
@@ -526,6 +635,8 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 
 	DevBuf<Hom> raw;
 	DevBuf<int32_t> raw_q;
+	DevBuf<uint32_t> d_n_raw(1, s);
+	d_n_raw.zero();
 	uint32_t n_raw = 0;
 	if (n_events) {
 		DevBuf<Event> tev(n_events, s);
@@ -549,7 +660,6 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 			},
 			[HC] __device__(int64_t t, uint32_t v) { HC[t] = v; }, OpMax(), 0u, true, s);
 		// a run ends where the next event is a left anchor or belongs to another query
-		DevBuf<uint32_t> d_n(1, s);
 		const int64_t ne = n_events;
 		auto run_end_pushed = [E, EQ, HC, border, thr, ne] __device__(int64_t t, Hom *h) -> bool {
 			const bool last = (t + 1 == ne) || EQ[t + 1] != EQ[t] || !ev_is_right(E, EQ, t + 1, border);
@@ -564,13 +674,10 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 			if (ok && h) *h = tmp;
 			return ok;
 		};
-		device_select(
-			n_events, [run_end_pushed] __device__(int64_t t) { return run_end_pushed(t, nullptr); },
-			[] __device__(int64_t, uint32_t) {}, d_n.get(), s);
-		n_raw = d2h_scalar(d_n.get(), s);
-		if (n_raw) {
-			raw.alloc(n_raw, s);
-			raw_q.alloc(n_raw, s);
+		// one pass: there are at most as many homologies as events
+		raw.alloc(n_events, s);
+		raw_q.alloc(n_events, s);
+		{
 			Hom *R = raw.get();
 			int32_t *RQ = raw_q.get();
 			device_select(
@@ -581,17 +688,43 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 					R[w] = h;
 					RQ[w] = EQ[t];
 				},
-				d_n.get(), s);
+				d_n_raw.get(), s);
 		}
 	}
 	ST.assemble_ms = lap.lap();
 
+	// per-query ranges of the raw lists, then the per-query sort + filter in shared memory
 	DevBuf<int64_t> d_raw_offs((size_t)nq + 1, s);
-	k_query_offsets<<<div_up(nq + 1, 128), 128, 0, s>>>(raw_q.get(), n_raw, nq, d_raw_offs.get());
+	DevBuf<Hom> fin(n_events, s);
+	DevBuf<int32_t> fin_count(nq, s), fin_flags(nq, s);
+	k_query_offsets<<<div_up(nq + 1, 128), 128, 0, s>>>(raw_q.get(), d_n_raw.get(), nq, d_raw_offs.get());
 	KERNEL_CHECK();
+	CUDA_CHECK(cudaFuncSetAttribute(k_sort_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmem)));
+	k_sort_filter<<<nq, FIN_THREADS, sizeof(FinSmem), s>>>(d_raw_offs.get(), raw.get(), fin.get(), fin_count.get(),
+	                                                       fin_flags.get());
+	KERNEL_CHECK();
+	std::vector<int32_t> h_fin_count((size_t)nq), h_fin_flags((size_t)nq);
 	CUDA_CHECK(cudaMemcpyAsync(out.raw_offs.data(), d_raw_offs.get(), ((size_t)nq + 1) * sizeof(int64_t),
 	                           cudaMemcpyDeviceToHost, s));
+	CUDA_CHECK(cudaMemcpyAsync(h_fin_count.data(), fin_count.get(), (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+	CUDA_CHECK(cudaMemcpyAsync(h_fin_flags.data(), fin_flags.get(), (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+	CUDA_CHECK(cudaMemcpyAsync(&n_raw, d_n_raw.get(), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 	CUDA_CHECK(cudaStreamSynchronize(s));
+	bool general_path = false;
+	for (int32_t q = 0; q < nq; q++)
+		general_path = general_path || h_fin_flags[q] != 0;
+	if (!general_path) {
+		// done: the survivors of query q sit at fin[raw_offs[q] ...)
+		for (int32_t q = 0; q < nq; q++) {
+			out.begin[q] = out.raw_offs[q];
+			out.count[q] = h_fin_count[q];
+		}
+		out.homs = std::move(fin);
+		CUDA_CHECK(cudaMemcpyAsync(out.d_begin.get(), out.begin.data(), (size_t)nq * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+		CUDA_CHECK(cudaMemcpyAsync(out.d_count.get(), out.count.data(), (size_t)nq * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+		CUDA_CHECK(cudaStreamSynchronize(s)); // the host vectors are pageable
+		n_raw = 0;                            // skip the general path below
+	}
 
 	// 6. sort by (query, projected start) and keep the heaviest chain per query
 	if (n_raw) {
@@ -659,7 +792,7 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 					},
 					d_n.get(), s);
 			}
-			k_query_offsets<<<div_up(nq + 1, 128), 128, 0, s>>>(fq.get(), n_final, nq, out.d_offs.get());
+			k_query_offsets<<<div_up(nq + 1, 128), 128, 0, s>>>(fq.get(), d_n.get(), nq, out.d_offs.get());
 			KERNEL_CHECK();
 			CUDA_CHECK(cudaMemcpyAsync(out.offs.data(), out.d_offs.get(), ((size_t)nq + 1) * sizeof(int64_t),
 			                           cudaMemcpyDeviceToHost, s));
@@ -687,6 +820,16 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 			                           cudaMemcpyHostToDevice, s));
 			CUDA_CHECK(cudaStreamSynchronize(s));
 		}
+	}
+	if (general_path) {
+		ST.general_path++;
+		for (int32_t q = 0; q < nq; q++) {
+			out.begin[q] = out.offs[q];
+			out.count[q] = out.offs[q + 1] - out.offs[q];
+		}
+		CUDA_CHECK(cudaMemcpyAsync(out.d_begin.get(), out.begin.data(), (size_t)nq * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+		CUDA_CHECK(cudaMemcpyAsync(out.d_count.get(), out.count.data(), (size_t)nq * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+		CUDA_CHECK(cudaStreamSynchronize(s));
 	}
 	ST.filter_ms = lap.lap();
 	if (opt.keep_raw) {

@@ -17,6 +17,7 @@ struct AnchorStats {
 	int64_t open_events = 0;   // matches longer than the per-thread cap
 	int64_t unresolved = 0;    // bridges that gave up and were continued serially
 	int64_t tie_fallback = 0;  // batches whose sort went through std::sort on the host
+	int64_t general_path = 0;  // batches sorted/filtered by the global path (a list > 2048, or ties)
 	float walk_ms = 0, open_ms = 0, bridge_ms = 0, path_ms = 0, assemble_ms = 0, filter_ms = 0, total_ms = 0;
 };
 
@@ -28,9 +29,11 @@ struct AnchorOptions {
 };
 
 struct AnchorResult {
-	DevBuf<Hom> homs;          // filtered lists of all queries, concatenated
-	std::vector<int64_t> offs; // nq + 1 offsets into homs (host)
-	DevBuf<int64_t> d_offs;    // same on the device
+	DevBuf<Hom> homs;                  // filtered lists; query q owns homs[begin[q] .. begin[q] + count[q])
+	std::vector<int64_t> begin, count; // (the lists need not be packed back to back)
+	DevBuf<int64_t> d_begin, d_count;  // same on the device
+	std::vector<int64_t> offs;         // scratch of the general path: nq + 1 packed offsets
+	DevBuf<int64_t> d_offs;
 	DevBuf<Hom> raw;           // push-order lists before sort/filter (keep_raw)
 	std::vector<int64_t> raw_offs;
 };

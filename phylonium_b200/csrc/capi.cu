@@ -135,6 +135,7 @@ void record_anchor_stats(phylo_ctx *c, const AnchorStats &t)
 	s["anchor.open"] = (double)t.open_events;
 	s["anchor.unresolved"] = (double)t.unresolved;
 	s["anchor.tie_fallback"] = (double)t.tie_fallback;
+	s["anchor.general_path"] = (double)t.general_path;
 	s["anchor.walk_ms"] = t.walk_ms;
 	s["anchor.open_ms"] = t.open_ms;
 	s["anchor.bridge_ms"] = t.bridge_ms;
@@ -272,7 +273,8 @@ void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_
 	if ((uint64_t)c->rows.genomes != total || c->rows.n != c->esa.n) rows_alloc(c->rows, (int64_t)total, c->esa.n, s);
 	if (N) {
 		CUDA_CHECK(cudaMemcpyAsync(d_qi.get(), c->qi.data(), N * sizeof(QueryInfo), cudaMemcpyHostToDevice, s));
-		rows_build(c->rows, (int64_t)first, dQ, d_qi.get(), (int32_t)N, c->anchors.homs.get(), c->anchors.d_offs.get(), s);
+		rows_build(c->rows, (int64_t)first, dQ, d_qi.get(), (int32_t)N, c->anchors.homs.get(), c->anchors.d_begin.get(),
+		           c->anchors.d_count.get(), s);
 	}
 	c->stats["rows.ms"] = wt.stop();
 	c->mapped = true;
@@ -362,6 +364,8 @@ void phylo_ctx_destroy(phylo_ctx *c)
 	c->anchors.homs.release();
 	c->anchors.raw.release();
 	c->anchors.d_offs.release();
+	c->anchors.d_begin.release();
+	c->anchors.d_count.release();
 	c->rows.data.release();
 	c->d_subst.release();
 	c->d_hom.release();
@@ -592,9 +596,8 @@ int phylo_homology_counts(const phylo_ctx *c, uint64_t *counts, int raw)
 {
 	if (!c || !counts) return PHYLO_ERR_INVALID;
 	if (!c->mapped) return PHYLO_ERR_INVALID;
-	const auto &o = raw ? c->anchors.raw_offs : c->anchors.offs;
 	for (uint64_t k = 0; k < c->N; k++)
-		counts[k] = (uint64_t)(o[k + 1] - o[k]);
+		counts[k] = raw ? (uint64_t)(c->anchors.raw_offs[k + 1] - c->anchors.raw_offs[k]) : (uint64_t)c->anchors.count[k];
 	return PHYLO_OK;
 }
 
@@ -606,15 +609,16 @@ int phylo_get_homologies(const phylo_ctx *cc, uint64_t index, int raw, phylo_hom
 		if (!c->mapped) throw std::invalid_argument("phylo_map_queries has not been called");
 		if (index >= c->N) throw std::invalid_argument("sequence index out of range");
 		if (raw && !c->keep_raw) throw std::invalid_argument("raw lists need option keep_raw");
-		const auto &o = raw ? c->anchors.raw_offs : c->anchors.offs;
 		const Hom *src = raw ? c->anchors.raw.get() : c->anchors.homs.get();
-		const uint64_t cnt = (uint64_t)(o[index + 1] - o[index]);
+		const uint64_t first = (uint64_t)(raw ? c->anchors.raw_offs[index] : c->anchors.begin[index]);
+		const uint64_t cnt = raw ? (uint64_t)(c->anchors.raw_offs[index + 1] - c->anchors.raw_offs[index])
+		                         : (uint64_t)c->anchors.count[index];
 		if (written) *written = cnt;
 		const uint64_t take = cnt < cap ? cnt : cap;
 		if (!take) return;
 		if (!out) throw std::invalid_argument("out is NULL");
 		std::vector<Hom> h(take);
-		CUDA_CHECK(cudaMemcpyAsync(h.data(), src + o[index], take * sizeof(Hom), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_CHECK(cudaMemcpyAsync(h.data(), src + first, take * sizeof(Hom), cudaMemcpyDeviceToHost, c->stream));
 		CUDA_CHECK(cudaStreamSynchronize(c->stream));
 		for (uint64_t k = 0; k < take; k++) {
 			out[k].direction = h[k].dir;

@@ -24,13 +24,14 @@ namespace
 
 __global__ void k_build_rows(uint32_t *__restrict__ rows, int64_t genome_words, int64_t W, int32_t n,
                              int64_t first_row, const uint8_t *__restrict__ Q, const QueryInfo *__restrict__ qi,
-                             int32_t count, const Hom *__restrict__ homs, const int64_t *__restrict__ offs)
+                             int32_t count, const Hom *__restrict__ homs, const int64_t *__restrict__ begin,
+                             const int64_t *__restrict__ hcount)
 {
 	const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const int32_t k = blockIdx.y;
 	if (w >= W || k >= count) return;
-	const Hom *H = homs + offs[k];
-	const int32_t h = (int32_t)(offs[k + 1] - offs[k]);
+	const Hom *H = homs + begin[k];
+	const int32_t h = (int32_t)hcount[k];
 	const uint8_t *q = Q + qi[k].qoff;
 	const int64_t c0 = w * 32;
 	uint32_t pv = 0, p0 = 0, p1 = 0, pd = 0, pb = 0;
@@ -221,7 +222,7 @@ void rows_alloc(RowStore &rs, int64_t genomes, int32_t n, cudaStream_t s)
 }
 
 void rows_build(RowStore &rs, int64_t first_row, const uint8_t *d_Q, const QueryInfo *d_qi, int32_t count,
-                const Hom *d_homs, const int64_t *d_offs, cudaStream_t s)
+                const Hom *d_homs, const int64_t *d_begin, const int64_t *d_count, cudaStream_t s)
 {
 	if (count <= 0) return;
 	if (first_row < 0 || first_row + count > rs.genomes) throw std::invalid_argument("row store too small");
@@ -229,7 +230,7 @@ void rows_build(RowStore &rs, int64_t first_row, const uint8_t *d_Q, const Query
 		const int32_t c = count - k0 < 32768 ? count - k0 : 32768;
 		dim3 grid(div_up(rs.W, 128), c);
 		k_build_rows<<<grid, 128, 0, s>>>(rs.data.get(), rs.genome_words(), rs.W, rs.n, first_row + k0, d_Q, d_qi + k0, c,
-		                                  d_homs, d_offs + k0);
+		                                  d_homs, d_begin + k0, d_count + k0);
 		KERNEL_CHECK();
 	}
 }

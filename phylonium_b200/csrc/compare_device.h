@@ -31,10 +31,10 @@ struct RowStore {
 
 void rows_alloc(RowStore &rs, int64_t genomes, int32_t n, cudaStream_t s);
 
-// rows of `count` genomes (their homology lists in d_homs / d_offs, bases in d_Q / d_qi)
-// written to rs.row(first_row + k)
+// rows of `count` genomes (genome k's sorted, disjoint homologies are
+// d_homs[d_begin[k] .. d_begin[k] + d_count[k]), bases in d_Q / d_qi) written to rs.row(first_row + k)
 void rows_build(RowStore &rs, int64_t first_row, const uint8_t *d_Q, const QueryInfo *d_qi, int32_t count,
-                const Hom *d_homs, const int64_t *d_offs, cudaStream_t s);
+                const Hom *d_homs, const int64_t *d_begin, const int64_t *d_count, cudaStream_t s);
 
 // substitutions / homologs (N*N, row-major, symmetric, zero diagonal) for the tile pairs
 // tile_rank, tile_rank + tile_world, … ; the rest of the matrix is left zero.

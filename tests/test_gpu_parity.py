@@ -179,6 +179,62 @@ def test_pair_counts_and_matrix(pb, oracle, ctx, name, flags):
                     assert abs(dev[i, j] - ref_val) <= 1e-12 * max(1.0, abs(ref_val))  # tolerance of the north star
 
 
+def test_equal_starts_take_the_host_sort(pb, oracle):
+    """two homologies of one query with the same reference start: the reference's result
+    hangs on libstdc++'s unstable std::sort, so the library runs that very call"""
+    rng = np.random.default_rng(41)
+    r = datasets.random_dna(rng, 20000)
+    dup = r[4000:9000]
+
+    def other(b):  # a base different from b, so that the copies start and end exactly at the duplicate
+        return b"C" if b != ord("C") else b"G"
+
+    # first copy at query position 0; the second one right after a full match of another
+    # reference stretch plus one mismatching base, so that the walk lands on its first base
+    post, stretch, bad = other(r[9000]), r[12000:13000], other(r[13000])
+    q = dup + post + stretch + bad + dup + post + datasets.random_dna(rng, 300)
+    assert len(np.unique(esa_starts := oracle.esa(r).anchor_homologies(oracle.threshold(r), q)["index_reference_projected"])) < len(esa_starts)
+    genomes = [r, q, datasets.mutate(rng, r, 0.01)]
+    thr = oracle.threshold(r)
+    esa = oracle.esa(r)
+    with pb.Context(keep_raw=1) as ctx:
+        ctx.esa_build(r)
+        ctx.map_queries(genomes, thr)
+        assert ctx.stat("anchor.tie_fallback") == 1 and ctx.stat("anchor.general_path") == 1
+        for k, q in enumerate(genomes):
+            raw = esa.anchor_homologies(thr, q)
+            assert np.array_equal(ctx.homologies(k, raw=True), raw)
+            assert np.array_equal(ctx.homologies(k), oracle.sort_filter(raw))
+        subst, homol = ctx.compare_all()
+    want = oracle.process(genomes, 0, 0, threads=2)
+    assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
+
+
+def test_thousands_of_homologies_take_the_global_sort(pb, oracle):
+    """more homologies in one list than the per-query shared-memory sort holds"""
+    rng = np.random.default_rng(43)
+    blocks = [datasets.random_dna(rng, 150) for _ in range(2600)]
+    r = b"".join(blocks)
+    order = rng.permutation(len(blocks))
+    q1 = b"".join(blocks[i] for i in order)
+    q2 = b"".join(datasets.revcomp(blocks[i]) if i % 3 == 0 else blocks[i] for i in order[::-1])
+    genomes = [r, q1, q2, datasets.mutate(rng, r, 0.02)]
+    thr = oracle.threshold(r)
+    esa = oracle.esa(r)
+    with pb.Context(keep_raw=1) as ctx:
+        ctx.esa_build(r)
+        ctx.map_queries(genomes, thr)
+        assert ctx.homology_counts(raw=True).max() > 2048
+        assert ctx.stat("anchor.general_path") == 1 and ctx.stat("anchor.tie_fallback") == 0
+        for k, q in enumerate(genomes):
+            raw = esa.anchor_homologies(thr, q)
+            assert np.array_equal(ctx.homologies(k, raw=True), raw)
+            assert np.array_equal(ctx.homologies(k), oracle.sort_filter(raw))
+        subst, homol = ctx.compare_all()
+    want = oracle.process(genomes, 0, 0, threads=2)
+    assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
+
+
 def test_reference_need_not_be_first(pb, oracle, ctx):
     genomes = datasets.multi_contig_set()
     for ref_index in (2, 5):
