@@ -83,14 +83,17 @@ template <typename F> int guarded(phylo_ctx *ctx, F &&f)
 struct WallTimer {
 	cudaEvent_t a, b;
 	cudaStream_t s;
-	explicit WallTimer(cudaStream_t st) : s(st)
+	bool on; // only with option "timings": stop() synchronises
+	WallTimer(cudaStream_t st, bool enabled) : s(st), on(enabled)
 	{
+		if (!on) return;
 		CUDA_CHECK(cudaEventCreate(&a));
 		CUDA_CHECK(cudaEventCreate(&b));
 		CUDA_CHECK(cudaEventRecord(a, s));
 	}
 	float stop()
 	{
+		if (!on) return 0.f;
 		CUDA_CHECK(cudaEventRecord(b, s));
 		CUDA_CHECK(cudaEventSynchronize(b));
 		float ms = 0;
@@ -99,6 +102,7 @@ struct WallTimer {
 	}
 	~WallTimer()
 	{
+		if (!on) return;
 		cudaEventDestroy(a);
 		cudaEventDestroy(b);
 	}
@@ -266,7 +270,7 @@ void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_
 	record_anchor_stats(c, st);
 
 	// reference-coordinate rows for the all-pairs stage
-	WallTimer wt(s);
+	WallTimer wt(s, c->timings);
 	const uint64_t total = c->rows_total ? c->rows_total : N;
 	const uint64_t first = c->rows_total ? c->rows_first : 0;
 	if (first + N > total) throw std::invalid_argument("rows: first_row + N exceeds total_genomes");
@@ -286,7 +290,7 @@ void do_compare(phylo_ctx *c, int flags, int rank, int world, unsigned long long
 	if (!c->mapped) throw std::invalid_argument("phylo_map_queries has not been called");
 	if (world < 1 || rank < 0 || rank >= world) throw std::invalid_argument("bad tile rank/world");
 	const uint64_t total = c->rows_total ? c->rows_total : c->N;
-	WallTimer wt(c->stream);
+	WallTimer wt(c->stream, c->timings);
 	compare_all_device(c->rows, (int64_t)total, (flags & PHYLO_FLAG_COMPLETE_DELETION) != 0, rank, world, d_subst, d_hom,
 	                   c->stream);
 	c->stats["compare.ms"] = wt.stop();

@@ -46,19 +46,27 @@ __global__ void k_build_text(const uint8_t *__restrict__ ref, int32_t n, uint8_t
 {
 	const int32_t m = 2 * n + 1;
 	int gc = 0;
-	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += (int64_t)gridDim.x * blockDim.x) {
-		uint8_t c = 0;
-		if (i < n) {
-			c = ref[i];
-			if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == '!')) atomicExch(flags, 1);
-			gc += ((c & 'G' & 'C') == ('G' & 'C'));
-		} else if (i == n) {
-			c = '#';
-		} else if (i < m) {
-			c = ref[2 * (int64_t)n - i]; // S[n+1+k] = comp(R[n-1-k])
-			if (c >= 'A') c ^= (c & 2) ? 4 : 21;
+	// 16 bytes of S per thread and iteration, one 128-bit store (padded is a multiple of 256)
+	for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; i0 < padded;
+	     i0 += (int64_t)gridDim.x * blockDim.x * 16) {
+		uint8_t out[16];
+#pragma unroll
+		for (int t = 0; t < 16; t++) {
+			const int64_t i = i0 + t;
+			uint8_t c = 0;
+			if (i < n) {
+				c = ref[i];
+				if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == '!')) atomicExch(flags, 1);
+				gc += ((c & 'G' & 'C') == ('G' & 'C'));
+			} else if (i == n) {
+				c = '#';
+			} else if (i < m) {
+				c = ref[2 * (int64_t)n - i]; // S[n+1+k] = comp(R[n-1-k])
+				if (c >= 'A') c ^= (c & 2) ? 4 : 21;
+			}
+			out[t] = c;
 		}
-		S[i] = c;
+		*reinterpret_cast<uint4 *>(S + i0) = *reinterpret_cast<const uint4 *>(out);
 	}
 #pragma unroll
 	for (int d = 16; d > 0; d >>= 1)
@@ -114,28 +122,38 @@ constexpr int32_t LCP_TIE = -2;
 
 __global__ void k_keys_to_lcp(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ sa,
                               const uint8_t *__restrict__ S, int32_t m, int32_t *__restrict__ SA,
-                              int32_t *__restrict__ LCP, uint8_t *__restrict__ FVC, int kc)
+                              int32_t *__restrict__ LCP, uint8_t *__restrict__ FVC, int kc,
+                              int32_t *__restrict__ heads, uint32_t *__restrict__ counters)
 {
 	const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= m) return;
-	const uint64_t key = keys[j];
-	const uint32_t pos = sa[j];
-	SA[j] = (int32_t)pos;
-	if (j == 0) {
-		LCP[0] = -1; // esa.cxx:313-314
-		LCP[m] = -1;
-		FVC[0] = pos > 0 ? S[pos - 1] : 0; // esa.cxx:247-248 reads S[SA[0] + LCP[0]] with LCP[0] = -1
-		return;
+	bool head = false; // first member of a tie group (same key as the next suffix, not as the previous)
+	if (j < m) {
+		const uint64_t key = keys[j];
+		const uint32_t pos = sa[j];
+		SA[j] = (int32_t)pos;
+		const uint64_t x = j > 0 ? key ^ keys[j - 1] : 1;
+		if (j == 0) {
+			LCP[0] = -1; // esa.cxx:313-314
+			LCP[m] = -1;
+			FVC[0] = pos > 0 ? S[pos - 1] : 0; // esa.cxx:247-248 reads S[SA[0] + LCP[0]] with LCP[0] = -1
+		} else if (x == 0) {
+			LCP[j] = LCP_TIE;
+		} else {
+			// equal leading 3-bit codes: the key occupies bits [0, 3 kc)
+			const int l = (__clzll((long long)x) - (64 - 3 * kc)) / 3;
+			LCP[j] = l;
+			FVC[j] = text_char((uint32_t)(key >> (3 * (kc - 1 - l))) & 7u);
+		}
+		head = x != 0 && j + 1 < m && keys[j + 1] == key;
 	}
-	const uint64_t x = key ^ keys[j - 1];
-	if (x == 0) {
-		LCP[j] = LCP_TIE;
-		return;
-	}
-	// equal leading 3-bit codes: the key occupies bits [0, 3 kc)
-	const int l = (__clzll((long long)x) - (64 - 3 * kc)) / 3;
-	LCP[j] = l;
-	FVC[j] = text_char((uint32_t)(key >> (3 * (kc - 1 - l))) & 7u);
+	// heads[] receives the first SA index of every tie group; one atomic per warp
+	const uint32_t bal = __ballot_sync(0xffffffffu, head);
+	if (!bal) return;
+	const int lane = threadIdx.x & 31;
+	uint32_t base = 0;
+	if (lane == __ffs(bal) - 1) base = atomicAdd(&counters[0], (uint32_t)__popc(bal));
+	base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+	if (head) heads[base + __popc(bal & ((1u << lane) - 1))] = (int32_t)j;
 }
 
 // ---------------------------------------------------------------- small tie groups
@@ -148,26 +166,6 @@ __global__ void k_keys_to_lcp(const uint64_t *__restrict__ keys, const uint32_t 
 
 constexpr int SMALL_GROUP = 8;    // largest group handled by direct comparison
 constexpr int SMALL_COMPARE = 256; // characters beyond the key a comparison may look at
-
-// heads[] receives the first SA index of every tie group
-__global__ void k_tie_heads(const uint64_t *__restrict__ keys, int32_t m, int32_t *__restrict__ heads,
-                            uint32_t *__restrict__ counters)
-{
-	const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	bool head = false;
-	if (j + 1 < m) {
-		const uint64_t k = keys[j];
-		head = (k == keys[j + 1]) && !(j > 0 && keys[j - 1] == k);
-	}
-	// one atomic per warp: with short keys hundreds of thousands of groups get appended
-	const uint32_t bal = __ballot_sync(0xffffffffu, head);
-	if (!bal) return;
-	const int lane = threadIdx.x & 31;
-	uint32_t base = 0;
-	if (lane == __ffs(bal) - 1) base = atomicAdd(&counters[0], (uint32_t)__popc(bal));
-	base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-	if (head) heads[base + __popc(bal & ((1u << lane) - 1))] = (int32_t)j;
-}
 
 // returns the number of equal characters beyond offset `from`, or -1 when the cap is hit;
 // less = suffix a sorts before suffix b (the zeros behind S make the shorter one smaller)
@@ -650,18 +648,16 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 		T.sort_ms = lap.lap();
 
 		// 4. LCP/FVC from neighbouring keys; SA in its final place for all untied suffixes
+		DevBuf<int32_t> heads((size_t)m / 2 + 1, s);
+		DevBuf<uint32_t> counters(2, s);
+		counters.zero();
 		k_keys_to_lcp<<<div_up(m, 256), 256, 0, s>>>(K1, V1, esa.S.get(), m, esa.SA.get(), esa.LCP.get(),
-		                                             esa.FVC.get(), kc);
+		                                             esa.FVC.get(), kc, heads.get(), counters.get());
 		KERNEL_CHECK();
 
 		// 5a. small tie groups by direct comparison
 		uint32_t h_counters[2] = {0, 0};
 		{
-			DevBuf<int32_t> heads((size_t)m / 2 + 1, s);
-			DevBuf<uint32_t> counters(2, s);
-			counters.zero();
-			k_tie_heads<<<div_up(m, 256), 256, 0, s>>>(K1, m, heads.get(), counters.get());
-			KERNEL_CHECK();
 			k_small_groups<<<NUM_SMS_B200 * 4, 128, 0, s>>>(heads.get(), counters.get(), K1, esa.S.get(), m, esa.SA.get(),
 			                                               esa.LCP.get(), esa.FVC.get(), kc);
 			KERNEL_CHECK();

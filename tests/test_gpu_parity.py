@@ -258,6 +258,39 @@ def test_many_genomes_tiles(pb, oracle, ctx):
     assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
 
 
+def test_config4_shape_scaled(pb, oracle, ctx):
+    """BASELINE.json configs[3] in small: many genomes (67 x 200 kbp, d up to 0.05), all 2211
+    pairs; also with complete deletion"""
+    n, N = 200000, 67
+    dists = [0.05 * i / (N - 1) for i in range(1, N)]
+    genomes = oracle_lib.port().simf_set(4, n, dists)
+    for flags in (0, 4):
+        want = oracle.process(genomes, 0, flags, threads=16)
+        subst, homol = ctx.process(genomes, 0, flags)
+        assert np.array_equal(homol, want["homologs"]) and np.array_equal(subst, want["subst"])
+
+
+def test_config5_shape_scaled(pb, oracle, ctx):
+    """BASELINE.json configs[4] in small: multi-contig genomes, every third contig reverse
+    complemented, cut points shifted per genome"""
+    L, N, ncontig = 600000, 6, 12
+    base = oracle_lib.port().simf_set(5, L, [0.02 * i / (N - 1) for i in range(1, N)])
+    genomes = []
+    for g, seq in enumerate(base):
+        step = L // ncontig
+        cuts = [c * step + (1000 * g if g % 2 else 0) for c in range(1, ncontig)]
+        pieces, prev = [], 0
+        for c, cut in enumerate(cuts + [L]):
+            piece = seq[prev:cut]
+            pieces.append(datasets.revcomp(piece) if (c + g) % 3 == 0 else piece)
+            prev = cut
+        genomes.append(b"!".join(pieces))
+    want = oracle.process(genomes, 0, 0, threads=16)
+    subst, homol = ctx.process(genomes, 0, 0)
+    assert np.array_equal(homol, want["homologs"]) and np.array_equal(subst, want["subst"])
+    assert (homol[0, 1:] > 0.9 * L).all()
+
+
 def test_config1_simf(pb, oracle, ctx):
     """BASELINE.json configs[0]: 2 x 100 kbp, d = 0.01, the reference's own CPU-runnable case"""
     genomes = oracle_lib.port().simf_set(1, 100000, [0.01])
