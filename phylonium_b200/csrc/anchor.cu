@@ -3,17 +3,20 @@
 // chunk-parallel walk reproduces the reference's sequential walk exactly.
 //
 // Launch sequence for one batch of queries (all on one stream):
-//   k_walk_chunks     one thread per CH-base chunk: cold walk, events, dead bitmap, exit
+//   k_walk_chunks     one warp per CH-base chunk: cold walk, events, dead bitmap, exit
 //   k_resolve_open    one warp per over-long match: link it to the next open match on the
 //                     same diagonal or scan on cooperatively to the mismatch
 //   k_open_jump       pointer jumping over those links
 //   k_apply_open      final lengths / exit states of open events
-//   k_bridge          one thread per chunk: from the exit state to the merge point
+//   k_bridge          one warp per chunk: from the exit state to the merge point
 //   k_resolve_path    one block per query: pointer doubling from walker 0 marks the true path
 //   (k_continue)      only if a give-up sits on a true path: exact serial continuation
 //   k_copy_events     true events, compacted per query
 //   assemble          right/left classification (max-scan for run heads) -> homologies
-//   sort + k_filter   radix sort by (query, projected start); chaining DP per query
+//   k_sort_filter     one block per query: bitonic sort by projected start in shared memory,
+//                     overlap check, chaining DP, survivors
+//   (general path)    a list longer than 2048, or equal starts: global radix sort by (query,
+//                     start) + k_filter, or std::sort on the host for the tie case
 #include "anchor_device.h"
 #include "filter.h"
 #include "primitives.cuh"

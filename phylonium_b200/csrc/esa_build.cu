@@ -9,20 +9,24 @@
 //   6-mer interval cache                                   (esa.cxx:90-228)
 //
 // GPU formulation (all streaming except where noted):
-//   1. k_build_text      S and its zero padding.
-//   2. k_make_keys       63-bit key per suffix = its first 21 characters in 3-bit codes
-//                        (end < '!' < '#' < A < C < G < T, i.e. unsigned byte order).
-//   3. radix sort        (key, index) pairs, 8 passes of 8 bits (primitives.cuh).
+//   1. k_build_text      S and its zero padding, alphabet check, G/C count.
+//   2. k_make_keys       key per suffix = its first c characters in 3-bit codes
+//                        (end < '!' < '#' < A < C < G < T, i.e. unsigned byte order);
+//                        c from the text length (16 for a 5 Mbp reference, at most 21).
+//   3. radix sort        (key, index) pairs, ceil(3c / 8) passes of 8 bits (primitives.cuh).
 //   4. k_keys_to_lcp     neighbours with different keys give LCP (count of equal leading
 //                        codes) and FVC (the next code of the right neighbour) straight
-//                        from the sorted keys — no random access.  Equal keys mark a tie.
-//   5. refinement        only suffixes inside tie groups: prefix doubling on the compacted
-//                        set — key = (group rank, rank of suffix + h), h = 21, 42, 84, … —
-//                        until every group is a singleton; ranks live in an ISA array.
-//                        Random access, but over the tied fraction only.
-//   6. k_tie_lcp         LCP/FVC of the tied neighbours by direct comparison from offset 21.
-//   7. min-pyramid + k_cld   child table from its closed form (cld_search.h).
-//   8. k_table           K-mer table for the descents (esa_search.h).
+//                        from the sorted keys — no random access.  Equal keys mark a tie;
+//                        the first member of every tie group is appended to a list.
+//   5a. k_small_groups   tie groups of up to 8 suffixes: sorted by direct comparison, with
+//                        their LCP and FVC (all there is on non-repetitive text).
+//   5b. refinement       what is left (repeats): prefix doubling on the compacted set —
+//                        key = (group rank, rank of suffix + h), h = c, 2c, 4c, … — until
+//                        every group is a singleton; ranks live in an ISA array.  Random
+//                        access, but over the tied fraction only.  k_tie_lcp: their LCP/FVC.
+//   6. k_pyramid_level, k_cld, k_cld_long   child table from its closed form (cld_search.h).
+//   7. k_pack_nodes, k_table   interleaved records and K-mer table for the descents
+//                        (esa_search.h).
 #include "cld_search.h"
 #include "esa_device.h"
 #include "esa_search.h"

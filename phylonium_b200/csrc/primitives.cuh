@@ -194,7 +194,7 @@ __device__ __forceinline__ uint32_t warp_peers8(uint32_t d)
 	uint32_t peers = 0xffffffffu;
 #pragma unroll
 	for (int b = 0; b < 8; b++) {
-		const bool bit = (d >> b) & 1u;
+		const bool bit = (d & (1u << b)) != 0; // one LOP3 with predicate output
 		const uint32_t bal = __ballot_sync(0xffffffffu, bit);
 		peers &= bit ? bal : ~bal;
 	}

@@ -288,7 +288,7 @@ def test_config5_shape_scaled(pb, oracle, ctx):
     want = oracle.process(genomes, 0, 0, threads=16)
     subst, homol = ctx.process(genomes, 0, 0)
     assert np.array_equal(homol, want["homologs"]) and np.array_equal(subst, want["subst"])
-    assert (homol[0, 1:] > 0.9 * L).all()
+    assert (homol[0, 1:] > 0.7 * L).all()  # reversed contigs are found too
 
 
 def test_config1_simf(pb, oracle, ctx):
