@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--genomes", type=int, default=8, help="genomes per GPU (configs[1]: 8)")
     ap.add_argument("--chunk", type=int, default=0, help="walker chunk length (0 = library default)")
     ap.add_argument("--kmer-k", type=int, default=None, help="K of the descent table (library default: from m)")
+    ap.add_argument("--sort-path", type=int, default=0, help="suffix sorter: 0 = pick (packed words), 1 = general")
     ap.add_argument("--index", default="replicate", choices=["replicate", "broadcast"],
                     help="multi-GPU: every rank builds the index, or rank 0 builds and broadcasts it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -223,6 +224,7 @@ def run_b200(args):
         ctx.set_option("chunk", args.chunk)
     if args.kmer_k is not None:
         ctx.set_option("kmer_k", args.kmer_k)
+    ctx.set_option("sort_path", args.sort_path)
     d_counts = torch.zeros(2, total * total, dtype=torch.int64, device=dev)
     d_subst, d_homol = d_counts[0], d_counts[1]
     if rank == 0:
@@ -286,6 +288,8 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = int(round((ctx.stat("launches") - launches0) / max(1, args.steps)))
     ms = sum(step_ms) / len(step_ms)
+    srt = sorted(step_ms)
+    step_stats = {"min": srt[0], "median": srt[len(srt) // 2], "max": srt[-1]}
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -327,7 +331,8 @@ def run_b200(args):
             for k in ("esa.text_ms", "esa.keys_ms", "esa.sort_ms", "esa.refine_ms", "esa.lcp_ms", "esa.cld_ms",
                       "esa.table_ms", "esa.total_ms", "anchor.walk_ms", "anchor.open_ms", "anchor.bridge_ms",
                       "anchor.path_ms", "anchor.assemble_ms", "anchor.filter_ms", "anchor.total_ms", "rows.ms",
-                      "compare.ms", "esa.scatter_ms_avg", "esa.scatter_launches"):
+                      "compare.ms", "esa.scatter_ms_avg", "esa.scatter_launches", "esa.first_pass_ms", "esa.hist_ms_avg",
+                      "esa.scan_ms_avg"):
                 acc[k] = acc.get(k, 0.0) + ctx.stat(k) / reps
         ctx.set_option("timings", 0)
         phases = {k: round(v, 4) for k, v in acc.items()}
@@ -336,12 +341,15 @@ def run_b200(args):
         phases["threshold"] = thr_box[0]
         peak, peak_src = measured_peak()
         m = 2 * L + 1
+        packed = ctx.stat("esa.packed") == 1
         if acc.get("esa.scatter_ms_avg", -1) > 0:
-            # dominant kernel: rs_scatter, one radix pass over (u64 key, u32 index) pairs:
-            # 12 B read + 12 B written per suffix
-            bytes_per_launch = 24.0 * m
+            # dominant kernel: one radix pass of the suffix sort.  pk_scatter moves one packed
+            # 64-bit word per suffix (8 B read + 8 B written); the general sorter's rs_scatter a
+            # u64 key and a u32 index (12 B + 12 B)
+            bytes_per_launch = (16.0 if packed else 24.0) * m
             achieved = bytes_per_launch / (acc["esa.scatter_ms_avg"] * 1e-3) / 1e9
-            roofline = {"kernel": "rs_scatter (radix sort pass of the suffix sort)", "bound": "hbm",
+            roofline = {"kernel": ("pk_scatter<false>" if packed else "rs_scatter") + " (radix pass of the suffix sort)",
+                        "bound": "hbm",
                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": None, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": bytes_per_launch,
@@ -380,7 +388,7 @@ def run_b200(args):
                        "step": "ESA build + anchoring of all genomes + all-pairs counts (process())",
                        "parallelism": (f"queries sharded x{world}, index {args.index}d, rows all-gathered, "
                                        f"matrix tiles dealt to ranks + all-reduce") if world > 1 else "single GPU"},
-            "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": launches, "step_ms": step_stats, "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
             "phases": phases,
         }
         print(json.dumps(line), flush=True)

@@ -124,6 +124,9 @@ void record_esa_stats(phylo_ctx *c, const EsaTimings &t)
 	s["esa.scatter_ms_avg"] = t.scatter_ms_avg;
 	s["esa.scatter_launches"] = t.sort_passes;
 	s["esa.key_chars"] = t.key_chars;
+	s["esa.packed"] = t.packed ? 1 : 0;
+	s["esa.dirty"] = (double)t.dirty;
+	s["esa.first_pass_ms"] = t.first_pass_ms;
 	s["esa.refine_rounds"] = t.refine_rounds;
 	s["esa.tied"] = (double)t.tied;
 	s["esa.tie_groups"] = (double)t.tie_groups;
@@ -348,12 +351,6 @@ int phylo_ctx_create(int device, phylo_ctx **out)
 		delete c;
 		return fail(nullptr, PHYLO_ERR_CUDA, "could not create the copy stream");
 	}
-	// keep freed temporaries in the pool instead of returning them to the driver
-	cudaMemPool_t pool;
-	if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-		uint64_t keep = ~0ull;
-		cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-	}
 	*out = c;
 	return PHYLO_OK;
 }
@@ -375,6 +372,9 @@ void phylo_ctx_destroy(phylo_ctx *c)
 	c->d_hom.release();
 	cudaStreamSynchronize(c->stream);
 	cudaStreamSynchronize(c->copy_stream);
+	// blocks cached for this context's streams go back to the driver
+	g_block_cache.trim(c->device, c->own_stream);
+	if (c->stream != c->own_stream) g_block_cache.trim(c->device, c->stream);
 	cudaStreamDestroy(c->copy_stream);
 	cudaEventDestroy(c->ev_main);
 	cudaEventDestroy(c->ev_copy);
@@ -386,6 +386,7 @@ int phylo_set_stream(phylo_ctx *c, void *stream)
 {
 	return guarded(c, [&] {
 		CUDA_CHECK(cudaStreamSynchronize(c->stream));
+		if (c->stream != c->own_stream) g_block_cache.trim(c->device, c->stream);
 		c->stream = stream ? (cudaStream_t)stream : c->own_stream;
 	});
 }
@@ -411,6 +412,9 @@ int phylo_set_option(phylo_ctx *c, const char *key, int64_t value)
 		} else if (k == "sort_mode") {
 			if (value < 0 || value > 2) throw std::invalid_argument("sort_mode must be 0, 1 or 2");
 			g_rs_mode = (int)value; // process-wide
+		} else if (k == "sort_path") {
+			if (value < 0 || value > 2) throw std::invalid_argument("sort_path must be 0, 1 or 2");
+			g_sort_path = (int)value; // process-wide
 		} else if (k == "key_chars") {
 			if (value < 0 || value > 21) throw std::invalid_argument("key_chars must be in [0, 21]");
 			c->opt_key_chars = value;

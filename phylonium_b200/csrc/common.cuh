@@ -4,8 +4,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
+#include <utility>
 
 namespace phy
 {
@@ -40,7 +44,111 @@ inline int div_up(int64_t a, int64_t b)
 	return (int)((a + b - 1) / b);
 }
 
-// Stream-ordered device buffer (cudaMallocAsync); freed on the same stream.
+// Device memory for the library's buffers.  A step of the pipeline asks for the same few
+// dozen buffers in the same order every time, so freed blocks are kept and handed out again:
+// after the first step no allocation reaches the driver (cudaMallocAsync's pool re-maps
+// memory when the size pattern changes, which showed up as idle gaps of 0.1..40 ms on B200).
+// Blocks are cached per (device, stream): a block freed on a stream is only reused on that
+// stream, where the earlier work on it is ordered before the later one.
+class BlockCache
+{
+	struct Block {
+		size_t size;
+		int device;
+		cudaStream_t stream;
+	};
+	std::mutex mu_;
+	std::map<std::pair<int, cudaStream_t>, std::multimap<size_t, void *>> free_;
+	std::unordered_map<void *, Block> live_;
+	size_t cached_bytes_ = 0;
+
+	static size_t round_size(size_t b)
+	{
+		const size_t q = b <= (1u << 20) ? 512 : (2u << 20);
+		return (b + q - 1) / q * q;
+	}
+
+  public:
+	void *alloc(size_t bytes, cudaStream_t s)
+	{
+		if (!bytes) return nullptr;
+		int dev = 0;
+		cuda_check(cudaGetDevice(&dev), "cudaGetDevice", __FILE__, __LINE__);
+		const size_t want = round_size(bytes);
+		std::lock_guard<std::mutex> lock(mu_);
+		auto &pool = free_[{dev, s}];
+		auto it = pool.lower_bound(want);
+		void *p = nullptr;
+		size_t got = want;
+		if (it != pool.end() && it->first <= want + want / 2) {
+			p = it->second;
+			got = it->first;
+			pool.erase(it);
+			cached_bytes_ -= got;
+		} else {
+			cudaError_t e = cudaMalloc(&p, want);
+			if (e == cudaErrorMemoryAllocation) {
+				cudaGetLastError();
+				trim_locked(); // give everything cached back to the driver and try once more
+				e = cudaMalloc(&p, want);
+			}
+			cuda_check(e, "cudaMalloc", __FILE__, __LINE__);
+		}
+		live_[p] = Block{got, dev, s};
+		return p;
+	}
+	void free(void *p)
+	{
+		if (!p) return;
+		std::lock_guard<std::mutex> lock(mu_);
+		auto it = live_.find(p);
+		if (it == live_.end()) return;
+		const Block b = it->second;
+		live_.erase(it);
+		free_[{b.device, b.stream}].emplace(b.size, p);
+		cached_bytes_ += b.size;
+	}
+	// returns the cached blocks of one stream (or of all, stream == (cudaStream_t)-1) to the driver
+	void trim(int device, cudaStream_t stream)
+	{
+		std::lock_guard<std::mutex> lock(mu_);
+		for (auto it = free_.begin(); it != free_.end();) {
+			if (it->first.first == device && (stream == (cudaStream_t)-1 || it->first.second == stream)) {
+				for (auto &kv : it->second) {
+					cudaFree(kv.second);
+					cached_bytes_ -= kv.first;
+				}
+				it = free_.erase(it);
+			} else {
+				++it;
+			}
+		}
+	}
+	size_t cached_bytes() const { return cached_bytes_; }
+
+  private:
+	void trim_locked()
+	{
+		cudaDeviceSynchronize();
+		int dev = 0;
+		cudaGetDevice(&dev);
+		for (auto it = free_.begin(); it != free_.end();) {
+			if (it->first.first == dev) {
+				for (auto &kv : it->second) {
+					cudaFree(kv.second);
+					cached_bytes_ -= kv.first;
+				}
+				it = free_.erase(it);
+			} else {
+				++it;
+			}
+		}
+	}
+};
+
+inline BlockCache g_block_cache;
+
+// Device buffer from the block cache; `stream` is the stream the buffer is used on.
 template <typename T> class DevBuf
 {
 	T *p_ = nullptr;
@@ -71,11 +179,11 @@ template <typename T> class DevBuf
 		release();
 		s_ = s;
 		n_ = n;
-		if (n) CUDA_CHECK(cudaMallocAsync((void **)&p_, n * sizeof(T), s));
+		if (n) p_ = static_cast<T *>(g_block_cache.alloc(n * sizeof(T), s));
 	}
 	void release()
 	{
-		if (p_) cudaFreeAsync(p_, s_);
+		if (p_) g_block_cache.free(p_);
 		p_ = nullptr;
 		n_ = 0;
 	}

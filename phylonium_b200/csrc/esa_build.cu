@@ -31,6 +31,7 @@
 #include "esa_device.h"
 #include "esa_search.h"
 #include "primitives.cuh"
+#include "suffix_sort.cuh"
 
 #include <vector>
 
@@ -44,12 +45,13 @@ constexpr int KEY_CHARS = 21; // most characters a 63-bit key can hold
 
 // ---------------------------------------------------------------- text
 
-// flags[0]: bad byte seen; flags[1]: number of G/C bytes (gc_content, sequence.cxx:152-165)
+// flags[0]: bad byte seen; flags[1]: number of G/C bytes (gc_content, sequence.cxx:152-165);
+// flags[2]: number of '!' (contig separators), which bounds the dirty suffixes of suffix_sort.cuh
 __global__ void k_build_text(const uint8_t *__restrict__ ref, int32_t n, uint8_t *__restrict__ S, int32_t padded,
                              int *__restrict__ flags)
 {
 	const int32_t m = 2 * n + 1;
-	int gc = 0;
+	int gc = 0, bangs = 0;
 	// 16 bytes of S per thread and iteration, one 128-bit store (padded is a multiple of 256)
 	for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; i0 < padded;
 	     i0 += (int64_t)gridDim.x * blockDim.x * 16) {
@@ -62,6 +64,7 @@ __global__ void k_build_text(const uint8_t *__restrict__ ref, int32_t n, uint8_t
 				c = ref[i];
 				if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == '!')) atomicExch(flags, 1);
 				gc += ((c & 'G' & 'C') == ('G' & 'C'));
+				bangs += (c == '!');
 			} else if (i == n) {
 				c = '#';
 			} else if (i < m) {
@@ -76,6 +79,12 @@ __global__ void k_build_text(const uint8_t *__restrict__ ref, int32_t n, uint8_t
 	for (int d = 16; d > 0; d >>= 1)
 		gc += __shfl_xor_sync(0xffffffffu, gc, d);
 	if ((threadIdx.x & 31) == 0 && gc) atomicAdd(flags + 1, gc);
+	if (__any_sync(0xffffffffu, bangs != 0)) {
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1)
+			bangs += __shfl_xor_sync(0xffffffffu, bangs, d);
+		if ((threadIdx.x & 31) == 0) atomicAdd(flags + 2, bangs);
+	}
 }
 
 // ---------------------------------------------------------------- keys
@@ -160,6 +169,54 @@ __global__ void k_keys_to_lcp(const uint64_t *__restrict__ keys, const uint32_t 
 	if (head) heads[base + __popc(bal & ((1u << lane) - 1))] = (int32_t)j;
 }
 
+// The same for the packed words of suffix_sort.cuh (2-bit codes in the top half, dirty flag,
+// index).  Next to a dirty suffix LCP and FVC come from the text: its key is not its text.
+__global__ void k_words_to_lcp(const uint64_t *__restrict__ words, const uint8_t *__restrict__ S, int32_t m,
+                               int32_t *__restrict__ SA, int32_t *__restrict__ LCP, uint8_t *__restrict__ FVC,
+                               int32_t *__restrict__ heads, uint32_t *__restrict__ counters)
+{
+	const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	bool head = false;
+	if (j < m) {
+		const uint64_t e = words[j];
+		const uint32_t key = (uint32_t)(e >> 32), low = (uint32_t)e, pos = low & PK_INDEX;
+		SA[j] = (int32_t)pos;
+		bool first_of_key = true;
+		if (j == 0) {
+			LCP[0] = -1; // esa.cxx:313-314
+			LCP[m] = -1;
+			FVC[0] = pos > 0 ? S[pos - 1] : 0; // esa.cxx:247-248 reads S[SA[0] + LCP[0]] with LCP[0] = -1
+		} else {
+			const uint64_t ep = words[j - 1];
+			const uint32_t x = key ^ (uint32_t)(ep >> 32);
+			if ((low | (uint32_t)ep) & PK_DIRTY) {
+				const uint8_t *a = S + ((uint32_t)ep & PK_INDEX), *b = S + pos;
+				int32_t l = 0;
+				while (a[l] == b[l]) // two different suffixes; S ends in zeros
+					l++;
+				LCP[j] = l;
+				FVC[j] = b[l];
+			} else if (x == 0) {
+				LCP[j] = LCP_TIE;
+				first_of_key = false;
+			} else {
+				const int l = __clz((int)x) >> 1;
+				LCP[j] = l;
+				FVC[j] = (uint8_t)(0x54474341u >> (8 * ((key >> (30 - 2 * l)) & 3u)));
+			}
+		}
+		// dirty suffixes lead their key group and are final; a tie group is made of clean ones
+		head = first_of_key && !(low & PK_DIRTY) && j + 1 < m && (uint32_t)(words[j + 1] >> 32) == key;
+	}
+	const uint32_t bal = __ballot_sync(0xffffffffu, head);
+	if (!bal) return;
+	const int lane = threadIdx.x & 31;
+	uint32_t base = 0;
+	if (lane == __ffs(bal) - 1) base = atomicAdd(&counters[0], (uint32_t)__popc(bal));
+	base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+	if (head) heads[base + __popc(bal & ((1u << lane) - 1))] = (int32_t)j;
+}
+
 // ---------------------------------------------------------------- small tie groups
 //
 // On non-repetitive text the few suffixes that tie on their sort key come in groups of
@@ -187,7 +244,9 @@ __device__ __forceinline__ int32_t suffix_compare(const uint8_t *__restrict__ S,
 	return -1;
 }
 
-// counters[0] = number of groups, counters[1] = groups left for the doubling rounds
+// counters[0] = number of groups, counters[1] = groups left for the doubling rounds.
+// PACKED: keys[] holds the words of suffix_sort.cuh, the sort key is their top half.
+template <bool PACKED>
 __global__ void k_small_groups(const int32_t *__restrict__ heads, uint32_t *__restrict__ counters,
                                const uint64_t *__restrict__ keys, const uint8_t *__restrict__ S, int32_t m,
                                int32_t *__restrict__ SA, int32_t *__restrict__ LCP, uint8_t *__restrict__ FVC, int kc)
@@ -195,9 +254,9 @@ __global__ void k_small_groups(const int32_t *__restrict__ heads, uint32_t *__re
 	const uint32_t groups = counters[0];
 	for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
 		const int32_t j0 = heads[g];
-		const uint64_t key = keys[j0];
+		const uint64_t key = PACKED ? keys[j0] >> 32 : keys[j0];
 		int32_t size = 1;
-		while (size <= SMALL_GROUP && j0 + size < m && keys[j0 + size] == key)
+		while (size <= SMALL_GROUP && j0 + size < m && (PACKED ? keys[j0 + size] >> 32 : keys[j0 + size]) == key)
 			size++;
 		bool hard = size > SMALL_GROUP;
 		int32_t sa[SMALL_GROUP];
@@ -589,6 +648,15 @@ int esa_default_key_chars(int32_t m)
 	return c > KEY_CHARS ? KEY_CHARS : c;
 }
 
+int esa_default_packed_chars(int32_t m)
+{
+	// whole radix passes of four 2-bit characters; 4^c >= 16 m keeps ties rare
+	int c = 4;
+	while (c < PK_MAX_CHARS && (1ll << (2 * c)) < 16 * (int64_t)m)
+		c += 4;
+	return c;
+}
+
 void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k, int key_chars, cudaStream_t s,
                       EsaTimings *tm)
 {
@@ -604,10 +672,6 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 	Timer total(s, timed);
 	Timer lap(s, timed);
 
-	int kc = key_chars > 0 ? key_chars : esa_default_key_chars(m);
-	if (kc > KEY_CHARS) kc = KEY_CHARS;
-	T.key_chars = kc;
-
 	esa.release();
 	esa.n = n;
 	esa.m = m;
@@ -618,56 +682,118 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 	esa.FVC.alloc(m, s);
 
 	// 1. text
-	DevBuf<int> bad(2, s);
+	DevBuf<int> bad(3, s);
 	bad.zero();
 	k_build_text<<<NUM_SMS_B200 * 8, 256, 0, s>>>(d_ref, n, esa.S.get(), padded, bad.get());
 	KERNEL_CHECK();
+	int64_t bangs = 0;
 	{
-		int h_flags[2];
+		int h_flags[3];
 		CUDA_CHECK(cudaMemcpyAsync(h_flags, bad.get(), sizeof h_flags, cudaMemcpyDeviceToHost, s));
 		CUDA_CHECK(cudaStreamSynchronize(s));
 		if (h_flags[0]) throw std::invalid_argument("reference contains bytes outside {A,C,G,T,!}");
 		esa.gc_count = h_flags[1];
+		bangs = h_flags[2];
 	}
 	T.text_ms = lap.lap();
 
+	// Which sorter: packed words (2-bit codes, <= 16 characters, suffix_sort.cuh) unless the
+	// caller asks for longer keys, the text has so many separators that ordering the dirty
+	// suffixes pairwise would cost more than it saves, or 16 characters are hopelessly few.
+	const int64_t dirty_bound = 16 * (2 * bangs + 2); // 16 suffixes in front of every byte below 'A'
+	const bool packed = g_sort_path != 1 && key_chars <= PK_MAX_CHARS && dirty_bound <= PK_DIRTY_CAP && m <= (1 << 30);
+	int kc;
+	if (packed) {
+		kc = key_chars > 0 ? key_chars : esa_default_packed_chars(m);
+	} else {
+		kc = key_chars > 0 ? key_chars : esa_default_key_chars(m);
+		if (kc > KEY_CHARS) kc = KEY_CHARS;
+	}
+	T.key_chars = kc;
+	T.packed = packed;
+
 	{
 		// 2. keys, 3. sort
-		DevBuf<uint64_t> keys(m, s), keys_alt(m, s);
-		DevBuf<uint32_t> vals(m, s), vals_alt(m, s);
-		k_make_keys<<<div_up(m, KEY_TILE), KEY_THREADS, 0, s>>>(esa.S.get(), m, padded, keys.get(), kc);
-		KERNEL_CHECK();
-		T.keys_ms = lap.lap();
-		RsProfile prof;
-		const bool flipped = radix_sort_pairs(keys.get(), vals.get(), keys_alt.get(), vals_alt.get(), m, 0, 3 * kc, true, s,
-		                                      timed ? &prof : nullptr);
-		if (timed && prof.passes) {
-			T.sort_passes = prof.passes;
-			T.hist_ms_avg = prof.hist_ms / prof.passes;
-			T.scan_ms_avg = prof.scan_ms / prof.passes;
-			T.scatter_ms_avg = prof.scatter_ms / prof.passes;
+		const size_t key_words = packed ? pk_padded_words(m) : (size_t)m;
+		DevBuf<uint64_t> keys(key_words, s), keys_alt(key_words, s);
+		DevBuf<uint32_t> vals, vals_alt, dirty_list, dirty_sorted, dirty_ctl;
+		const uint64_t *K1 = nullptr;
+		if (packed) {
+			const uint32_t cap = (uint32_t)dirty_bound;
+			dirty_list.alloc(cap, s);
+			dirty_sorted.alloc(cap, s);
+			dirty_ctl.alloc(2, s); // [0] number of dirty suffixes, [1] error flag of k_dirty_fix
+			dirty_ctl.zero();
+			PkProfile prof;
+			uint64_t *W = suffix_sort_packed(esa.S.get(), m, padded, kc, keys.get(), keys_alt.get(), dirty_list.get(),
+			                                 dirty_ctl.get(), cap, s, timed ? &prof : nullptr);
+			if (timed) {
+				T.first_pass_ms = prof.first_ms;
+				if (prof.passes) {
+					T.sort_passes = prof.passes;
+					T.hist_ms_avg = prof.hist_ms / prof.passes;
+					T.scan_ms_avg = prof.scan_ms / prof.passes;
+					T.scatter_ms_avg = prof.scatter_ms / prof.passes;
+				}
+			}
+			k_dirty_rank<<<div_up(cap, 8), 256, 0, s>>>(dirty_list.get(), dirty_ctl.get(), esa.S.get(), dirty_sorted.get());
+			KERNEL_CHECK();
+			k_dirty_fix<<<div_up(cap, 8), 256, 0, s>>>(dirty_sorted.get(), dirty_ctl.get(), esa.S.get(), m, kc, W,
+			                                           (int *)(dirty_ctl.get() + 1));
+			KERNEL_CHECK();
+			K1 = W;
+			T.sort_ms = lap.lap();
+		} else {
+			vals.alloc(m, s);
+			vals_alt.alloc(m, s);
+			k_make_keys<<<div_up(m, KEY_TILE), KEY_THREADS, 0, s>>>(esa.S.get(), m, padded, keys.get(), kc);
+			KERNEL_CHECK();
+			T.keys_ms = lap.lap();
+			RsProfile prof;
+			const bool flipped = radix_sort_pairs(keys.get(), vals.get(), keys_alt.get(), vals_alt.get(), m, 0, 3 * kc, true, s,
+			                                      timed ? &prof : nullptr);
+			if (timed && prof.passes) {
+				T.sort_passes = prof.passes;
+				T.hist_ms_avg = prof.hist_ms / prof.passes;
+				T.scan_ms_avg = prof.scan_ms / prof.passes;
+				T.scatter_ms_avg = prof.scatter_ms / prof.passes;
+			}
+			K1 = flipped ? keys_alt.get() : keys.get();
+			T.sort_ms = lap.lap();
 		}
-		const uint64_t *K1 = flipped ? keys_alt.get() : keys.get();
-		const uint32_t *V1 = flipped ? vals_alt.get() : vals.get();
-		T.sort_ms = lap.lap();
 
 		// 4. LCP/FVC from neighbouring keys; SA in its final place for all untied suffixes
 		DevBuf<int32_t> heads((size_t)m / 2 + 1, s);
 		DevBuf<uint32_t> counters(2, s);
 		counters.zero();
-		k_keys_to_lcp<<<div_up(m, 256), 256, 0, s>>>(K1, V1, esa.S.get(), m, esa.SA.get(), esa.LCP.get(),
-		                                             esa.FVC.get(), kc, heads.get(), counters.get());
+		if (packed) {
+			k_words_to_lcp<<<div_up(m, 256), 256, 0, s>>>(K1, esa.S.get(), m, esa.SA.get(), esa.LCP.get(), esa.FVC.get(),
+			                                              heads.get(), counters.get());
+		} else {
+			const uint32_t *V1 = K1 == keys.get() ? vals.get() : vals_alt.get();
+			k_keys_to_lcp<<<div_up(m, 256), 256, 0, s>>>(K1, V1, esa.S.get(), m, esa.SA.get(), esa.LCP.get(),
+			                                             esa.FVC.get(), kc, heads.get(), counters.get());
+		}
 		KERNEL_CHECK();
 
 		// 5a. small tie groups by direct comparison
 		uint32_t h_counters[2] = {0, 0};
 		{
-			k_small_groups<<<NUM_SMS_B200 * 4, 128, 0, s>>>(heads.get(), counters.get(), K1, esa.S.get(), m, esa.SA.get(),
-			                                               esa.LCP.get(), esa.FVC.get(), kc);
+			if (packed)
+				k_small_groups<true><<<NUM_SMS_B200 * 4, 128, 0, s>>>(heads.get(), counters.get(), K1, esa.S.get(), m,
+				                                                     esa.SA.get(), esa.LCP.get(), esa.FVC.get(), kc);
+			else
+				k_small_groups<false><<<NUM_SMS_B200 * 4, 128, 0, s>>>(heads.get(), counters.get(), K1, esa.S.get(), m,
+				                                                      esa.SA.get(), esa.LCP.get(), esa.FVC.get(), kc);
 			KERNEL_CHECK();
+			uint32_t h_dirty[2] = {0, 0};
+			if (packed) CUDA_CHECK(cudaMemcpyAsync(h_dirty, dirty_ctl.get(), sizeof h_dirty, cudaMemcpyDeviceToHost, s));
 			CUDA_CHECK(cudaMemcpyAsync(h_counters, counters.get(), sizeof h_counters, cudaMemcpyDeviceToHost, s));
 			CUDA_CHECK(cudaStreamSynchronize(s));
 			T.tie_groups = h_counters[0];
+			T.dirty = h_dirty[0];
+			if (h_dirty[1] || h_dirty[0] > (uint64_t)dirty_bound)
+				throw std::runtime_error("suffix sort: dirty suffixes inconsistent with their key groups");
 		}
 
 		// 5b. refinement of the tie groups that are left (repeats): prefix doubling

@@ -13,6 +13,9 @@ struct EsaTimings {
 	float text_ms = 0, keys_ms = 0, sort_ms = 0, refine_ms = 0, lcp_ms = 0, cld_ms = 0, table_ms = 0, total_ms = 0;
 	float hist_ms_avg = 0, scan_ms_avg = 0, scatter_ms_avg = 0; // per radix pass of the main sort
 	int sort_passes = 0;
+	float first_pass_ms = 0; // packed sorter: the pass that reads the text (histogram + scan + scatter)
+	bool packed = false;     // sorted as packed 2-bit words (suffix_sort.cuh) or as 3-bit keys + indices
+	int64_t dirty = 0;       // packed sorter: suffixes with a byte below 'A' among their key characters
 	int key_chars = 0; // characters per sort key actually used
 	int refine_rounds = 0;
 	int64_t tie_groups = 0; // groups of suffixes with equal sort keys
@@ -67,5 +70,10 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t stream);
 
 int esa_default_k(int32_t m);
+
+// option "sort_path": 0 pick, 1 always the general sorter (3-bit codes, 64-bit keys), 2 same as 0
+inline int g_sort_path = 0;
+// most dirty suffixes the packed sorter orders by pairwise comparison (about 1000 contigs)
+constexpr int64_t PK_DIRTY_CAP = 32768;
 
 } // namespace phy

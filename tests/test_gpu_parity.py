@@ -84,6 +84,90 @@ def test_esa_any_sort_key_length(pb, oracle, name, key_chars):
         assert ctx.stat("esa.key_chars") == key_chars
 
 
+def _contig_torture():
+    """references whose contig separators sit in repeats, poly-A runs and next to each other:
+    the suffixes that start within 16 characters of a separator ("dirty" in suffix_sort.cuh)
+    tie with each other and with clean suffixes in every possible way"""
+    rng = np.random.default_rng(77)
+    rep = datasets.random_dna(rng, 300)
+    refs = {
+        "seps_in_polyA": b"A" * 40 + b"!" + b"A" * 23 + b"!" + b"A" * 7 + b"!" + b"AAAC" + b"A" * 60,
+        "same_contig_many_times": b"!".join([rep] * 12),
+        "contigs_end_in_repeat": b"!".join(datasets.random_dna(rng, 50 + 7 * k) + rep for k in range(20)),
+        "contigs_start_with_repeat": b"!".join(rep[: 20 + k] + datasets.random_dna(rng, 40) for k in range(30)),
+        "short_contigs": b"!".join(datasets.random_dna(rng, 1 + (k % 19)) for k in range(400)),
+        "adjacent_separators": b"ACGT!!ACGT!!!A!C!G!T!!" + datasets.random_dna(rng, 100) + b"!",
+        "separator_first_and_last": b"!" + datasets.random_dna(rng, 500) + b"!",
+        "all_T_then_seps": b"T" * 100 + b"!" + b"T" * 100 + b"!" + b"T" * 15 + b"!" + b"T" * 16 + b"!" + b"T" * 17,
+        "many_contigs": b"!".join(datasets.random_dna(rng, 30 + (k % 11)) for k in range(900)),
+    }
+    return refs
+
+
+@pytest.mark.parametrize("name", sorted(_contig_torture()))
+@pytest.mark.parametrize("key_chars", [0, 3, 8, 16])
+def test_esa_separators_packed_sorter(pb, oracle, name, key_chars):
+    ref = _contig_torture()[name]
+    want = oracle.esa(ref).arrays()
+    with pb.Context(key_chars=key_chars) as ctx:
+        ctx.esa_build(ref)
+        got = ctx.esa_arrays()
+        assert ctx.stat("esa.packed") == 1 and ctx.stat("esa.dirty") >= 3
+        for k in ("SA", "LCP", "CLD", "FVC"):
+            assert np.array_equal(got[k], want[k]), k
+
+
+def test_esa_too_many_separators_take_the_general_sorter(pb, oracle):
+    rng = np.random.default_rng(5)
+    ref = b"!".join(datasets.random_dna(rng, 20) for _ in range(1100))
+    want = oracle.esa(ref).arrays()
+    with pb.Context() as ctx:
+        ctx.esa_build(ref)
+        got = ctx.esa_arrays()
+        assert ctx.stat("esa.packed") == 0
+        for k in ("SA", "LCP", "CLD", "FVC"):
+            assert np.array_equal(got[k], want[k]), k
+
+
+@pytest.mark.parametrize("name", SETS)
+def test_esa_general_sorter(pb, oracle, name):
+    """sort_path 1: 3-bit codes, 64-bit keys + 32-bit indices (what long keys and
+    separator-rich references use)"""
+    ref = datasets.ALL_SETS[name]()[0]
+    want = oracle.esa(ref).arrays()
+    try:
+        with pb.Context(sort_path=1) as ctx:
+            ctx.esa_build(ref)
+            got = ctx.esa_arrays()
+            assert ctx.stat("esa.packed") == 0
+            for k in ("SA", "LCP", "CLD", "FVC"):
+                assert np.array_equal(got[k], want[k]), k
+    finally:
+        with pb.Context(sort_path=0):
+            pass
+
+
+def test_esa_packed_equals_general_on_a_large_text(pb):
+    """1 Mbp with separators: both sorters must give the same index (no oracle needed)"""
+    rng = np.random.default_rng(11)
+    parts = [datasets.random_dna(rng, 100_000) for _ in range(9)]
+    parts.append(parts[2][:5000])  # a repeat next to a separator
+    parts.append(b"A" * 1000)
+    ref = b"!".join(parts)
+    res = []
+    try:
+        for path in (0, 1):
+            with pb.Context(sort_path=path) as ctx:
+                ctx.esa_build(ref)
+                assert ctx.stat("esa.packed") == 1 - path
+                res.append(ctx.esa_arrays())
+    finally:
+        with pb.Context(sort_path=0):
+            pass
+    for k in ("SA", "LCP", "CLD", "FVC"):
+        assert np.array_equal(res[0][k], res[1][k]), k
+
+
 @pytest.mark.parametrize("mode", [1, 2])
 def test_both_radix_sort_schemes(pb, oracle, mode):
     """the look-back ("onesweep") passes are normally used only for very large inputs"""
