@@ -67,8 +67,11 @@ struct Timer {
 // walker's scalar logic redundantly (same addresses: broadcast loads, merged stores) and
 // share the byte comparisons, 32 bases per step (match_run<true>).
 constexpr int WALK_WARPS_PER_BLOCK = 4;
+#ifndef WALK_MIN_BLOCKS
+#define WALK_MIN_BLOCKS 16
+#endif
 
-__global__ void __launch_bounds__(32 * WALK_WARPS_PER_BLOCK) k_walk_chunks(WalkParams P, int *__restrict__ any_open)
+__global__ void __launch_bounds__(32 * WALK_WARPS_PER_BLOCK, WALK_MIN_BLOCKS) k_walk_chunks(WalkParams P, int *__restrict__ any_open)
 {
 	const int32_t w = blockIdx.x * WALK_WARPS_PER_BLOCK + (threadIdx.x >> 5);
 	if (w >= P.total_chunks) return;

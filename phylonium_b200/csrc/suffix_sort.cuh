@@ -28,16 +28,22 @@
 namespace phy
 {
 
-#ifndef PK_ITEMS_N
-#define PK_ITEMS_N 16
+// geometry of the scatter kernel (switchable for tools/sortbench.cu)
+#ifndef PKS_THREADS_N
+#define PKS_THREADS_N 256
 #endif
-#ifndef PK_MIN_BLOCKS
-#define PK_MIN_BLOCKS 3
+#ifndef PKS_MIN_BLOCKS
+#define PKS_MIN_BLOCKS 3
 #endif
-constexpr int PK_THREADS = 256;
-constexpr int PK_ITEMS = PK_ITEMS_N;
+constexpr int PK_THREADS = 256; // histogram and scan kernels
+constexpr int PK_ITEMS = 16;
 constexpr int PK_TILE = PK_THREADS * PK_ITEMS; // suffixes per tile
 constexpr int PK_WARPS = PK_THREADS / 32;
+constexpr int PKS_THREADS = PKS_THREADS_N;      // scatter kernel: same tile, more or fewer items per thread
+constexpr int PKS_ITEMS = PK_TILE / PKS_THREADS;
+constexpr int PKS_WARPS = PKS_THREADS / 32;
+static_assert(PKS_THREADS >= RS_BINS && PKS_THREADS % 32 == 0 && PKS_ITEMS * PKS_THREADS == PK_TILE && PKS_ITEMS % 2 == 0,
+              "scatter geometry");
 constexpr int PK_WORDS = PK_TILE / 16 + 1; // 16-character text words a tile looks at
 constexpr int PK_MAX_CHARS = 16;
 constexpr uint32_t PK_DIRTY = 0x80000000u;
@@ -337,10 +343,10 @@ template <bool FROM_TEXT> struct PkSmem {
 	// words: staging of the incoming tile, then its digit-sorted order; double buffered when
 	// the input is words (the next tile streams in while this one is ranked)
 	uint64_t buf[FROM_TEXT ? 1 : 2][PK_TILE];
-	uint16_t warp_cnt[PK_WARPS][RS_BINS]; // per-warp digit counts, then the warp's first slot in the tile order
-	uint32_t gdelta[RS_BINS];             // global position of (digit, tile) minus its slot in the tile order
-	uint32_t digit_base[RS_BINS];         // words with a smaller digit
-	uint32_t scan_tmp[32];
+	uint16_t warp_cnt[PKS_WARPS][RS_BINS]; // per-warp digit counts, then the warp's first slot in the tile order
+	uint32_t gdelta[RS_BINS];              // global position of (digit, tile) minus its slot in the tile order
+	uint32_t digit_base[RS_BINS];          // words with a smaller digit
+	uint32_t scan_tmp[2][8];               // warp totals of the digit scan, by tile parity
 	uint4 raw[FROM_TEXT ? 2 : 1][FROM_TEXT ? PK_RAW_CHUNKS : 1]; // text of this and the next tile
 	uint32_t codes[FROM_TEXT ? PK_WORDS + 2 : 1];
 	uint32_t spec[FROM_TEXT ? PK_WORDS + 2 : 1];
@@ -352,8 +358,10 @@ template <bool FROM_TEXT> struct PkSmem {
 // digit's run leaves as one contiguous store.  offsets[tile * 256 + d] and totals[d] from
 // pk_scan_counts.  FROM_TEXT: the words are made here from the text (all ones from index n
 // on), and the index of every dirty suffix is appended to dirty_list.
+// Five block barriers per tile; the kernel is bound by the logic pipe and by shared-memory
+// latency, not by HBM (profiles/), so the count of both is what was tuned.
 template <bool FROM_TEXT>
-static __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS)
+static __global__ void __launch_bounds__(PKS_THREADS, PKS_MIN_BLOCKS)
 pk_scatter(const uint64_t *__restrict__ in, const uint8_t *__restrict__ S, int32_t padded, uint64_t *__restrict__ out,
            int64_t n, int shift, int ntiles, PkMasks mk, const uint32_t *__restrict__ offsets,
            const uint32_t *__restrict__ totals, uint32_t *__restrict__ dirty_list, uint32_t *__restrict__ dirty_count,
@@ -367,7 +375,7 @@ pk_scatter(const uint64_t *__restrict__ in, const uint8_t *__restrict__ S, int32
 	auto prefetch = [&](int tile, int slot) {
 		if (FROM_TEXT) {
 			const int64_t tile_base = (int64_t)tile * PK_TILE;
-			for (int c = threadIdx.x; c < PK_RAW_CHUNKS; c += PK_THREADS) {
+			for (int c = threadIdx.x; c < PK_RAW_CHUNKS; c += PKS_THREADS) {
 				const int64_t o = tile_base + 16 * (int64_t)c;
 				const bool ok = o + 16 <= padded;
 				pk_cp_async16(&sm.raw[slot][c], S + (ok ? o : 0), ok ? 16 : 0);
@@ -376,45 +384,62 @@ pk_scatter(const uint64_t *__restrict__ in, const uint8_t *__restrict__ S, int32
 			const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(in) + (size_t)tile * (PK_TILE / 2) + threadIdx.x;
 			ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(sm.buf[slot]) + threadIdx.x;
 #pragma unroll
-			for (int r = 0; r < PK_ITEMS / 2; r++)
-				pk_cp_async16(dst + r * PK_THREADS, src + r * PK_THREADS, 16);
+			for (int r = 0; r < PKS_ITEMS / 2; r++)
+				pk_cp_async16(dst + r * PKS_THREADS, src + r * PKS_THREADS, 16);
 		}
+	};
+	auto zero_counters = [&] {
+		for (int b = threadIdx.x; b < PKS_WARPS * RS_BINS / 2; b += PKS_THREADS)
+			reinterpret_cast<uint32_t *>(&sm.warp_cnt[0][0])[b] = 0;
 	};
 
 	int tile = blockIdx.x;
 	uint32_t my_offset = 0;
 	if (tile < ntiles) {
 		prefetch(tile, 0);
-		my_offset = offsets[(size_t)tile * RS_BINS + threadIdx.x];
+		if (threadIdx.x < RS_BINS) my_offset = offsets[(size_t)tile * RS_BINS + threadIdx.x];
 	}
 	pk_cp_async_commit();
 	{
-		const uint32_t tot = totals[threadIdx.x];
-		sm.digit_base[threadIdx.x] = block_scan_exclusive<uint32_t>(tot, OpSum(), 0u, (uint32_t *)nullptr, sm.scan_tmp);
+		// digit_base = exclusive scan of the digit totals
+		uint32_t v = threadIdx.x < RS_BINS ? totals[threadIdx.x] : 0, inc = v;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+			if (lane >= d) inc += o;
+		}
+		if (lane == 31 && warp < 8) sm.scan_tmp[0][warp] = inc;
+		__syncthreads();
+		if (threadIdx.x < RS_BINS) {
+			uint32_t before = 0;
+#pragma unroll
+			for (int w = 0; w < 8; w++)
+				if (w < warp) before += sm.scan_tmp[0][w];
+			sm.digit_base[threadIdx.x] = before + inc - v;
+		}
 	}
+	zero_counters();
 	uint16_t *const my_cnt = sm.warp_cnt[warp];
-	const int warp_base = warp * (32 * PK_ITEMS);
+	const int warp_base = warp * (32 * PKS_ITEMS);
 
 	for (int it = 0; tile < ntiles; tile += gridDim.x, it++) {
 		const int slot = FROM_TEXT ? 0 : (it & 1);
 		const uint32_t tile_base = (uint32_t)tile * PK_TILE;
 		uint64_t *const buf = sm.buf[slot];
 
+		pk_cp_async_wait<0>(); // this tile's copies have landed
+		__syncthreads();       // (1) ... for everybody; the previous tile has left; the counters are zero
 		// the next tile starts to arrive
 		const int next = tile + gridDim.x;
 		const uint32_t offset_now = my_offset;
 		if (next < ntiles) {
 			prefetch(next, (it & 1) ^ 1);
-			my_offset = offsets[(size_t)next * RS_BINS + threadIdx.x];
+			if (threadIdx.x < RS_BINS) my_offset = offsets[(size_t)next * RS_BINS + threadIdx.x];
 		}
 		pk_cp_async_commit();
-		for (int b = threadIdx.x; b < PK_WARPS * RS_BINS / 2; b += PK_THREADS)
-			reinterpret_cast<uint32_t *>(&sm.warp_cnt[0][0])[b] = 0;
-		pk_cp_async_wait<1>(); // this tile's copies (all but the newest group) have landed
-		__syncthreads();
 		if (FROM_TEXT) {
 			const uint4 *raw = sm.raw[it & 1];
-			for (int w = threadIdx.x; w <= PK_WORDS; w += PK_THREADS) {
+			for (int w = threadIdx.x; w <= PK_WORDS; w += PKS_THREADS) {
 				uint32_t ca, sa, cb, sb;
 				pk_pack16(raw[w], ca, sa);
 				pk_pack16(raw[w + 1], cb, sb);
@@ -425,10 +450,10 @@ pk_scatter(const uint64_t *__restrict__ in, const uint8_t *__restrict__ S, int32
 		}
 
 		// warp-striped: item r of lane l sits at warp_base + r * 32 + l (tile order)
-		uint64_t e[PK_ITEMS];
-		uint32_t rank[PK_ITEMS / 2]; // two 16-bit ranks per register
+		uint64_t e[PKS_ITEMS];
+		uint32_t rank[PKS_ITEMS / 2]; // two 16-bit ranks per register
 #pragma unroll
-		for (int r = 0; r < PK_ITEMS; r++) {
+		for (int r = 0; r < PKS_ITEMS; r++) {
 			const int t = warp_base + r * 32 + lane;
 			if (FROM_TEXT) {
 				const uint32_t index = tile_base + t;
@@ -447,7 +472,7 @@ pk_scatter(const uint64_t *__restrict__ in, const uint8_t *__restrict__ S, int32
 		}
 		// stable rank of every item among the items of its warp with the same digit
 #pragma unroll
-		for (int r = 0; r < PK_ITEMS; r++) {
+		for (int r = 0; r < PKS_ITEMS; r++) {
 			const uint32_t d = pk_digit(e[r], shift);
 			const uint32_t peers = pk_warp_peers(d);
 			const uint32_t before = my_cnt[d];
@@ -460,38 +485,50 @@ pk_scatter(const uint64_t *__restrict__ in, const uint8_t *__restrict__ S, int32
 			else
 				rank[r / 2] = rk;
 		}
-		__syncthreads();
+		__syncthreads(); // (2)
 		// thread d: per-warp counts of digit d -> the warps' first slots; digit d's first slot
-		{
-			const int d = threadIdx.x;
-			uint32_t c[PK_WARPS], run = 0;
+		uint32_t c[PKS_WARPS], run = 0, inc = 0;
+		if (threadIdx.x < RS_BINS) {
 #pragma unroll
-			for (int w = 0; w < PK_WARPS; w++) {
-				c[w] = sm.warp_cnt[w][d];
+			for (int w = 0; w < PKS_WARPS; w++) {
+				c[w] = sm.warp_cnt[w][threadIdx.x];
 				run += c[w];
 			}
-			uint32_t slot0 = block_scan_exclusive<uint32_t>(run, OpSum(), 0u, (uint32_t *)nullptr, sm.scan_tmp);
-			sm.gdelta[d] = sm.digit_base[d] + offset_now - slot0;
+			inc = run;
 #pragma unroll
-			for (int w = 0; w < PK_WARPS; w++) {
-				sm.warp_cnt[w][d] = (uint16_t)slot0;
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+				if (lane >= d) inc += o;
+			}
+			if (lane == 31) sm.scan_tmp[it & 1][warp] = inc;
+		}
+		__syncthreads(); // (3)
+		if (threadIdx.x < RS_BINS) {
+			uint32_t slot0 = inc - run;
+#pragma unroll
+			for (int w = 0; w < 8; w++)
+				if (w < warp) slot0 += sm.scan_tmp[it & 1][w];
+			sm.gdelta[threadIdx.x] = sm.digit_base[threadIdx.x] + offset_now - slot0;
+#pragma unroll
+			for (int w = 0; w < PKS_WARPS; w++) {
+				sm.warp_cnt[w][threadIdx.x] = (uint16_t)slot0;
 				slot0 += c[w];
 			}
 		}
-		__syncthreads();
+		__syncthreads(); // (4)
 		// exchange: every word to its place in the tile's digit order
 #pragma unroll
-		for (int r = 0; r < PK_ITEMS; r++)
+		for (int r = 0; r < PKS_ITEMS; r++)
 			buf[my_cnt[pk_digit(e[r], shift)] + ((r & 1) ? rank[r / 2] >> 16 : rank[r / 2] & 0xffffu)] = e[r];
-		__syncthreads();
+		__syncthreads(); // (5)
+		zero_counters();
 		// every digit's run leaves as one contiguous store
 #pragma unroll
-		for (int r = 0; r < PK_ITEMS; r++) {
-			const uint32_t p = r * PK_THREADS + threadIdx.x;
+		for (int r = 0; r < PKS_ITEMS; r++) {
+			const uint32_t p = r * PKS_THREADS + threadIdx.x;
 			const uint64_t w = buf[p];
 			out[sm.gdelta[pk_digit(w, shift)] + p] = w;
 		}
-		__syncthreads(); // buf is the landing area of the tile after next
 	}
 	pk_cp_async_wait<0>();
 }
@@ -610,7 +647,7 @@ template <bool FROM_TEXT> inline int pk_scatter_grid(int ntiles)
 		CUDA_CHECK(cudaFuncSetAttribute(pk_scatter<FROM_TEXT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		                                (int)sizeof(PkSmem<FROM_TEXT>)));
 		int per_sm = 0, dev = 0, sms = 0;
-		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_scatter<FROM_TEXT>, PK_THREADS,
+		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_scatter<FROM_TEXT>, PKS_THREADS,
 		                                                         sizeof(PkSmem<FROM_TEXT>)));
 		CUDA_CHECK(cudaGetDevice(&dev));
 		CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -652,10 +689,10 @@ inline uint64_t *suffix_sort_packed(const uint8_t *S, int32_t m, int32_t padded,
 		KERNEL_CHECK();
 		mark();
 		if (p == 0)
-			pk_scatter<true><<<grid_text, PK_THREADS, sizeof(PkSmem<true>), s>>>(
+			pk_scatter<true><<<grid_text, PKS_THREADS, sizeof(PkSmem<true>), s>>>(
 				nullptr, S, padded, out, m, shift, ntiles, mk, counts.get(), tot, dirty_list, dirty_count, dirty_cap);
 		else
-			pk_scatter<false><<<grid_words, PK_THREADS, sizeof(PkSmem<false>), s>>>(
+			pk_scatter<false><<<grid_words, PKS_THREADS, sizeof(PkSmem<false>), s>>>(
 				in, nullptr, 0, out, m, shift, ntiles, mk, counts.get(), tot, nullptr, nullptr, 0);
 		KERNEL_CHECK();
 		mark();

@@ -44,7 +44,7 @@ int main(int argc, char **argv)
 		cudaEventRecord(e1, s);
 		pk_scan_counts<<<RS_BINS / 8, PK_THREADS, 0, s>>>(counts.get(), ntiles, totals.get());
 		cudaEventRecord(e2, s);
-		pk_scatter<false><<<grid, PK_THREADS, sizeof(PkSmem<false>), s>>>(a.get(), nullptr, 0, b.get(), m, shift, ntiles, mk,
+		pk_scatter<false><<<grid, PKS_THREADS, sizeof(PkSmem<false>), s>>>(a.get(), nullptr, 0, b.get(), m, shift, ntiles, mk,
 		                                                                 counts.get(), totals.get(), nullptr, nullptr, 0);
 		cudaEventRecord(e3, s);
 		cudaStreamSynchronize(s);
