@@ -354,7 +354,8 @@ struct FinSmem {
 
 __global__ void __launch_bounds__(FIN_THREADS)
 k_sort_filter(const int64_t *__restrict__ raw_offs, const Hom *__restrict__ raw, Hom *__restrict__ fin,
-              int32_t *__restrict__ fin_count, int32_t *__restrict__ fin_flags)
+              int32_t *__restrict__ fin_count, int32_t *__restrict__ fin_flags, int64_t *__restrict__ d_begin,
+              int64_t *__restrict__ d_count)
 {
 	extern __shared__ __align__(16) unsigned char fin_smem_raw[];
 	FinSmem &sm = *reinterpret_cast<FinSmem *>(fin_smem_raw);
@@ -430,6 +431,8 @@ k_sort_filter(const int64_t *__restrict__ raw_offs, const Hom *__restrict__ raw,
 	if (threadIdx.x == 0) {
 		fin_count[q] = (int32_t)carry;
 		fin_flags[q] = 0;
+		d_begin[q] = lo; // what the row builder reads (no host round trip on this path)
+		d_count[q] = carry;
 	}
 }
 
@@ -505,7 +508,10 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	out.d_count.alloc((size_t)nq, s);
 	out.d_begin.zero();
 	out.d_count.zero();
-	if (total_chunks == 0) return;
+	if (total_chunks == 0) {
+		if (opt.input_flags) ST.input_flags = d2h_scalar(opt.input_flags, s);
+		return;
+	}
 
 	const int32_t cap_ev = CH / (thr + 1) + 2;
 	DevBuf<QueryInfo> d_qi(nq, s);
@@ -581,13 +587,37 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	DevBuf<uint8_t> reach(total_chunks, s);
 	std::vector<DevBuf<Event>> overflow;
 	std::vector<int32_t> h_status((size_t)nq);
+	// number of true events per (walker, bridge), scanned right after every path resolution so
+	// that its total comes back with the same synchronisation as the path status
+	DevBuf<uint32_t> cnt((size_t)2 * total_chunks + 1, s);
+	uint32_t n_events = 0;
 	for (int iter = 0;; iter++) {
 		k_resolve_path<<<nq, 1024, 0, s>>>(P, jump_a.get(), jump_b.get(), reach.get(), from.get(), status.get());
 		KERNEL_CHECK();
+		{
+			uint32_t *c = cnt.get();
+			const ChunkRec *rc = rec.get();
+			const uint8_t *rh = reach.get();
+			const int32_t *fr = from.get();
+			const int64_t n2 = 2 * (int64_t)total_chunks;
+			device_scan<uint32_t>(
+				n2 + 1,
+				[rc, rh, fr, n2] __device__(int64_t i) -> uint32_t {
+					if (i >= n2) return 0u;
+					const int64_t g = i >> 1;
+					if (!rh[g]) return 0u;
+					return (i & 1) ? (uint32_t)rc[g].n_bridge : (uint32_t)(rc[g].n_events - fr[g]);
+				},
+				[c] __device__(int64_t i, uint32_t v) { c[i] = v; }, OpSum(), 0u, false, s);
+		}
 		CUDA_CHECK(cudaMemcpyAsync(h_status.data(), status.get(), nq * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
 		int h_flags[4];
 		CUDA_CHECK(cudaMemcpyAsync(h_flags, flags.get(), sizeof h_flags, cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaMemcpyAsync(&n_events, cnt.get() + 2 * (int64_t)total_chunks, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+		if (opt.input_flags)
+			CUDA_CHECK(cudaMemcpyAsync(&ST.input_flags, opt.input_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
 		CUDA_CHECK(cudaStreamSynchronize(s));
+		if (ST.input_flags) return; // the caller reports what is wrong with the input
 		if (h_flags[1]) throw std::runtime_error("internal error: open match left unresolved");
 		ST.open_events += (iter == 0 && h_flags[0]) ? 1 : 0;
 		std::vector<int32_t> stuck;
@@ -619,24 +649,6 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	ST.path_ms = lap.lap();
 
 	// 5. true events, compacted; then homologies
-	DevBuf<uint32_t> cnt((size_t)2 * total_chunks + 1, s);
-	{
-		uint32_t *c = cnt.get();
-		const ChunkRec *rc = rec.get();
-		const uint8_t *rh = reach.get();
-		const int32_t *fr = from.get();
-		const int64_t n2 = 2 * (int64_t)total_chunks;
-		device_scan<uint32_t>(
-			n2 + 1,
-			[rc, rh, fr, n2] __device__(int64_t i) -> uint32_t {
-				if (i >= n2) return 0u;
-				const int64_t g = i >> 1;
-				if (!rh[g]) return 0u;
-				return (i & 1) ? (uint32_t)rc[g].n_bridge : (uint32_t)(rc[g].n_events - fr[g]);
-			},
-			[c] __device__(int64_t i, uint32_t v) { c[i] = v; }, OpSum(), 0u, false, s);
-	}
-	const uint32_t n_events = d2h_scalar(cnt.get() + 2 * (int64_t)total_chunks, s);
 	ST.events = n_events;
 
 	DevBuf<Hom> raw;
@@ -707,7 +719,7 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	KERNEL_CHECK();
 	CUDA_CHECK(cudaFuncSetAttribute(k_sort_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmem)));
 	k_sort_filter<<<nq, FIN_THREADS, sizeof(FinSmem), s>>>(d_raw_offs.get(), raw.get(), fin.get(), fin_count.get(),
-	                                                       fin_flags.get());
+	                                                       fin_flags.get(), out.d_begin.get(), out.d_count.get());
 	KERNEL_CHECK();
 	std::vector<int32_t> h_fin_count((size_t)nq), h_fin_flags((size_t)nq);
 	CUDA_CHECK(cudaMemcpyAsync(out.raw_offs.data(), d_raw_offs.get(), ((size_t)nq + 1) * sizeof(int64_t),
@@ -725,11 +737,8 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 			out.begin[q] = out.raw_offs[q];
 			out.count[q] = h_fin_count[q];
 		}
-		out.homs = std::move(fin);
-		CUDA_CHECK(cudaMemcpyAsync(out.d_begin.get(), out.begin.data(), (size_t)nq * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-		CUDA_CHECK(cudaMemcpyAsync(out.d_count.get(), out.count.data(), (size_t)nq * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-		CUDA_CHECK(cudaStreamSynchronize(s)); // the host vectors are pageable
-		n_raw = 0;                            // skip the general path below
+		out.homs = std::move(fin); // d_begin / d_count were written by k_sort_filter
+		n_raw = 0;                 // skip the general path below
 	}
 
 	// 6. sort by (query, projected start) and keep the heaviest chain per query

@@ -18,6 +18,7 @@ struct AnchorStats {
 	int64_t unresolved = 0;    // bridges that gave up and were continued serially
 	int64_t tie_fallback = 0;  // batches whose sort went through std::sort on the host
 	int64_t general_path = 0;  // batches sorted/filtered by the global path (a list > 2048, or ties)
+	int input_flags = 0;       // copy of *AnchorOptions::input_flags; != 0: nothing was mapped
 	float walk_ms = 0, open_ms = 0, bridge_ms = 0, path_ms = 0, assemble_ms = 0, filter_ms = 0, total_ms = 0;
 };
 
@@ -26,6 +27,9 @@ struct AnchorOptions {
 	int32_t cap = 0;      // comparison cap per thread; 0 = 2 * chunk
 	bool keep_raw = false; // also keep the unsorted, unfiltered lists (tests)
 	bool timings = false;
+	// device int set by the caller's input validation kernel (same stream); read back with the
+	// first synchronisation of the mapping instead of one of its own
+	const int *input_flags = nullptr;
 };
 
 struct AnchorResult {

@@ -22,6 +22,33 @@ namespace phy
 namespace
 {
 
+// 32 query bytes (any alignment) -> three 32-bit planes, byte t -> bit t: bit 1 and bit 2 of
+// the byte (the 2-bit code (c & 6) >> 1) and "byte is '!'" (the only valid byte with bit 6
+// clear).  Reads the aligned words that cover src[0, 32), i.e. up to 3 bytes past src + 32.
+__device__ __forceinline__ void planes_of_32_bytes(const uint8_t *src, uint32_t &c0, uint32_t &c1, uint32_t &bang)
+{
+	const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+	const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+	const uint32_t sh = (uint32_t)(a & 3) * 8;
+	uint32_t x[9];
+#pragma unroll
+	for (int i = 0; i < 9; i++)
+		x[i] = __ldg(w + i);
+	c0 = c1 = bang = 0;
+#pragma unroll
+	for (int i = 0; i < 8; i++) {
+		const uint32_t y = __funnelshift_r(x[i], x[i + 1], sh); // bytes src[4 i .. 4 i + 3]
+		// one flag per byte -> four adjacent bits (multiply gathers them in the top byte)
+		const uint32_t f0 = (y >> 1) & 0x01010101u, f1 = (y >> 2) & 0x01010101u, fb = (~y >> 6) & 0x01010101u;
+		c0 |= (((f0 * 0x01020408u) >> 24) & 0xfu) << (4 * i);
+		c1 |= (((f1 * 0x01020408u) >> 24) & 0xfu) << (4 * i);
+		bang |= (((fb * 0x01020408u) >> 24) & 0xfu) << (4 * i);
+	}
+}
+
+// One thread per 32 reference columns of one genome.  A word that lies inside one homology
+// (nearly all of them) is made from 32 contiguous query bytes with word-wide logic; words at
+// homology borders go column by column.
 __global__ void k_build_rows(uint32_t *__restrict__ rows, int64_t genome_words, int64_t W, int32_t n,
                              int64_t first_row, const uint8_t *__restrict__ Q, const QueryInfo *__restrict__ qi,
                              int32_t count, const Hom *__restrict__ homs, const int64_t *__restrict__ begin,
@@ -33,6 +60,7 @@ __global__ void k_build_rows(uint32_t *__restrict__ rows, int64_t genome_words, 
 	const Hom *H = homs + begin[k];
 	const int32_t h = (int32_t)hcount[k];
 	const uint8_t *q = Q + qi[k].qoff;
+	const int64_t qlen = qi[k].qlen;
 	const int64_t c0 = w * 32;
 	uint32_t pv = 0, p0 = 0, p1 = 0, pd = 0, pb = 0;
 	if (c0 < n && h > 0) {
@@ -45,7 +73,31 @@ __global__ void k_build_rows(uint32_t *__restrict__ rows, int64_t genome_words, 
 			else
 				hi = mid;
 		}
-		for (int32_t x = lo; x < h && H[x].iproj < c0 + 32; x++) {
+		bool done = false;
+		if (lo < h) {
+			const Hom hm = H[lo];
+			const int64_t start = hm.iproj, end = (int64_t)hm.iproj + hm.len;
+			if (start <= c0 && end >= c0 + 32) {
+				// query bytes of columns c0 .. c0 + 31, in ascending query order
+				const int64_t q0 = hm.dir ? (int64_t)hm.iq + (end - 1 - (c0 + 31)) : (int64_t)hm.iq + (c0 - start);
+				if (q0 >= 0 && q0 + 36 <= qlen + 1) { // the aligned loads stay inside the sequence and its terminator
+					uint32_t a, b, g;
+					planes_of_32_bytes(q + q0, a, b, g);
+					if (hm.dir) { // column p holds byte end - 1 - p: reverse, and complement the code
+						a = __brev(a);
+						b = ~__brev(b);
+						g = __brev(g);
+						pd = 0xffffffffu;
+					}
+					pv = 0xffffffffu;
+					p0 = a;
+					p1 = b;
+					pb = g;
+					done = true;
+				}
+			}
+		}
+		for (int32_t x = lo; !done && x < h && H[x].iproj < c0 + 32; x++) {
 			const Hom hm = H[x];
 			const int64_t start = hm.iproj, end = (int64_t)hm.iproj + hm.len;
 			const int64_t a = start > c0 ? start : c0;

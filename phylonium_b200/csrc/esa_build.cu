@@ -33,6 +33,7 @@
 #include "primitives.cuh"
 #include "suffix_sort.cuh"
 
+#include <algorithm>
 #include <vector>
 
 namespace phy
@@ -549,6 +550,61 @@ __global__ void k_table(EsaView e, int32_t K, Interval *__restrict__ table)
 	table[code] = esa_table_entry(e, code, K);
 }
 
+// The table level by level (esa_search.h, esa_table_extend).  Levels 0 .. k0 are small and
+// are made by one block, level L in buf[L & 1]; every further level is one launch with one
+// descent step per entry.  final_out: this level is the table itself, only `cur` is kept.
+constexpr int TABLE_HEAD_LEVELS = 6;
+
+__device__ __forceinline__ TableBuild table_load(const TableBuild *p)
+{
+	const int4 a = __ldg(reinterpret_cast<const int4 *>(p)), b = __ldg(reinterpret_cast<const int4 *>(p) + 1);
+	TableBuild t;
+	t.cur = Interval{a.x, a.y, a.z, a.w};
+	t.par = Interval{b.x, b.y, b.z, b.w};
+	return t;
+}
+
+__device__ __forceinline__ void table_store(TableBuild *p, const TableBuild &t)
+{
+	reinterpret_cast<int4 *>(p)[0] = make_int4(t.cur.l, t.cur.i, t.cur.j, t.cur.m);
+	reinterpret_cast<int4 *>(p)[1] = make_int4(t.par.l, t.par.i, t.par.j, t.par.m);
+}
+
+__global__ void __launch_bounds__(1024)
+k_table_head(EsaView e, int32_t k0, TableBuild *buf0, TableBuild *buf1, Interval *__restrict__ final_out)
+{
+	TableBuild *buf[2] = {buf0, buf1};
+	if (threadIdx.x == 0) buf[0][0] = esa_table_root(e);
+	__syncthreads();
+	for (int32_t k = 0; k < k0; k++) {
+		const TableBuild *prev = buf[k & 1];
+		TableBuild *next = buf[(k + 1) & 1];
+		const uint32_t entries = 1u << (2 * (k + 1));
+		for (uint32_t code = threadIdx.x; code < entries; code += blockDim.x) {
+			const TableBuild r = esa_table_extend(e, prev[code >> 2], k, (uint8_t)(0x54474341u >> (8 * (code & 3))));
+			if (final_out && k + 1 == k0)
+				final_out[code] = r.cur;
+			else
+				next[code] = r;
+		}
+		__syncthreads(); // one block: the level is visible to all its threads
+	}
+	if (k0 == 0 && final_out && threadIdx.x == 0) final_out[0] = buf[0][0].cur;
+}
+
+__global__ void __launch_bounds__(256)
+k_table_level(EsaView e, int32_t k, const TableBuild *__restrict__ prev, TableBuild *__restrict__ next,
+              Interval *__restrict__ final_out)
+{
+	const uint32_t code = blockIdx.x * blockDim.x + threadIdx.x;
+	if (code >= (1u << (2 * (k + 1)))) return;
+	const TableBuild r = esa_table_extend(e, table_load(prev + (code >> 2)), k, (uint8_t)(0x54474341u >> (8 * (code & 3))));
+	if (final_out)
+		reinterpret_cast<int4 *>(final_out)[code] = make_int4(r.cur.l, r.cur.i, r.cur.j, r.cur.m);
+	else
+		table_store(next + code, r);
+}
+
 int bits_for(uint64_t v)
 {
 	int b = 0;
@@ -590,7 +646,9 @@ struct Timer {
 
 int esa_default_k(int32_t m)
 {
-	// about one table record per 4..16 suffixes; 4^K records of 16 bytes
+	// about one table record per 4..16 suffixes; 4^K records of 16 bytes.  One level more
+	// makes the walk 20 % faster on B200 but costs ~5 random sectors per record to build:
+	// worth it from a few dozen queries per index on (phylo_process decides, capi.cu)
 	int k = 1;
 	while (k < 12 && (1ll << (2 * (k + 1))) * 4 <= (int64_t)m)
 		k++;
@@ -630,8 +688,29 @@ void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t s)
 	esa.table.alloc(entries, s);
 	EsaView v = esa.view();
 	v.K = 0;
-	k_table<<<div_up(entries, 128), 128, 0, s>>>(v, K, esa.table.get());
-	KERNEL_CHECK();
+	if (g_table_direct == 1 || (g_table_direct == 0 && K <= 10)) {
+		// every entry by its own descent from the root: the upper levels of neighbouring
+		// entries are the same cache lines, so up to K = 10 this beats the five extra launches
+		// of the level-wise build (measured on B200: 0.150 vs 0.193 ms at K = 10, 0.317 vs
+		// 0.265 ms at K = 11); both give the same table
+		k_table<<<div_up(entries, 128), 128, 0, s>>>(v, K, esa.table.get());
+		KERNEL_CHECK();
+	} else {
+		const int32_t k0 = K < TABLE_HEAD_LEVELS ? K : TABLE_HEAD_LEVELS;
+		// level L lives in buf[L & 1]; the largest stored level is K - 1
+		const size_t big = (size_t)1 << (2 * (K > 0 ? K - 1 : 0)), small = K > 1 ? big / 4 : 1;
+		const size_t head = (size_t)1 << (2 * k0);
+		DevBuf<TableBuild> buf_a(std::max(((K - 1) & 1) ? small : big, head), s), buf_b(std::max(((K - 1) & 1) ? big : small, head), s);
+		TableBuild *buf[2] = {buf_a.get(), buf_b.get()};
+		k_table_head<<<1, 1024, 0, s>>>(v, k0, buf[0], buf[1], k0 == K ? esa.table.get() : nullptr);
+		KERNEL_CHECK();
+		for (int32_t k = k0; k < K; k++) {
+			const uint32_t n_next = 1u << (2 * (k + 1));
+			k_table_level<<<div_up(n_next, 256), 256, 0, s>>>(v, k, buf[k & 1], buf[(k + 1) & 1],
+			                                                  k + 1 == K ? esa.table.get() : nullptr);
+			KERNEL_CHECK();
+		}
+	}
 	esa.K = K;
 }
 

@@ -255,4 +255,52 @@ PHY_HD Interval esa_table_entry(const EsaView &e, uint32_t code, int32_t K)
 	return ij;
 }
 
+// ---- the same table built level by level -------------------------------------------------
+//
+// esa_table_entry walks K characters down from the root for every K-mer.  The entry of a
+// (k+1)-mer is a function of the entry of its k-mer prefix and one more character, so the
+// table can be grown one level at a time, one descent step per entry instead of k + 1:
+// 4/3 * 4^K steps altogether instead of K * 4^K (esa_build.cu).  What the step needs besides
+// the prefix's entry is the node that entry was reached from: if the entry sits inside an
+// edge label longer than k and the next label character differs from c, the descent falls
+// back to that parent (esa_table_entry: "mismatch inside the edge label").
+struct TableBuild {
+	Interval cur; // esa_table_entry(code, k)
+	Interval par; // the explicit node cur was entered from (used while cur.l > k)
+};
+
+PHY_HD TableBuild esa_table_root(const EsaView &e)
+{
+	TableBuild t;
+	t.cur = esa_root(e);
+	t.par = t.cur;
+	return t;
+}
+
+// entry of the (k+1)-mer "prefix c" from the entry P of its k-mer prefix
+PHY_HD TableBuild esa_table_extend(const EsaView &e, const TableBuild &P, int32_t k, uint8_t c)
+{
+	TableBuild r = P;
+	const Interval cur = P.cur;
+	if (cur.i == cur.j) { // singleton {verified, i, i, SA[i]}
+		if (cur.l == k && e.S[cur.m + k] == c) r.cur.l = k + 1;
+		return r;
+	}
+	if (cur.l < k) return r; // the descent failed at an earlier character: same state
+	if (cur.l > k) {         // inside the label of cur: one more label character
+		if (e.S[esa_node(e, cur.i).sa + k] != c) r.cur = P.par;
+		return r;
+	}
+	// cur is an explicit node at depth k: one descent step
+	int32_t sa;
+	const Interval nx = esa_get_interval(e, cur, c, sa);
+	if (interval_empty(nx)) return r; // resuming repeats the failing step
+	r.par = cur;
+	if (nx.i == nx.j)
+		r.cur = Interval{k + 1, nx.i, nx.i, sa};
+	else
+		r.cur = nx; // nx.l >= k + 1 characters, k + 1 of them verified
+	return r;
+}
+
 } // namespace phy

@@ -200,19 +200,22 @@ pk_histogram(const uint64_t *__restrict__ in, const uint8_t *__restrict__ S, int
 }
 
 // counts[tile * 256 + d] -> number of words with digit d in the tiles before `tile` (in
-// place); totals[d] = number of words with digit d.  One block per 8 digits: a thread reads the 8 counts of a tile as one 32-byte
-// sector, two tiles per round.
-constexpr int PK_SCAN_TILES = 2; // tiles per thread and round
-static __global__ void __launch_bounds__(PK_THREADS)
+// place); totals[d] = number of words with digit d.  One block per 8 digits: a thread reads
+// the 8 counts of a tile as one 32-byte sector, four tiles per round.
+constexpr int PK_SCAN_THREADS = 1024;
+constexpr int PK_SCAN_WARPS = PK_SCAN_THREADS / 32;
+constexpr int PK_SCAN_TILES = 4; // tiles per thread and round: 4096 tiles (16.7 M suffixes) per round
+static __global__ void __launch_bounds__(PK_SCAN_THREADS)
 pk_scan_counts(uint32_t *__restrict__ counts, int ntiles, uint32_t *__restrict__ totals)
 {
-	__shared__ uint32_t wsum[PK_WARPS][8];
+	__shared__ uint32_t wsum[PK_SCAN_WARPS][8], wtot[8];
+	static_assert(PK_SCAN_WARPS == 32, "the warp totals are scanned by one warp");
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	uint32_t carry[8];
 #pragma unroll
 	for (int k = 0; k < 8; k++)
 		carry[k] = 0;
-	for (int base = 0; base < ntiles; base += PK_THREADS * PK_SCAN_TILES) {
+	for (int base = 0; base < ntiles; base += PK_SCAN_THREADS * PK_SCAN_TILES) {
 		uint32_t v[PK_SCAN_TILES][8];
 		uint32_t sum[8];
 #pragma unroll
@@ -246,18 +249,26 @@ pk_scan_counts(uint32_t *__restrict__ counts, int ntiles, uint32_t *__restrict__
 			if (lane == 31) wsum[warp][k] = inc[k];
 		}
 		__syncthreads();
+		if (warp == 0) { // warp totals -> exclusive prefixes, block totals
+#pragma unroll
+			for (int k = 0; k < 8; k++) {
+				const uint32_t x = wsum[lane][k];
+				uint32_t y = x;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					const uint32_t o = __shfl_up_sync(0xffffffffu, y, d);
+					if (lane >= d) y += o;
+				}
+				wsum[lane][k] = y - x;
+				if (lane == 31) wtot[k] = y;
+			}
+		}
+		__syncthreads();
 		uint32_t total[8];
 #pragma unroll
 		for (int k = 0; k < 8; k++) {
-			uint32_t before = 0, all = 0;
-#pragma unroll
-			for (int w = 0; w < PK_WARPS; w++) {
-				const uint32_t x = wsum[w][k];
-				if (w < warp) before += x;
-				all += x;
-			}
-			total[k] = all;
-			inc[k] += before + carry[k] - sum[k]; // now: exclusive prefix of this thread's first tile
+			total[k] = wtot[k];
+			inc[k] += wsum[warp][k] + carry[k] - sum[k]; // now: exclusive prefix of this thread's first tile
 		}
 #pragma unroll
 		for (int u = 0; u < PK_SCAN_TILES; u++) {
@@ -685,7 +696,7 @@ inline uint64_t *suffix_sort_packed(const uint8_t *S, int32_t m, int32_t padded,
 			pk_histogram<false><<<ntiles, PK_THREADS, 0, s>>>(in, nullptr, 0, m, shift, mk, counts.get());
 		KERNEL_CHECK();
 		mark();
-		pk_scan_counts<<<RS_BINS / 8, PK_THREADS, 0, s>>>(counts.get(), ntiles, tot);
+		pk_scan_counts<<<RS_BINS / 8, PK_SCAN_THREADS, 0, s>>>(counts.get(), ntiles, tot);
 		KERNEL_CHECK();
 		mark();
 		if (p == 0)

@@ -10,6 +10,8 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../../phylonium_b200/csrc/cld_search.h"
@@ -63,6 +65,22 @@ HostEsa make_esa(const uint8_t *S, const int64_t *SA, const int64_t *LCP, const 
 		e.table.resize((size_t)1 << (2 * K));
 		for (uint32_t code = 0; code < e.table.size(); code++)
 			e.table[code] = esa_table_entry(e.view, code, K);
+		// the level-by-level construction of esa_build.cu must give the very same records
+		std::vector<TableBuild> level(1, esa_table_root(e.view));
+		for (int32_t k = 0; k < K; k++) {
+			std::vector<TableBuild> next(level.size() * 4);
+			for (size_t code = 0; code < next.size(); code++)
+				next[code] = esa_table_extend(e.view, level[code >> 2], k, (uint8_t) "ACGT"[code & 3]);
+			level.swap(next);
+		}
+		for (uint32_t code = 0; code < e.table.size(); code++) {
+			const Interval a = e.table[code], b = level[code].cur;
+			if (a.l != b.l || a.i != b.i || a.j != b.j || a.m != b.m) {
+				fprintf(stderr, "emul: hierarchical table differs at K=%d code=%u: (%d %d %d %d) vs (%d %d %d %d)\n", K, code,
+				        a.l, a.i, a.j, a.m, b.l, b.i, b.j, b.m);
+				abort();
+			}
+		}
 		e.view.table = e.table.data();
 		e.view.K = K;
 	}

@@ -42,7 +42,7 @@ int main(int argc, char **argv)
 		cudaEventRecord(e0, s);
 		pk_histogram<false><<<ntiles, PK_THREADS, 0, s>>>(a.get(), nullptr, 0, m, shift, mk, counts.get());
 		cudaEventRecord(e1, s);
-		pk_scan_counts<<<RS_BINS / 8, PK_THREADS, 0, s>>>(counts.get(), ntiles, totals.get());
+		pk_scan_counts<<<RS_BINS / 8, PK_SCAN_THREADS, 0, s>>>(counts.get(), ntiles, totals.get());
 		cudaEventRecord(e2, s);
 		pk_scatter<false><<<grid, PKS_THREADS, sizeof(PkSmem<false>), s>>>(a.get(), nullptr, 0, b.get(), m, shift, ntiles, mk,
 		                                                                 counts.get(), totals.get(), nullptr, nullptr, 0);
