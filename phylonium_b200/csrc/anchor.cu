@@ -124,14 +124,73 @@ __global__ void k_resolve_open(WalkParams P, int *__restrict__ ctl, int32_t *__r
 	}
 }
 
-// resolves chains lnk -> lnk -> … -> end by pointer jumping over the open chunks only;
-// one block, ping-pong buffers (indexed by chunk, touched only at open chunks)
+// resolves chains lnk -> lnk -> … -> end by pointer jumping over the open chunks only; one
+// block.  Up to OPEN_SMEM open chunks (the usual case: the reference mapped onto itself is one
+// chain of length / CH links) the links live in shared memory under compact indices — a round
+// is then two barriers instead of dependent trips to L2; longer lists ping-pong in global
+// memory (buffers indexed by chunk, touched only at open chunks).
+constexpr int OPEN_SMEM = 8192;
+
 __global__ void __launch_bounds__(1024)
 k_open_jump(const int *__restrict__ ctl, const int32_t *__restrict__ open_list, int32_t *lnk_a, int32_t *end_a,
             int32_t *lnk_b, int32_t *end_b, int rounds)
 {
 	if (!ctl[0]) return;
 	const int32_t count = ctl[2];
+	if (count <= OPEN_SMEM) {
+		extern __shared__ int32_t open_smem[];
+		int32_t *sl = open_smem, *se = open_smem + OPEN_SMEM;
+		// lnk_b is free here: chunk -> position in open_list
+		for (int32_t k = threadIdx.x; k < count; k += blockDim.x)
+			lnk_b[open_list[k]] = k;
+		__syncthreads();
+		for (int32_t k = threadIdx.x; k < count; k += blockDim.x) {
+			const int32_t g = open_list[k];
+			const int32_t l = lnk_a[g];
+			sl[k] = l >= 0 ? lnk_b[l] : -1;
+			se[k] = end_a[g];
+		}
+		__syncthreads();
+		constexpr int PER = OPEN_SMEM / 1024;
+		for (int r = 0; r < rounds; r++) {
+			int32_t nl[PER], ne[PER];
+			bool any = false;
+#pragma unroll
+			for (int u = 0; u < PER; u++) {
+				const int32_t k = threadIdx.x + u * 1024;
+				if (k >= count) break;
+				int32_t l = sl[k], e = se[k];
+				if (l >= 0) {
+					const int32_t l2 = sl[l];
+					if (l2 < 0) {
+						e = se[l];
+						l = -1;
+					} else {
+						l = l2;
+						any = true;
+					}
+				}
+				nl[u] = l;
+				ne[u] = e;
+			}
+			__syncthreads(); // everybody has read this round's links
+#pragma unroll
+			for (int u = 0; u < PER; u++) {
+				const int32_t k = threadIdx.x + u * 1024;
+				if (k >= count) break;
+				sl[k] = nl[u];
+				se[k] = ne[u];
+			}
+			if (!__syncthreads_or(any)) break;
+		}
+		for (int32_t k = threadIdx.x; k < count; k += blockDim.x) {
+			const int32_t g = open_list[k];
+			const int32_t l = sl[k];
+			lnk_a[g] = l >= 0 ? open_list[l] : -1;
+			end_a[g] = se[k];
+		}
+		return;
+	}
 	int32_t *la = lnk_a, *ea = end_a, *lb = lnk_b, *eb = end_b;
 	for (int r = 0; r < rounds; r++) {
 		bool any = false;
@@ -569,8 +628,10 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 		k_resolve_open<<<div_up((int64_t)total_chunks * 32, 256), 256, 0, s>>>(P, flags.get(), lnk_a.get(), end_a.get(),
 		                                                                       open_list.get());
 		KERNEL_CHECK();
-		k_open_jump<<<1, 1024, 0, s>>>(flags.get(), open_list.get(), lnk_a.get(), end_a.get(), lnk_b.get(), end_b.get(),
-		                               rounds_for(total_chunks));
+		CUDA_CHECK(cudaFuncSetAttribute(k_open_jump, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                                2 * OPEN_SMEM * (int)sizeof(int32_t)));
+		k_open_jump<<<1, 1024, 2 * OPEN_SMEM * sizeof(int32_t), s>>>(flags.get(), open_list.get(), lnk_a.get(), end_a.get(),
+		                                                             lnk_b.get(), end_b.get(), rounds_for(total_chunks));
 		KERNEL_CHECK();
 		k_apply_open<<<div_up(total_chunks, 256), 256, 0, s>>>(P, flags.get(), lnk_a.get(), end_a.get(), flags.get() + 1);
 		KERNEL_CHECK();

@@ -382,8 +382,11 @@ struct CldTable {
 	}
 };
 
+// Also writes the interleaved records the descent reads (EsaNode: SA, LCP, CLD, FVC), so
+// that no separate packing pass re-reads the arrays.
 __global__ void __launch_bounds__(CLD_THREADS)
-k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ long_list, uint32_t *__restrict__ long_count)
+k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ long_list, uint32_t *__restrict__ long_count,
+      const int32_t *__restrict__ SA, const uint8_t *__restrict__ FVC, EsaNode *__restrict__ node)
 {
 	__shared__ CldTable T;
 	const int32_t *__restrict__ LCP = py.level[0];
@@ -414,9 +417,12 @@ k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ lo
 				const int s = T.first_le_right(t + 1, a);
 				if (s >= 0) res = (T.st[0][s] == a) ? s : T.first_le_right(t + 1, T.range_min(t + 1, s - 1));
 			}
-			if (res >= 0) CLD[i] = (int32_t)(lo + res);
+			const int32_t cld = res >= 0 ? (int32_t)(lo + res) : 0; // far entries: k_cld_long fills it in
+			if (res >= 0) CLD[i] = cld;
+			reinterpret_cast<int4 *>(node)[i] = make_int4(SA[i], a, cld, FVC[i]);
 		} else if (i == m) {
 			CLD[i] = 0;
+			reinterpret_cast<int4 *>(node)[i] = make_int4(0, LCP[m], 0, 0);
 		}
 		// far away: queue the entry for the warp-cooperative kernel (one atomic per warp)
 		const bool far = i < m && res < 0;
@@ -515,7 +521,7 @@ __device__ __forceinline__ int32_t coop_range_min(const Pyramid &py, int32_t a, 
 // entries whose scans are long: one warp each, 32 positions per step
 __global__ void __launch_bounds__(256)
 k_cld_long(Pyramid py, const int32_t *__restrict__ long_list, const uint32_t *__restrict__ long_count,
-           int32_t *__restrict__ CLD)
+           int32_t *__restrict__ CLD, EsaNode *__restrict__ node)
 {
 	const uint32_t count = *long_count;
 	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -537,7 +543,10 @@ k_cld_long(Pyramid py, const int32_t *__restrict__ long_list, const uint32_t *__
 				res = coop_first_le_right(py, i + 1, mv);
 			}
 		}
-		if ((threadIdx.x & 31) == 0) CLD[i] = res;
+		if ((threadIdx.x & 31) == 0) {
+			CLD[i] = res;
+			node[i].cld = res;
+		}
 	}
 }
 
@@ -672,13 +681,16 @@ __global__ void k_pack_nodes(const int32_t *__restrict__ SA, const int32_t *__re
 }
 } // namespace
 
-void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t s)
+void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t s, bool nodes_ready)
 {
-	// the descent reads interleaved records: pack them first (13 B read, 16 B written per suffix)
-	esa.node.alloc((size_t)esa.m + 1, s);
-	k_pack_nodes<<<div_up((int64_t)esa.m + 1, 256), 256, 0, s>>>(esa.SA.get(), esa.LCP.get(), esa.CLD.get(),
-	                                                            esa.FVC.get(), esa.m, esa.node.get());
-	KERNEL_CHECK();
+	// the descent reads interleaved records; the build writes them with the child table, an
+	// imported index packs them here (13 B read, 16 B written per suffix)
+	if (!nodes_ready) {
+		esa.node.alloc((size_t)esa.m + 1, s);
+		k_pack_nodes<<<div_up((int64_t)esa.m + 1, 256), 256, 0, s>>>(esa.SA.get(), esa.LCP.get(), esa.CLD.get(),
+		                                                            esa.FVC.get(), esa.m, esa.node.get());
+		KERNEL_CHECK();
+	}
 	int K = kmer_k < 0 ? esa_default_k(esa.m) : kmer_k;
 	if (K > 12) K = 12;
 	esa.K = 0;
@@ -1007,16 +1019,18 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 		DevBuf<int32_t> long_list((size_t)m + 1, s);
 		DevBuf<uint32_t> long_count(1, s);
 		long_count.zero();
+		esa.node.alloc((size_t)m + 1, s);
 		k_cld<<<div_up((int64_t)m + 1, CLD_TILE), CLD_THREADS, 0, s>>>(py, m, esa.CLD.get(), long_list.get(),
-		                                                               long_count.get());
+		                                                               long_count.get(), esa.SA.get(), esa.FVC.get(),
+		                                                               esa.node.get());
 		KERNEL_CHECK();
-		k_cld_long<<<NUM_SMS_B200 * 8, 256, 0, s>>>(py, long_list.get(), long_count.get(), esa.CLD.get());
+		k_cld_long<<<NUM_SMS_B200 * 8, 256, 0, s>>>(py, long_list.get(), long_count.get(), esa.CLD.get(), esa.node.get());
 		KERNEL_CHECK();
 		T.cld_ms = lap.lap();
 	}
 
 	// 8. K-mer table
-	esa_build_table(esa, kmer_k, s);
+	esa_build_table(esa, kmer_k, s, true);
 	T.table_ms = lap.lap();
 	T.total_ms = total.lap();
 }

@@ -67,7 +67,8 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
                       EsaTimings *timings);
 
 // builds only the table (used after importing S/SA/LCP/CLD/FVC from another GPU)
-void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t stream);
+// nodes_ready: esa.node already holds the interleaved records
+void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t stream, bool nodes_ready = false);
 
 int esa_default_k(int32_t m);
 
