@@ -10,9 +10,13 @@
 // bit-planes once per genome (N * n bytes read, 5/8 * N * n written); k_compare_pairs then
 // needs only AND/XOR/POPC on 32 columns at a time.
 //
-// k_compare_pairs: one warp per (4 x 4 genome tile, column chunk).  The 32 lanes take 32
-// consecutive words, so every row-plane load is one coalesced 128-byte request; the 16
-// pair counters live in registers and are reduced with shuffles once per chunk.
+// k_compare_tiles: one block of 16 warps per (16 x 16 genome tile, column chunk).  The rows of
+// the 32 genomes stream through shared memory in steps of 32 words, double buffered with
+// cp.async; every warp owns a 4 x 4 sub-tile whose 16 pair counters live in registers and are
+// reduced with shuffles once per chunk.  Tiles none of whose genomes has a reverse-strand
+// homology or a '!' (the flag word behind every row) skip the D and B planes: 3 instead of 5
+// planes to load and half the logic per pair.  Work units (tile pair, chunk) are dealt
+// round-robin to the ranks of a sharded run.
 #include "compare_device.h"
 #include "primitives.cuh"
 
@@ -122,6 +126,12 @@ __global__ void k_build_rows(uint32_t *__restrict__ rows, int64_t genome_words, 
 	row[PL_C1 * W + w] = p1;
 	row[PL_D * W + w] = pd;
 	row[PL_B * W + w] = pb;
+	// flag word behind the planes: does this genome use the D / B planes at all?
+	const uint32_t f = (pd ? ROW_FLAG_D : 0u) | (pb ? ROW_FLAG_B : 0u);
+	if (f) {
+		uint32_t *flag = row + ROW_PLANES * W;
+		if ((*(volatile uint32_t *)flag & f) != f) atomicOr(flag, f);
+	}
 }
 
 // vall[w] = AND over all genomes of V (complete deletion, process.cxx:725-776 in row form)
@@ -136,29 +146,49 @@ __global__ void k_and_valid(const uint32_t *__restrict__ rows, int64_t genome_wo
 	vall[w] = v;
 }
 
-constexpr int PT = 4; // genomes per tile side
-
-__global__ void __launch_bounds__(128)
-k_compare_pairs(const uint32_t *__restrict__ rows, int64_t genome_words, int64_t W, int64_t N, int32_t tiles_side,
-                int64_t n_tile_pairs, int32_t chunks, int64_t chunk_words, int tile_rank, int tile_world,
-                const uint32_t *__restrict__ vall, unsigned long long *__restrict__ subst,
-                unsigned long long *__restrict__ homol)
+constexpr int PT = 4;        // genomes per side of a warp's sub-tile
+constexpr int CMP_STEP = 32; // words per step: one per lane
+// CT = genomes per side of a block's tile: 16 (16 warps), or 8 (4 warps) when there are so few
+// genomes that 16 x 16 tiles would be mostly padding
+__host__ __device__ constexpr int cmp_threads(int CT)
 {
-	const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const int lane = threadIdx.x & 31;
-	const int64_t my_pairs = (n_tile_pairs - tile_rank + tile_world - 1) / tile_world;
-	if (warp >= my_pairs * chunks) return;
-	const int64_t tp = (warp / chunks) * tile_world + tile_rank; // tile pair index
-	const int32_t chunk = (int32_t)(warp % chunks);
-	// unrank tp -> (ti <= tj): row ti holds tiles_side - ti pairs
-	int32_t ti = 0;
-	int64_t rem = tp;
-	while (rem >= tiles_side - ti) {
-		rem -= tiles_side - ti;
-		ti++;
-	}
-	const int32_t tj = ti + (int32_t)rem;
-	const int64_t gi0 = (int64_t)ti * PT, gj0 = (int64_t)tj * PT;
+	return (CT / PT) * (CT / PT) * 32;
+}
+
+__device__ __forceinline__ void cmp_cp_async16(void *smem_dst, const void *gsrc, int src_bytes)
+{
+	const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+// one (tile pair, chunk) unit; P = planes to look at (3: V, C0, C1; 5: all)
+template <int P, int CT>
+__device__ __forceinline__ void compare_tile(uint32_t *stage, const uint32_t *__restrict__ rows, int64_t genome_words,
+                                             int64_t W, int64_t N, int64_t gi0, int64_t gj0, int64_t w_begin, int64_t w_end,
+                                             const uint32_t *__restrict__ vall, unsigned long long *__restrict__ subst,
+                                             unsigned long long *__restrict__ homol)
+{
+	// stage[buf][slot][plane][32]: slots 0..15 the I genomes, 16..31 the J genomes
+	constexpr int SLOT_WORDS = P * CMP_STEP;
+	constexpr int BUF_WORDS = 2 * CT * SLOT_WORDS;
+	constexpr int PIECES = 2 * CT * P * (CMP_STEP / 4); // 16-byte pieces per step
+	constexpr int CMP_THREADS = cmp_threads(CT);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int wi = warp / (CT / PT), wj = warp % (CT / PT);
+	// sub-tiles of padding genomes, or below the diagonal of a diagonal tile, have nothing to count
+	const bool active = gi0 + PT * wi < N && gj0 + PT * wj < N && (gi0 != gj0 || wi <= wj);
+
+	auto prefetch = [&](int64_t w0, int buf) {
+		for (int piece = threadIdx.x; piece < PIECES; piece += CMP_THREADS) {
+			const int slot = piece / (P * 8), rem = piece % (P * 8), plane = rem >> 3, part = rem & 7;
+			const int64_t g = slot < CT ? gi0 + slot : gj0 + (slot - CT);
+			const int64_t w = w0 + 4 * part;
+			const bool ok = g < N && w < w_end; // w_end and W are multiples of 4
+			const uint32_t *src = rows + (ok ? g * genome_words + plane * W + w : 0);
+			cmp_cp_async16(stage + buf * BUF_WORDS + slot * SLOT_WORDS + plane * CMP_STEP + 4 * part, src, ok ? 16 : 0);
+		}
+		asm volatile("cp.async.commit_group;\n" ::: "memory");
+	};
 
 	uint32_t cs[PT][PT], ch[PT][PT];
 #pragma unroll
@@ -167,60 +197,107 @@ k_compare_pairs(const uint32_t *__restrict__ rows, int64_t genome_words, int64_t
 		for (int b = 0; b < PT; b++)
 			cs[a][b] = ch[a][b] = 0;
 
-	const int64_t w_begin = (int64_t)chunk * chunk_words;
-	const int64_t w_end = w_begin + chunk_words < W ? w_begin + chunk_words : W;
-	for (int64_t w = w_begin + lane; w < w_end; w += 32) {
+	prefetch(w_begin, 0);
+	int buf = 0;
+	for (int64_t w0 = w_begin; w0 < w_end; w0 += CMP_STEP, buf ^= 1) {
+		asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+		__syncthreads(); // this step's words are in; everybody is done with the other buffer
+		if (w0 + CMP_STEP < w_end) prefetch(w0 + CMP_STEP, buf ^ 1);
+		if (!active) continue;
+		const uint32_t *st = stage + buf * BUF_WORDS + lane;
+		uint32_t mask = 0xffffffffu;
+		if (vall && w0 + lane < w_end) mask = vall[w0 + lane];
+		// the I side stays in registers, the J side is read genome by genome
 		uint32_t av[PT], a0[PT], a1[PT], ad[PT], ab[PT];
-		uint32_t bv[PT], b0[PT], b1[PT], bd[PT], bb[PT];
-		const uint32_t mask = vall ? vall[w] : 0xffffffffu;
 #pragma unroll
 		for (int a = 0; a < PT; a++) {
-			const bool ok = gi0 + a < N;
-			const uint32_t *r = rows + (ok ? gi0 + a : 0) * genome_words + w;
-			av[a] = ok ? (r[PL_V * W] & mask) : 0u;
-			a0[a] = r[PL_C0 * W];
-			a1[a] = r[PL_C1 * W];
-			ad[a] = r[PL_D * W];
-			ab[a] = r[PL_B * W];
+			const uint32_t *r = st + (PT * wi + a) * SLOT_WORDS;
+			av[a] = r[PL_V * CMP_STEP] & mask;
+			a0[a] = r[PL_C0 * CMP_STEP];
+			a1[a] = r[PL_C1 * CMP_STEP];
+			if (P == 5) {
+				ad[a] = r[PL_D * CMP_STEP];
+				ab[a] = r[PL_B * CMP_STEP];
+			}
 		}
 #pragma unroll
 		for (int b = 0; b < PT; b++) {
-			const bool ok = gj0 + b < N;
-			const uint32_t *r = rows + (ok ? gj0 + b : 0) * genome_words + w;
-			bv[b] = ok ? r[PL_V * W] : 0u;
-			b0[b] = r[PL_C0 * W];
-			b1[b] = r[PL_C1 * W];
-			bd[b] = r[PL_D * W];
-			bb[b] = r[PL_B * W];
-		}
+			const uint32_t *r = st + (CT + PT * wj + b) * SLOT_WORDS;
+			const uint32_t bv = r[PL_V * CMP_STEP], b0 = r[PL_C0 * CMP_STEP], b1 = r[PL_C1 * CMP_STEP];
+			uint32_t bd = 0, bb = 0;
+			if (P == 5) {
+				bd = r[PL_D * CMP_STEP];
+				bb = r[PL_B * CMP_STEP];
+			}
 #pragma unroll
-		for (int a = 0; a < PT; a++) {
-#pragma unroll
-			for (int b = 0; b < PT; b++) {
-				const uint32_t both = av[a] & bv[b];
-				const uint32_t diff = (a0[a] ^ b0[b]) | (a1[a] ^ b1[b]) | (~(ad[a] ^ bd[b]) & (ab[a] ^ bb[b]));
+			for (int a = 0; a < PT; a++) {
+				const uint32_t both = av[a] & bv;
+				uint32_t diff = (a0[a] ^ b0) | (a1[a] ^ b1);
+				if (P == 5) diff |= ~(ad[a] ^ bd) & (ab[a] ^ bb);
 				ch[a][b] += __popc(both);
 				cs[a][b] += __popc(both & diff);
 			}
 		}
 	}
+	if (!active) return;
 #pragma unroll
 	for (int a = 0; a < PT; a++) {
 #pragma unroll
 		for (int b = 0; b < PT; b++) {
-			uint32_t s = cs[a][b], h = ch[a][b];
+			uint32_t sv = cs[a][b], hv = ch[a][b];
 #pragma unroll
 			for (int d = 16; d > 0; d >>= 1) {
-				s += __shfl_xor_sync(0xffffffffu, s, d);
-				h += __shfl_xor_sync(0xffffffffu, h, d);
+				sv += __shfl_xor_sync(0xffffffffu, sv, d);
+				hv += __shfl_xor_sync(0xffffffffu, hv, d);
 			}
-			const int64_t i = gi0 + a, j = gj0 + b;
-			if (lane == 0 && i < j && j < N && h) {
-				atomicAdd(&subst[i * N + j], (unsigned long long)s);
-				atomicAdd(&homol[i * N + j], (unsigned long long)h);
+			const int64_t i = gi0 + PT * wi + a, j = gj0 + PT * wj + b;
+			if (lane == 0 && i < j && j < N && hv) {
+				atomicAdd(&subst[i * N + j], (unsigned long long)sv);
+				atomicAdd(&homol[i * N + j], (unsigned long long)hv);
 			}
 		}
 	}
+}
+
+template <int CT>
+__global__ void __launch_bounds__(cmp_threads(CT), CT == 16 ? 2 : 8)
+k_compare_tiles(const uint32_t *__restrict__ rows, int64_t genome_words, int64_t W, int64_t N, int32_t tiles_side,
+                int64_t units, int32_t chunks, int64_t chunk_words, int tile_rank, int tile_world,
+                const uint32_t *__restrict__ vall, unsigned long long *__restrict__ subst,
+                unsigned long long *__restrict__ homol)
+{
+	extern __shared__ __align__(16) uint32_t cmp_stage[];
+	__shared__ uint32_t tile_flags;
+	const int64_t unit = (int64_t)blockIdx.x * tile_world + tile_rank; // units are dealt round-robin
+	if (unit >= units) return;
+	const int64_t tp = unit / chunks;
+	const int32_t chunk = (int32_t)(unit % chunks);
+	// unrank tp -> (ti <= tj): row ti holds tiles_side - ti pairs
+	int32_t ti = 0;
+	int64_t rem = tp;
+	while (rem >= tiles_side - ti) {
+		rem -= tiles_side - ti;
+		ti++;
+	}
+	const int32_t tj = ti + (int32_t)rem;
+	const int64_t gi0 = (int64_t)ti * CT, gj0 = (int64_t)tj * CT;
+	const int64_t w_begin = (int64_t)chunk * chunk_words;
+	const int64_t w_end = w_begin + chunk_words < W ? w_begin + chunk_words : W;
+
+	if (threadIdx.x == 0) tile_flags = 0;
+	__syncthreads();
+	if (threadIdx.x < 2 * CT) {
+		const int64_t g = threadIdx.x < CT ? gi0 + threadIdx.x : gj0 + (threadIdx.x - CT);
+		if (g < N) {
+			const uint32_t f = rows[g * genome_words + ROW_PLANES * W];
+			if (f) atomicOr(&tile_flags, f);
+		}
+	}
+	__syncthreads();
+	if (tile_flags)
+		compare_tile<5, CT>(cmp_stage, rows, genome_words, W, N, gi0, gj0, w_begin, w_end, vall, subst, homol);
+	else
+		compare_tile<3, CT>(cmp_stage, rows, genome_words, W, N, gi0, gj0, w_begin, w_end, vall, subst, homol);
 }
 
 __global__ void k_symmetrize(unsigned long long *__restrict__ subst, unsigned long long *__restrict__ homol, int64_t N)
@@ -269,7 +346,7 @@ void rows_alloc(RowStore &rs, int64_t genomes, int32_t n, cudaStream_t s)
 	rs.n = n;
 	rs.W = (((int64_t)n + 31) / 32 + 3) / 4 * 4;
 	rs.genomes = genomes;
-	rs.data.alloc((size_t)(genomes * ROW_PLANES * rs.W), s);
+	rs.data.alloc((size_t)(genomes * rs.genome_words()), s);
 	rs.data.zero(); // rows never written (padding genomes of a sharded run) are all-invalid
 }
 
@@ -278,6 +355,9 @@ void rows_build(RowStore &rs, int64_t first_row, const uint8_t *d_Q, const Query
 {
 	if (count <= 0) return;
 	if (first_row < 0 || first_row + count > rs.genomes) throw std::invalid_argument("row store too small");
+	// the flag words behind the rows about to be written
+	CUDA_CHECK(cudaMemset2DAsync(rs.row(first_row) + ROW_PLANES * rs.W, (size_t)rs.genome_words() * sizeof(uint32_t), 0,
+	                             ROW_FLAG_WORDS * sizeof(uint32_t), (size_t)count, s));
 	for (int32_t k0 = 0; k0 < count; k0 += 32768) { // gridDim.y limit
 		const int32_t c = count - k0 < 32768 ? count - k0 : 32768;
 		dim3 grid(div_up(rs.W, 128), c);
@@ -300,24 +380,39 @@ void compare_all_device(const RowStore &rs, int64_t N, bool complete_deletion, i
 		k_and_valid<<<div_up(rs.W, 256), 256, 0, s>>>(rs.data.get(), rs.genome_words(), rs.W, N, vall.get());
 		KERNEL_CHECK();
 	}
-	const int32_t tiles_side = (int32_t)((N + PT - 1) / PT);
+	const int CT = N <= 24 ? 8 : 16; // sharding.py mirrors this choice
+	const int32_t tiles_side = (int32_t)((N + CT - 1) / CT);
 	const int64_t n_tile_pairs = (int64_t)tiles_side * (tiles_side + 1) / 2;
-	const int64_t my_pairs = (n_tile_pairs - tile_rank + tile_world - 1) / tile_world;
-	if (my_pairs > 0) {
-		// enough warps to fill the machine a few times over, chunks of at least 256 words
-		const int64_t want_warps = (int64_t)NUM_SMS_B200 * 64 * 4;
-		int64_t chunks = (want_warps + my_pairs - 1) / my_pairs;
+	{
+		// enough blocks to fill the machine a few times over, chunks of at least 256 words
+		const int64_t want_blocks = (int64_t)NUM_SMS_B200 * 8 * tile_world;
+		int64_t chunks = (want_blocks + n_tile_pairs - 1) / n_tile_pairs;
 		const int64_t max_chunks = (rs.W + 255) / 256;
 		if (chunks > max_chunks) chunks = max_chunks;
 		if (chunks < 1) chunks = 1;
 		int64_t chunk_words = (rs.W + chunks - 1) / chunks;
-		chunk_words = (chunk_words + 31) / 32 * 32;
+		chunk_words = (chunk_words + CMP_STEP - 1) / CMP_STEP * CMP_STEP;
 		chunks = (rs.W + chunk_words - 1) / chunk_words;
-		const int64_t warps = my_pairs * chunks;
-		k_compare_pairs<<<div_up(warps * 32, 128), 128, 0, s>>>(rs.data.get(), rs.genome_words(), rs.W, N, tiles_side,
-		                                                        n_tile_pairs, (int32_t)chunks, chunk_words, tile_rank,
-		                                                        tile_world, vall.get(), d_subst, d_homologs);
-		KERNEL_CHECK();
+		const int64_t units = n_tile_pairs * chunks;
+		const int64_t my_units = (units - tile_rank + tile_world - 1) / tile_world;
+		const size_t smem = (size_t)2 * 2 * CT * ROW_PLANES * CMP_STEP * sizeof(uint32_t);
+		static bool attr_set = false;
+		if (!attr_set) {
+			CUDA_CHECK(cudaFuncSetAttribute(k_compare_tiles<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                                2 * 2 * 16 * ROW_PLANES * CMP_STEP * (int)sizeof(uint32_t)));
+			attr_set = true;
+		}
+		if (my_units > 0) {
+			if (CT == 16)
+				k_compare_tiles<16><<<(unsigned)my_units, cmp_threads(16), smem, s>>>(
+					rs.data.get(), rs.genome_words(), rs.W, N, tiles_side, units, (int32_t)chunks, chunk_words, tile_rank,
+					tile_world, vall.get(), d_subst, d_homologs);
+			else
+				k_compare_tiles<8><<<(unsigned)my_units, cmp_threads(8), smem, s>>>(
+					rs.data.get(), rs.genome_words(), rs.W, N, tiles_side, units, (int32_t)chunks, chunk_words, tile_rank,
+					tile_world, vall.get(), d_subst, d_homologs);
+			KERNEL_CHECK();
+		}
 	}
 	k_symmetrize<<<div_up(N * N, 256), 256, 0, s>>>(d_subst, d_homologs, N);
 	KERNEL_CHECK();

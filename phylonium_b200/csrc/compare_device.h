@@ -17,16 +17,22 @@ namespace phy
 //   B   the query byte is the contig separator '!'
 // Two genomes differ in a column iff the codes differ, or — same strand only — the '!'
 // flags differ (seqcmp compares bytes, revseqcmp only bits 1-2).
+// Behind the planes of a genome sit ROW_FLAG_WORDS words; the first says whether any bit of
+// the D / B planes is set (genomes without reverse-strand homologies and separators, the
+// common case, let the all-pairs kernel skip those planes).  The flags travel with the rows
+// in the all-gather of a sharded run.
 constexpr int ROW_PLANES = 5;
+constexpr int ROW_FLAG_WORDS = 4;
 enum : int { PL_V = 0, PL_C0 = 1, PL_C1 = 2, PL_D = 3, PL_B = 4 };
+enum : uint32_t { ROW_FLAG_D = 1, ROW_FLAG_B = 2 };
 
 struct RowStore {
-	DevBuf<uint32_t> data; // genomes * ROW_PLANES * W
+	DevBuf<uint32_t> data; // genomes * (ROW_PLANES * W + ROW_FLAG_WORDS)
 	int64_t genomes = 0;   // capacity in genomes
 	int64_t W = 0;         // words per plane, multiple of 4
 	int32_t n = 0;         // reference length (columns)
-	uint32_t *row(int64_t g) const { return data.get() + g * ROW_PLANES * W; }
-	int64_t genome_words() const { return ROW_PLANES * W; }
+	uint32_t *row(int64_t g) const { return data.get() + g * genome_words(); }
+	int64_t genome_words() const { return ROW_PLANES * W + ROW_FLAG_WORDS; }
 };
 
 void rows_alloc(RowStore &rs, int64_t genomes, int32_t n, cudaStream_t s);

@@ -5,8 +5,8 @@
   queries  genome g belongs to rank g // per_rank (contiguous blocks, so that a rank's
            reference-coordinate rows are one contiguous slice of the row store)
   rows     all-gather of the bit-plane rows: afterwards every GPU holds all rows
-  matrix   4x4 tile pairs dealt round-robin to ranks; partial N x N count matrices are
-           summed with one all-reduce (every cell is written by exactly one rank)
+  matrix   work units (16x16 genome tile pair, chunk of reference columns) dealt round-robin
+           to ranks; the partial N x N count matrices are summed with one all-reduce
 
 torch.distributed is plumbing only; the collectives move buffers that live inside the
 phylo contexts (wrapped without copying).  The same helpers run under the gloo backend
@@ -46,11 +46,36 @@ def owner_of(plan: ShardPlan, genome: int) -> int:
     return genome // plan.per_rank
 
 
-def tile_pairs_of_rank(n_genomes: int, rank: int, world: int, tile: int = 4) -> List[tuple]:
-    """the (ti, tj) tile pairs rank `rank` computes — same enumeration as k_compare_pairs"""
+NUM_SMS = 148
+STEP_WORDS = 32  # words per step (compare.cu: CMP_STEP)
+
+
+def tile_side(n_genomes: int) -> int:
+    """genomes per side of a block's tile (compare.cu: CT)"""
+    return 8 if n_genomes <= 24 else 16
+
+
+def compare_units(n_genomes: int, words: int, world: int):
+    """(tile pairs, chunks, chunk_words) of the all-pairs stage — the same arithmetic as
+    compare_all_device (compare.cu); `words` = 32-bit words per row plane"""
+    tile = tile_side(n_genomes)
     side = (n_genomes + tile - 1) // tile
     pairs = [(ti, tj) for ti in range(side) for tj in range(ti, side)]
-    return pairs[rank::world]
+    want_blocks = NUM_SMS * 8 * world
+    chunks = (want_blocks + len(pairs) - 1) // max(1, len(pairs))
+    chunks = max(1, min(chunks, (words + 255) // 256))
+    chunk_words = (words + chunks - 1) // chunks
+    chunk_words = (chunk_words + STEP_WORDS - 1) // STEP_WORDS * STEP_WORDS
+    chunks = (words + chunk_words - 1) // chunk_words
+    return pairs, chunks, chunk_words
+
+
+def units_of_rank(n_genomes: int, words: int, rank: int, world: int) -> List[tuple]:
+    """the (ti, tj, chunk) work units rank `rank` computes: unit u = pair * chunks + chunk
+    belongs to rank u mod world — same enumeration as k_compare_tiles"""
+    pairs, chunks, _ = compare_units(n_genomes, words, world)
+    units = [(ti, tj, c) for (ti, tj) in pairs for c in range(chunks)]
+    return units[rank::world]
 
 
 class DeviceBuffer:

@@ -1,8 +1,8 @@
 """Host-side logic of the multi-GPU path on CPU: two processes, gloo backend.
 
-Checks the shard plan, that the tile enumeration gives every genome pair to exactly one rank
-(so that summing the partial matrices reproduces the full matrix) and the in-place
-all-gather of the genome-major row store."""
+Checks the shard plan, that the work-unit enumeration gives every (genome pair, column chunk)
+to exactly one rank (so that summing the partial matrices reproduces the full matrix) and the
+in-place all-gather of the genome-major row store."""
 import os
 import socket
 
@@ -37,19 +37,23 @@ def _worker(rank, world, port, total, results):
         for g in range(total):
             want[g * bpg : (g + 1) * bpg] = (g * 7 + 1) % 251
         ok_rows = bool((store == want).all())
-        # --- matrix: each rank fills the cells of its tile pairs only
+        # --- matrix: each rank adds up the contributions of its work units only
         n = plan.padded_total
+        words = 1000
+        pairs, chunks, _ = sharding.compare_units(n, words, world)
         rng = np.random.default_rng(5)
-        full = rng.integers(1, 1000, size=(n, n))
-        full = np.triu(full, 1)
+        contrib = rng.integers(1, 1000, size=(chunks, n, n))  # what chunk c adds to cell (i, j)
+        contrib = np.triu(contrib, 1)
+        full = contrib.sum(axis=0)
         full = full + full.T
         part = np.zeros_like(full)
-        for ti, tj in sharding.tile_pairs_of_rank(n, rank, world):
-            for i in range(ti * 4, min(n, ti * 4 + 4)):
-                for j in range(tj * 4, min(n, tj * 4 + 4)):
+        T = sharding.tile_side(n)
+        for ti, tj, c in sharding.units_of_rank(n, words, rank, world):
+            for i in range(ti * T, min(n, ti * T + T)):
+                for j in range(tj * T, min(n, tj * T + T)):
                     if i < j:
-                        part[i, j] = full[i, j]
-                        part[j, i] = full[i, j]
+                        part[i, j] += contrib[c, i, j]
+                        part[j, i] += contrib[c, i, j]
         a = torch.from_numpy(part.copy())
         b = torch.from_numpy(part.copy())
         sharding.reduce_matrix(a, b)
@@ -81,10 +85,13 @@ def test_plan_and_tiles_cover_everything():
             owned = [g for p in plans for g in range(p.first, p.first + p.count)]
             assert owned == list(range(total))
             n = plans[0].padded_total
-            seen = set()
-            for r in range(world):
-                for t in sharding.tile_pairs_of_rank(n, r, world):
-                    assert t not in seen
-                    seen.add(t)
-            side = (n + 3) // 4
-            assert len(seen) == side * (side + 1) // 2
+            for words in (1, 255, 4000, 156252):
+                pairs, chunks, chunk_words = sharding.compare_units(n, words, world)
+                assert chunks * chunk_words >= words > (chunks - 1) * chunk_words
+                seen = set()
+                for r in range(world):
+                    for u in sharding.units_of_rank(n, words, r, world):
+                        assert u not in seen
+                        seen.add(u)
+                side = (n + sharding.tile_side(n) - 1) // sharding.tile_side(n)
+                assert len(seen) == side * (side + 1) // 2 * chunks
