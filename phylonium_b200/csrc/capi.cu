@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <functional>
 #include <cstring>
 #include <map>
 #include <string>
@@ -35,7 +36,14 @@ struct phylo_ctx {
 	const uint8_t *dQ = nullptr; // q_own or the caller's device buffer
 	std::vector<QueryInfo> qi;
 	uint64_t N = 0; // sequences of the last map call
-	AnchorResult anchors;
+	// the sequences are mapped in batches (bounded scratch memory; in phylo_process a batch is
+	// mapped while the next one is still on its way over PCIe)
+	struct Batch {
+		uint64_t first = 0, count = 0;
+		AnchorResult res;
+	};
+	std::vector<Batch> batches;
+	std::vector<cudaEvent_t> batch_events; // phylo_process: "the copies of batch b have landed"
 	bool mapped = false;
 
 	RowStore rows;
@@ -236,7 +244,48 @@ void do_esa_build(phylo_ctx *c, const uint8_t *d_ref, uint64_t n, uint64_t query
 	c->esa_ready = true;
 }
 
-void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_t *lens, uint64_t N, uint64_t thr)
+// about this many sequence bytes per batch
+constexpr uint64_t MAP_BATCH_BYTES = 512ull << 20;
+
+// batch b = sequences [ends[b - 1], ends[b])
+std::vector<uint64_t> plan_batches(const uint64_t *lens, uint64_t N)
+{
+	std::vector<uint64_t> ends;
+	uint64_t bytes = 0;
+	for (uint64_t k = 0; k < N; k++) {
+		bytes += lens[k];
+		if (bytes >= MAP_BATCH_BYTES || k + 1 == N) {
+			ends.push_back(k + 1);
+			bytes = 0;
+		}
+	}
+	return ends;
+}
+
+void accumulate(AnchorStats &sum, const AnchorStats &st)
+{
+	sum.chunks += st.chunks;
+	sum.events += st.events;
+	sum.open_events += st.open_events;
+	sum.unresolved += st.unresolved;
+	sum.tie_fallback += st.tie_fallback;
+	sum.general_path += st.general_path;
+	sum.walk_ms += st.walk_ms;
+	sum.open_ms += st.open_ms;
+	sum.bridge_ms += st.bridge_ms;
+	sum.path_ms += st.path_ms;
+	sum.assemble_ms += st.assemble_ms;
+	sum.filter_ms += st.filter_ms;
+	sum.total_ms += st.total_ms;
+}
+
+// ends: batch boundaries (plan_batches); ready: per batch, an event the stream waits for
+// before it touches the batch's bytes (NULL: everything is already ordered on the stream);
+// before_batch(b) is called before batch b is waited for (phylo_process queues the copies of
+// a later batch there)
+void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_t *lens, uint64_t N, uint64_t thr,
+            const std::vector<uint64_t> *ends_in = nullptr, const std::vector<cudaEvent_t> *ready = nullptr,
+            const std::function<void(size_t)> &before_batch = nullptr)
 {
 	if (!c->esa_ready) throw std::invalid_argument("phylo_esa_build has not been called");
 	if (thr < 1 || thr > 0x3fffffffull) throw std::invalid_argument("threshold out of range");
@@ -244,6 +293,7 @@ void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_
 	c->mapped = false;
 	c->dQ = dQ;
 	c->N = N;
+	c->batches.clear();
 	c->qi.assign((size_t)N, QueryInfo());
 	for (uint64_t k = 0; k < N; k++) {
 		if (lens[k] > 0x7fffff00ull) throw std::invalid_argument("sequence too long for 32-bit indices");
@@ -256,44 +306,67 @@ void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_
 	opt.cap = (int32_t)c->opt_cap;
 	opt.keep_raw = c->keep_raw;
 	opt.timings = c->timings;
-	AnchorStats st;
-	DevBuf<QueryInfo> d_qi;
-	DevBuf<int> bad(1, s);
-	if (N) {
+
+	const uint64_t total = c->rows_total ? c->rows_total : N;
+	const uint64_t first_row = c->rows_total ? c->rows_first : 0;
+	if (first_row + N > total) throw std::invalid_argument("rows: first_row + N exceeds total_genomes");
+	if ((uint64_t)c->rows.genomes != total || c->rows.n != c->esa.n) rows_alloc(c->rows, (int64_t)total, c->esa.n, s);
+
+	const std::vector<uint64_t> ends = ends_in ? *ends_in : plan_batches(lens, N);
+	AnchorStats sum;
+	float rows_ms = 0;
+	c->batches.resize(ends.size());
+	uint64_t b0 = 0;
+	for (size_t b = 0; b < ends.size(); b++) {
+		const uint64_t b1 = ends[b], cnt = b1 - b0;
+		phylo_ctx::Batch &B = c->batches[b];
+		B.first = b0;
+		B.count = cnt;
+		if (before_batch) before_batch(b);
+		if (ready) CUDA_CHECK(cudaStreamWaitEvent(s, (*ready)[b], 0));
+		std::vector<QueryInfo> qi(c->qi.begin() + (size_t)b0, c->qi.begin() + (size_t)b1);
 		// the walk relies on the alphabet and on the zero byte behind every sequence; the
 		// verdict is read back with the first synchronisation of the mapping
-		d_qi.alloc((size_t)N, s);
-		CUDA_CHECK(cudaMemcpyAsync(d_qi.get(), c->qi.data(), N * sizeof(QueryInfo), cudaMemcpyHostToDevice, s));
+		DevBuf<QueryInfo> d_qi((size_t)cnt, s);
+		DevBuf<int> bad(1, s);
+		CUDA_CHECK(cudaMemcpyAsync(d_qi.get(), qi.data(), cnt * sizeof(QueryInfo), cudaMemcpyHostToDevice, s));
 		bad.zero();
-		for (uint64_t k0 = 0; k0 < N; k0 += 32768) {
-			const int32_t cnt = (int32_t)(N - k0 < 32768 ? N - k0 : 32768);
+		for (uint64_t k0 = 0; k0 < cnt; k0 += 32768) {
+			const int32_t part = (int32_t)(cnt - k0 < 32768 ? cnt - k0 : 32768);
 			uint64_t longest = 0;
-			for (uint64_t k = k0; k < k0 + (uint64_t)cnt; k++)
-				longest = std::max<uint64_t>(longest, lens[k]);
-			dim3 grid((unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (longest / 16 + 256) / 256), 4096), cnt);
-			k_validate_queries<<<grid, 256, 0, s>>>(dQ, d_qi.get() + k0, cnt, bad.get());
+			for (uint64_t k = k0; k < k0 + (uint64_t)part; k++)
+				longest = std::max<uint64_t>(longest, lens[b0 + k]);
+			dim3 grid((unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (longest / 16 + 256) / 256), 4096), part);
+			k_validate_queries<<<grid, 256, 0, s>>>(dQ, d_qi.get() + k0, part, bad.get());
 			KERNEL_CHECK();
 		}
 		opt.input_flags = bad.get();
-	}
-	anchor_queries_device(c->esa, dQ, c->qi, (int32_t)thr, opt, s, c->anchors, &st);
-	if (st.input_flags & 1) throw std::invalid_argument("a sequence contains bytes outside {A,C,G,T,!}");
-	if (st.input_flags & 2) throw std::invalid_argument("a sequence is not followed by a zero byte in the device buffer");
-	record_anchor_stats(c, st);
+		AnchorStats st;
+		anchor_queries_device(c->esa, dQ, qi, (int32_t)thr, opt, s, B.res, &st);
+		if (st.input_flags & 1) throw std::invalid_argument("a sequence contains bytes outside {A,C,G,T,!}");
+		if (st.input_flags & 2) throw std::invalid_argument("a sequence is not followed by a zero byte in the device buffer");
+		accumulate(sum, st);
 
-	// reference-coordinate rows for the all-pairs stage
-	WallTimer wt(s, c->timings);
-	const uint64_t total = c->rows_total ? c->rows_total : N;
-	const uint64_t first = c->rows_total ? c->rows_first : 0;
-	if (first + N > total) throw std::invalid_argument("rows: first_row + N exceeds total_genomes");
-	if ((uint64_t)c->rows.genomes != total || c->rows.n != c->esa.n) rows_alloc(c->rows, (int64_t)total, c->esa.n, s);
-	if (N) {
-		CUDA_CHECK(cudaMemcpyAsync(d_qi.get(), c->qi.data(), N * sizeof(QueryInfo), cudaMemcpyHostToDevice, s));
-		rows_build(c->rows, (int64_t)first, dQ, d_qi.get(), (int32_t)N, c->anchors.homs.get(), c->anchors.d_begin.get(),
-		           c->anchors.d_count.get(), s);
+		// reference-coordinate rows for the all-pairs stage
+		WallTimer wt(s, c->timings);
+		CUDA_CHECK(cudaMemcpyAsync(d_qi.get(), qi.data(), cnt * sizeof(QueryInfo), cudaMemcpyHostToDevice, s));
+		rows_build(c->rows, (int64_t)(first_row + b0), dQ, d_qi.get(), (int32_t)cnt, B.res.homs.get(), B.res.d_begin.get(),
+		           B.res.d_count.get(), s);
+		rows_ms += wt.stop();
+		b0 = b1;
 	}
-	c->stats["rows.ms"] = wt.stop();
+	record_anchor_stats(c, sum);
+	c->stats["rows.ms"] = rows_ms;
+	c->stats["map.batches"] = (double)ends.size();
 	c->mapped = true;
+}
+
+// batch that holds sequence `index`
+const phylo_ctx::Batch &batch_of(const phylo_ctx *c, uint64_t index)
+{
+	for (const auto &B : c->batches)
+		if (index >= B.first && index < B.first + B.count) return B;
+	throw std::invalid_argument("sequence index out of range");
 }
 
 void do_compare(phylo_ctx *c, int flags, int rank, int world, unsigned long long *d_subst,
@@ -371,11 +444,10 @@ void phylo_ctx_destroy(phylo_ctx *c)
 	cudaStreamSynchronize(c->stream);
 	c->esa.release();
 	c->q_own.release();
-	c->anchors.homs.release();
-	c->anchors.raw.release();
-	c->anchors.d_offs.release();
-	c->anchors.d_begin.release();
-	c->anchors.d_count.release();
+	c->batches.clear();
+	for (cudaEvent_t e : c->batch_events)
+		cudaEventDestroy(e);
+	c->batch_events.clear();
 	c->rows.data.release();
 	c->d_subst.release();
 	c->d_hom.release();
@@ -616,8 +688,10 @@ int phylo_homology_counts(const phylo_ctx *c, uint64_t *counts, int raw)
 {
 	if (!c || !counts) return PHYLO_ERR_INVALID;
 	if (!c->mapped) return PHYLO_ERR_INVALID;
-	for (uint64_t k = 0; k < c->N; k++)
-		counts[k] = raw ? (uint64_t)(c->anchors.raw_offs[k + 1] - c->anchors.raw_offs[k]) : (uint64_t)c->anchors.count[k];
+	for (const auto &B : c->batches)
+		for (uint64_t k = 0; k < B.count; k++)
+			counts[B.first + k] =
+				raw ? (uint64_t)(B.res.raw_offs[k + 1] - B.res.raw_offs[k]) : (uint64_t)B.res.count[k];
 	return PHYLO_OK;
 }
 
@@ -629,10 +703,11 @@ int phylo_get_homologies(const phylo_ctx *cc, uint64_t index, int raw, phylo_hom
 		if (!c->mapped) throw std::invalid_argument("phylo_map_queries has not been called");
 		if (index >= c->N) throw std::invalid_argument("sequence index out of range");
 		if (raw && !c->keep_raw) throw std::invalid_argument("raw lists need option keep_raw");
-		const Hom *src = raw ? c->anchors.raw.get() : c->anchors.homs.get();
-		const uint64_t first = (uint64_t)(raw ? c->anchors.raw_offs[index] : c->anchors.begin[index]);
-		const uint64_t cnt = raw ? (uint64_t)(c->anchors.raw_offs[index + 1] - c->anchors.raw_offs[index])
-		                         : (uint64_t)c->anchors.count[index];
+		const phylo_ctx::Batch &B = batch_of(c, index);
+		const uint64_t k = index - B.first;
+		const Hom *src = raw ? B.res.raw.get() : B.res.homs.get();
+		const uint64_t first = (uint64_t)(raw ? B.res.raw_offs[k] : B.res.begin[k]);
+		const uint64_t cnt = raw ? (uint64_t)(B.res.raw_offs[k + 1] - B.res.raw_offs[k]) : (uint64_t)B.res.count[k];
 		if (written) *written = cnt;
 		const uint64_t take = cnt < cap ? cnt : cap;
 		if (!take) return;
@@ -723,10 +798,32 @@ int phylo_process(phylo_ctx *c, const char *const *seqs, const uint64_t *lens, u
 			CUDA_CHECK(cudaMemcpyAsync(dq + offs[ref_index], seqs[ref_index], lens[ref_index], cudaMemcpyHostToDevice, s));
 		CUDA_CHECK(cudaEventRecord(c->ev_main, s));
 		CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
-		for (uint64_t k = 0; k < N; k++)
-			if (k != ref_index && lens[k])
-				CUDA_CHECK(cudaMemcpyAsync(dq + offs[k], seqs[k], lens[k], cudaMemcpyHostToDevice, c->copy_stream));
-		CUDA_CHECK(cudaEventRecord(c->ev_copy, c->copy_stream));
+		// The other sequences follow on the copy stream, batch by batch, with an event behind
+		// every batch: batch b is mapped while the later ones are still crossing PCIe.  At most
+		// COPY_QUEUE copies are queued ahead of the batch being mapped — a thousand queued copies
+		// fill the driver's queue and block the host until they have drained, with the index
+		// build not yet launched (measured: 1000 x 3 Mbp) — but never fewer than two batches.
+		const std::vector<uint64_t> ends = plan_batches(lens, N);
+		while (c->batch_events.size() < ends.size()) {
+			cudaEvent_t e;
+			CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+			c->batch_events.push_back(e);
+		}
+		constexpr uint64_t COPY_QUEUE = 256;
+		size_t queued = 0;
+		auto queue_copies = [&](size_t current) { // `current` = the batch about to be mapped
+			const uint64_t seq0 = current ? ends[current - 1] : 0;
+			size_t last = current + 2;
+			while (last + 1 < ends.size() && ends[last + 1] - seq0 <= COPY_QUEUE)
+				last++;
+			for (; queued <= last && queued < ends.size(); queued++) {
+				for (uint64_t k = queued ? ends[queued - 1] : 0; k < ends[queued]; k++)
+					if (k != ref_index && lens[k])
+						CUDA_CHECK(cudaMemcpyAsync(dq + offs[k], seqs[k], lens[k], cudaMemcpyHostToDevice, c->copy_stream));
+				CUDA_CHECK(cudaEventRecord(c->batch_events[queued], c->copy_stream));
+			}
+		};
+		queue_copies(0);
 
 		uint64_t query_bases = 0;
 		for (uint64_t k = 0; k < N; k++)
@@ -738,8 +835,8 @@ int phylo_process(phylo_ctx *c, const char *const *seqs, const uint64_t *lens, u
 		const uint64_t thr = phylo_min_anchor_length(0.025, gc, 2 * lens[ref_index] + 1);
 		c->stats["threshold"] = (double)thr;
 
-		CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_copy, 0));
-		do_map(c, dq, offs.data(), lens, N, thr);
+		const std::vector<cudaEvent_t> ready(c->batch_events.begin(), c->batch_events.begin() + ends.size());
+		do_map(c, dq, offs.data(), lens, N, thr, &ends, &ready, queue_copies);
 
 		const uint64_t tot = c->rows_total ? c->rows_total : c->N;
 		ensure_matrix(c, tot);
