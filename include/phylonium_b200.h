@@ -79,6 +79,8 @@ int phylo_set_stream(phylo_ctx *ctx, void *stream);
  *   "cap"      per-thread comparison cap (default 2 * chunk)
  *   "kmer_k"   K of the descent table, 0 = none, -1 = from the text length (default)
  *   "key_chars" characters per suffix-sort key (1..21), 0 = from the text length (default)
+ *   "map_batch_bytes" sequences are mapped in batches of about this many bytes (default
+ *               512 MiB): bounds the scratch memory; process-wide
  *   "table_direct" how the descent table is built: 0 = by K (default), 1 = entry by entry
  *               from the root, 2 = level by level; process-wide
  *   "sort_path" suffix sorter: 0 = packed 2-bit words when the key fits 16 characters and the

@@ -244,8 +244,8 @@ void do_esa_build(phylo_ctx *c, const uint8_t *d_ref, uint64_t n, uint64_t query
 	c->esa_ready = true;
 }
 
-// about this many sequence bytes per batch
-constexpr uint64_t MAP_BATCH_BYTES = 512ull << 20;
+// about this many sequence bytes per batch (option "map_batch_bytes")
+inline uint64_t g_map_batch_bytes = 512ull << 20;
 
 // batch b = sequences [ends[b - 1], ends[b])
 std::vector<uint64_t> plan_batches(const uint64_t *lens, uint64_t N)
@@ -254,7 +254,7 @@ std::vector<uint64_t> plan_batches(const uint64_t *lens, uint64_t N)
 	uint64_t bytes = 0;
 	for (uint64_t k = 0; k < N; k++) {
 		bytes += lens[k];
-		if (bytes >= MAP_BATCH_BYTES || k + 1 == N) {
+		if (bytes >= g_map_batch_bytes || k + 1 == N) {
 			ends.push_back(k + 1);
 			bytes = 0;
 		}
@@ -496,6 +496,9 @@ int phylo_set_option(phylo_ctx *c, const char *key, int64_t value)
 		} else if (k == "sort_path") {
 			if (value < 0 || value > 2) throw std::invalid_argument("sort_path must be 0, 1 or 2");
 			g_sort_path = (int)value; // process-wide
+		} else if (k == "map_batch_bytes") {
+			if (value < 1) throw std::invalid_argument("map_batch_bytes must be >= 1");
+			g_map_batch_bytes = (uint64_t)value; // process-wide
 		} else if (k == "table_direct") {
 			if (value < 0 || value > 2) throw std::invalid_argument("table_direct must be 0, 1 or 2");
 			g_table_direct = (int)value; // process-wide

@@ -359,6 +359,36 @@ def test_reference_need_not_be_first(pb, oracle, ctx):
         assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
 
 
+@pytest.mark.parametrize("batch_bytes", [1, 9000, 30000])
+def test_mapping_in_batches(pb, oracle, batch_bytes):
+    """phylo_process / phylo_map_queries map the sequences batch by batch (512 MiB by default);
+    tiny batches here: every count, the per-sequence homology lists and the raw lists must not
+    depend on where the batch borders fall"""
+    rng = np.random.default_rng(31)
+    r = datasets.random_dna(rng, 6000)
+    genomes = [r] + [datasets.mutate(rng, r, 0.003 * (k + 1)) for k in range(10)]
+    genomes[4] = datasets.revcomp(genomes[4])
+    genomes[7] = genomes[7][:2500] + b"!" + genomes[7][2500:]
+    genomes[9] = b""
+    want = oracle.process(genomes, 0, 0, threads=4)
+    try:
+        with pb.Context(keep_raw=1, map_batch_bytes=batch_bytes) as ctx:
+            subst, homol = ctx.process(genomes, 0, 0)
+            assert ctx.stat("map.batches") > 1
+            assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
+            with pb.Context(keep_raw=1, map_batch_bytes=1 << 40) as one:
+                one.process(genomes, 0, 0)
+                assert one.stat("map.batches") == 1
+                assert np.array_equal(ctx.homology_counts(), one.homology_counts())
+                assert np.array_equal(ctx.homology_counts(raw=True), one.homology_counts(raw=True))
+                for k in range(len(genomes)):
+                    assert np.array_equal(ctx.homologies(k), one.homologies(k)), k
+                    assert np.array_equal(ctx.homologies(k, raw=True), one.homologies(k, raw=True)), k
+    finally:
+        with pb.Context(map_batch_bytes=512 << 20):
+            pass
+
+
 def test_many_genomes_tiles(pb, oracle, ctx):
     """more genomes than one 4x4 tile, odd count: diagonal and ragged tiles"""
     rng = np.random.default_rng(17)
