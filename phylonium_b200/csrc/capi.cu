@@ -443,6 +443,7 @@ void phylo_ctx_destroy(phylo_ctx *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	c->esa.release();
+	c->esa.destroy_side();
 	c->q_own.release();
 	c->batches.clear();
 	for (cudaEvent_t e : c->batch_events)

@@ -997,25 +997,36 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 		}
 	}
 
-	// 7. child table
+	// 7. child table.  The min-pyramid is only read by k_cld_long (the entries whose scans are
+	// long): it is built on a side stream while k_cld works through the bulk of the entries.
 	{
+		if (!esa.side) {
+			CUDA_CHECK(cudaStreamCreateWithFlags(&esa.side, cudaStreamNonBlocking));
+			CUDA_CHECK(cudaEventCreateWithFlags(&esa.ev_fork, cudaEventDisableTiming));
+			CUDA_CHECK(cudaEventCreateWithFlags(&esa.ev_join, cudaEventDisableTiming));
+		}
+		cudaStream_t side = esa.side;
+		cudaEvent_t ev_fork = esa.ev_fork, ev_join = esa.ev_join;
 		Pyramid py;
 		std::vector<DevBuf<int32_t>> levels;
 		py.level[0] = esa.LCP.get();
 		py.size[0] = m + 1;
 		py.levels = 1;
+		CUDA_CHECK(cudaEventRecord(ev_fork, s));
+		CUDA_CHECK(cudaStreamWaitEvent(side, ev_fork, 0));
 		while (py.size[py.levels - 1] > 1) {
 			if (py.levels >= PYR_MAX_LEVELS) throw std::runtime_error("pyramid too deep");
 			const int32_t n_in = py.size[py.levels - 1];
 			const int32_t n_out = (n_in + 31) / 32;
 			levels.emplace_back((size_t)n_out, s);
-			k_pyramid_level<<<div_up((int64_t)n_out * 32, 256), 256, 0, s>>>(py.level[py.levels - 1], n_in,
-			                                                                 levels.back().get(), n_out);
+			k_pyramid_level<<<div_up((int64_t)n_out * 32, 256), 256, 0, side>>>(py.level[py.levels - 1], n_in,
+			                                                                    levels.back().get(), n_out);
 			KERNEL_CHECK();
 			py.level[py.levels] = levels.back().get();
 			py.size[py.levels] = n_out;
 			py.levels++;
 		}
+		CUDA_CHECK(cudaEventRecord(ev_join, side));
 		DevBuf<int32_t> long_list((size_t)m + 1, s);
 		DevBuf<uint32_t> long_count(1, s);
 		long_count.zero();
@@ -1024,6 +1035,7 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 		                                                               long_count.get(), esa.SA.get(), esa.FVC.get(),
 		                                                               esa.node.get());
 		KERNEL_CHECK();
+		CUDA_CHECK(cudaStreamWaitEvent(s, ev_join, 0));
 		k_cld_long<<<NUM_SMS_B200 * 8, 256, 0, s>>>(py, long_list.get(), long_count.get(), esa.CLD.get(), esa.node.get());
 		KERNEL_CHECK();
 		T.cld_ms = lap.lap();

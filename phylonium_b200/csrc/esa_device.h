@@ -32,6 +32,18 @@ struct EsaDevice {
 	DevBuf<int32_t> CLD; // m + 1
 	DevBuf<EsaNode> node;   // m + 1: SA/LCP/CLD/FVC interleaved for the descent (esa_search.h)
 	DevBuf<Interval> table; // 4^K
+	// side stream of the build (min-pyramid next to the child-table kernel), made on first use
+	cudaStream_t side = nullptr;
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	void destroy_side()
+	{
+		if (!side) return;
+		cudaStreamSynchronize(side);
+		cudaStreamDestroy(side);
+		cudaEventDestroy(ev_fork);
+		cudaEventDestroy(ev_join);
+		side = nullptr;
+	}
 	EsaView view() const
 	{
 		EsaView v;

@@ -103,8 +103,24 @@ template <bool COOP> PHY_HD int32_t match_run(const uint8_t *a, const uint8_t *b
 			if (bal) return from + (__ffs(bal) - 1);
 		}
 		// then 128 bytes per round, all eight loads in flight before the first ballot:
-		// the loop is bound by the latency of a round trip to L2/HBM, not by bandwidth
-		for (int32_t base = from + 32; base < to; base += 128) {
+		// the loop is bound by the latency of a round trip to L2/HBM, not by bandwidth.
+		// Whole rounds first (no bounds checks: a third of the walk's instructions were
+		// spent here), then one checked round for the rest.
+		int32_t base = from + 32;
+		for (; base + 128 <= to; base += 128) {
+			uint8_t va[4], vb[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				va[u] = a[base + 32 * u + lane];
+				vb[u] = b[base + 32 * u + lane];
+			}
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const uint32_t bal = __ballot_sync(0xffffffffu, va[u] != vb[u]);
+				if (bal) return base + 32 * u + (__ffs(bal) - 1);
+			}
+		}
+		for (; base < to; base += 128) {
 			uint8_t va[4], vb[4];
 #pragma unroll
 			for (int u = 0; u < 4; u++) {
