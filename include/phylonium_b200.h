@@ -79,6 +79,8 @@ int phylo_set_stream(phylo_ctx *ctx, void *stream);
  *   "cap"      per-thread comparison cap (default 2 * chunk)
  *   "kmer_k"   K of the descent table, 0 = none, -1 = from the text length (default)
  *   "key_chars" characters per suffix-sort key (1..21), 0 = from the text length (default)
+ *   "scan_mode" prefix scans: 1 = one launch with decoupled look-back (default), 0 = three
+ *               launches (reduce, scan of the tile sums, apply); process-wide
  *   "map_batch_bytes" sequences are mapped in batches of about this many bytes (default
  *               512 MiB): bounds the scratch memory; process-wide
  *   "table_direct" how the descent table is built: 0 = by K (default), 1 = entry by entry

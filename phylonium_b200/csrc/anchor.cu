@@ -568,7 +568,10 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	out.d_begin.zero();
 	out.d_count.zero();
 	if (total_chunks == 0) {
-		if (opt.input_flags) ST.input_flags = d2h_scalar(opt.input_flags, s);
+		if (opt.input_flags) {
+			if (opt.input_flags_ready) CUDA_CHECK(cudaStreamWaitEvent(s, opt.input_flags_ready, 0));
+			ST.input_flags = d2h_scalar(opt.input_flags, s);
+		}
 		return;
 	}
 
@@ -675,8 +678,10 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 		int h_flags[4];
 		CUDA_CHECK(cudaMemcpyAsync(h_flags, flags.get(), sizeof h_flags, cudaMemcpyDeviceToHost, s));
 		CUDA_CHECK(cudaMemcpyAsync(&n_events, cnt.get() + 2 * (int64_t)total_chunks, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-		if (opt.input_flags)
+		if (opt.input_flags) {
+			if (opt.input_flags_ready && iter == 0) CUDA_CHECK(cudaStreamWaitEvent(s, opt.input_flags_ready, 0));
 			CUDA_CHECK(cudaMemcpyAsync(&ST.input_flags, opt.input_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
+		}
 		CUDA_CHECK(cudaStreamSynchronize(s));
 		if (ST.input_flags) return; // the caller reports what is wrong with the input
 		if (h_flags[1]) throw std::runtime_error("internal error: open match left unresolved");

@@ -30,6 +30,9 @@ struct AnchorOptions {
 	// device int set by the caller's input validation kernel (same stream); read back with the
 	// first synchronisation of the mapping instead of one of its own
 	const int *input_flags = nullptr;
+	// if set: recorded (on another stream) behind the validation kernel; the mapping stream
+	// waits for it only right before it reads input_flags, so the validation runs next to the walk
+	cudaEvent_t input_flags_ready = nullptr;
 };
 
 struct AnchorResult {

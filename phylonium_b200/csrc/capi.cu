@@ -44,6 +44,8 @@ struct phylo_ctx {
 	};
 	std::vector<Batch> batches;
 	std::vector<cudaEvent_t> batch_events; // phylo_process: "the copies of batch b have landed"
+	cudaStream_t check_stream = nullptr;   // input validation next to the walk
+	cudaEvent_t ev_check_fork = nullptr, ev_check_done = nullptr;
 	bool mapped = false;
 
 	RowStore rows;
@@ -331,15 +333,32 @@ void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_
 		DevBuf<int> bad(1, s);
 		CUDA_CHECK(cudaMemcpyAsync(d_qi.get(), qi.data(), cnt * sizeof(QueryInfo), cudaMemcpyHostToDevice, s));
 		bad.zero();
+		// ... on a stream of its own, next to the walk
+		if (!c->check_stream) {
+			CUDA_CHECK(cudaStreamCreateWithFlags(&c->check_stream, cudaStreamNonBlocking));
+			CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_check_fork, cudaEventDisableTiming));
+			CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_check_done, cudaEventDisableTiming));
+		}
+		CUDA_CHECK(cudaEventRecord(c->ev_check_fork, s));
+		CUDA_CHECK(cudaStreamWaitEvent(c->check_stream, c->ev_check_fork, 0));
 		for (uint64_t k0 = 0; k0 < cnt; k0 += 32768) {
 			const int32_t part = (int32_t)(cnt - k0 < 32768 ? cnt - k0 : 32768);
 			uint64_t longest = 0;
 			for (uint64_t k = k0; k < k0 + (uint64_t)part; k++)
 				longest = std::max<uint64_t>(longest, lens[b0 + k]);
 			dim3 grid((unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (longest / 16 + 256) / 256), 4096), part);
-			k_validate_queries<<<grid, 256, 0, s>>>(dQ, d_qi.get() + k0, part, bad.get());
+			k_validate_queries<<<grid, 256, 0, c->check_stream>>>(dQ, d_qi.get() + k0, part, bad.get());
 			KERNEL_CHECK();
 		}
+		CUDA_CHECK(cudaEventRecord(c->ev_check_done, c->check_stream));
+		opt.input_flags_ready = c->ev_check_done;
+		// whatever happens below, the mapping stream is behind the validation before d_qi and
+		// bad (declared above, released after this guard) can be handed out again
+		struct JoinGuard {
+			cudaStream_t s;
+			cudaEvent_t e;
+			~JoinGuard() { cudaStreamWaitEvent(s, e, 0); }
+		} join_guard{s, c->ev_check_done};
 		opt.input_flags = bad.get();
 		AnchorStats st;
 		anchor_queries_device(c->esa, dQ, qi, (int32_t)thr, opt, s, B.res, &st);
@@ -444,6 +463,12 @@ void phylo_ctx_destroy(phylo_ctx *c)
 	cudaStreamSynchronize(c->stream);
 	c->esa.release();
 	c->esa.destroy_side();
+	if (c->check_stream) {
+		cudaStreamSynchronize(c->check_stream);
+		cudaStreamDestroy(c->check_stream);
+		cudaEventDestroy(c->ev_check_fork);
+		cudaEventDestroy(c->ev_check_done);
+	}
 	c->q_own.release();
 	c->batches.clear();
 	for (cudaEvent_t e : c->batch_events)
@@ -497,6 +522,8 @@ int phylo_set_option(phylo_ctx *c, const char *key, int64_t value)
 		} else if (k == "sort_path") {
 			if (value < 0 || value > 2) throw std::invalid_argument("sort_path must be 0, 1 or 2");
 			g_sort_path = (int)value; // process-wide
+		} else if (k == "scan_mode") {
+			g_scan_single_pass = value != 0; // process-wide
 		} else if (k == "map_batch_bytes") {
 			if (value < 1) throw std::invalid_argument("map_batch_bytes must be >= 1");
 			g_map_batch_bytes = (uint64_t)value; // process-wide

@@ -18,6 +18,9 @@ namespace phy
 
 // ----------------------------------------------------------------------------- scan
 
+// option "scan_mode": 1 = one launch per scan (decoupled look-back, default), 0 = three
+inline int g_scan_single_pass = 1;
+
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
@@ -107,6 +110,86 @@ template <typename T> struct ScanPtrOut {
 	__device__ __forceinline__ void operator()(int64_t i, T v) const { p[i] = v; }
 };
 
+// ---- single-pass scan (decoupled look-back) -----------------------------------------------
+// One launch instead of reduce + scan + apply: a block takes the next tile from an atomic
+// counter, publishes the tile's aggregate, then adds up its predecessors' status words — a
+// warp looks at 32 of them at a time — until it meets one that already holds an inclusive
+// prefix.  status[t] = flag << 32 | value (32-bit T only); the status array and the counter
+// are zeroed by one memset before the launch.
+constexpr unsigned long long SP_AGGREGATE = 1ull << 32, SP_INCLUSIVE = 2ull << 32;
+
+template <typename T, typename InF, typename OutF, typename Op>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_single_pass_kernel(int64_t n, InF in, OutF out, Op op, T identity, bool inclusive, unsigned long long *status,
+                        uint32_t *tile_counter)
+{
+	static_assert(sizeof(T) == 4, "status words carry 32-bit values");
+	__shared__ T smem[32];
+	__shared__ uint32_t s_tile;
+	__shared__ T s_prefix;
+	if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+	T v[SCAN_ITEMS];
+	T acc = identity;
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; k++) {
+		const int64_t i = base + k;
+		v[k] = i < n ? in(i) : identity;
+		acc = op(acc, v[k]);
+	}
+	T total;
+	const T exc = block_scan_exclusive(acc, op, identity, &total, smem);
+	if (threadIdx.x < 32) {
+		const int lane = threadIdx.x;
+		T prefix = identity;
+		if (tile == 0) {
+			if (lane == 0) atomicExch(status, SP_INCLUSIVE | (unsigned long long)(uint32_t)total);
+		} else {
+			if (lane == 0) atomicExch(status + tile, SP_AGGREGATE | (unsigned long long)(uint32_t)total);
+			// windows of 32 predecessors, nearest first: lane l looks at tile - 1 - l
+			int64_t top = (int64_t)tile - 1;
+			for (;;) {
+				const int64_t t = top - lane;
+				unsigned long long w = SP_INCLUSIVE; // before tile 0: an inclusive prefix of `identity`
+				T val = identity;
+				if (t >= 0) {
+					do {
+						w = *(volatile unsigned long long *)(status + t);
+					} while ((w >> 32) == 0);
+					val = (T)(uint32_t)w;
+				}
+				const uint32_t incl = __ballot_sync(0xffffffffu, (w >> 32) == 2);
+				// lanes up to and including the nearest inclusive one contribute
+				const int stop = incl ? __ffs(incl) - 1 : 31;
+				T part = lane <= stop ? val : identity;
+				// (the tree below does not keep the tiles in order: op must commute — sum, max)
+#pragma unroll
+				for (int d = 16; d > 0; d >>= 1) {
+					const T o = __shfl_down_sync(0xffffffffu, part, d);
+					part = op(o, part);
+				}
+				part = __shfl_sync(0xffffffffu, part, 0);
+				prefix = op(part, prefix);
+				if (incl) break;
+				top -= 32;
+			}
+			if (lane == 0) atomicExch(status + tile, SP_INCLUSIVE | (unsigned long long)(uint32_t)op(prefix, total));
+		}
+		if (lane == 0) s_prefix = prefix;
+	}
+	__syncthreads();
+	T run = op(s_prefix, exc);
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; k++) {
+		const int64_t i = base + k;
+		const T incl = op(run, v[k]);
+		if (i < n) out(i, inclusive ? incl : run);
+		run = incl;
+	}
+}
+
 // out(i, scan value); exclusive: value before element i, inclusive: including it.
 template <typename T, typename InF, typename OutF, typename Op>
 void device_scan(int64_t n, InF in, OutF out, Op op, T identity, bool inclusive, cudaStream_t s)
@@ -115,6 +198,14 @@ void device_scan(int64_t n, InF in, OutF out, Op op, T identity, bool inclusive,
 	const int nblocks = div_up(n, SCAN_TILE);
 	if (nblocks == 1) {
 		scan_apply_kernel<T><<<1, SCAN_THREADS, 0, s>>>(n, in, out, op, identity, (const T *)nullptr, inclusive);
+		KERNEL_CHECK();
+		return;
+	}
+	if (g_scan_single_pass) {
+		DevBuf<unsigned long long> status((size_t)nblocks + 1, s); // [nblocks]: the tile counter
+		status.zero();
+		scan_single_pass_kernel<T><<<nblocks, SCAN_THREADS, 0, s>>>(n, in, out, op, identity, inclusive, status.get(),
+		                                                            reinterpret_cast<uint32_t *>(status.get() + nblocks));
 		KERNEL_CHECK();
 		return;
 	}
