@@ -355,23 +355,18 @@ constexpr int CLD_SPAN = CLD_TILE + 2 * CLD_HALO + 1;
 struct CldTable {
 	int32_t st[CLD_LEVELS][CLD_SPAN];
 
-	// first position >= from with value <= v, or -1 if it is not within reach
-	__device__ __forceinline__ int first_le_right(int from, int32_t v) const
+	// first position >= from (left == false) or last position <= from (left == true) with
+	// value <= v, or -1 if it is not within reach: both directions in one instruction stream
+	__device__ __forceinline__ int gallop(int from, int32_t v, bool left) const
 	{
 		int pos = from;
+		const int neg = left ? -1 : 0;
 #pragma unroll
-		for (int k = CLD_LEVELS - 1; k >= 0; k--)
-			if (pos + (1 << k) <= CLD_SPAN && st[k][pos] > v) pos += 1 << k;
-		return (pos < CLD_SPAN && st[0][pos] <= v) ? pos : -1;
-	}
-	// last position <= from with value <= v, or -1
-	__device__ __forceinline__ int last_le_left(int from, int32_t v) const
-	{
-		int pos = from;
-#pragma unroll
-		for (int k = CLD_LEVELS - 1; k >= 0; k--)
-			if (pos - (1 << k) + 1 >= 0 && st[k][pos - (1 << k) + 1] > v) pos -= 1 << k;
-		return (pos >= 0 && st[0][pos] <= v) ? pos : -1;
+		for (int k = CLD_LEVELS - 1; k >= 0; k--) {
+			const int w = pos - (neg & ((1 << k) - 1)); // first entry of the window of 2^k that starts/ends at pos
+			if (w >= 0 && w + (1 << k) <= CLD_SPAN && st[k][w] > v) pos += left ? -(1 << k) : (1 << k);
+		}
+		return (pos >= 0 && pos < CLD_SPAN && st[0][pos] <= v) ? pos : -1;
 	}
 	// minimum over [a, b], 1 <= b - a + 1 <= 256 (two windows of 128 still cover 256)
 	__device__ __forceinline__ int32_t range_min(int a, int b) const
@@ -410,12 +405,20 @@ k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ lo
 		if (i < m) {
 			const int t = (int)(i - lo);
 			const int32_t a = T.st[0][t], b = T.st[0][t + 1];
-			if (b < a) { // up: leftmost minimum of (p, i], p = last position left of i with LCP <= b
-				const int p = T.last_le_left(t - 1, b);
-				if (p >= 0) res = T.first_le_right(p + 1, T.range_min(p + 1, t));
-			} else { // next l-index, or leftmost minimum of (i, s), s = first position right of i with LCP <= a
-				const int s = T.first_le_right(t + 1, a);
-				if (s >= 0) res = (T.st[0][s] == a) ? s : T.first_le_right(t + 1, T.range_min(t + 1, s - 1));
+			// One code path for both cases (lanes of a warp are a mix of them, and divergent
+			// branches would run one after the other): a gallop to the left for p = last position
+			// left of i with LCP <= b ("up", b < a), or to the right for s = first position right
+			// of i with LCP <= a; then the leftmost minimum of (p, i] or (i, s) — unless LCP[s] == a,
+			// when s itself is the next l-index.
+			const bool up = b < a;
+			const int x = T.gallop(up ? t - 1 : t + 1, up ? b : a, up);
+			if (x >= 0) {
+				if (!up && T.st[0][x] == a) {
+					res = x;
+				} else {
+					const int from = up ? x + 1 : t + 1, to = up ? t : x - 1;
+					res = T.gallop(from, T.range_min(from, to), false);
+				}
 			}
 			const int32_t cld = res >= 0 ? (int32_t)(lo + res) : 0; // far entries: k_cld_long fills it in
 			if (res >= 0) CLD[i] = cld;
