@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--chunk", type=int, default=0, help="walker chunk length (0 = library default)")
     ap.add_argument("--kmer-k", type=int, default=None, help="K of the descent table (library default: from m)")
     ap.add_argument("--sort-path", type=int, default=0, help="suffix sorter: 0 = pick (packed words), 1 = general")
-    ap.add_argument("--table-direct", action="store_true", help="build the K-mer table entry by entry (A/B)")
+    ap.add_argument("--table-direct", type=int, default=0, help="K-mer table build: 0/1 entry by entry, 2 level by level (A/B)")
     ap.add_argument("--index", default="replicate", choices=["replicate", "broadcast"],
                     help="multi-GPU: every rank builds the index, or rank 0 builds and broadcasts it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -252,7 +252,7 @@ def run_b200(args):
         ctx.set_option("kmer_k", args.kmer_k)
     ctx.set_option("sort_path", args.sort_path)
     if args.table_direct:
-        ctx.set_option("table_direct", 1)
+        ctx.set_option("table_direct", args.table_direct)
     d_counts = torch.zeros(2, total * total, dtype=torch.int64, device=dev)
     d_subst, d_homol = d_counts[0], d_counts[1]
     if rank == 0:

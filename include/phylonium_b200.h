@@ -83,8 +83,8 @@ int phylo_set_stream(phylo_ctx *ctx, void *stream);
  *               launches (reduce, scan of the tile sums, apply); process-wide
  *   "map_batch_bytes" sequences are mapped in batches of about this many bytes (default
  *               512 MiB): bounds the scratch memory; process-wide
- *   "table_direct" how the descent table is built: 0 = by K (default), 1 = entry by entry
- *               from the root, 2 = level by level; process-wide
+ *   "table_direct" how the descent table is built: 0 / 1 = entry by entry from the root
+ *               (default), 2 = level by level (cross-check); process-wide
  *   "sort_path" suffix sorter: 0 = packed 2-bit words when the key fits 16 characters and the
  *               reference has at most ~1000 contigs, else the general one (default); 1 = always
  *               the general sorter (3-bit codes, 64-bit keys); process-wide

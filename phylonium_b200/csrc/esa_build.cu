@@ -703,11 +703,11 @@ void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t s, bool nodes_read
 	esa.table.alloc(entries, s);
 	EsaView v = esa.view();
 	v.K = 0;
-	if (g_table_direct == 1 || (g_table_direct == 0 && K <= 10)) {
+	if (g_table_direct != 2) {
 		// every entry by its own descent from the root: the upper levels of neighbouring
-		// entries are the same cache lines, so up to K = 10 this beats the five extra launches
-		// of the level-wise build (measured on B200: 0.150 vs 0.193 ms at K = 10, 0.317 vs
-		// 0.265 ms at K = 11); both give the same table
+		// entries are the same cache lines, so this is as fast as or faster than the level-wise
+		// build with its extra launches (measured on B200: 0.097 vs 0.193 ms at K = 10, 0.262 vs
+		// 0.265 ms at K = 11; a head + one-launch tail variant: 0.149 / 0.302); same table
 		k_table<<<div_up(entries, 128), 128, 0, s>>>(v, K, esa.table.get());
 		KERNEL_CHECK();
 	} else {
