@@ -39,6 +39,21 @@ inline uint64_t g_kernel_launches = 0;
 
 constexpr int NUM_SMS_B200 = 148;
 
+// Per-device "done once" flags (kernel attributes are per device: a process that drives
+// several GPUs has to set them on each).
+struct PerDeviceOnce {
+	bool done[64] = {};
+	// true the first time it is asked on the current device
+	bool first()
+	{
+		int dev = 0;
+		if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+		if (done[dev]) return false;
+		done[dev] = true;
+		return true;
+	}
+};
+
 inline int div_up(int64_t a, int64_t b)
 {
 	return (int)((a + b - 1) / b);

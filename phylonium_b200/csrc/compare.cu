@@ -396,12 +396,10 @@ void compare_all_device(const RowStore &rs, int64_t N, bool complete_deletion, i
 		const int64_t units = n_tile_pairs * chunks;
 		const int64_t my_units = (units - tile_rank + tile_world - 1) / tile_world;
 		const size_t smem = (size_t)2 * 2 * CT * ROW_PLANES * CMP_STEP * sizeof(uint32_t);
-		static bool attr_set = false;
-		if (!attr_set) {
+		static PerDeviceOnce once;
+		if (once.first())
 			CUDA_CHECK(cudaFuncSetAttribute(k_compare_tiles<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 			                                2 * 2 * 16 * ROW_PLANES * CMP_STEP * (int)sizeof(uint32_t)));
-			attr_set = true;
-		}
 		if (my_units > 0) {
 			if (CT == 16)
 				k_compare_tiles<16><<<(unsigned)my_units, cmp_threads(16), smem, s>>>(

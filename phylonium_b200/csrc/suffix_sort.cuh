@@ -653,18 +653,20 @@ struct PkProfile {
 // blocks of pk_scatter<FROM_TEXT> that fit the device at once (persistent grid)
 template <bool FROM_TEXT> inline int pk_scatter_grid(int ntiles)
 {
-	static int resident = 0;
-	if (!resident) {
+	static int resident[64] = {};
+	int dev = 0;
+	CUDA_CHECK(cudaGetDevice(&dev));
+	if (dev < 0 || dev >= 64) dev = 0;
+	if (!resident[dev]) {
 		CUDA_CHECK(cudaFuncSetAttribute(pk_scatter<FROM_TEXT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		                                (int)sizeof(PkSmem<FROM_TEXT>)));
-		int per_sm = 0, dev = 0, sms = 0;
+		int per_sm = 0, sms = 0;
 		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_scatter<FROM_TEXT>, PKS_THREADS,
 		                                                         sizeof(PkSmem<FROM_TEXT>)));
-		CUDA_CHECK(cudaGetDevice(&dev));
 		CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-		resident = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : NUM_SMS_B200);
+		resident[dev] = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : NUM_SMS_B200);
 	}
-	return ntiles < resident ? ntiles : resident;
+	return ntiles < resident[dev] ? ntiles : resident[dev];
 }
 
 inline uint64_t *suffix_sort_packed(const uint8_t *S, int32_t m, int32_t padded, int kc, uint64_t *buf_a,

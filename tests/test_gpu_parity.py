@@ -389,6 +389,53 @@ def test_mapping_in_batches(pb, oracle, batch_bytes):
             pass
 
 
+def _kitchen_sink(n=600_000, seed=41):
+    """a 5-contig reference with a 20 kbp repeat and low-complexity stretches; genomes that are
+    mutated, cut, inverted, shuffled, reverse complemented, truncated or unrelated"""
+    rng = np.random.default_rng(seed)
+    contigs = [datasets.random_dna(rng, n // 5) for _ in range(5)]
+    repeat = contigs[0][5000:25000]
+    contigs[2] = contigs[2][:40000] + repeat + contigs[2][40000:]
+    contigs[3] = contigs[3][:1000] + b"A" * 300 + b"ACAC" * 100 + contigs[3][1000:]
+    ref = b"!".join(contigs)
+    flat = ref.replace(b"!", b"")
+    genomes = [ref]
+    for d in (0.001, 0.01, 0.03, 0.06):
+        genomes.append(datasets.mutate(rng, flat, d))
+    genomes.append(datasets.indel(rng, datasets.mutate(rng, flat, 0.01), 60, 200))
+    blocks = [flat[i : i + 30000] for i in range(0, len(flat), 30000)]
+    order = rng.permutation(len(blocks))
+    genomes.append(b"".join(datasets.revcomp(blocks[k]) if k % 3 == 0 else blocks[k] for k in order))
+    genomes.append(datasets.revcomp(datasets.mutate(rng, flat, 0.02)))
+    genomes.append(b"!".join(datasets.mutate(rng, c, 0.005) for c in reversed(contigs)))
+    genomes.append(datasets.mutate(rng, flat, 0.02)[: n // 3])
+    genomes.append(datasets.random_dna(rng, 50000))
+    genomes.append(ref)
+    return genomes
+
+
+def test_kitchen_sink_600kbp(pb, oracle):
+    """everything at once at a size where chunks, batches and tiles are many: counts, with and
+    without complete deletion, and every homology list"""
+    genomes = _kitchen_sink()
+    try:
+        with pb.Context(keep_raw=1, map_batch_bytes=2_000_000) as ctx:
+            for flags in (0, 4):
+                want = oracle.process(genomes, 0, flags, threads=8)
+                subst, homol = ctx.process(genomes, 0, flags)
+                assert np.array_equal(homol, want["homologs"]) and np.array_equal(subst, want["subst"]), flags
+            assert ctx.stat("map.batches") > 1
+            thr = oracle.threshold(genomes[0])
+            esa = oracle.esa(genomes[0])
+            for k, q in enumerate(genomes):
+                raw = esa.anchor_homologies(thr, q)
+                assert np.array_equal(ctx.homologies(k, raw=True), raw), (k, "raw")
+                assert np.array_equal(ctx.homologies(k), oracle.sort_filter(raw)), (k, "filtered")
+    finally:
+        with pb.Context(map_batch_bytes=512 << 20):
+            pass
+
+
 def test_many_genomes_tiles(pb, oracle, ctx):
     """more genomes than one 4x4 tile, odd count: diagonal and ragged tiles"""
     rng = np.random.default_rng(17)

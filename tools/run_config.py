@@ -78,6 +78,7 @@ def main():
     ap.add_argument("--no-check", action="store_true", help="skip the CPU checker")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--flags", type=int, default=0, help="4 = complete deletion")
+    ap.add_argument("--option", action="append", default=[], help="library option key=value (repeatable)")
     args = ap.parse_args()
 
     import torch
@@ -119,6 +120,9 @@ def main():
     lens = np.array([len(g) for g in genomes], dtype=np.uint64)
 
     ctx = pb.Context(0)
+    for kv in args.option:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     out = (np.zeros((N, N), np.uint64), np.zeros((N, N), np.uint64))
     times = []
     for rep in range(args.reps + 1):
