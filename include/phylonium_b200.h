@@ -143,6 +143,17 @@ int phylo_get_homologies(const phylo_ctx *ctx, uint64_t index, int raw, phylo_ho
  * row-major, symmetric, zero diagonal — the two counters of evo_model
  * (src/evo_model.h:17-19). */
 int phylo_compare_all(phylo_ctx *ctx, int flags, uint64_t *subst, uint64_t *homologs);
+/* The core genome after complete deletion, for the reference's option -p (print reference
+ * positions, src/process.cxx:471-513, get_segsites :665-723).  Call after phylo_map_queries
+ * or phylo_process.  Three bitmaps of *words 32-bit words each (bit b of word w = reference
+ * column 32 w + b; pass words = ceil(n / 32) rounded up to a multiple of 4, or query it with
+ * all three pointers NULL):
+ *   core    the column is covered by a homology of every sequence
+ *   border  some sequence's homology starts at the column: a new "part" starts there
+ *   seg     core column where some sequence differs from sequence 0 (bytes on the same
+ *           strand, complement rule across strands)
+ * A part of the reference's output is a maximal run of core columns without a border inside. */
+int phylo_core_sites(phylo_ctx *ctx, uint32_t *core, uint32_t *border, uint32_t *seg, uint64_t *words);
 /* evo_model::estimate_raw/JC/ani on the device for the last matrix; dist: N*N doubles,
  * diagonal 0 (src/io.cxx:157).  Hosts that must print bit-identical text should use
  * their own libm on the integer counts instead. */

@@ -59,6 +59,7 @@ SIGNATURES = {
     "phylo_esa_finish_import": (C.c_int, [C.c_void_p]),
     "phylo_rows_configure": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
     "phylo_rows_device": (C.c_int, [C.c_void_p, _vpp, _u64p, _u64p]),
+    "phylo_core_sites": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "phylo_compare_tiles_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
@@ -231,6 +232,14 @@ class Context:
 
     def compare_tiles_dev(self, d_subst: int, d_homologs: int, rank: int, world: int, flags: int = 0):
         self._check(self.lib.phylo_compare_tiles_dev(self.h, flags, rank, world, d_subst, d_homologs))
+
+    def core_sites(self):
+        """(core, border, seg) bitmaps as uint32 arrays (bit b of word w = reference column 32 w + b)"""
+        words = C.c_uint64(0)
+        self._check(self.lib.phylo_core_sites(self.h, None, None, None, C.byref(words)))
+        core, border, seg = (np.zeros(words.value, np.uint32) for _ in range(3))
+        self._check(self.lib.phylo_core_sites(self.h, core.ctypes.data, border.ctypes.data, seg.ctypes.data, C.byref(words)))
+        return core, border, seg
 
     def estimate(self, kind: int = DIST_JC, total: int | None = None) -> np.ndarray:
         N = total if total is not None else self.N

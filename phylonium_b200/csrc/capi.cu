@@ -790,6 +790,33 @@ int phylo_compare_tiles_dev(phylo_ctx *c, int flags, int rank, int world, void *
 	});
 }
 
+int phylo_core_sites(phylo_ctx *c, uint32_t *core, uint32_t *border, uint32_t *seg, uint64_t *words)
+{
+	return guarded(c, [&] {
+		if (!words) throw std::invalid_argument("NULL argument");
+		if (!c->mapped) throw std::invalid_argument("phylo_map_queries has not been called");
+		const uint64_t W = (uint64_t)c->rows.W;
+		if (!core && !border && !seg) {
+			*words = W;
+			return;
+		}
+		if (!core || !border || !seg) throw std::invalid_argument("NULL argument");
+		if (*words < W) throw std::invalid_argument("phylo_core_sites: bitmaps too short");
+		if (c->rows_total) throw std::invalid_argument("phylo_core_sites works on an unsharded context");
+		*words = W;
+		cudaStream_t s = c->stream;
+		DevBuf<uint32_t> d_core(W, s), d_border(W, s), d_seg(W, s);
+		d_border.zero();
+		core_sites_device(c->rows, (int64_t)c->N, d_core.get(), d_seg.get(), s);
+		for (const auto &B : c->batches)
+			hom_borders_device(B.res.homs.get(), B.res.d_begin.get(), B.res.d_count.get(), (int32_t)B.count, d_border.get(), s);
+		CUDA_CHECK(cudaMemcpyAsync(core, d_core.get(), W * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaMemcpyAsync(border, d_border.get(), W * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaMemcpyAsync(seg, d_seg.get(), W * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaStreamSynchronize(s));
+	});
+}
+
 int phylo_estimate(phylo_ctx *c, int kind, double *dist)
 {
 	return guarded(c, [&] {

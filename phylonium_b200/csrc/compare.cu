@@ -300,6 +300,37 @@ k_compare_tiles(const uint32_t *__restrict__ rows, int64_t genome_words, int64_t
 		compare_tile<3, CT>(cmp_stage, rows, genome_words, W, N, gi0, gj0, w_begin, w_end, vall, subst, homol);
 }
 
+// seg[w] = core columns where some genome differs from genome 0 (process.cxx:484-490:
+// get_segsites of queries[0] against every query, OR-ed), core = columns every genome covers
+__global__ void k_seg_sites(const uint32_t *__restrict__ rows, int64_t genome_words, int64_t W, int64_t N,
+                            const uint32_t *__restrict__ core, uint32_t *__restrict__ seg)
+{
+	const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= W) return;
+	const uint32_t *r0 = rows + w;
+	const uint32_t a0 = r0[PL_C0 * W], a1 = r0[PL_C1 * W], ad = r0[PL_D * W], ab = r0[PL_B * W];
+	uint32_t any = 0;
+	for (int64_t g = 1; g < N; g++) {
+		const uint32_t *r = rows + g * genome_words + w;
+		any |= (a0 ^ r[PL_C0 * W]) | (a1 ^ r[PL_C1 * W]) | (~(ad ^ r[PL_D * W]) & (ab ^ r[PL_B * W]));
+	}
+	seg[w] = any & core[w];
+}
+
+// border bit at the first reference column of every homology of `count` genomes
+__global__ void k_hom_borders(const Hom *__restrict__ homs, const int64_t *__restrict__ begin,
+                              const int64_t *__restrict__ hcount, int32_t count, uint32_t *__restrict__ border)
+{
+	const int32_t k = blockIdx.y;
+	if (k >= count) return;
+	const Hom *H = homs + begin[k];
+	const int64_t h = hcount[k];
+	for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < h; x += (int64_t)gridDim.x * blockDim.x) {
+		const uint32_t c = (uint32_t)H[x].iproj;
+		atomicOr(&border[c >> 5], 1u << (c & 31));
+	}
+}
+
 __global__ void k_symmetrize(unsigned long long *__restrict__ subst, unsigned long long *__restrict__ homol, int64_t N)
 {
 	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -414,6 +445,25 @@ void compare_all_device(const RowStore &rs, int64_t N, bool complete_deletion, i
 	}
 	k_symmetrize<<<div_up(N * N, 256), 256, 0, s>>>(d_subst, d_homologs, N);
 	KERNEL_CHECK();
+}
+
+void core_sites_device(const RowStore &rs, int64_t N, uint32_t *d_core, uint32_t *d_seg, cudaStream_t s)
+{
+	if (N > rs.genomes) throw std::invalid_argument("row store holds fewer genomes than N");
+	k_and_valid<<<div_up(rs.W, 256), 256, 0, s>>>(rs.data.get(), rs.genome_words(), rs.W, N, d_core);
+	KERNEL_CHECK();
+	k_seg_sites<<<div_up(rs.W, 256), 256, 0, s>>>(rs.data.get(), rs.genome_words(), rs.W, N, d_core, d_seg);
+	KERNEL_CHECK();
+}
+
+void hom_borders_device(const Hom *d_homs, const int64_t *d_begin, const int64_t *d_count, int32_t count,
+                        uint32_t *d_border, cudaStream_t s)
+{
+	for (int32_t k0 = 0; k0 < count; k0 += 32768) {
+		const int32_t c = count - k0 < 32768 ? count - k0 : 32768;
+		k_hom_borders<<<dim3(8, c), 128, 0, s>>>(d_homs, d_begin + k0, d_count + k0, c, d_border);
+		KERNEL_CHECK();
+	}
 }
 
 void estimate_device(const unsigned long long *d_subst, const unsigned long long *d_homologs, int64_t N, int kind,

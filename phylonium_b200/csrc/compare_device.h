@@ -47,6 +47,13 @@ void rows_build(RowStore &rs, int64_t first_row, const uint8_t *d_Q, const Query
 void compare_all_device(const RowStore &rs, int64_t N, bool complete_deletion, int tile_rank, int tile_world,
                         unsigned long long *d_subst, unsigned long long *d_homologs, cudaStream_t s);
 
+// Core genome in row form (the reference's -p option, process.cxx:471-513): d_core[w] = columns
+// covered by all N genomes, d_seg[w] = core columns where some genome differs from genome 0
+// (W words each); hom_borders_device sets the bit of the first column of every homology.
+void core_sites_device(const RowStore &rs, int64_t N, uint32_t *d_core, uint32_t *d_seg, cudaStream_t s);
+void hom_borders_device(const Hom *d_homs, const int64_t *d_begin, const int64_t *d_count, int32_t count,
+                        uint32_t *d_border, cudaStream_t s);
+
 // kind 0 raw, 1 Jukes-Cantor, 2 ANI (evo_model.cxx:100-131); diagonal 0
 void estimate_device(const unsigned long long *d_subst, const unsigned long long *d_homologs, int64_t N, int kind,
                      double *d_out, cudaStream_t s);

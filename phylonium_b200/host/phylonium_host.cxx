@@ -95,6 +95,50 @@ double evo_model::estimate_JC(bool zero_on_error) const noexcept
 	return dist <= 0.0 ? 0.0 : dist;
 }
 
+// ------------------------------------------------------------------ reference positions (-p)
+
+// src/process.cxx:471-513: after complete deletion all sequences cover the same parts of the
+// reference; for every part print its range, the positions at which some sequence differs
+// from the first one, and the reference's bases.  The library hands back the core genome as
+// bitmaps over the reference columns (phylo_core_sites).
+static std::string REFPOS_FILE_NAME;
+
+static void write_reference_positions(phylo_ctx *ctx, const sequence &subject)
+{
+	uint64_t words = 0;
+	if (phylo_core_sites(ctx, nullptr, nullptr, nullptr, &words) != PHYLO_OK) errx(1, "%s", phylo_last_error(ctx));
+	std::vector<uint32_t> core(words), border(words), seg(words);
+	if (phylo_core_sites(ctx, core.data(), border.data(), seg.data(), &words) != PHYLO_OK)
+		errx(1, "%s", phylo_last_error(ctx));
+	auto bit = [](const std::vector<uint32_t> &v, size_t c) { return (v[c >> 5] >> (c & 31)) & 1u; };
+	std::ofstream out(REFPOS_FILE_NAME);
+	const size_t n = subject.size();
+	size_t counter = 1;
+	size_t c = 0;
+	while (c < n) {
+		if (!core[c >> 5]) { // nothing in this word
+			c = ((c >> 5) + 1) << 5;
+			continue;
+		}
+		if (!bit(core, c)) {
+			c++;
+			continue;
+		}
+		const size_t start = c;
+		std::vector<size_t> pos;
+		do {
+			if (bit(seg, c)) pos.push_back(c - start);
+			c++;
+		} while (c < n && bit(core, c) && !bit(border, c));
+		const size_t end = c;
+		out << ">part" << counter++ << "\t(" << (start + 1) << ".." << (end + 1) << ")  " << pos.size();
+		for (size_t p : pos)
+			out << "  " << (p + 1);
+		out << std::endl;
+		out << std::string(subject.c_str() + start, subject.c_str() + end) << std::endl;
+	}
+}
+
 // ------------------------------------------------------------------ the seam
 
 std::vector<evo_model> process(const sequence &subject, const std::vector<sequence> &queries)
@@ -119,6 +163,7 @@ std::vector<evo_model> process(const sequence &subject, const std::vector<sequen
 	const int rc = phylo_process(ctx, ptr.data(), len.data(), N, ref, FLAGS & flags::complete_deletion, subst.data(),
 	                             homol.data());
 	if (rc != PHYLO_OK) errx(1, "%s", phylo_last_error(ctx));
+	if (FLAGS & flags::print_positions) write_reference_positions(ctx, subject);
 	std::vector<evo_model> matrix(N * N);
 	for (size_t k = 0; k < N * N; k++)
 		matrix[k] = evo_model(subst[k], homol[k]);
@@ -274,6 +319,7 @@ static void usage(int status)
 		"Options:\n"
 		"  -2, --2pass          Enable two-pass algorithm\n"
 		"  --complete-deletion  Delete the whole aligned column in case of gaps\n"
+		"  -p FILE              Print reference positions to FILE (implies complete deletion)\n"
 		"  -r FILE              Set the reference genome\n"
 		"  -t, --threads=N      Accepted for compatibility (the work runs on the GPU)\n"
 		"  -v, --verbose        Print additional information\n"
@@ -300,7 +346,7 @@ int main(int argc, char *argv[])
 	                                       {nullptr, 0, nullptr, 0}};
 	for (;;) {
 		int idx = 0;
-		const int c = getopt_long(argc, argv, "2hr:t:v", long_options, &idx);
+		const int c = getopt_long(argc, argv, "2hp:r:t:v", long_options, &idx);
 		if (c == -1) break;
 		switch (c) {
 			case 0: {
@@ -325,11 +371,19 @@ int main(int argc, char *argv[])
 			}
 			case '2': two_pass = true; break;
 			case 'h': usage(EXIT_SUCCESS); break;
+			case 'p': // src/phylonium.cxx:183-188
+				FLAGS |= flags::print_positions | flags::complete_deletion;
+				REFPOS_FILE_NAME = optarg;
+				break;
 			case 'r': reference_name = optarg; break;
 			case 't': break;
 			case 'v': FLAGS |= (FLAGS & flags::verbose) ? flags::extra_verbose : flags::verbose; break;
 			default: usage(EXIT_FAILURE);
 		}
+	}
+	if (FLAGS & flags::print_positions) { // src/phylonium.cxx:233-240: avoid overwriting files
+		std::ifstream file(REFPOS_FILE_NAME);
+		if (file.good()) errx(1, "output file '%s' already exists", REFPOS_FILE_NAME.c_str());
 	}
 	std::vector<std::string> files(argv + optind, argv + argc);
 	if (!reference_name.empty()) { // src/phylonium.cxx:384-391: the list gets sorted and made unique

@@ -58,7 +58,7 @@ class evo_model
 	double coverage(size_t length) const noexcept { return (double)homologs / length; }
 };
 
-enum flags { none = 0, verbose = 1, extra_verbose = 2, complete_deletion = 4, dist_ani = 32, dist_raw = 64 };
+enum flags { none = 0, verbose = 1, extra_verbose = 2, complete_deletion = 4, print_positions = 16, dist_ani = 32, dist_raw = 64 };
 extern int FLAGS;
 extern int RETURN_CODE;
 extern size_t reference_index;

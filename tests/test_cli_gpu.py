@@ -62,3 +62,20 @@ def test_same_stdout(fasta_dir, opts):
     assert b.stdout, b.stderr
     assert a.stdout == b.stdout, (a.stderr, b.stderr)
     assert a.returncode == b.returncode
+
+
+@pytest.mark.parametrize("ref", ["alpha.fasta", "gamma.fas", "delta.fasta"])
+def test_reference_positions_file(fasta_dir, ref, tmp_path):
+    """-p FILE: the parts of the core genome, their segregating sites and the reference bases
+    (src/process.cxx:471-513) — the file and the matrix must be byte-identical"""
+    files = ["alpha.fasta", "beta.fa", "gamma.fas", "delta.fasta", "epsilon.fasta"]
+    pa, pb_ = tmp_path / "ours.pos", tmp_path / "theirs.pos"
+    a = subprocess.run([OURS, "-r", ref, "-p", str(pa)] + files, cwd=fasta_dir, capture_output=True)
+    b = subprocess.run([THEIRS, "-t", "2", "-r", ref, "-p", str(pb_)] + files, cwd=fasta_dir, capture_output=True)
+    assert b.stdout, b.stderr
+    assert a.stdout == b.stdout, (a.stderr, b.stderr)
+    assert pb_.read_bytes(), "the reference wrote nothing"
+    assert pa.read_bytes() == pb_.read_bytes()
+    # an existing file is not overwritten (src/phylonium.cxx:233-240)
+    again = subprocess.run([OURS, "-r", ref, "-p", str(pa)] + files, cwd=fasta_dir, capture_output=True)
+    assert again.returncode == 1 and b"already exists" in again.stderr
