@@ -8,6 +8,7 @@
 #include "phylonium_host.h"
 
 #include <algorithm>
+#include <cerrno>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -18,6 +19,7 @@
 #include <iostream>
 #include <limits>
 #include <numeric>
+#include <random>
 
 #include "../../include/phylonium_b200.h"
 
@@ -102,6 +104,7 @@ double evo_model::estimate_JC(bool zero_on_error) const noexcept
 // from the first one, and the reference's bases.  The library hands back the core genome as
 // bitmaps over the reference columns (phylo_core_sites).
 static std::string REFPOS_FILE_NAME;
+static size_t BOOTSTRAP = 0; // replicates to print after the matrix itself (-b N prints N matrices)
 
 static void write_reference_positions(phylo_ctx *ctx, const sequence &subject)
 {
@@ -266,6 +269,26 @@ void print_matrix(const std::vector<sequence> &queries, const std::vector<evo_mo
 		}
 	}
 	just_print(names, dist);
+	// -b: more matrices from resampled substitution counts (src/io.cxx:188-200 and
+	// evo_model::bootstrap, src/evo_model.cxx:136-147: binomial in the number of homologous
+	// positions, every cell on its own).  Like the reference's, the generator is seeded from
+	// std::random_device, so replicates differ from run to run.
+	if (BOOTSTRAP) {
+		static std::mt19937 prng{std::random_device{}()};
+		std::vector<double> neu(N * N);
+		for (size_t rep = 0; rep < BOOTSTRAP; rep++) {
+			for (size_t k = 0; k < N * N; k++) {
+				evo_model em = matrix[k];
+				if (em.homologs) {
+					const double rate = em.substitutions / (double)em.homologs;
+					std::binomial_distribution<long long> d((long long)em.homologs, rate);
+					em.substitutions = (uint64_t)d(prng);
+				}
+				neu[k] = FLAGS & flags::dist_raw ? em.estimate_raw() : FLAGS & flags::dist_ani ? em.estimate_ani() : em.estimate_JC();
+			}
+			just_print(names, neu);
+		}
+	}
 	if (FLAGS & flags::verbose) {
 		uint64_t aligned = 0, total = 0;
 		for (size_t i = 0; i < N; i++) {
@@ -318,6 +341,7 @@ static void usage(int status)
 		"\tFILES... can be any sequence of FASTA files, each file representing one genome.\n\n"
 		"Options:\n"
 		"  -2, --2pass          Enable two-pass algorithm\n"
+		"  -b, --bootstrap=N    Print additional bootstrap matrices\n"
 		"  --complete-deletion  Delete the whole aligned column in case of gaps\n"
 		"  -p FILE              Print reference positions to FILE (implies complete deletion)\n"
 		"  -r FILE              Set the reference genome\n"
@@ -336,6 +360,7 @@ int main(int argc, char *argv[])
 	bool two_pass = false;
 	std::string reference_name;
 	static struct option long_options[] = {{"2pass", no_argument, nullptr, '2'},
+	                                       {"bootstrap", required_argument, nullptr, 'b'},
 	                                       {"complete-deletion", no_argument, nullptr, 0},
 	                                       {"distance", required_argument, nullptr, 0},
 	                                       {"progress", required_argument, nullptr, 0},
@@ -346,7 +371,7 @@ int main(int argc, char *argv[])
 	                                       {nullptr, 0, nullptr, 0}};
 	for (;;) {
 		int idx = 0;
-		const int c = getopt_long(argc, argv, "2hp:r:t:v", long_options, &idx);
+		const int c = getopt_long(argc, argv, "2b:hp:r:t:v", long_options, &idx);
 		if (c == -1) break;
 		switch (c) {
 			case 0: {
@@ -370,6 +395,18 @@ int main(int argc, char *argv[])
 				break;
 			}
 			case '2': two_pass = true; break;
+			case 'b': { // src/phylonium.cxx:165-180
+				errno = 0;
+				char *end;
+				const unsigned long bootstrap = strtoul(optarg, &end, 10);
+				if (errno || end == optarg || *end != '\0' || bootstrap == 0) {
+					RETURN_CODE |= EXIT_FAILURE;
+					warnx("Expected a positive number for -b argument, but '%s' was given. Ignoring -b argument.", optarg);
+					break;
+				}
+				BOOTSTRAP = bootstrap - 1;
+				break;
+			}
 			case 'h': usage(EXIT_SUCCESS); break;
 			case 'p': // src/phylonium.cxx:183-188
 				FLAGS |= flags::print_positions | flags::complete_deletion;

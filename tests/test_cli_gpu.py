@@ -79,3 +79,28 @@ def test_reference_positions_file(fasta_dir, ref, tmp_path):
     # an existing file is not overwritten (src/phylonium.cxx:233-240)
     again = subprocess.run([OURS, "-r", ref, "-p", str(pa)] + files, cwd=fasta_dir, capture_output=True)
     assert again.returncode == 1 and b"already exists" in again.stderr
+
+
+def test_bootstrap_matrices(fasta_dir):
+    """-b 5: the matrix itself (byte-identical to the reference's first one) and four
+    replicates with resampled substitution counts; the replicates are random in both programs
+    (seeded from std::random_device), so only their shape and plausibility are checked"""
+    files = ["alpha.fasta", "beta.fa", "gamma.fas", "delta.fasta", "epsilon.fasta"]
+    a = subprocess.run([OURS, "-r", "alpha.fasta", "-b", "5"] + files, cwd=fasta_dir, capture_output=True)
+    b = subprocess.run([THEIRS, "-t", "2", "-r", "alpha.fasta", "-b", "5"] + files, cwd=fasta_dir, capture_output=True)
+    la, lb = a.stdout.decode().splitlines(), b.stdout.decode().splitlines()
+    assert len(la) == len(lb) == 5 * 6
+    assert la[:6] == lb[:6]
+
+    def matrix(lines):
+        return np.array([[float(x) for x in l.split()[1:]] for l in lines[1:6]])
+
+    first = matrix(la[:6])
+    for rep in range(1, 5):
+        block = la[6 * rep : 6 * rep + 6]
+        assert block[0] == "5" and [l.split()[0] for l in block[1:]] == [l.split()[0] for l in la[1:6]]
+        m = matrix(block)
+        assert (np.diag(m) == 0).all()
+        off = ~np.eye(5, dtype=bool)
+        assert np.allclose(m[off], first[off], rtol=0.25), rep  # thousands of substitutions per cell
+        assert not np.array_equal(m, first)
