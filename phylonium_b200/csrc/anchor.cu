@@ -60,26 +60,32 @@ struct Timer {
 
 // ------------------------------------------------------------------ phase 1
 
-// Walkers are latency-bound pointer chasers that diverge from the first step on.  Threads
-// of one warp that sit at different PCs are serialised (their memory latencies add up),
-// so each walker gets a warp of its own: every walker is then an independent instruction
-// stream and the SM overlaps their latencies (64 walkers per SM).  All 32 lanes execute the
-// walker's scalar logic redundantly (same addresses: broadcast loads, merged stores) and
-// share the byte comparisons, 32 bases per step (match_run<true>).
-constexpr int WALK_WARPS_PER_BLOCK = 4;
+// Walkers are latency-bound pointer chasers that diverge from the first step on.  A thread
+// per walker does not work: threads of one warp that sit at different PCs are serialised and
+// their memory latencies add up.  A walker therefore gets a group of WALK_LANES lanes
+// (esa_search.h, "lane groups"): all of them execute the walker's scalar logic redundantly
+// (same addresses: broadcast loads, merged stores) and share the byte comparisons, 32 bases
+// per step.  Measured on B200 (8 x 5 Mbp): a whole warp per walker 0.41 ms, 16 lanes 0.50 ms,
+// 8 lanes 0.55 ms, one thread 6.7 ms — more walkers in flight per SM do not make up for the
+// warp's walkers taking turns, so the default is the whole warp.
+#ifndef WALK_LANES
+#define WALK_LANES 32
+#endif
+constexpr int WALK_THREADS = 128;
+constexpr int WALKERS_PER_BLOCK = WALK_THREADS / WALK_LANES;
 #ifndef WALK_MIN_BLOCKS
 #define WALK_MIN_BLOCKS 16
 #endif
 
-__global__ void __launch_bounds__(32 * WALK_WARPS_PER_BLOCK, WALK_MIN_BLOCKS) k_walk_chunks(WalkParams P, int *__restrict__ any_open)
+__global__ void __launch_bounds__(WALK_THREADS, WALK_MIN_BLOCKS) k_walk_chunks(WalkParams P, int *__restrict__ any_open)
 {
-	const int32_t w = blockIdx.x * WALK_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+	const int32_t w = blockIdx.x * WALKERS_PER_BLOCK + threadIdx.x / WALK_LANES;
 	if (w >= P.total_chunks) return;
 	// walkers of divergent genomes take several times longer than those of close ones and a
 	// genome's chunks are numbered consecutively: spread them over the launch order so that
 	// the last wave is not made of the slow ones only
 	const int32_t g = (int32_t)(((int64_t)w * P.perm_mul) % P.total_chunks);
-	walk_chunk<true>(P, g);
+	walk_chunk<WALK_LANES>(P, g);
 	if (P.rec[g].open) *any_open = 1;
 }
 
@@ -250,14 +256,14 @@ __global__ void k_apply_open(WalkParams P, const int *__restrict__ any_open, con
 
 // ------------------------------------------------------------------ phase 3
 
-__global__ void __launch_bounds__(32 * WALK_WARPS_PER_BLOCK) k_bridge(WalkParams P)
+__global__ void __launch_bounds__(WALK_THREADS) k_bridge(WalkParams P)
 {
-	const int32_t w = blockIdx.x * WALK_WARPS_PER_BLOCK + (threadIdx.x >> 5); // one walker per warp
+	const int32_t w = blockIdx.x * WALKERS_PER_BLOCK + threadIdx.x / WALK_LANES; // one walker per lane group
 	if (w >= P.total_chunks) return;
 	const int32_t g = (int32_t)(((int64_t)w * P.perm_mul) % P.total_chunks);
 	ChunkRec &r = P.rec[g];
-	const int32_t link = bridge_walk<true>(P, g, r.exit, 0, r.bridge_ev, P.cap_ev, P.CH, P.CAP);
-	__syncwarp();
+	const int32_t link = bridge_walk<WALK_LANES>(P, g, r.exit, 0, r.bridge_ev, P.cap_ev, P.CH, P.CAP);
+	__syncwarp(coop_mask<WALK_LANES>());
 	r.link = link;
 }
 
@@ -620,7 +626,7 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	P.chunk_query = d_cq.get();
 
 	// 1. cold walks
-	k_walk_chunks<<<div_up(total_chunks, WALK_WARPS_PER_BLOCK), 32 * WALK_WARPS_PER_BLOCK, 0, s>>>(P, flags.get());
+	k_walk_chunks<<<div_up(total_chunks, WALKERS_PER_BLOCK), WALK_THREADS, 0, s>>>(P, flags.get());
 	KERNEL_CHECK();
 	ST.walk_ms = lap.lap();
 
@@ -642,7 +648,7 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	ST.open_ms = lap.lap();
 
 	// 3. bridges
-	k_bridge<<<div_up(total_chunks, WALK_WARPS_PER_BLOCK), 32 * WALK_WARPS_PER_BLOCK, 0, s>>>(P);
+	k_bridge<<<div_up(total_chunks, WALKERS_PER_BLOCK), WALK_THREADS, 0, s>>>(P);
 	KERNEL_CHECK();
 	ST.bridge_ms = lap.lap();
 

@@ -86,53 +86,89 @@ PHY_HD Interval esa_get_interval(const EsaView &e, Interval ij, uint8_t a, int32
 	return ij;
 }
 
+// Lane groups.  A walker of anchor.cu is run by COOP consecutive lanes of a warp (32, 16 or
+// 8; 0 = one plain thread, as in the CPU emulation): all of them execute the walker's scalar
+// logic redundantly and share the byte comparisons.  With fewer than 32 lanes per walker a
+// warp carries several walkers, which may sit at different program counters; the group
+// primitives below only ever name the lanes of one group.
+#if defined(__CUDACC__)
+template <int COOP> __device__ __forceinline__ int coop_lane()
+{
+	return threadIdx.x & (COOP - 1);
+}
+template <int COOP> __device__ __forceinline__ int coop_shift()
+{
+	return (threadIdx.x & 31) & ~(COOP - 1);
+}
+template <int COOP> __device__ __forceinline__ uint32_t coop_mask()
+{
+	return COOP == 32 ? 0xffffffffu : ((1u << (COOP & 31)) - 1u) << coop_shift<COOP>();
+}
+// ballot over the group, bit 0 = the group's first lane
+template <int COOP> __device__ __forceinline__ uint32_t coop_ballot(bool p)
+{
+	return __ballot_sync(coop_mask<COOP>(), p) >> coop_shift<COOP>();
+}
+#endif
+
 // First k in [from, to) with a[k] != b[k], or `to`.
-// COOP = true: called by all 32 lanes of a warp with identical arguments (the walkers of
-// anchor.cu run their scalar logic redundantly on every lane); the lanes then compare 32
-// bytes per step and agree on the result through a ballot.  COOP = false: plain loop.
-template <bool COOP> PHY_HD int32_t match_run(const uint8_t *a, const uint8_t *b, int32_t from, int32_t to)
+// COOP > 0: called by all lanes of a group with identical arguments; the lanes then compare
+// 32 bytes per step — 32 / COOP each — and agree on the result through a ballot.
+// COOP = 0: plain loop.
+template <int COOP> PHY_HD int32_t match_run(const uint8_t *a, const uint8_t *b, int32_t from, int32_t to)
 {
 #if defined(__CUDA_ARCH__)
 	if (COOP) {
-		const int lane = threadIdx.x & 31;
+		constexpr int PER = 32 / (COOP ? COOP : 32); // bytes per lane and step
+		const int gl = coop_lane<COOP ? COOP : 32>();
+		// position of the first mismatch among the 32 bytes from `base` on, or -1; lanes past
+		// `lim` (exclusive) do not count
+		auto step = [&](int32_t base, int32_t lim, bool checked) -> int32_t {
+			uint32_t miss = 0; // bit t: my byte t differs
+#pragma unroll
+			for (int t = 0; t < PER; t++) {
+				const int32_t x = base + gl * PER + t;
+				if (!checked || x < lim) miss |= (uint32_t)(a[x] != b[x]) << t;
+			}
+			const uint32_t bal = coop_ballot<COOP ? COOP : 32>(miss != 0);
+			if (!bal) return -1;
+			const int first = __ffs(bal) - 1;
+			if (PER == 1) return base + first;
+			const uint32_t m = __shfl_sync(coop_mask<COOP ? COOP : 32>(), miss, coop_shift<COOP ? COOP : 32>() + first);
+			return base + first * PER + (__ffs(m) - 1);
+		};
 		// first 32 bytes alone: most comparisons at high divergence end here
 		{
-			const int32_t x = from + lane;
-			const bool miss = x < to && a[x] != b[x];
-			const uint32_t bal = __ballot_sync(0xffffffffu, miss);
-			if (bal) return from + (__ffs(bal) - 1);
+			const int32_t r = step(from, to, true);
+			if (r >= 0) return r;
 		}
-		// then 128 bytes per round, all eight loads in flight before the first ballot:
-		// the loop is bound by the latency of a round trip to L2/HBM, not by bandwidth.
-		// Whole rounds first (no bounds checks: a third of the walk's instructions were
-		// spent here), then one checked round for the rest.
+		// Whole steps first (no bounds checks: a third of the walk's instructions were spent
+		// here), four of them in flight together — the loop is bound by the latency of a round
+		// trip to L2/HBM, not by bandwidth — then checked steps for the rest.
 		int32_t base = from + 32;
-		for (; base + 128 <= to; base += 128) {
-			uint8_t va[4], vb[4];
+		if (COOP == 32) {
+			for (; base + 128 <= to; base += 128) {
+				uint8_t va[4], vb[4];
 #pragma unroll
-			for (int u = 0; u < 4; u++) {
-				va[u] = a[base + 32 * u + lane];
-				vb[u] = b[base + 32 * u + lane];
+				for (int u = 0; u < 4; u++) {
+					va[u] = a[base + 32 * u + gl];
+					vb[u] = b[base + 32 * u + gl];
+				}
+#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					const uint32_t bal = __ballot_sync(0xffffffffu, va[u] != vb[u]);
+					if (bal) return base + 32 * u + (__ffs(bal) - 1);
+				}
 			}
-#pragma unroll
-			for (int u = 0; u < 4; u++) {
-				const uint32_t bal = __ballot_sync(0xffffffffu, va[u] != vb[u]);
-				if (bal) return base + 32 * u + (__ffs(bal) - 1);
+		} else {
+			for (; base + 32 <= to; base += 32) {
+				const int32_t r = step(base, to, false);
+				if (r >= 0) return r;
 			}
 		}
-		for (; base < to; base += 128) {
-			uint8_t va[4], vb[4];
-#pragma unroll
-			for (int u = 0; u < 4; u++) {
-				const int32_t x = base + 32 * u + lane;
-				va[u] = x < to ? a[x] : 0;
-				vb[u] = x < to ? b[x] : 0;
-			}
-#pragma unroll
-			for (int u = 0; u < 4; u++) {
-				const uint32_t bal = __ballot_sync(0xffffffffu, va[u] != vb[u]);
-				if (bal) return base + 32 * u + (__ffs(bal) - 1);
-			}
+		for (; base < to; base += 32) {
+			const int32_t r = step(base, to, true);
+			if (r >= 0) return r;
 		}
 		return to;
 	}
@@ -146,7 +182,7 @@ template <bool COOP> PHY_HD int32_t match_run(const uint8_t *a, const uint8_t *b
 // Extension of a singleton: characters [k, …) of the query against S[sa + k …).
 // Stops at the first mismatch (the NUL after S counts as one), at qlen, or — still
 // matching — once `cap` characters are verified (open).
-template <bool COOP = false>
+template <int COOP = 0>
 PHY_HD Match esa_extend_singleton(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t k, int32_t idx, int32_t sa,
                                   int32_t cap)
 {
@@ -163,7 +199,7 @@ PHY_HD Match esa_extend_singleton(const EsaView &e, const uint8_t *q, int32_t ql
 
 // src/esa.cxx:446-513 — continue a match of q[0..k) that sits in the proper interval ij
 // (i < j, k == ij.l).
-template <bool COOP = false>
+template <int COOP = 0>
 PHY_HD Match esa_match_from(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t k, Interval ij, int32_t cap)
 {
 	Match res;
@@ -196,7 +232,7 @@ PHY_HD Match esa_match_from(const EsaView &e, const uint8_t *q, int32_t qlen, in
 }
 
 // src/esa.cxx:525-531
-template <bool COOP = false> PHY_HD Match esa_match_root(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t cap)
+template <int COOP = 0> PHY_HD Match esa_match_root(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t cap)
 {
 	return esa_match_from<COOP>(e, q, qlen, 0, esa_root(e), cap);
 }
@@ -204,18 +240,30 @@ template <bool COOP = false> PHY_HD Match esa_match_root(const EsaView &e, const
 // src/esa.cxx:542-563 with the K-mer table in the role of the cache.
 // Table records: i == j: singleton with l verified characters and m = SA[i];
 //                i <  j: interval with lcp value l (min(K, l) characters verified).
-template <bool COOP = false> PHY_HD Match esa_match(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t cap)
+template <int COOP = 0> PHY_HD Match esa_match(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t cap)
 {
 	const int32_t K = e.K;
 	if (K <= 0 || qlen <= K) return esa_match_root<COOP>(e, q, qlen, cap);
 	uint32_t code = 0;
 #if defined(__CUDA_ARCH__)
 	if (COOP) {
-		// lane t reads character t; the 2-bit codes are OR-ed together across the warp
-		const int lane = threadIdx.x & 31;
-		const int c = lane < K ? kmer_code(q[lane]) : 0;
-		if (__any_sync(0xffffffffu, c < 0)) return esa_match_root<COOP>(e, q, qlen, cap);
-		code = __reduce_or_sync(0xffffffffu, lane < K ? ((uint32_t)c << (2 * (K - 1 - lane))) : 0u);
+		// the group's lanes read the K <= 12 characters (lane t: t, t + COOP, …); the 2-bit
+		// codes are OR-ed together across the group
+		constexpr int C = COOP ? COOP : 32;
+		const int gl = coop_lane<C>();
+		uint32_t part = 0;
+		bool bad = false;
+#pragma unroll
+		for (int t0 = 0; t0 < 12; t0 += C) {
+			const int t = t0 + gl;
+			if (t < K) {
+				const int c = kmer_code(q[t]);
+				bad = bad || c < 0;
+				part |= (uint32_t)(c & 3) << (2 * (K - 1 - t));
+			}
+		}
+		if (__any_sync(coop_mask<C>(), bad)) return esa_match_root<COOP>(e, q, qlen, cap);
+		code = __reduce_or_sync(coop_mask<C>(), part);
 	} else
 #endif
 	{

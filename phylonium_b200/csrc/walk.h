@@ -56,7 +56,7 @@ PHY_HD bool walk_is_dead(const WalkState &st, int32_t thr)
 // One iteration of the while loop at process.cxx:245-282, without the homology
 // bookkeeping.  q points at the query's first base.
 // COOP: see match_run in esa_search.h.
-template <bool COOP = false>
+template <int COOP = 0>
 PHY_HD StepOut walk_step(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t thr, int32_t cap,
                          const WalkState &st)
 {
@@ -150,7 +150,7 @@ struct WalkParams {
 // ---------------------------------------------------------------------------------
 // Phase 1: cold walk of one chunk
 
-template <bool COOP = false> PHY_HD void walk_chunk(const WalkParams &P, int32_t g)
+template <int COOP = 0> PHY_HD void walk_chunk(const WalkParams &P, int32_t g)
 {
 	const int32_t qid = P.chunk_query[g];
 	const QueryInfo qi = P.qi[qid];
@@ -298,7 +298,7 @@ PHY_HD bool dead_visited(const WalkParams &P, int32_t g, int32_t rel)
 // (in query bases); budget < 0 means until merged or the query ends.  `out` receives
 // the accepted anchors (at most out_cap); cap is the comparison cap for this walk.
 // Returns LINK_*; fills r.link_chunk / r.link_from / r.n_bridge / r.bstate.
-template <bool COOP = false>
+template <int COOP = 0>
 PHY_HD int32_t bridge_walk(const WalkParams &P, int32_t g, WalkState st, int32_t nb, Event *out,
                            int64_t out_cap, int32_t budget, int32_t cap)
 {
