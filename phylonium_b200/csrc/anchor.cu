@@ -77,16 +77,29 @@ constexpr int WALKERS_PER_BLOCK = WALK_THREADS / WALK_LANES;
 #define WALK_MIN_BLOCKS 16
 #endif
 
-__global__ void __launch_bounds__(WALK_THREADS, WALK_MIN_BLOCKS) k_walk_chunks(WalkParams P, int *__restrict__ any_open)
+// Walkers of divergent genomes take several times longer than those of close ones (one takes
+// ~190 us at d = 0.05, a few us at d = 0.001).  With one walker per launched group a block keeps
+// its slot until its slowest walker is done and the second wave of blocks starts late: the
+// kernel took two "slowest walker" times.  So the groups are persistent and pull the next
+// chunk from a counter; the launch-order permutation still spreads a genome's chunks (which
+// are numbered consecutively) over the queue.
+__device__ __forceinline__ int32_t next_walker(int *counter)
 {
-	const int32_t w = blockIdx.x * WALKERS_PER_BLOCK + threadIdx.x / WALK_LANES;
-	if (w >= P.total_chunks) return;
-	// walkers of divergent genomes take several times longer than those of close ones and a
-	// genome's chunks are numbered consecutively: spread them over the launch order so that
-	// the last wave is not made of the slow ones only
-	const int32_t g = (int32_t)(((int64_t)w * P.perm_mul) % P.total_chunks);
-	walk_chunk<WALK_LANES>(P, g);
-	if (P.rec[g].open) *any_open = 1;
+	int32_t w = 0;
+	if (coop_lane<WALK_LANES>() == 0) w = atomicAdd(counter, 1);
+	return __shfl_sync(coop_mask<WALK_LANES>(), w, coop_shift<WALK_LANES>());
+}
+
+// ctl[0]: any open match, ctl[3]: the work counter (zero at launch)
+__global__ void __launch_bounds__(WALK_THREADS, WALK_MIN_BLOCKS) k_walk_chunks(WalkParams P, int *__restrict__ ctl)
+{
+	for (;;) {
+		const int32_t w = next_walker(ctl + 3);
+		if (w >= P.total_chunks) return;
+		const int32_t g = (int32_t)(((int64_t)w * P.perm_mul) % P.total_chunks);
+		walk_chunk<WALK_LANES>(P, g);
+		if (P.rec[g].open) ctl[0] = 1;
+	}
 }
 
 // ------------------------------------------------------------------ phase 2: open matches
@@ -256,15 +269,17 @@ __global__ void k_apply_open(WalkParams P, const int *__restrict__ any_open, con
 
 // ------------------------------------------------------------------ phase 3
 
-__global__ void __launch_bounds__(WALK_THREADS) k_bridge(WalkParams P)
+__global__ void __launch_bounds__(WALK_THREADS) k_bridge(WalkParams P, int *__restrict__ counter)
 {
-	const int32_t w = blockIdx.x * WALKERS_PER_BLOCK + threadIdx.x / WALK_LANES; // one walker per lane group
-	if (w >= P.total_chunks) return;
-	const int32_t g = (int32_t)(((int64_t)w * P.perm_mul) % P.total_chunks);
-	ChunkRec &r = P.rec[g];
-	const int32_t link = bridge_walk<WALK_LANES>(P, g, r.exit, 0, r.bridge_ev, P.cap_ev, P.CH, P.CAP);
-	__syncwarp(coop_mask<WALK_LANES>());
-	r.link = link;
+	for (;;) {
+		const int32_t w = next_walker(counter); // one walker per lane group, pulled from a counter
+		if (w >= P.total_chunks) return;
+		const int32_t g = (int32_t)(((int64_t)w * P.perm_mul) % P.total_chunks);
+		ChunkRec &r = P.rec[g];
+		const int32_t link = bridge_walk<WALK_LANES>(P, g, r.exit, 0, r.bridge_ev, P.cap_ev, P.CH, P.CAP);
+		__syncwarp(coop_mask<WALK_LANES>());
+		r.link = link;
+	}
 }
 
 // ------------------------------------------------------------------ phase 4
@@ -591,7 +606,7 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	DevBuf<uint32_t> dead((size_t)total_chunks * (CH / 32), s);
 	dead.zero();
 	DevBuf<ChunkRec> rec(total_chunks, s);
-	DevBuf<int> flags(4, s); // [0] any_open, [1] error
+	DevBuf<int> flags(8, s); // [0] any_open, [1] error, [2] open chunks, [3] / [4] work counters of walk / bridge
 	flags.zero();
 
 	WalkParams P;
@@ -626,7 +641,8 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	P.chunk_query = d_cq.get();
 
 	// 1. cold walks
-	k_walk_chunks<<<div_up(total_chunks, WALKERS_PER_BLOCK), WALK_THREADS, 0, s>>>(P, flags.get());
+	const int walk_blocks = std::min(div_up(total_chunks, WALKERS_PER_BLOCK), NUM_SMS_B200 * WALK_MIN_BLOCKS);
+	k_walk_chunks<<<walk_blocks, WALK_THREADS, 0, s>>>(P, flags.get());
 	KERNEL_CHECK();
 	ST.walk_ms = lap.lap();
 
@@ -648,7 +664,7 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	ST.open_ms = lap.lap();
 
 	// 3. bridges
-	k_bridge<<<div_up(total_chunks, WALKERS_PER_BLOCK), WALK_THREADS, 0, s>>>(P);
+	k_bridge<<<walk_blocks, WALK_THREADS, 0, s>>>(P, flags.get() + 4);
 	KERNEL_CHECK();
 	ST.bridge_ms = lap.lap();
 

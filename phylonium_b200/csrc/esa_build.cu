@@ -422,10 +422,11 @@ k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ lo
 			}
 			const int32_t cld = res >= 0 ? (int32_t)(lo + res) : 0; // far entries: k_cld_long fills it in
 			if (res >= 0) CLD[i] = cld;
-			reinterpret_cast<int4 *>(node)[i] = make_int4(SA[i], a, cld, FVC[i]);
+			const int32_t lcp_of_cld = res >= 0 ? T.st[0][res] : 0x7ffffff0; // far: no hint yet
+			reinterpret_cast<int4 *>(node)[i] = make_int4(SA[i], a, cld, esa_pack_fvc(FVC[i], lcp_of_cld));
 		} else if (i == m) {
 			CLD[i] = 0;
-			reinterpret_cast<int4 *>(node)[i] = make_int4(0, LCP[m], 0, 0);
+			reinterpret_cast<int4 *>(node)[i] = make_int4(0, LCP[m], 0, esa_pack_fvc(0, LCP[0]));
 		}
 		// far away: queue the entry for the warp-cooperative kernel (one atomic per warp)
 		const bool far = i < m && res < 0;
@@ -549,6 +550,7 @@ k_cld_long(Pyramid py, const int32_t *__restrict__ long_list, const uint32_t *__
 		if ((threadIdx.x & 31) == 0) {
 			CLD[i] = res;
 			node[i].cld = res;
+			node[i].fvc = esa_pack_fvc((uint8_t)node[i].fvc, LCP[res]);
 		}
 	}
 }
@@ -679,7 +681,7 @@ __global__ void k_pack_nodes(const int32_t *__restrict__ SA, const int32_t *__re
 	v.x = i < m ? SA[i] : 0;
 	v.y = LCP[i];
 	v.z = CLD[i];
-	v.w = i < m ? FVC[i] : 0;
+	v.w = esa_pack_fvc(i < m ? FVC[i] : 0, LCP[CLD[i]]);
 	reinterpret_cast<int4 *>(node)[i] = v;
 }
 } // namespace

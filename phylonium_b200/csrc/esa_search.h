@@ -28,11 +28,18 @@ PHY_HD EsaNode esa_node(const EsaView &e, int32_t idx)
 #endif
 }
 
+// LCP[nx.cld] for the record nx of some index x: from the hint, or by looking it up
+PHY_HD int32_t esa_child_lcp(const EsaView &e, const EsaNode &nx)
+{
+	const uint32_t hint = (uint32_t)nx.fvc >> 8;
+	return hint != ESA_HINT_NONE ? (int32_t)hint - 1 : esa_node(e, nx.cld).lcp;
+}
+
 PHY_HD Interval esa_root(const EsaView &e)
 {
 	// src/esa.cxx:527-528: m = left_child(m_size) = CLD[m_size - 1]
-	const int32_t mr = esa_node(e, e.m - 1).cld;
-	return Interval{esa_node(e, mr).lcp, 0, e.m - 1, mr};
+	const EsaNode last = esa_node(e, e.m - 1);
+	return Interval{esa_child_lcp(e, last), 0, e.m - 1, last.cld};
 }
 
 PHY_HD bool interval_empty(const Interval &ij)
@@ -54,15 +61,16 @@ PHY_HD Interval esa_get_interval(const EsaView &e, Interval ij, uint8_t a, int32
 	}
 	int32_t m = ij.m;
 	const int32_t l = ij.l;
-	EsaNode nm = esa_node(e, m); // independent of the text load below
+	// the record of the next l-index m and, speculatively, of m - 1 (whose CLD and hint give the
+	// child [i, m - 1] if that is the one we are after): both are independent of the text load
+	// below and of each other, so a step down costs two round trips to memory instead of four
+	EsaNode nm = esa_node(e, m);
+	EsaNode np = esa_node(e, m - 1);
 	const uint8_t c0 = e.S[ni.sa + l];
 	uint8_t c = c0;
 	for (;;) {
 		if (c == a) {
-			if (i != m - 1) {
-				const int32_t up = esa_node(e, m - 1).cld; // left_child(m)
-				return Interval{esa_node(e, up).lcp, i, m - 1, up};
-			}
+			if (i != m - 1) return Interval{esa_child_lcp(e, np), i, m - 1, np.cld}; // left_child(m)
 			return Interval{ni.lcp, i, i, -1};
 		}
 		if (c > a) break;
@@ -72,6 +80,7 @@ PHY_HD Interval esa_get_interval(const EsaView &e, Interval ij, uint8_t a, int32
 		if (i == j) break;
 		m = nm.cld; // right_child(m)
 		nm = esa_node(e, m);
+		np = esa_node(e, m - 1);
 		if (nm.lcp != l) break;
 		c = (uint8_t)ni.fvc;
 	}

@@ -24,10 +24,20 @@ struct Interval {
 	int32_t l, i, j, m;
 };
 
-// everything the descent needs to know about one suffix-array index, in one 16-byte load
+// everything the descent needs to know about one suffix-array index, in one 16-byte load.
+// fvc: low byte FVC[x]; upper 24 bits a hint, LCP[CLD[x]] + 1 (0xffffff: too large, look it
+// up) — the lcp value of the child interval CLD[x] points at, which the descent needs right
+// after CLD[x] itself; with the hint that is no second dependent load.
 struct alignas(16) EsaNode {
 	int32_t sa, lcp, cld, fvc;
 };
+constexpr uint32_t ESA_HINT_NONE = 0xffffffu;
+
+PHY_HD int32_t esa_pack_fvc(uint8_t fvc, int32_t lcp_of_cld)
+{
+	const uint32_t hint = (uint32_t)(lcp_of_cld + 1) < ESA_HINT_NONE ? (uint32_t)(lcp_of_cld + 1) : ESA_HINT_NONE;
+	return (int32_t)((uint32_t)fvc | (hint << 8));
+}
 
 struct EsaView {
 	const uint8_t *S;   // m bytes, followed by >= 64 zero bytes

@@ -50,7 +50,8 @@ HostEsa make_esa(const uint8_t *S, const int64_t *SA, const int64_t *LCP, const 
 	}
 	e.node.resize((size_t)m + 1);
 	for (int32_t i = 0; i <= m; i++)
-		e.node[i] = EsaNode{i < m ? e.SA[i] : 0, e.LCP[i], e.CLD[i], i < m ? (int32_t)e.FVC[i] : 0};
+		e.node[i] = EsaNode{i < m ? e.SA[i] : 0, e.LCP[i], e.CLD[i],
+		                    esa_pack_fvc(i < m ? e.FVC[i] : 0, e.LCP[e.CLD[i]])};
 	e.view.node = e.node.data();
 	e.view.S = e.S.data();
 	e.view.SA = e.SA.data();
