@@ -72,6 +72,25 @@ int fail(phylo_ctx *ctx, int code, const std::string &msg)
 	return code;
 }
 
+// The block cache (common.cuh) keeps freed scratch for the next call.  A caller that maps very
+// differently sized inputs one after the other would pile up blocks that never fit again: once
+// more than half of the device memory sits idle in the cache, give it back.
+void trim_scratch_if_large(phylo_ctx *ctx)
+{
+	static size_t limit[64] = {};
+	const int dev = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
+	if (!limit[dev]) {
+		size_t free_b = 0, total_b = 0;
+		if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return;
+		limit[dev] = total_b / 2;
+	}
+	if (g_block_cache.cached_bytes() > limit[dev]) {
+		cudaStreamSynchronize(ctx->stream);
+		g_block_cache.trim(ctx->device, ctx->stream);
+		if (ctx->stream != ctx->own_stream) g_block_cache.trim(ctx->device, ctx->own_stream);
+	}
+}
+
 template <typename F> int guarded(phylo_ctx *ctx, F &&f)
 {
 	if (!ctx) return fail(nullptr, PHYLO_ERR_INVALID, "context is NULL");
@@ -79,6 +98,7 @@ template <typename F> int guarded(phylo_ctx *ctx, F &&f)
 		cudaError_t e = cudaSetDevice(ctx->device);
 		if (e != cudaSuccess) return fail(ctx, PHYLO_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
 		f();
+		trim_scratch_if_large(ctx);
 		return PHYLO_OK;
 	} catch (const std::invalid_argument &e) {
 		return fail(ctx, PHYLO_ERR_INVALID, e.what());
