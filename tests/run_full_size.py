@@ -2,14 +2,15 @@
 """Run one of BASELINE.json's configurations at full (or scaled) size through the C ABI on one
 GPU, time it, and check every count against the CPU checker (oracle/_ref or the port).
 
-    python tools/run_config.py --config 3            # 100 x 5 Mbp
-    python tools/run_config.py --config 4            # 1000 x 3 Mbp
-    python tools/run_config.py --config 5 --scale 0.1   # 16 x 25 Mbp, multi-contig
+    python tests/run_full_size.py --config 3            # 100 x 5 Mbp
+    python tests/run_full_size.py --config 4            # 1000 x 3 Mbp
+    python tests/run_full_size.py --config 5 --scale 0.1   # 16 x 25 Mbp, multi-contig
 
 Genomes come from the product-side simf generator (phylonium_b200/simgen.py); config 5 is
 split into 25 contigs per genome as BASELINE.md §2 / SURVEY.md §8d describe (cut points every
 len/25 bases, shifted by 1000 g for odd g; contig c reverse-complemented iff (c + g) % 3 == 0).
-The checker is test infrastructure: it is only used here to verify, never on the timed path.
+This script is test infrastructure like the rest of tests/ (it is not collected by pytest: the
+full sizes take minutes): the checker (oracle/) is only used to verify, never on the timed path.
 Prints one JSON line (also appended to gpurun_out/configs.jsonl)."""
 from __future__ import annotations
 
@@ -25,7 +26,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # oracle_lib
 
 _COMP = np.zeros(256, dtype=np.uint8)
 for _a, _b in zip(b"ACGT!", b"TGCA!"):
