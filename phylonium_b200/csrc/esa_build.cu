@@ -285,6 +285,7 @@ __global__ void k_small_groups(const int32_t *__restrict__ heads, uint32_t *__re
 			continue;
 		}
 		SA[j0] = sa[0];
+		if (j0 == 0) FVC[0] = sa[0] > 0 ? S[sa[0] - 1] : 0; // esa.cxx:247-248 with LCP[0] = -1, for the final SA[0]
 		for (int32_t t = 1; t < size; t++) {
 			bool less;
 			const int32_t l = kc + suffix_compare(S, sa[t - 1], sa[t], kc, less);
@@ -314,6 +315,10 @@ __global__ void k_tie_lcp(const uint32_t *__restrict__ slots, uint32_t count, co
 	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= count) return;
 	const uint32_t j = slots[r];
+	if (j == 0) { // the first suffix was part of a tie group: its FVC quirk value follows the final SA[0]
+		FVC[0] = SA[0] > 0 ? S[SA[0] - 1] : 0;
+		return;
+	}
 	if (LCP[j] != LCP_TIE) return; // group head: its LCP came from the keys
 	const uint8_t *a = S + SA[j - 1];
 	const uint8_t *b = S + SA[j];

@@ -168,6 +168,43 @@ def test_esa_packed_equals_general_on_a_large_text(pb):
         assert np.array_equal(res[0][k], res[1][k]), k
 
 
+@pytest.mark.parametrize("key_chars", [1, 2, 5, 11, 21])
+@pytest.mark.parametrize("name", ["multi_contig", "repeats", "rearranged", "tiny"])
+def test_esa_general_sorter_any_key_length(pb, oracle, name, key_chars):
+    """the general sorter with short keys: nearly everything goes through the refinement,
+    including the first suffixes of the array (found by tests/fuzz_gpu.py: FVC[0] follows the
+    final SA[0])"""
+    ref = datasets.ALL_SETS[name]()[0]
+    want = oracle.esa(ref).arrays()
+    try:
+        with pb.Context(key_chars=key_chars, sort_path=1) as ctx:
+            ctx.esa_build(ref)
+            got = ctx.esa_arrays()
+            assert ctx.stat("esa.packed") == 0
+            for k in ("SA", "LCP", "CLD", "FVC"):
+                assert np.array_equal(got[k], want[k]), k
+    finally:
+        with pb.Context(sort_path=0):
+            pass
+
+
+def test_esa_first_suffix_in_a_tie_group(pb, oracle):
+    """several contigs that start alike: the smallest suffixes ('!...') tie on their sort key"""
+    ref = b"!".join([b"ACGTACGTACGTACGTACGTACGTAAAC" + (b"A" if k % 2 else b"C") * k for k in range(1, 12)])
+    want = oracle.esa(ref).arrays()
+    try:
+        for path in (0, 1):
+            for kc in (0, 2, 21):
+                with pb.Context(key_chars=kc, sort_path=path) as ctx:
+                    ctx.esa_build(ref)
+                    got = ctx.esa_arrays()
+                    for k in ("SA", "LCP", "CLD", "FVC"):
+                        assert np.array_equal(got[k], want[k]), (path, kc, k)
+    finally:
+        with pb.Context(sort_path=0):
+            pass
+
+
 @pytest.mark.parametrize("mode", [1, 2])
 def test_both_radix_sort_schemes(pb, oracle, mode):
     """the look-back ("onesweep") passes are normally used only for very large inputs"""
