@@ -26,8 +26,10 @@ import datasets  # noqa: E402
 import oracle_lib  # noqa: E402
 
 
-def make_family(rng):
+def make_family(rng, big=False):
     n = int(rng.integers(1, 40000)) if rng.random() < 0.85 else int(rng.integers(1, 40))
+    if big:
+        n = int(rng.integers(50000, 400000))
     kind = rng.random()
     if kind < 0.15:
         unit = datasets.random_dna(rng, int(rng.integers(1, 12)))
@@ -41,8 +43,8 @@ def make_family(rng):
     if n > 50 and rng.random() < 0.3:  # low complexity
         b = int(rng.integers(0, len(ref)))
         ref = ref[:b] + b"A" * int(rng.integers(5, 120)) + ref[b:]
-    if len(ref) > 10 and rng.random() < 0.4:  # contigs
-        for _ in range(int(rng.integers(1, 8))):
+    if len(ref) > 10 and rng.random() < 0.4:  # contigs (sometimes more than the packed sorter takes)
+        for _ in range(int(rng.integers(1, 8)) if not big or rng.random() < 0.7 else int(rng.integers(900, 1300))):
             b = int(rng.integers(0, len(ref) + 1))
             ref = ref[:b] + b"!" + ref[b:]
     flat = ref.replace(b"!", b"") or b"A"
@@ -78,6 +80,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=120)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--big", action="store_true", help="references of 50..400 kbp, sometimes with > 1000 contigs")
     args = ap.parse_args()
     import phylonium_b200 as pb
 
@@ -88,7 +91,7 @@ def main():
     try:
         while time.time() < t_end:
             rng = np.random.default_rng([args.seed, rounds])
-            genomes = make_family(rng)
+            genomes = make_family(rng, args.big)
             ref_index = int(rng.integers(0, len(genomes)))
             if len(genomes[ref_index]) == 0:
                 ref_index = 0
