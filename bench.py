@@ -134,6 +134,19 @@ def measured_traffic(kernel: str, m: int):
     return None
 
 
+def measured_random_access(kernel: str, m: int):
+    """sectors/request and cache hit rates of the random-access kernel from the committed
+    ncu capture (profiles/traffic.json)"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        for row in json.load(open(p)):
+            if row["kernel"] == kernel and int(row["m"]) == int(m) and "random_access" in row:
+                return dict(row["random_access"], kernel=kernel, source=row["source"])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -411,7 +424,8 @@ def run_b200(args):
                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": measured_traffic(kname, m), "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": bytes_per_launch,
-                        "ms_per_launch": acc["esa.scatter_ms_avg"]}
+                        "ms_per_launch": acc["esa.scatter_ms_avg"],
+                        "random_access_kernel": measured_random_access("k_walk_chunks", m)}
 
     # ---- CPU baseline next to it (rank 0, N = 1) ------------------------------------------------
     cpu = None
