@@ -74,22 +74,24 @@ const char *phylo_version(void);
  * outlive the buffers allocated while it was set. */
 int phylo_set_stream(phylo_ctx *ctx, void *stream);
 
-/* tuning knobs; results never depend on them (tests sweep them):
+/* tuning knobs, per context; results never depend on them (tests sweep them):
  *   "chunk"    bases per speculative walker (default 2048)
  *   "cap"      per-thread comparison cap (default 2 * chunk)
  *   "kmer_k"   K of the descent table, 0 = none, -1 = from the text length (default)
  *   "key_chars" characters per suffix-sort key (1..21), 0 = from the text length (default)
  *   "scan_mode" prefix scans: 1 = one launch with decoupled look-back (default), 0 = three
- *               launches (reduce, scan of the tile sums, apply); process-wide
+ *               launches (reduce, scan of the tile sums, apply)
  *   "map_batch_bytes" sequences are mapped in batches of about this many bytes (default
- *               512 MiB): bounds the scratch memory; process-wide
+ *               512 MiB): bounds the scratch memory
  *   "table_direct" how the descent table is built: 0 / 1 = entry by entry from the root
- *               (default), 2 = level by level (cross-check); process-wide
+ *               (default), 2 = level by level (cross-check)
  *   "sort_path" suffix sorter: 0 = packed 2-bit words when the key fits 16 characters and the
  *               reference has at most ~1000 contigs, else the general one (default); 1 = always
- *               the general sorter (3-bit codes, 64-bit keys); process-wide
+ *               the general sorter (3-bit codes, 64-bit keys)
  *   "sort_mode" radix sort scheme: 0 = by size (default), 1 = histogram+scan+scatter per
- *              pass, 2 = single-pass look-back ("onesweep"); process-wide
+ *              pass, 2 = single-pass look-back ("onesweep")
+ *   "stage_threads" worker threads that stage sequences from ordinary (pageable) host memory
+ *               through pinned buffers in phylo_process; 0 = from the core count (default)
  *   "keep_raw" keep unsorted/unfiltered homology lists for phylo_get_homologies(raw=1)
  *   "timings"  record per-phase device times (adds synchronisation) */
 int phylo_set_option(phylo_ctx *ctx, const char *key, int64_t value);
@@ -166,6 +168,11 @@ int phylo_estimate(phylo_ctx *ctx, int kind, double *dist);
 int phylo_process(phylo_ctx *ctx, const char *const *seqs, const uint64_t *lens, uint64_t N, uint64_t ref_index,
                   int flags, uint64_t *subst, uint64_t *homologs);
 
+/* The second pass of the reference's --2pass option (src/phylonium.cxx:289-296): process()
+ * again with another sequence as the reference.  The sequences of the last phylo_process
+ * (or phylo_map_queries) call are still in device memory; nothing crosses the bus again. */
+int phylo_process_again(phylo_ctx *ctx, uint64_t ref_index, int flags, uint64_t *subst, uint64_t *homologs);
+
 /* ---- device-resident variants (benchmarks, multi-GPU plumbing) --------------------------- */
 
 /* Same stages with inputs/outputs already in device memory of ctx's device.
@@ -193,6 +200,21 @@ int phylo_esa_device_arrays(const phylo_ctx *ctx, void **S, uint64_t *S_bytes, v
 int phylo_esa_finish_import(phylo_ctx *ctx);
 int phylo_rows_configure(phylo_ctx *ctx, uint64_t total_genomes, uint64_t first_row);
 int phylo_rows_device(const phylo_ctx *ctx, void **rows, uint64_t *bytes_per_genome, uint64_t *total_genomes);
+/* Exchange of the rows without a collective: every rank hands the address of its row store to
+ * the others (across processes: a CUDA IPC handle of PHYLO_IPC_HANDLE_BYTES bytes from
+ * phylo_rows_ipc_export, all ranks' handles concatenated in rank order into
+ * phylo_rows_ipc_import; inside one process: the pointers of phylo_rows_device into
+ * phylo_rows_set_peers, NULL to switch it off again).  From then on phylo_map_queries[_dev]
+ * copies every batch of rows it builds into all peers' stores over NVLink while it maps the
+ * next batch, and leaves the context's stream ordered behind those copies.  The caller needs
+ * one barrier across ranks on that stream (any collective) between the mapping and
+ * phylo_compare_tiles_dev, and another one before the next mapping overwrites the rows.
+ * The handles die with the row store: exchange them again after a phylo_rows_configure that
+ * changes the store's size. */
+#define PHYLO_IPC_HANDLE_BYTES 64
+int phylo_rows_ipc_export(phylo_ctx *ctx, void *handle);
+int phylo_rows_ipc_import(phylo_ctx *ctx, const void *handles, int world, int rank);
+int phylo_rows_set_peers(phylo_ctx *ctx, void *const *peer_rows, int world, int rank);
 int phylo_compare_tiles_dev(phylo_ctx *ctx, int flags, int rank, int world, void *d_subst, void *d_homologs);
 
 #ifdef __cplusplus

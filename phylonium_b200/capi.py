@@ -51,6 +51,7 @@ SIGNATURES = {
     "phylo_compare_all": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "phylo_estimate": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "phylo_process": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]),
+    "phylo_process_again": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]),
     "phylo_esa_build_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "phylo_map_queries_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "phylo_compare_all_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -59,6 +60,9 @@ SIGNATURES = {
     "phylo_esa_finish_import": (C.c_int, [C.c_void_p]),
     "phylo_rows_configure": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
     "phylo_rows_device": (C.c_int, [C.c_void_p, _vpp, _u64p, _u64p]),
+    "phylo_rows_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "phylo_rows_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "phylo_rows_set_peers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "phylo_core_sites": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "phylo_compare_tiles_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
@@ -271,6 +275,14 @@ class Context:
         self.N = N
         return out
 
+    def process_again(self, ref_index: int, flags: int = 0, out=None):
+        """second pass of --2pass: same sequences (still on the device), another reference"""
+        N = self.N
+        if out is None:
+            out = (np.zeros((N, N), np.uint64), np.zeros((N, N), np.uint64))
+        self._check(self.lib.phylo_process_again(self.h, ref_index, flags, out[0].ctypes.data, out[1].ctypes.data))
+        return out
+
     # ---- multi-GPU plumbing ---------------------------------------------------
     def esa_alloc(self, n: int):
         self._check(self.lib.phylo_esa_alloc(self.h, n))
@@ -299,3 +311,24 @@ class Context:
         b, t = C.c_uint64(), C.c_uint64()
         self._check(self.lib.phylo_rows_device(self.h, C.byref(p), C.byref(b), C.byref(t)))
         return p.value, b.value, t.value
+
+    IPC_HANDLE_BYTES = 64
+
+    def rows_ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(self.IPC_HANDLE_BYTES)
+        self._check(self.lib.phylo_rows_ipc_export(self.h, buf))
+        return buf.raw
+
+    def rows_ipc_import(self, handles, rank: int):
+        """handles: one 64-byte handle per rank, in rank order"""
+        blob = b"".join(handles)
+        assert len(blob) == self.IPC_HANDLE_BYTES * len(handles)
+        self._check(self.lib.phylo_rows_ipc_import(self.h, blob, len(handles), rank))
+
+    def rows_set_peers(self, ptrs, rank: int):
+        """same-process peers: the row store addresses of all ranks (None switches the push off)"""
+        if not ptrs:
+            self._check(self.lib.phylo_rows_set_peers(self.h, None, 0, 0))
+            return
+        arr = (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p)) for p in ptrs])
+        self._check(self.lib.phylo_rows_set_peers(self.h, arr, len(ptrs), rank))

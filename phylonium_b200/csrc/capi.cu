@@ -7,8 +7,10 @@
 #include "esa_device.h"
 #include "esa_search.h"
 #include "primitives.cuh"
+#include "staging.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <functional>
 #include <cstring>
@@ -26,8 +28,9 @@ struct phylo_ctx {
 	cudaEvent_t ev_main = nullptr, ev_copy = nullptr;
 	std::string err;
 
-	int64_t opt_chunk = 2048, opt_cap = 0, opt_kmer = -1, opt_key_chars = 0;
+	int64_t opt_chunk = 2048, opt_cap = 0, opt_kmer = -1, opt_key_chars = 0, opt_stage_threads = 0;
 	bool keep_raw = false, timings = false;
+	Tuning tuning; // this context's copy of the tuning options (common.cuh)
 
 	EsaDevice esa;
 	bool esa_ready = false;
@@ -51,6 +54,19 @@ struct phylo_ctx {
 	RowStore rows;
 	uint64_t rows_total = 0; // 0: follow N
 	uint64_t rows_first = 0;
+	// sharded runs: the row stores of the other ranks (peer memory, same layout as ours).  Every
+	// batch of rows is copied into all of them as soon as it is built (phylo_rows_ipc_import /
+	// phylo_rows_set_peers), on a stream of its own: the exchange runs while the next batch is mapped.
+	std::vector<uint32_t *> peer_rows;
+	std::vector<void *> peer_ipc; // what cudaIpcOpenMemHandle returned (closed with the context)
+	int peer_rank = 0;
+	cudaStream_t push_stream = nullptr;
+	cudaEvent_t ev_rows = nullptr, ev_pushed = nullptr;
+
+	// sequences of the last phylo_process / phylo_map_queries, still in q_own (phylo_process_again)
+	std::vector<uint64_t> q_offs, q_lens;
+	bool q_resident = false;
+	HostStager stager; // pageable host buffers go through pinned bounce rings (staging.h)
 
 	DevBuf<unsigned long long> d_subst, d_hom;
 	uint64_t matN = 0;
@@ -77,7 +93,7 @@ int fail(phylo_ctx *ctx, int code, const std::string &msg)
 // more than half of the device memory sits idle in the cache, give it back.
 void trim_scratch_if_large(phylo_ctx *ctx)
 {
-	static size_t limit[64] = {};
+	static std::atomic<size_t> limit[64] = {};
 	const int dev = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
 	if (!limit[dev]) {
 		size_t free_b = 0, total_b = 0;
@@ -91,12 +107,22 @@ void trim_scratch_if_large(phylo_ctx *ctx)
 	}
 }
 
+void clear_peers(phylo_ctx *c)
+{
+	if (c->push_stream) cudaStreamSynchronize(c->push_stream);
+	for (void *p : c->peer_ipc)
+		if (p) cudaIpcCloseMemHandle(p);
+	c->peer_ipc.clear();
+	c->peer_rows.clear();
+}
+
 template <typename F> int guarded(phylo_ctx *ctx, F &&f)
 {
 	if (!ctx) return fail(nullptr, PHYLO_ERR_INVALID, "context is NULL");
 	try {
 		cudaError_t e = cudaSetDevice(ctx->device);
 		if (e != cudaSuccess) return fail(ctx, PHYLO_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+		g_tuning = ctx->tuning; // the host code of the kernels reads the calling context's options
 		f();
 		trim_scratch_if_large(ctx);
 		return PHYLO_OK;
@@ -246,10 +272,18 @@ __global__ void k_get_matches(EsaView e, const uint8_t *__restrict__ text, const
 	out[3 * k + 2] = mt.j;
 }
 
+// One bound for every way an index comes into being (build, build_dev, alloc for import): the
+// same as esa_build_device's, so that m = 2n + 1 plus its padding stays inside int32.
+void check_ref_length(uint64_t n)
+{
+	if (n < 1 || 2 * n + 1 > 0x7fffffffull - 128 - 320)
+		throw std::invalid_argument("reference length must be in [1, 2^30 - 225)");
+}
+
 // query_bases: how much text will be mapped on this index, if the caller knows (0 = unknown)
 void do_esa_build(phylo_ctx *c, const uint8_t *d_ref, uint64_t n, uint64_t query_bases = 0)
 {
-	if (n < 1 || n > 0x3fffffffull) throw std::invalid_argument("reference length must be in [1, 2^30)");
+	check_ref_length(n);
 	c->esa_ready = false;
 	c->mapped = false;
 	EsaTimings t;
@@ -266,17 +300,21 @@ void do_esa_build(phylo_ctx *c, const uint8_t *d_ref, uint64_t n, uint64_t query
 	c->esa_ready = true;
 }
 
-// about this many sequence bytes per batch (option "map_batch_bytes")
-inline uint64_t g_map_batch_bytes = 512ull << 20;
-
-// batch b = sequences [ends[b - 1], ends[b])
+// batch b = sequences [ends[b - 1], ends[b]).  With many short sequences a batch ends on a
+// multiple of 16 of them: the all-pairs stage works on tiles of 16 genomes and can then start
+// on the tiles of a batch as soon as that batch is mapped.
 std::vector<uint64_t> plan_batches(const uint64_t *lens, uint64_t N)
 {
+	const uint64_t limit = g_tuning.map_batch_bytes;
+	uint64_t longest = 0;
+	for (uint64_t k = 0; k < N; k++)
+		longest = std::max(longest, lens[k]);
+	const uint64_t align = (N > 24 && 16 * longest <= limit / 2) ? 16 : 1;
 	std::vector<uint64_t> ends;
 	uint64_t bytes = 0;
 	for (uint64_t k = 0; k < N; k++) {
 		bytes += lens[k];
-		if (bytes >= g_map_batch_bytes || k + 1 == N) {
+		if ((bytes >= limit && (k + 1) % align == 0) || k + 1 == N) {
 			ends.push_back(k + 1);
 			bytes = 0;
 		}
@@ -301,13 +339,35 @@ void accumulate(AnchorStats &sum, const AnchorStats &st)
 	sum.total_ms += st.total_ms;
 }
 
-// ends: batch boundaries (plan_batches); ready: per batch, an event the stream waits for
-// before it touches the batch's bytes (NULL: everything is already ordered on the stream);
-// before_batch(b) is called before batch b is waited for (phylo_process queues the copies of
-// a later batch there)
+// What phylo_process hangs into the mapping: its batch plan, a call before batch b is touched
+// (queue later copies, make the stream wait for this batch's bytes) and one after the rows of
+// batch b have been built (compare what can be compared already).
+struct MapHooks {
+	const std::vector<uint64_t> *ends = nullptr;
+	std::function<void(size_t)> before_batch, after_batch;
+};
+
+// copies rows [first, first + count) of this context's store into the peers' stores
+void push_rows(phylo_ctx *c, uint64_t first, uint64_t count)
+{
+	if (c->peer_rows.empty() || !count) return;
+	if (!c->push_stream) {
+		CUDA_CHECK(cudaStreamCreateWithFlags(&c->push_stream, cudaStreamNonBlocking));
+		CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_rows, cudaEventDisableTiming));
+		CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_pushed, cudaEventDisableTiming));
+	}
+	CUDA_CHECK(cudaEventRecord(c->ev_rows, c->stream));
+	CUDA_CHECK(cudaStreamWaitEvent(c->push_stream, c->ev_rows, 0));
+	const size_t off = (size_t)first * (size_t)c->rows.genome_words();
+	const size_t bytes = (size_t)count * (size_t)c->rows.genome_words() * sizeof(uint32_t);
+	for (size_t p = 0; p < c->peer_rows.size(); p++) {
+		if ((int)p == c->peer_rank || !c->peer_rows[p]) continue;
+		CUDA_CHECK(cudaMemcpyAsync(c->peer_rows[p] + off, c->rows.data.get() + off, bytes, cudaMemcpyDefault, c->push_stream));
+	}
+}
+
 void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_t *lens, uint64_t N, uint64_t thr,
-            const std::vector<uint64_t> *ends_in = nullptr, const std::vector<cudaEvent_t> *ready = nullptr,
-            const std::function<void(size_t)> &before_batch = nullptr)
+            const MapHooks &hooks = MapHooks())
 {
 	if (!c->esa_ready) throw std::invalid_argument("phylo_esa_build has not been called");
 	if (thr < 1 || thr > 0x3fffffffull) throw std::invalid_argument("threshold out of range");
@@ -332,9 +392,14 @@ void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_
 	const uint64_t total = c->rows_total ? c->rows_total : N;
 	const uint64_t first_row = c->rows_total ? c->rows_first : 0;
 	if (first_row + N > total) throw std::invalid_argument("rows: first_row + N exceeds total_genomes");
-	if ((uint64_t)c->rows.genomes != total || c->rows.n != c->esa.n) rows_alloc(c->rows, (int64_t)total, c->esa.n, s);
+	if ((uint64_t)c->rows.genomes != total || c->rows.n != c->esa.n) {
+		if (!c->peer_rows.empty())
+			throw std::invalid_argument("the row store changed size after the peers exchanged its address: "
+			                            "call phylo_rows_configure and exchange the handles again");
+		rows_alloc(c->rows, (int64_t)total, c->esa.n, s);
+	}
 
-	const std::vector<uint64_t> ends = ends_in ? *ends_in : plan_batches(lens, N);
+	const std::vector<uint64_t> ends = hooks.ends ? *hooks.ends : plan_batches(lens, N);
 	AnchorStats sum;
 	float rows_ms = 0;
 	c->batches.resize(ends.size());
@@ -344,8 +409,7 @@ void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_
 		phylo_ctx::Batch &B = c->batches[b];
 		B.first = b0;
 		B.count = cnt;
-		if (before_batch) before_batch(b);
-		if (ready) CUDA_CHECK(cudaStreamWaitEvent(s, (*ready)[b], 0));
+		if (hooks.before_batch) hooks.before_batch(b);
 		std::vector<QueryInfo> qi(c->qi.begin() + (size_t)b0, c->qi.begin() + (size_t)b1);
 		// the walk relies on the alphabet and on the zero byte behind every sequence; the
 		// verdict is read back with the first synchronisation of the mapping
@@ -392,7 +456,14 @@ void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_
 		rows_build(c->rows, (int64_t)(first_row + b0), dQ, d_qi.get(), (int32_t)cnt, B.res.homs.get(), B.res.d_begin.get(),
 		           B.res.d_count.get(), s);
 		rows_ms += wt.stop();
+		push_rows(c, first_row + b0, cnt);
+		if (hooks.after_batch) hooks.after_batch(b);
 		b0 = b1;
+	}
+	if (!c->peer_rows.empty() && c->push_stream) {
+		// whatever the caller puts on the stream next (its barrier across ranks) is behind our pushes
+		CUDA_CHECK(cudaEventRecord(c->ev_pushed, c->push_stream));
+		CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_pushed, 0));
 	}
 	record_anchor_stats(c, sum);
 	c->stats["rows.ms"] = rows_ms;
@@ -489,6 +560,14 @@ void phylo_ctx_destroy(phylo_ctx *c)
 		cudaEventDestroy(c->ev_check_fork);
 		cudaEventDestroy(c->ev_check_done);
 	}
+	c->stager.release();
+	clear_peers(c);
+	if (c->push_stream) {
+		cudaStreamSynchronize(c->push_stream);
+		cudaStreamDestroy(c->push_stream);
+		cudaEventDestroy(c->ev_rows);
+		cudaEventDestroy(c->ev_pushed);
+	}
 	c->q_own.release();
 	c->batches.clear();
 	for (cudaEvent_t e : c->batch_events)
@@ -538,21 +617,24 @@ int phylo_set_option(phylo_ctx *c, const char *key, int64_t value)
 			c->opt_kmer = value;
 		} else if (k == "sort_mode") {
 			if (value < 0 || value > 2) throw std::invalid_argument("sort_mode must be 0, 1 or 2");
-			g_rs_mode = (int)value; // process-wide
+			c->tuning.rs_mode = (int)value;
 		} else if (k == "sort_path") {
 			if (value < 0 || value > 2) throw std::invalid_argument("sort_path must be 0, 1 or 2");
-			g_sort_path = (int)value; // process-wide
+			c->tuning.sort_path = (int)value;
 		} else if (k == "scan_mode") {
-			g_scan_single_pass = value != 0; // process-wide
+			c->tuning.scan_single_pass = value != 0;
 		} else if (k == "map_batch_bytes") {
 			if (value < 1) throw std::invalid_argument("map_batch_bytes must be >= 1");
-			g_map_batch_bytes = (uint64_t)value; // process-wide
+			c->tuning.map_batch_bytes = (uint64_t)value;
 		} else if (k == "table_direct") {
 			if (value < 0 || value > 2) throw std::invalid_argument("table_direct must be 0, 1 or 2");
-			g_table_direct = (int)value; // process-wide
+			c->tuning.table_direct = (int)value;
 		} else if (k == "key_chars") {
 			if (value < 0 || value > 21) throw std::invalid_argument("key_chars must be in [0, 21]");
 			c->opt_key_chars = value;
+		} else if (k == "stage_threads") {
+			if (value < 0 || value > 64) throw std::invalid_argument("stage_threads must be in [0, 64]");
+			c->opt_stage_threads = value;
 		} else if (k == "keep_raw") {
 			c->keep_raw = value != 0;
 		} else if (k == "timings") {
@@ -567,7 +649,7 @@ int phylo_get_stat(const phylo_ctx *c, const char *key, double *out)
 {
 	if (!c || !key || !out) return PHYLO_ERR_INVALID;
 	if (std::string(key) == "launches") {
-		*out = (double)g_kernel_launches; // process-wide count of kernel launches so far
+		*out = (double)g_kernel_launches.load(); // process-wide count of kernel launches so far
 		return PHYLO_OK;
 	}
 	auto it = c->stats.find(key);
@@ -630,7 +712,7 @@ int phylo_esa_build(phylo_ctx *c, const char *ref, uint64_t n)
 {
 	return guarded(c, [&] {
 		if (!ref) throw std::invalid_argument("ref is NULL");
-		if (n < 1 || n > 0x3fffffffull) throw std::invalid_argument("reference length must be in [1, 2^30)");
+		check_ref_length(n);
 		DevBuf<uint8_t> d(n, c->stream);
 		CUDA_CHECK(cudaMemcpyAsync(d.get(), ref, n, cudaMemcpyHostToDevice, c->stream));
 		do_esa_build(c, d.get(), n);
@@ -716,12 +798,17 @@ int phylo_map_queries(phylo_ctx *c, const char *const *queries, const uint64_t *
 		}
 		cudaStream_t s = c->stream;
 		CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
+		c->stager.drain();
+		c->q_resident = false;
 		c->q_own.alloc(total + 64, s);
 		c->q_own.zero();
 		for (uint64_t k = 0; k < N; k++)
 			if (lens[k])
 				CUDA_CHECK(cudaMemcpyAsync(c->q_own.get() + offs[k], queries[k], lens[k], cudaMemcpyHostToDevice, s));
 		do_map(c, c->q_own.get(), offs.data(), lens, N, threshold);
+		c->q_offs = offs;
+		c->q_lens.assign(lens, lens + N);
+		c->q_resident = true;
 	});
 }
 
@@ -730,6 +817,7 @@ int phylo_map_queries_dev(phylo_ctx *c, const void *d_queries, const uint64_t *o
 {
 	return guarded(c, [&] {
 		if (N && (!d_queries || !offs || !lens)) throw std::invalid_argument("NULL argument");
+		c->q_resident = false;
 		c->q_own.release();
 		do_map(c, (const uint8_t *)d_queries, offs, lens, N, threshold);
 	});
@@ -801,12 +889,16 @@ int phylo_compare_tiles_dev(phylo_ctx *c, int flags, int rank, int world, void *
 	return guarded(c, [&] {
 		if (!d_subst || !d_homologs) throw std::invalid_argument("NULL argument");
 		do_compare(c, flags, rank, world, (unsigned long long *)d_subst, (unsigned long long *)d_homologs);
+		if (world > 1) {
+			// one rank's share of the tiles: not a matrix phylo_estimate could work on
+			c->matN = 0;
+			return;
+		}
 		const uint64_t total = c->matN;
 		ensure_matrix(c, total);
 		const size_t bytes = (size_t)(total * total) * sizeof(uint64_t);
 		CUDA_CHECK(cudaMemcpyAsync(c->d_subst.get(), d_subst, bytes, cudaMemcpyDeviceToDevice, c->stream));
 		CUDA_CHECK(cudaMemcpyAsync(c->d_hom.get(), d_homologs, bytes, cudaMemcpyDeviceToDevice, c->stream));
-		CUDA_CHECK(cudaStreamSynchronize(c->stream));
 	});
 }
 
@@ -841,7 +933,7 @@ int phylo_estimate(phylo_ctx *c, int kind, double *dist)
 {
 	return guarded(c, [&] {
 		if (!dist) throw std::invalid_argument("dist is NULL");
-		if (!c->matN) throw std::invalid_argument("no matrix yet");
+		if (!c->matN) throw std::invalid_argument("no full matrix in this context (none computed yet, or only one rank's tiles)");
 		if (kind < 0 || kind > 2) throw std::invalid_argument("unknown estimator");
 		const uint64_t n2 = c->matN * c->matN;
 		DevBuf<double> d(n2, c->stream);
@@ -851,24 +943,106 @@ int phylo_estimate(phylo_ctx *c, int kind, double *dist)
 	});
 }
 
+namespace
+{
+
+// index + threshold + mapping + all pairs on sequences that are already in (or on their way
+// into) the context's device buffer; hooks.ends / before_batch as for do_map.  The all-pairs
+// stage runs tile column by tile column as the batches get mapped, so that what is left to do
+// after the last sequence has arrived is the last batch's share only.
+void process_resident(phylo_ctx *c, uint64_t N, uint64_t ref_index, int flags, MapHooks hooks, uint64_t *subst,
+                      uint64_t *homologs)
+{
+	const uint8_t *dq = c->q_own.get();
+	const uint64_t *offs = c->q_offs.data(), *lens = c->q_lens.data();
+	cudaStream_t s = c->stream;
+	uint64_t query_bases = 0;
+	for (uint64_t k = 0; k < N; k++)
+		query_bases += lens[k];
+	do_esa_build(c, dq + offs[ref_index], lens[ref_index], query_bases);
+	// process.cxx:416-417; the G/C count comes out of the text kernel, the division and the
+	// threshold search are the reference's double arithmetic on the host
+	const double gc = (double)c->esa.gc_count / (double)lens[ref_index];
+	const uint64_t thr = phylo_min_anchor_length(0.025, gc, 2 * lens[ref_index] + 1);
+	c->stats["threshold"] = (double)thr;
+
+	const uint64_t tot = c->rows_total ? c->rows_total : N;
+	ensure_matrix(c, tot);
+	const std::vector<uint64_t> ends = hooks.ends ? *hooks.ends : plan_batches(lens, N);
+	hooks.ends = &ends;
+	const bool complete_deletion = (flags & PHYLO_FLAG_COMPLETE_DELETION) != 0;
+	const bool incremental = !complete_deletion && !c->rows_total; // complete deletion needs every row first
+	const int64_t CT = compare_tile_side((int64_t)tot);
+	const int64_t tiles_side = ((int64_t)tot + CT - 1) / CT;
+	int64_t tiles_done = 0;
+	float compare_ms = 0;
+	hooks.after_batch = [&](size_t b) {
+		if (!incremental) return;
+		const int64_t ready = b + 1 == ends.size() ? tiles_side : (int64_t)ends[b] / CT;
+		if (ready <= tiles_done) return;
+		WallTimer wt(s, c->timings);
+		compare_all_device(c->rows, (int64_t)tot, false, 0, 1, c->d_subst.get(), c->d_hom.get(), s, tiles_done, ready,
+		                   tiles_done == 0, false);
+		compare_ms += wt.stop();
+		tiles_done = ready;
+	};
+	do_map(c, dq, offs, lens, N, thr, hooks);
+	{
+		WallTimer wt(s, c->timings);
+		compare_all_device(c->rows, (int64_t)tot, complete_deletion, 0, 1, c->d_subst.get(), c->d_hom.get(), s, tiles_done,
+		                   -1, tiles_done == 0, true);
+		compare_ms += wt.stop();
+	}
+	c->stats["compare.ms"] = compare_ms;
+	c->stats["compare.increments"] = (double)ends.size();
+	c->matN = tot;
+	const size_t bytes = (size_t)(tot * tot) * sizeof(uint64_t);
+	CUDA_CHECK(cudaMemcpyAsync(subst, c->d_subst.get(), bytes, cudaMemcpyDeviceToHost, s));
+	CUDA_CHECK(cudaMemcpyAsync(homologs, c->d_hom.get(), bytes, cudaMemcpyDeviceToHost, s));
+	CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+// after a failed call nothing of ours may still be reading the caller's buffers
+void quiesce(phylo_ctx *c)
+{
+	c->stager.drain();
+	cudaStreamSynchronize(c->copy_stream);
+	cudaStreamSynchronize(c->stream);
+	if (c->push_stream) cudaStreamSynchronize(c->push_stream);
+	cudaGetLastError();
+}
+
+} // namespace
+
 int phylo_process(phylo_ctx *c, const char *const *seqs, const uint64_t *lens, uint64_t N, uint64_t ref_index, int flags,
                   uint64_t *subst, uint64_t *homologs)
 {
 	if (!c) return fail(nullptr, PHYLO_ERR_INVALID, "context is NULL");
 	if (!seqs || !lens || !subst || !homologs || ref_index >= N)
 		return fail(c, PHYLO_ERR_INVALID, "bad arguments to phylo_process");
-	return guarded(c, [&] {
+	const int rc = guarded(c, [&] {
 		// one device buffer for all sequences; the reference goes first on the main stream,
 		// the other sequences follow on the copy stream while the index is being built
-		std::vector<uint64_t> offs((size_t)N);
+		c->q_resident = false;
+		c->q_offs.assign((size_t)N, 0);
+		c->q_lens.assign(lens, lens + N);
 		uint64_t total = 0;
+		bool pageable = false;
 		for (uint64_t k = 0; k < N; k++) {
 			if (!seqs[k] && lens[k]) throw std::invalid_argument("NULL sequence");
-			offs[k] = total;
+			c->q_offs[k] = total;
 			total = (total + lens[k] + 1 + 15) / 16 * 16;
 		}
+		// where do the sequences live?  one probe: callers do not mix pinned and ordinary memory
+		for (uint64_t k = 0; k < N && !pageable; k++)
+			if (k != ref_index && lens[k]) {
+				pageable = HostStager::is_pageable(seqs[k]);
+				break;
+			}
+		const uint64_t *offs = c->q_offs.data();
 		cudaStream_t s = c->stream;
 		CUDA_CHECK(cudaStreamSynchronize(c->copy_stream)); // nothing may still write into the old buffer
+		c->stager.drain();
 		c->q_own.alloc(total + 64, s);
 		c->q_own.zero();
 		uint8_t *dq = c->q_own.get();
@@ -876,66 +1050,96 @@ int phylo_process(phylo_ctx *c, const char *const *seqs, const uint64_t *lens, u
 			CUDA_CHECK(cudaMemcpyAsync(dq + offs[ref_index], seqs[ref_index], lens[ref_index], cudaMemcpyHostToDevice, s));
 		CUDA_CHECK(cudaEventRecord(c->ev_main, s));
 		CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
-		// The other sequences follow on the copy stream, batch by batch, with an event behind
-		// every batch: batch b is mapped while the later ones are still crossing PCIe.  At most
-		// COPY_QUEUE copies are queued ahead of the batch being mapped — a thousand queued copies
-		// fill the driver's queue and block the host until they have drained, with the index
-		// build not yet launched (measured: 1000 x 3 Mbp) — but never fewer than two batches.
 		const std::vector<uint64_t> ends = plan_batches(lens, N);
-		while (c->batch_events.size() < ends.size()) {
-			cudaEvent_t e;
-			CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-			c->batch_events.push_back(e);
-		}
-		constexpr uint64_t COPY_QUEUE = 256;
+		MapHooks hooks;
+		hooks.ends = &ends;
 		size_t queued = 0;
-		auto queue_copies = [&](size_t current) { // `current` = the batch about to be mapped
-			const uint64_t seq0 = current ? ends[current - 1] : 0;
-			size_t last = current + 2;
-			while (last + 1 < ends.size() && ends[last + 1] - seq0 <= COPY_QUEUE)
-				last++;
-			for (; queued <= last && queued < ends.size(); queued++) {
-				for (uint64_t k = queued ? ends[queued - 1] : 0; k < ends[queued]; k++)
-					if (k != ref_index && lens[k])
-						CUDA_CHECK(cudaMemcpyAsync(dq + offs[k], seqs[k], lens[k], cudaMemcpyHostToDevice, c->copy_stream));
-				CUDA_CHECK(cudaEventRecord(c->batch_events[queued], c->copy_stream));
+		if (pageable) {
+			// ordinary host memory: worker threads stage the pieces through pinned rings (staging.h)
+			uint64_t k = 0;
+			for (size_t b = 0; b < ends.size(); b++)
+				for (; k < ends[b]; k++)
+					if (k != ref_index && lens[k]) c->stager.add(dq + offs[k], seqs[k], lens[k], (int)b);
+			int threads = (int)c->opt_stage_threads;
+			if (threads <= 0) {
+				const unsigned hw = std::thread::hardware_concurrency();
+				threads = hw >= 16 ? 4 : hw >= 4 ? 2 : 1;
 			}
-		};
-		queue_copies(0);
-
-		uint64_t query_bases = 0;
-		for (uint64_t k = 0; k < N; k++)
-			query_bases += lens[k];
-		do_esa_build(c, dq + offs[ref_index], lens[ref_index], query_bases);
-		// process.cxx:416-417; the G/C count comes out of the text kernel, the division and the
-		// threshold search are the reference's double arithmetic on the host
-		const double gc = (double)c->esa.gc_count / (double)lens[ref_index];
-		const uint64_t thr = phylo_min_anchor_length(0.025, gc, 2 * lens[ref_index] + 1);
-		c->stats["threshold"] = (double)thr;
-
-		const std::vector<cudaEvent_t> ready(c->batch_events.begin(), c->batch_events.begin() + ends.size());
-		do_map(c, dq, offs.data(), lens, N, thr, &ends, &ready, queue_copies);
-
-		const uint64_t tot = c->rows_total ? c->rows_total : c->N;
-		ensure_matrix(c, tot);
-		do_compare(c, flags, 0, 1, c->d_subst.get(), c->d_hom.get());
-		const size_t bytes = (size_t)(tot * tot) * sizeof(uint64_t);
-		CUDA_CHECK(cudaMemcpyAsync(subst, c->d_subst.get(), bytes, cudaMemcpyDeviceToHost, s));
-		CUDA_CHECK(cudaMemcpyAsync(homologs, c->d_hom.get(), bytes, cudaMemcpyDeviceToHost, s));
-		CUDA_CHECK(cudaStreamSynchronize(s));
+			if (!c->stager.empty()) c->stager.start(c->device, (int)ends.size(), threads, c->ev_main);
+			hooks.before_batch = [&](size_t b) { c->stager.wait_batch((int)b, s); };
+		} else {
+			// pinned memory: plain asynchronous copies on the copy stream, batch by batch, with an
+			// event behind every batch: batch b is mapped while the later ones are still crossing
+			// PCIe.  At most COPY_QUEUE copies are queued ahead of the batch being mapped — a
+			// thousand queued copies fill the driver's queue and block the host until they have
+			// drained, with the index build not yet launched (measured: 1000 x 3 Mbp) — but never
+			// fewer than two batches.
+			while (c->batch_events.size() < ends.size()) {
+				cudaEvent_t e;
+				CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+				c->batch_events.push_back(e);
+			}
+			constexpr uint64_t COPY_QUEUE = 256;
+			auto queue_copies = [&, dq, offs](size_t current) { // `current` = the batch about to be mapped
+				const uint64_t seq0 = current ? ends[current - 1] : 0;
+				size_t last = current + 2;
+				while (last + 1 < ends.size() && ends[last + 1] - seq0 <= COPY_QUEUE)
+					last++;
+				for (; queued <= last && queued < ends.size(); queued++) {
+					for (uint64_t k = queued ? ends[queued - 1] : 0; k < ends[queued]; k++)
+						if (k != ref_index && lens[k])
+							CUDA_CHECK(cudaMemcpyAsync(dq + offs[k], seqs[k], lens[k], cudaMemcpyHostToDevice, c->copy_stream));
+					CUDA_CHECK(cudaEventRecord(c->batch_events[queued], c->copy_stream));
+				}
+			};
+			queue_copies(0);
+			hooks.before_batch = [&, queue_copies](size_t b) mutable {
+				queue_copies(b);
+				CUDA_CHECK(cudaStreamWaitEvent(s, c->batch_events[b], 0));
+			};
+		}
+		c->stats["process.pageable"] = pageable ? 1 : 0;
+		{
+			uint64_t bases = 0;
+			for (uint64_t k = 0; k < N; k++)
+				bases += lens[k];
+			c->stats["process.h2d_bytes"] = (double)bases;
+		}
+		process_resident(c, N, ref_index, flags, hooks, subst, homologs);
+		c->stager.finish();
+		c->q_resident = true;
 	});
+	if (rc != PHYLO_OK) quiesce(c);
+	return rc;
+}
+
+int phylo_process_again(phylo_ctx *c, uint64_t ref_index, int flags, uint64_t *subst, uint64_t *homologs)
+{
+	if (!c) return fail(nullptr, PHYLO_ERR_INVALID, "context is NULL");
+	const int rc = guarded(c, [&] {
+		if (!subst || !homologs) throw std::invalid_argument("NULL argument");
+		if (!c->q_resident) throw std::invalid_argument("phylo_process_again: no sequences resident on the device");
+		const uint64_t N = c->q_lens.size();
+		if (ref_index >= N) throw std::invalid_argument("reference index out of range");
+		if (!c->q_lens[ref_index]) throw std::invalid_argument("reference is empty");
+		CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
+		process_resident(c, N, ref_index, flags, MapHooks(), subst, homologs);
+		c->stats["process.h2d_bytes"] = 0;
+	});
+	if (rc != PHYLO_OK) quiesce(c);
+	return rc;
 }
 
 int phylo_esa_alloc(phylo_ctx *c, uint64_t n)
 {
 	return guarded(c, [&] {
-		if (n < 1 || n > 0x3fffffffull) throw std::invalid_argument("reference length must be in [1, 2^30)");
+		check_ref_length(n);
 		cudaStream_t s = c->stream;
 		c->esa_ready = false;
 		c->mapped = false;
 		c->esa.release();
 		const int32_t m = (int32_t)(2 * n + 1);
-		const int32_t padded = ((m + 64 + 255) / 256) * 256;
+		const int32_t padded = ((m + 64 + 255) / 256) * 256; // check_ref_length leaves room for the padding
 		c->esa.n = (int32_t)n;
 		c->esa.m = m;
 		c->esa.S.alloc(padded, s);
@@ -983,10 +1187,69 @@ int phylo_rows_configure(phylo_ctx *c, uint64_t total_genomes, uint64_t first_ro
 		if (total_genomes && first_row >= total_genomes) throw std::invalid_argument("first_row out of range");
 		c->rows_total = total_genomes;
 		c->rows_first = first_row;
-		if (total_genomes && c->esa.m && ((uint64_t)c->rows.genomes != total_genomes || c->rows.n != c->esa.n)) {
-			rows_alloc(c->rows, (int64_t)total_genomes, c->esa.n, c->stream);
+		if (total_genomes && c->esa.m) {
+			if ((uint64_t)c->rows.genomes != total_genomes || c->rows.n != c->esa.n) {
+				clear_peers(c); // the store moves: addresses handed to the peers are stale
+				rows_alloc(c->rows, (int64_t)total_genomes, c->esa.n, c->stream);
+			} else // no slot counts as a written row until a mapping (here or on a peer) fills it
+				rows_clear_flags(c->rows, c->stream);
 			CUDA_CHECK(cudaStreamSynchronize(c->stream));
 		}
+	});
+}
+
+int phylo_rows_ipc_export(phylo_ctx *c, void *handle)
+{
+	return guarded(c, [&] {
+		static_assert(sizeof(cudaIpcMemHandle_t) == PHYLO_IPC_HANDLE_BYTES, "handle size");
+		if (!handle) throw std::invalid_argument("handle is NULL");
+		if (!c->rows.data.get()) throw std::invalid_argument("no row store yet: call phylo_rows_configure after the index exists");
+		cudaIpcMemHandle_t h;
+		CUDA_CHECK(cudaIpcGetMemHandle(&h, c->rows.data.get()));
+		memcpy(handle, &h, sizeof h);
+	});
+}
+
+int phylo_rows_ipc_import(phylo_ctx *c, const void *handles, int world, int rank)
+{
+	return guarded(c, [&] {
+		if (!handles || world < 1 || rank < 0 || rank >= world) throw std::invalid_argument("bad arguments");
+		if (!c->rows.data.get()) throw std::invalid_argument("no row store yet");
+		clear_peers(c);
+		c->peer_rows.assign((size_t)world, nullptr);
+		c->peer_ipc.assign((size_t)world, nullptr);
+		c->peer_rank = rank;
+		for (int p = 0; p < world; p++) {
+			if (p == rank) {
+				c->peer_rows[p] = c->rows.data.get();
+				continue;
+			}
+			cudaIpcMemHandle_t h;
+			memcpy(&h, (const char *)handles + (size_t)p * sizeof h, sizeof h);
+			void *ptr = nullptr;
+			const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+			if (e != cudaSuccess) {
+				cudaGetLastError();
+				clear_peers(c);
+				throw CudaError(std::string("cudaIpcOpenMemHandle (row store of rank ") + std::to_string(p) + "): " + cudaGetErrorString(e));
+			}
+			c->peer_ipc[p] = ptr;
+			c->peer_rows[p] = (uint32_t *)ptr;
+		}
+	});
+}
+
+int phylo_rows_set_peers(phylo_ctx *c, void *const *peer_rows, int world, int rank)
+{
+	return guarded(c, [&] {
+		clear_peers(c);
+		if (!peer_rows || world <= 0) return; // back to a context that keeps its rows to itself
+		if (rank < 0 || rank >= world) throw std::invalid_argument("bad rank");
+		if (!c->rows.data.get()) throw std::invalid_argument("no row store yet");
+		c->peer_rank = rank;
+		c->peer_rows.assign((size_t)world, nullptr);
+		for (int p = 0; p < world; p++)
+			c->peer_rows[p] = p == rank ? c->rows.data.get() : (uint32_t *)peer_rows[p];
 	});
 }
 

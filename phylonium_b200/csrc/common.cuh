@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <stdexcept>
@@ -30,7 +31,7 @@ inline void cuda_check(cudaError_t e, const char *what, const char *file, int li
 #define CUDA_CHECK(x) ::phy::cuda_check((x), #x, __FILE__, __LINE__)
 // every kernel launch of the library goes through KERNEL_CHECK; the count is reported as
 // the "launches" statistic
-inline uint64_t g_kernel_launches = 0;
+inline std::atomic<uint64_t> g_kernel_launches{0};
 #define KERNEL_CHECK()                                                                              \
 	do {                                                                                            \
 		::phy::g_kernel_launches++;                                                                 \
@@ -39,18 +40,29 @@ inline uint64_t g_kernel_launches = 0;
 
 constexpr int NUM_SMS_B200 = 148;
 
+// Tuning options (phylo_set_option) belong to a context.  The kernels' host code reads them
+// from this thread-local copy, which every C-ABI call refreshes from its context on entry
+// (a context is used by one thread at a time): two contexts in one process — one per GPU —
+// never see each other's settings.
+struct Tuning {
+	int scan_single_pass = 1;  // "scan_mode": 1 = one launch with decoupled look-back, 0 = three launches
+	int rs_mode = 0;           // "sort_mode": 0 by size, 1 histogram + scan + scatter, 2 single-pass look-back
+	int sort_path = 0;         // "sort_path": 0 pick, 1 always the general sorter (3-bit codes, 64-bit keys)
+	int table_direct = 0;      // "table_direct": 0 / 1 entry by entry from the root, 2 level by level
+	uint64_t map_batch_bytes = 512ull << 20; // "map_batch_bytes"
+};
+inline thread_local Tuning g_tuning;
+
 // Per-device "done once" flags (kernel attributes are per device: a process that drives
 // several GPUs has to set them on each).
 struct PerDeviceOnce {
-	bool done[64] = {};
+	std::atomic<bool> done[64] = {};
 	// true the first time it is asked on the current device
 	bool first()
 	{
 		int dev = 0;
 		if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
-		if (done[dev]) return false;
-		done[dev] = true;
-		return true;
+		return !done[dev].exchange(true);
 	}
 };
 

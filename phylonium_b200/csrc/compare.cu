@@ -126,33 +126,48 @@ __global__ void k_build_rows(uint32_t *__restrict__ rows, int64_t genome_words, 
 	row[PL_C1 * W + w] = p1;
 	row[PL_D * W + w] = pd;
 	row[PL_B * W + w] = pb;
-	// flag word behind the planes: does this genome use the D / B planes at all?
+	// flag words behind the planes: does this genome use the D / B planes at all?  The second
+	// word marks the row as written (the padding rows of a sharded store never are).
 	const uint32_t f = (pd ? ROW_FLAG_D : 0u) | (pb ? ROW_FLAG_B : 0u);
 	if (f) {
 		uint32_t *flag = row + ROW_PLANES * W;
 		if ((*(volatile uint32_t *)flag & f) != f) atomicOr(flag, f);
 	}
+	if (w == 0) row[ROW_PLANES * W + ROW_WORD_REAL] = 1u;
 }
 
-// vall[w] = AND over all genomes of V (complete deletion, process.cxx:725-776 in row form)
+// vall[w] = AND over all genomes of V (complete deletion, process.cxx:725-776 in row form).
+// Rows that were never written — the padding slots of a sharded store — are not genomes and
+// do not take part (the reference intersects the real sequences only).
 __global__ void k_and_valid(const uint32_t *__restrict__ rows, int64_t genome_words, int64_t W, int64_t N,
                             uint32_t *__restrict__ vall)
 {
 	const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (w >= W) return;
 	uint32_t v = 0xffffffffu;
-	for (int64_t g = 0; g < N; g++)
-		v &= rows[g * genome_words + PL_V * W + w];
+	for (int64_t g = 0; g < N; g++) {
+		const uint32_t *row = rows + g * genome_words;
+		if (row[ROW_PLANES * W + ROW_WORD_REAL]) v &= row[PL_V * W + w];
+	}
 	vall[w] = v;
 }
 
-constexpr int PT = 4;        // genomes per side of a warp's sub-tile
-constexpr int CMP_STEP = 32; // words per step: one per lane
-// CT = genomes per side of a block's tile: 16 (16 warps), or 8 (4 warps) when there are so few
-// genomes that 16 x 16 tiles would be mostly padding
+constexpr int PT = 4; // genomes per side of a warp's sub-tile
+// CT = genomes per side of a block's tile: 16, or 8 when there are so few genomes that 16 x 16
+// tiles would be mostly padding.  A tile has (CT / PT)^2 sub-tiles of 4 x 4 pairs; a block of 8
+// warps takes two sub-tiles per warp (CT = 16), a block of 4 warps one (CT = 8).
 __host__ __device__ constexpr int cmp_threads(int CT)
 {
-	return (CT / PT) * (CT / PT) * 32;
+	return CT == 16 ? 256 : 128;
+}
+// words per lane and step: the 3-plane path adds up three words per pair with one carry-save
+// step before it counts bits; the 5-plane path (reverse strands, separators) goes word by word
+constexpr int CMP_WPL_FAST = 3, CMP_WPL_FULL = 1;
+__host__ __device__ constexpr size_t cmp_smem_bytes(int CT)
+{
+	// two buffers of 2 CT genomes x planes x (32 * words per lane) words; the larger of the two paths
+	const size_t fast = (size_t)2 * 2 * CT * 3 * 32 * CMP_WPL_FAST, full = (size_t)2 * 2 * CT * ROW_PLANES * 32 * CMP_WPL_FULL;
+	return (fast > full ? fast : full) * sizeof(uint32_t);
 }
 
 __device__ __forceinline__ void cmp_cp_async16(void *smem_dst, const void *gsrc, int src_bytes)
@@ -161,107 +176,185 @@ __device__ __forceinline__ void cmp_cp_async16(void *smem_dst, const void *gsrc,
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 
-// one (tile pair, chunk) unit; P = planes to look at (3: V, C0, C1; 5: all)
-template <int P, int CT>
+// acc += x * K on the multiply-add pipe (the logic pipe is what bounds this kernel)
+template <uint32_t K> __device__ __forceinline__ uint32_t cmp_mad(uint32_t x, uint32_t acc)
+{
+	uint32_t r;
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "n"(K), "r"(acc));
+	return r;
+}
+
+// One (tile pair, chunk) unit.  P = planes to look at (3: V, C0, C1; 5: all), WPL = words per
+// lane and step.  Per pair and word: both = Va & Vb, diff = both & (codes differ [or, on the
+// same strand, '!' flags differ]).  The two counts of a pair share one register (homologous
+// columns in the low half, substitutions in the high half) that is emptied into the matrix
+// before a half can overflow.
+//
+// Bit counting is the scarce resource: POPC issues at a quarter of the rate of logic
+// instructions (measured: the one-word-at-a-time version of this kernel sat on the XU pipe).
+// With WPL = 3 the three words of a pair go through one full-adder step first,
+//     ones = x0 ^ x1 ^ x2,  twos = maj(x0, x1, x2),  count = popc(ones) + 2 popc(twos),
+// two POPC instead of three for two more LOP3: logic and XU pipes come out even.
+template <int P, int CT, int WPL>
 __device__ __forceinline__ void compare_tile(uint32_t *stage, const uint32_t *__restrict__ rows, int64_t genome_words,
                                              int64_t W, int64_t N, int64_t gi0, int64_t gj0, int64_t w_begin, int64_t w_end,
                                              const uint32_t *__restrict__ vall, unsigned long long *__restrict__ subst,
                                              unsigned long long *__restrict__ homol)
 {
-	// stage[buf][slot][plane][32]: slots 0..15 the I genomes, 16..31 the J genomes
-	constexpr int SLOT_WORDS = P * CMP_STEP;
+	constexpr int STEP = 32 * WPL;                  // words per genome plane and step
+	constexpr int SLOT_WORDS = P * STEP;            // stage[buf][slot][plane][STEP]: slots 0..CT-1 the I genomes, then J
 	constexpr int BUF_WORDS = 2 * CT * SLOT_WORDS;
-	constexpr int PIECES = 2 * CT * P * (CMP_STEP / 4); // 16-byte pieces per step
-	constexpr int CMP_THREADS = cmp_threads(CT);
+	constexpr int PIECES = 2 * CT * P * (STEP / 4); // 16-byte pieces per step
+	constexpr int THREADS = cmp_threads(CT);
+	constexpr int SIDE = CT / PT, SUBS = SIDE * SIDE, WARPS = THREADS / 32, SPW = SUBS / WARPS;
+	constexpr int FLUSH_STEPS = 65535 / STEP; // a lane adds at most STEP per step to either half
+	static_assert(SUBS % WARPS == 0 && SPW >= 1, "sub-tiles per warp");
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int wi = warp / (CT / PT), wj = warp % (CT / PT);
-	// sub-tiles of padding genomes, or below the diagonal of a diagonal tile, have nothing to count
-	const bool active = gi0 + PT * wi < N && gj0 + PT * wj < N && (gi0 != gj0 || wi <= wj);
 
 	auto prefetch = [&](int64_t w0, int buf) {
-		for (int piece = threadIdx.x; piece < PIECES; piece += CMP_THREADS) {
-			const int slot = piece / (P * 8), rem = piece % (P * 8), plane = rem >> 3, part = rem & 7;
+		for (int piece = threadIdx.x; piece < PIECES; piece += THREADS) {
+			const int slot = piece / (P * (STEP / 4)), rem = piece % (P * (STEP / 4)), plane = rem / (STEP / 4),
+			          part = rem % (STEP / 4);
 			const int64_t g = slot < CT ? gi0 + slot : gj0 + (slot - CT);
 			const int64_t w = w0 + 4 * part;
 			const bool ok = g < N && w < w_end; // w_end and W are multiples of 4
 			const uint32_t *src = rows + (ok ? g * genome_words + plane * W + w : 0);
-			cmp_cp_async16(stage + buf * BUF_WORDS + slot * SLOT_WORDS + plane * CMP_STEP + 4 * part, src, ok ? 16 : 0);
+			cmp_cp_async16(stage + buf * BUF_WORDS + slot * SLOT_WORDS + plane * STEP + 4 * part, src, ok ? 16 : 0);
 		}
 		asm volatile("cp.async.commit_group;\n" ::: "memory");
 	};
 
-	uint32_t cs[PT][PT], ch[PT][PT];
+	// sub-tiles of padding genomes, or below the diagonal of a diagonal tile, have nothing to count
+	bool active[SPW];
+	int wi[SPW], wj[SPW];
+	uint32_t acc[SPW][PT][PT];
 #pragma unroll
-	for (int a = 0; a < PT; a++)
+	for (int u = 0; u < SPW; u++) {
+		const int sub = warp + u * WARPS;
+		wi[u] = sub / SIDE;
+		wj[u] = sub % SIDE;
+		active[u] = gi0 + PT * wi[u] < N && gj0 + PT * wj[u] < N && (gi0 != gj0 || wi[u] <= wj[u]);
 #pragma unroll
-		for (int b = 0; b < PT; b++)
-			cs[a][b] = ch[a][b] = 0;
-
-	prefetch(w_begin, 0);
-	int buf = 0;
-	for (int64_t w0 = w_begin; w0 < w_end; w0 += CMP_STEP, buf ^= 1) {
-		asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-		__syncthreads(); // this step's words are in; everybody is done with the other buffer
-		if (w0 + CMP_STEP < w_end) prefetch(w0 + CMP_STEP, buf ^ 1);
-		if (!active) continue;
-		const uint32_t *st = stage + buf * BUF_WORDS + lane;
-		uint32_t mask = 0xffffffffu;
-		if (vall && w0 + lane < w_end) mask = vall[w0 + lane];
-		// the I side stays in registers, the J side is read genome by genome
-		uint32_t av[PT], a0[PT], a1[PT], ad[PT], ab[PT];
+		for (int a = 0; a < PT; a++)
 #pragma unroll
-		for (int a = 0; a < PT; a++) {
-			const uint32_t *r = st + (PT * wi + a) * SLOT_WORDS;
-			av[a] = r[PL_V * CMP_STEP] & mask;
-			a0[a] = r[PL_C0 * CMP_STEP];
-			a1[a] = r[PL_C1 * CMP_STEP];
-			if (P == 5) {
-				ad[a] = r[PL_D * CMP_STEP];
-				ab[a] = r[PL_B * CMP_STEP];
-			}
-		}
+			for (int b = 0; b < PT; b++)
+				acc[u][a][b] = 0;
+	}
+	auto flush = [&] {
 #pragma unroll
-		for (int b = 0; b < PT; b++) {
-			const uint32_t *r = st + (CT + PT * wj + b) * SLOT_WORDS;
-			const uint32_t bv = r[PL_V * CMP_STEP], b0 = r[PL_C0 * CMP_STEP], b1 = r[PL_C1 * CMP_STEP];
-			uint32_t bd = 0, bb = 0;
-			if (P == 5) {
-				bd = r[PL_D * CMP_STEP];
-				bb = r[PL_B * CMP_STEP];
-			}
+		for (int u = 0; u < SPW; u++) {
+			if (!active[u]) continue;
 #pragma unroll
 			for (int a = 0; a < PT; a++) {
-				const uint32_t both = av[a] & bv;
-				uint32_t diff = (a0[a] ^ b0) | (a1[a] ^ b1);
-				if (P == 5) diff |= ~(ad[a] ^ bd) & (ab[a] ^ bb);
-				ch[a][b] += __popc(both);
-				cs[a][b] += __popc(both & diff);
+#pragma unroll
+				for (int b = 0; b < PT; b++) {
+					uint32_t hv = acc[u][a][b] & 0xffffu, sv = acc[u][a][b] >> 16;
+					acc[u][a][b] = 0;
+#pragma unroll
+					for (int d = 16; d > 0; d >>= 1) {
+						sv += __shfl_xor_sync(0xffffffffu, sv, d);
+						hv += __shfl_xor_sync(0xffffffffu, hv, d);
+					}
+					const int64_t i = gi0 + PT * wi[u] + a, j = gj0 + PT * wj[u] + b;
+					if (lane == 0 && i < j && j < N && hv) {
+						atomicAdd(&subst[i * N + j], (unsigned long long)sv);
+						atomicAdd(&homol[i * N + j], (unsigned long long)hv);
+					}
+				}
 			}
 		}
-	}
-	if (!active) return;
+	};
+
+	prefetch(w_begin, 0);
+	int buf = 0, steps = 0;
+	for (int64_t w0 = w_begin; w0 < w_end; w0 += STEP, buf ^= 1) {
+		asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+		__syncthreads(); // this step's words are in; everybody is done with the other buffer
+		if (w0 + STEP < w_end) prefetch(w0 + STEP, buf ^ 1);
+		const uint32_t *st = stage + buf * BUF_WORDS + lane;
+		uint32_t mask[WPL];
 #pragma unroll
-	for (int a = 0; a < PT; a++) {
+		for (int k = 0; k < WPL; k++)
+			mask[k] = (vall && w0 + 32 * k + lane < w_end) ? vall[w0 + 32 * k + lane] : 0xffffffffu;
 #pragma unroll
-		for (int b = 0; b < PT; b++) {
-			uint32_t sv = cs[a][b], hv = ch[a][b];
+		for (int u = 0; u < SPW; u++) {
+			if (!active[u]) continue;
+			// the I side stays in registers, the J side is read genome by genome
+			uint32_t av[PT][WPL], a0[PT][WPL], a1[PT][WPL], ad[PT][WPL], ab[PT][WPL];
 #pragma unroll
-			for (int d = 16; d > 0; d >>= 1) {
-				sv += __shfl_xor_sync(0xffffffffu, sv, d);
-				hv += __shfl_xor_sync(0xffffffffu, hv, d);
+			for (int a = 0; a < PT; a++) {
+				const uint32_t *r = st + (PT * wi[u] + a) * SLOT_WORDS;
+#pragma unroll
+				for (int k = 0; k < WPL; k++) {
+					av[a][k] = r[PL_V * STEP + 32 * k] & mask[k];
+					a0[a][k] = r[PL_C0 * STEP + 32 * k];
+					a1[a][k] = r[PL_C1 * STEP + 32 * k];
+					if (P == 5) {
+						ad[a][k] = r[PL_D * STEP + 32 * k];
+						ab[a][k] = r[PL_B * STEP + 32 * k];
+					}
+				}
 			}
-			const int64_t i = gi0 + PT * wi + a, j = gj0 + PT * wj + b;
-			if (lane == 0 && i < j && j < N && hv) {
-				atomicAdd(&subst[i * N + j], (unsigned long long)sv);
-				atomicAdd(&homol[i * N + j], (unsigned long long)hv);
+#pragma unroll
+			for (int b = 0; b < PT; b++) {
+				const uint32_t *r = st + (CT + PT * wj[u] + b) * SLOT_WORDS;
+				uint32_t bv[WPL], b0[WPL], b1[WPL], bd[WPL], bb[WPL];
+#pragma unroll
+				for (int k = 0; k < WPL; k++) {
+					bv[k] = r[PL_V * STEP + 32 * k];
+					b0[k] = r[PL_C0 * STEP + 32 * k];
+					b1[k] = r[PL_C1 * STEP + 32 * k];
+					if (P == 5) {
+						bd[k] = r[PL_D * STEP + 32 * k];
+						bb[k] = r[PL_B * STEP + 32 * k];
+					}
+				}
+#pragma unroll
+				for (int a = 0; a < PT; a++) {
+					uint32_t both[WPL], diff[WPL];
+#pragma unroll
+					for (int k = 0; k < WPL; k++) {
+						both[k] = av[a][k] & bv[k];
+						uint32_t d = (a0[a][k] ^ b0[k]) | (a1[a][k] ^ b1[k]);
+						if (P == 5) d |= ~(ad[a][k] ^ bd[k]) & (ab[a][k] ^ bb[k]);
+						diff[k] = d & both[k];
+					}
+					uint32_t c = acc[u][a][b];
+					if (WPL == 3) {
+						const uint32_t h1 = both[0] ^ both[1] ^ both[2];
+						const uint32_t h2 = (both[0] & both[1]) | (both[2] & (both[0] | both[1]));
+						const uint32_t s1 = diff[0] ^ diff[1] ^ diff[2];
+						const uint32_t s2 = (diff[0] & diff[1]) | (diff[2] & (diff[0] | diff[1]));
+						c = cmp_mad<1u>(__popc(h1), c);
+						c = cmp_mad<2u>(__popc(h2), c);
+						c = cmp_mad<65536u>(__popc(s1), c);
+						c = cmp_mad<131072u>(__popc(s2), c);
+					} else {
+#pragma unroll
+						for (int k = 0; k < WPL; k++) {
+							c = cmp_mad<1u>(__popc(both[k]), c);
+							c = cmp_mad<65536u>(__popc(diff[k]), c);
+						}
+					}
+					acc[u][a][b] = c;
+				}
 			}
 		}
+		if (++steps == FLUSH_STEPS) {
+			flush();
+			steps = 0;
+		}
 	}
+	flush();
 }
 
+// Work units are (tile pair, chunk of columns).  Tile pairs (ti <= tj) are numbered column by
+// column, tp = tj (tj + 1) / 2 + ti, so that "all pairs whose later tile is in [tj0, tj1)" —
+// what becomes computable when another batch of genomes has been mapped — is one range of
+// tp.  Unit u of this launch is tile pair tp_begin + (u * tile_world + tile_rank) / chunks.
 template <int CT>
-__global__ void __launch_bounds__(cmp_threads(CT), CT == 16 ? 2 : 8)
-k_compare_tiles(const uint32_t *__restrict__ rows, int64_t genome_words, int64_t W, int64_t N, int32_t tiles_side,
+__global__ void __launch_bounds__(cmp_threads(CT), CT == 16 ? 2 : 4)
+k_compare_tiles(const uint32_t *__restrict__ rows, int64_t genome_words, int64_t W, int64_t N, int64_t tp_begin,
                 int64_t units, int32_t chunks, int64_t chunk_words, int tile_rank, int tile_world,
                 const uint32_t *__restrict__ vall, unsigned long long *__restrict__ subst,
                 unsigned long long *__restrict__ homol)
@@ -270,17 +363,16 @@ k_compare_tiles(const uint32_t *__restrict__ rows, int64_t genome_words, int64_t
 	__shared__ uint32_t tile_flags;
 	const int64_t unit = (int64_t)blockIdx.x * tile_world + tile_rank; // units are dealt round-robin
 	if (unit >= units) return;
-	const int64_t tp = unit / chunks;
+	const int64_t tp = tp_begin + unit / chunks;
 	const int32_t chunk = (int32_t)(unit % chunks);
-	// unrank tp -> (ti <= tj): row ti holds tiles_side - ti pairs
-	int32_t ti = 0;
-	int64_t rem = tp;
-	while (rem >= tiles_side - ti) {
-		rem -= tiles_side - ti;
-		ti++;
-	}
-	const int32_t tj = ti + (int32_t)rem;
-	const int64_t gi0 = (int64_t)ti * CT, gj0 = (int64_t)tj * CT;
+	// unrank tp -> (ti <= tj): column tj holds tj + 1 pairs
+	int64_t tj = (int64_t)((sqrt(8.0 * (double)tp + 1.0) - 1.0) * 0.5);
+	while (tj * (tj + 1) / 2 > tp)
+		tj--;
+	while ((tj + 1) * (tj + 2) / 2 <= tp)
+		tj++;
+	const int64_t ti = tp - tj * (tj + 1) / 2;
+	const int64_t gi0 = ti * CT, gj0 = tj * CT;
 	const int64_t w_begin = (int64_t)chunk * chunk_words;
 	const int64_t w_end = w_begin + chunk_words < W ? w_begin + chunk_words : W;
 
@@ -289,15 +381,15 @@ k_compare_tiles(const uint32_t *__restrict__ rows, int64_t genome_words, int64_t
 	if (threadIdx.x < 2 * CT) {
 		const int64_t g = threadIdx.x < CT ? gi0 + threadIdx.x : gj0 + (threadIdx.x - CT);
 		if (g < N) {
-			const uint32_t f = rows[g * genome_words + ROW_PLANES * W];
+			const uint32_t f = rows[g * genome_words + ROW_PLANES * W + ROW_WORD_FLAGS];
 			if (f) atomicOr(&tile_flags, f);
 		}
 	}
 	__syncthreads();
 	if (tile_flags)
-		compare_tile<5, CT>(cmp_stage, rows, genome_words, W, N, gi0, gj0, w_begin, w_end, vall, subst, homol);
+		compare_tile<5, CT, CMP_WPL_FULL>(cmp_stage, rows, genome_words, W, N, gi0, gj0, w_begin, w_end, vall, subst, homol);
 	else
-		compare_tile<3, CT>(cmp_stage, rows, genome_words, W, N, gi0, gj0, w_begin, w_end, vall, subst, homol);
+		compare_tile<3, CT, CMP_WPL_FAST>(cmp_stage, rows, genome_words, W, N, gi0, gj0, w_begin, w_end, vall, subst, homol);
 }
 
 // seg[w] = core columns where some genome differs from genome 0 (process.cxx:484-490:
@@ -381,6 +473,13 @@ void rows_alloc(RowStore &rs, int64_t genomes, int32_t n, cudaStream_t s)
 	rs.data.zero(); // rows never written (padding genomes of a sharded run) are all-invalid
 }
 
+void rows_clear_flags(RowStore &rs, cudaStream_t s)
+{
+	if (!rs.genomes) return;
+	CUDA_CHECK(cudaMemset2DAsync(rs.row(0) + ROW_PLANES * rs.W, (size_t)rs.genome_words() * sizeof(uint32_t), 0,
+	                             ROW_FLAG_WORDS * sizeof(uint32_t), (size_t)rs.genomes, s));
+}
+
 void rows_build(RowStore &rs, int64_t first_row, const uint8_t *d_Q, const QueryInfo *d_qi, int32_t count,
                 const Hom *d_homs, const int64_t *d_begin, const int64_t *d_count, cudaStream_t s)
 {
@@ -398,12 +497,26 @@ void rows_build(RowStore &rs, int64_t first_row, const uint8_t *d_Q, const Query
 	}
 }
 
+int compare_tile_side(int64_t N)
+{
+	return N <= 24 ? 8 : 16; // sharding.py mirrors this choice
+}
+
 void compare_all_device(const RowStore &rs, int64_t N, bool complete_deletion, int tile_rank, int tile_world,
-                        unsigned long long *d_subst, unsigned long long *d_homologs, cudaStream_t s)
+                        unsigned long long *d_subst, unsigned long long *d_homologs, cudaStream_t s, int64_t tile_begin,
+                        int64_t tile_end, bool first, bool last)
 {
 	if (N > rs.genomes) throw std::invalid_argument("row store holds fewer genomes than N");
-	CUDA_CHECK(cudaMemsetAsync(d_subst, 0, (size_t)(N * N) * sizeof(unsigned long long), s));
-	CUDA_CHECK(cudaMemsetAsync(d_homologs, 0, (size_t)(N * N) * sizeof(unsigned long long), s));
+	const int CT = compare_tile_side(N);
+	const int64_t tiles_side = (N + CT - 1) / CT;
+	if (tile_end < 0 || tile_end > tiles_side) tile_end = tiles_side;
+	if (tile_begin < 0 || tile_begin > tile_end) throw std::invalid_argument("bad tile range");
+	if (complete_deletion && !(first && last))
+		throw std::invalid_argument("complete deletion needs all rows: no incremental comparison");
+	if (first) {
+		CUDA_CHECK(cudaMemsetAsync(d_subst, 0, (size_t)(N * N) * sizeof(unsigned long long), s));
+		CUDA_CHECK(cudaMemsetAsync(d_homologs, 0, (size_t)(N * N) * sizeof(unsigned long long), s));
+	}
 	if (N < 2) return;
 	DevBuf<uint32_t> vall;
 	if (complete_deletion) {
@@ -411,10 +524,10 @@ void compare_all_device(const RowStore &rs, int64_t N, bool complete_deletion, i
 		k_and_valid<<<div_up(rs.W, 256), 256, 0, s>>>(rs.data.get(), rs.genome_words(), rs.W, N, vall.get());
 		KERNEL_CHECK();
 	}
-	const int CT = N <= 24 ? 8 : 16; // sharding.py mirrors this choice
-	const int32_t tiles_side = (int32_t)((N + CT - 1) / CT);
-	const int64_t n_tile_pairs = (int64_t)tiles_side * (tiles_side + 1) / 2;
-	{
+	// tile pairs (ti <= tj) with tj in [tile_begin, tile_end), numbered column by column
+	const int64_t tp_begin = tile_begin * (tile_begin + 1) / 2;
+	const int64_t n_tile_pairs = tile_end * (tile_end + 1) / 2 - tp_begin;
+	if (n_tile_pairs > 0) {
 		// enough blocks to fill the machine a few times over, chunks of at least 256 words
 		const int64_t want_blocks = (int64_t)NUM_SMS_B200 * 8 * tile_world;
 		int64_t chunks = (want_blocks + n_tile_pairs - 1) / n_tile_pairs;
@@ -422,29 +535,34 @@ void compare_all_device(const RowStore &rs, int64_t N, bool complete_deletion, i
 		if (chunks > max_chunks) chunks = max_chunks;
 		if (chunks < 1) chunks = 1;
 		int64_t chunk_words = (rs.W + chunks - 1) / chunks;
-		chunk_words = (chunk_words + CMP_STEP - 1) / CMP_STEP * CMP_STEP;
+		chunk_words = (chunk_words + 31) / 32 * 32;
 		chunks = (rs.W + chunk_words - 1) / chunk_words;
 		const int64_t units = n_tile_pairs * chunks;
 		const int64_t my_units = (units - tile_rank + tile_world - 1) / tile_world;
-		const size_t smem = (size_t)2 * 2 * CT * ROW_PLANES * CMP_STEP * sizeof(uint32_t);
 		static PerDeviceOnce once;
-		if (once.first())
+		if (once.first()) {
 			CUDA_CHECK(cudaFuncSetAttribute(k_compare_tiles<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-			                                2 * 2 * 16 * ROW_PLANES * CMP_STEP * (int)sizeof(uint32_t)));
+			                                (int)cmp_smem_bytes(16)));
+			CUDA_CHECK(cudaFuncSetAttribute(k_compare_tiles<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                                (int)cmp_smem_bytes(8)));
+		}
+		if (my_units > 0x7fffffffll) throw std::invalid_argument("too many tile pairs for one launch");
 		if (my_units > 0) {
 			if (CT == 16)
-				k_compare_tiles<16><<<(unsigned)my_units, cmp_threads(16), smem, s>>>(
-					rs.data.get(), rs.genome_words(), rs.W, N, tiles_side, units, (int32_t)chunks, chunk_words, tile_rank,
+				k_compare_tiles<16><<<(unsigned)my_units, cmp_threads(16), cmp_smem_bytes(16), s>>>(
+					rs.data.get(), rs.genome_words(), rs.W, N, tp_begin, units, (int32_t)chunks, chunk_words, tile_rank,
 					tile_world, vall.get(), d_subst, d_homologs);
 			else
-				k_compare_tiles<8><<<(unsigned)my_units, cmp_threads(8), smem, s>>>(
-					rs.data.get(), rs.genome_words(), rs.W, N, tiles_side, units, (int32_t)chunks, chunk_words, tile_rank,
+				k_compare_tiles<8><<<(unsigned)my_units, cmp_threads(8), cmp_smem_bytes(8), s>>>(
+					rs.data.get(), rs.genome_words(), rs.W, N, tp_begin, units, (int32_t)chunks, chunk_words, tile_rank,
 					tile_world, vall.get(), d_subst, d_homologs);
 			KERNEL_CHECK();
 		}
 	}
-	k_symmetrize<<<div_up(N * N, 256), 256, 0, s>>>(d_subst, d_homologs, N);
-	KERNEL_CHECK();
+	if (last) {
+		k_symmetrize<<<div_up(N * N, 256), 256, 0, s>>>(d_subst, d_homologs, N);
+		KERNEL_CHECK();
+	}
 }
 
 void core_sites_device(const RowStore &rs, int64_t N, uint32_t *d_core, uint32_t *d_seg, cudaStream_t s)

@@ -25,6 +25,7 @@ constexpr int ROW_PLANES = 5;
 constexpr int ROW_FLAG_WORDS = 4;
 enum : int { PL_V = 0, PL_C0 = 1, PL_C1 = 2, PL_D = 3, PL_B = 4 };
 enum : uint32_t { ROW_FLAG_D = 1, ROW_FLAG_B = 2 };
+enum : int { ROW_WORD_FLAGS = 0, ROW_WORD_REAL = 1 }; // flag words: D/B use; "this row was written"
 
 struct RowStore {
 	DevBuf<uint32_t> data; // genomes * (ROW_PLANES * W + ROW_FLAG_WORDS)
@@ -36,16 +37,24 @@ struct RowStore {
 };
 
 void rows_alloc(RowStore &rs, int64_t genomes, int32_t n, cudaStream_t s);
+// marks every slot as "not written" (and without D / B planes)
+void rows_clear_flags(RowStore &rs, cudaStream_t s);
 
 // rows of `count` genomes (genome k's sorted, disjoint homologies are
 // d_homs[d_begin[k] .. d_begin[k] + d_count[k]), bases in d_Q / d_qi) written to rs.row(first_row + k)
 void rows_build(RowStore &rs, int64_t first_row, const uint8_t *d_Q, const QueryInfo *d_qi, int32_t count,
                 const Hom *d_homs, const int64_t *d_begin, const int64_t *d_count, cudaStream_t s);
 
-// substitutions / homologs (N*N, row-major, symmetric, zero diagonal) for the tile pairs
-// tile_rank, tile_rank + tile_world, … ; the rest of the matrix is left zero.
+// substitutions / homologs (N*N, row-major, symmetric, zero diagonal).  Work units are (tile
+// pair, column chunk); this call computes units tile_rank, tile_rank + tile_world, … and leaves
+// the rest of the matrix zero.  Tiles are compare_tile_side(N) genomes wide; only pairs of
+// tiles (ti <= tj) with tj in [tile_begin, tile_end) are compared (tile_end < 0: to the last
+// one), so a caller can compare as the rows arrive: `first` zeroes the matrix, `last` mirrors
+// the upper triangle.  Complete deletion needs all rows at once.
+int compare_tile_side(int64_t N);
 void compare_all_device(const RowStore &rs, int64_t N, bool complete_deletion, int tile_rank, int tile_world,
-                        unsigned long long *d_subst, unsigned long long *d_homologs, cudaStream_t s);
+                        unsigned long long *d_subst, unsigned long long *d_homologs, cudaStream_t s,
+                        int64_t tile_begin = 0, int64_t tile_end = -1, bool first = true, bool last = true);
 
 // Core genome in row form (the reference's -p option, process.cxx:471-513): d_core[w] = columns
 // covered by all N genomes, d_seg[w] = core columns where some genome differs from genome 0

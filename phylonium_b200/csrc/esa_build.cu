@@ -710,7 +710,7 @@ void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t s, bool nodes_read
 	esa.table.alloc(entries, s);
 	EsaView v = esa.view();
 	v.K = 0;
-	if (g_table_direct != 2) {
+	if (g_tuning.table_direct != 2) {
 		// every entry by its own descent from the root: the upper levels of neighbouring
 		// entries are the same cache lines, so this is as fast as or faster than the level-wise
 		// build with its extra launches (measured on B200: 0.097 vs 0.193 ms at K = 10, 0.262 vs
@@ -802,7 +802,7 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 	// caller asks for longer keys, the text has so many separators that ordering the dirty
 	// suffixes pairwise would cost more than it saves, or 16 characters are hopelessly few.
 	const int64_t dirty_bound = 16 * (2 * bangs + 2); // 16 suffixes in front of every byte below 'A'
-	const bool packed = g_sort_path != 1 && key_chars <= PK_MAX_CHARS && dirty_bound <= PK_DIRTY_CAP && m <= (1 << 30);
+	const bool packed = g_tuning.sort_path != 1 && key_chars <= PK_MAX_CHARS && dirty_bound <= PK_DIRTY_CAP && m <= (1 << 30);
 	int kc;
 	if (packed) {
 		kc = key_chars > 0 ? key_chars : esa_default_packed_chars(m);
@@ -1024,6 +1024,17 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 		py.levels = 1;
 		CUDA_CHECK(cudaEventRecord(ev_fork, s));
 		CUDA_CHECK(cudaStreamWaitEvent(side, ev_fork, 0));
+		// Whatever happens below (a throw unwinds `levels` into the main stream's block cache),
+		// the main stream is behind the side stream's kernels before any of those buffers can be
+		// handed out again.
+		struct SideJoin {
+			cudaStream_t main, side;
+			cudaEvent_t ev;
+			~SideJoin()
+			{
+				if (cudaEventRecord(ev, side) == cudaSuccess) cudaStreamWaitEvent(main, ev, 0);
+			}
+		} side_join{s, side, ev_join};
 		while (py.size[py.levels - 1] > 1) {
 			if (py.levels >= PYR_MAX_LEVELS) throw std::runtime_error("pyramid too deep");
 			const int32_t n_in = py.size[py.levels - 1];

@@ -84,11 +84,7 @@ void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t stream, bool nodes
 
 int esa_default_k(int32_t m);
 
-// option "sort_path": 0 pick, 1 always the general sorter (3-bit codes, 64-bit keys), 2 same as 0
-inline int g_sort_path = 0;
-// option "table_direct": 0 / 1 build the K-mer table entry by entry from the root (default),
-// 2 level by level (esa_search.h, esa_table_extend; same table, kept as a cross-check)
-inline int g_table_direct = 0;
+// options "sort_path" and "table_direct": see Tuning (common.cuh)
 // most dirty suffixes the packed sorter orders by pairwise comparison (about 1000 contigs)
 constexpr int64_t PK_DIRTY_CAP = 32768;
 

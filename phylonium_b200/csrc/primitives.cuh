@@ -18,8 +18,8 @@ namespace phy
 
 // ----------------------------------------------------------------------------- scan
 
-// option "scan_mode": 1 = one launch per scan (decoupled look-back, default), 0 = three
-inline int g_scan_single_pass = 1;
+// option "scan_mode" (Tuning::scan_single_pass): 1 = one launch per scan (decoupled look-back,
+// default), 0 = three
 
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
@@ -201,7 +201,7 @@ void device_scan(int64_t n, InF in, OutF out, Op op, T identity, bool inclusive,
 		KERNEL_CHECK();
 		return;
 	}
-	if (g_scan_single_pass) {
+	if (g_tuning.scan_single_pass) {
 		DevBuf<unsigned long long> status((size_t)nblocks + 1, s); // [nblocks]: the tile counter
 		status.zero();
 		scan_single_pass_kernel<T><<<nblocks, SCAN_THREADS, 0, s>>>(n, in, out, op, identity, inclusive, status.get(),
@@ -488,8 +488,7 @@ rs_scatter(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ va
 // (keys, vals) and (keys_alt, vals_alt); returns true if the result ended up in the
 // alternate buffers.  vals may be nullptr on input: values start as 0..n-1 and are written
 // to vals_alt/vals from the first pass on (vals must still be a valid buffer then).
-// 0: pick by size, 1: histogram + scan + scatter per pass, 2: onesweep (option "sort_mode")
-inline int g_rs_mode = 0;
+// Tuning::rs_mode — 0: pick by size, 1: histogram + scan + scatter per pass, 2: onesweep (option "sort_mode")
 constexpr int RS_ONESWEEP_MIN_TILES = 16384; // ~67 M pairs
 
 // optional per-kernel timing of a sort (CUDA events on the launching stream)
@@ -510,7 +509,7 @@ inline bool radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_alt,
 	// Two schemes.  Look-back ("onesweep") moves 24 B per element and pass instead of 32, but
 	// the first wave of resident tiles pays a serial look-back of ~0.1 ms per pass (measured
 	// on B200), so it only wins once there are many waves of tiles.
-	const bool onesweep = g_rs_mode == 2 || (g_rs_mode == 0 && ntiles >= RS_ONESWEEP_MIN_TILES);
+	const bool onesweep = g_tuning.rs_mode == 2 || (g_tuning.rs_mode == 0 && ntiles >= RS_ONESWEEP_MIN_TILES);
 	if (!onesweep) {
 		DevBuf<uint32_t> counts((size_t)ntiles * RS_BINS, s);
 		std::vector<cudaEvent_t> evs;

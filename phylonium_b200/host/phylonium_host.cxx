@@ -163,8 +163,18 @@ std::vector<evo_model> process(const sequence &subject, const std::vector<sequen
 	}
 	if (FLAGS & flags::verbose) std::cerr << "ref: " << subject.get_name() << std::endl;
 	std::vector<uint64_t> subst(N * N), homol(N * N);
-	const int rc = phylo_process(ctx, ptr.data(), len.data(), N, ref, FLAGS & flags::complete_deletion, subst.data(),
-	                             homol.data());
+	// The second call of --2pass (src/phylonium.cxx:289-296) hands over the very same strings:
+	// they are still on the device, only the index and the mapping are redone.
+	static std::vector<const char *> resident_ptr;
+	static std::vector<uint64_t> resident_len;
+	int rc;
+	if (ptr == resident_ptr && len == resident_len) {
+		rc = phylo_process_again(ctx, ref, FLAGS & flags::complete_deletion, subst.data(), homol.data());
+	} else {
+		rc = phylo_process(ctx, ptr.data(), len.data(), N, ref, FLAGS & flags::complete_deletion, subst.data(), homol.data());
+		resident_ptr = ptr;
+		resident_len = len;
+	}
 	if (rc != PHYLO_OK) errx(1, "%s", phylo_last_error(ctx));
 	if (FLAGS & flags::print_positions) write_reference_positions(ctx, subject);
 	std::vector<evo_model> matrix(N * N);

@@ -40,8 +40,11 @@ class EvoModel:
             return dist
         x = 1.0 - (4.0 / 3.0) * dist
         if x <= 0.0:
-            # log of a non-positive number: the reference prints inf / nan from libm
-            dist = math.inf if x == 0.0 else math.nan
+            # log of a non-positive number, as libm answers it (src/evo_model.cxx:124-131 calls
+            # log() unguarded): log(0) = -inf -> dist = +inf; log(x < 0) = -nan on glibc/x86, and
+            # the multiplication by -0.75 hands the NaN through with its sign, so the reference
+            # (and the C++ host here) print "-nan" for a saturated pair (raw distance > 0.75)
+            dist = math.inf if x == 0.0 else math.copysign(math.nan, -1.0)
         else:
             dist = -0.75 * math.log(x)
         return 0.0 if dist <= 0.0 else dist

@@ -26,24 +26,51 @@ class ShardPlan:
     world: int
     rank: int
     total: int      # genomes over all ranks
-    per_rank: int   # genomes per rank (the last ranks may hold padding rows)
-    first: int      # global index of this rank's first genome
+    per_rank: int   # row-store slots per rank (the last ones of a rank may be padding)
+    first: int      # first row-store slot of this rank
     count: int      # genomes this rank really owns
+    layout: str = "block"  # "block": genome g on rank g // per_rank; "interleaved": on rank g % world
 
     @property
     def padded_total(self) -> int:
         return self.per_rank * self.world
 
+    def genomes(self) -> List[int]:
+        """global indices of this rank's genomes, in the order of its row-store slots"""
+        if self.layout == "block":
+            return list(range(self.first, self.first + self.count))
+        return list(range(self.rank, self.total, self.world))
 
-def make_plan(total: int, world: int, rank: int) -> ShardPlan:
+    def slot_of(self, genome: int) -> int:
+        """row-store slot (= row/column of the count matrix) of a genome"""
+        if self.layout == "block":
+            return genome
+        return (genome % self.world) * self.per_rank + genome // self.world
+
+    def slots(self) -> List[int]:
+        """slot of genome 0, 1, ... total - 1: indexing the slot-ordered matrix with it on both
+        axes gives the matrix in genome order without the padding slots"""
+        return [self.slot_of(g) for g in range(self.total)]
+
+
+def make_plan(total: int, world: int, rank: int, layout: str = "block") -> ShardPlan:
+    """block: contiguous runs of genomes per rank.  interleaved: genome g on rank g % world —
+    when the divergence from the reference grows with the genome index (BASELINE.json's
+    configs) the anchoring time does too, and dealing the genomes round-robin is what keeps
+    the ranks balanced.  Either way a rank's rows are one contiguous slice of the store."""
     per_rank = (total + world - 1) // world
-    first = min(rank * per_rank, total)
-    count = max(0, min(per_rank, total - first))
-    return ShardPlan(world, rank, total, per_rank, rank * per_rank, count)
+    if layout == "block":
+        first = min(rank * per_rank, total)
+        count = max(0, min(per_rank, total - first))
+    elif layout == "interleaved":
+        count = len(range(rank, total, world))
+    else:
+        raise ValueError(layout)
+    return ShardPlan(world, rank, total, per_rank, rank * per_rank, count, layout)
 
 
 def owner_of(plan: ShardPlan, genome: int) -> int:
-    return genome // plan.per_rank
+    return genome // plan.per_rank if plan.layout == "block" else genome % plan.world
 
 
 NUM_SMS = 148
@@ -60,7 +87,7 @@ def compare_units(n_genomes: int, words: int, world: int):
     compare_all_device (compare.cu); `words` = 32-bit words per row plane"""
     tile = tile_side(n_genomes)
     side = (n_genomes + tile - 1) // tile
-    pairs = [(ti, tj) for ti in range(side) for tj in range(ti, side)]
+    pairs = [(ti, tj) for tj in range(side) for ti in range(tj + 1)]  # column by column, as k_compare_tiles
     want_blocks = NUM_SMS * 8 * world
     chunks = (want_blocks + len(pairs) - 1) // max(1, len(pairs))
     chunks = max(1, min(chunks, (words + 255) // 256))
@@ -128,6 +155,38 @@ def allgather_rows(ctx, plan: ShardPlan, device_index: int) -> int:
     store = DeviceBuffer(ptr, bytes_per_genome * total, device_index).tensor()
     allgather_store(store, plan, bytes_per_genome)
     return bytes_per_genome * total
+
+
+def setup_push(ctx, rank: int, world: int) -> None:
+    """Row exchange without a collective (include/phylonium_b200.h, phylo_rows_ipc_*): every
+    rank learns the address of every other rank's row store; from then on the mapping copies
+    each batch of rows into all of them over NVLink while it maps the next batch.  Call after
+    ctx.rows_configure (with an index in place) and again whenever the store changes size."""
+    mine = ctx.rows_ipc_export()
+    handles = [None] * world
+    dist.all_gather_object(handles, mine)
+    ctx.rows_ipc_import(handles, rank)
+
+
+_token = {}
+
+
+def rows_barrier(device) -> None:
+    """stream-ordered barrier across ranks: behind it, on this rank's current stream, the row
+    pushes of all ranks have landed (each rank's stream is ordered behind its own pushes)"""
+    t = _token.get(device)
+    if t is None:
+        t = _token[device] = torch.zeros(1, dtype=torch.int32, device=device)
+    dist.all_reduce(t)
+
+
+def genome_order(counts: torch.Tensor, plan: ShardPlan) -> torch.Tensor:
+    """counts: (..., padded_total * padded_total) in row-store slot order -> (..., total, total)
+    in genome order"""
+    n = plan.padded_total
+    idx = torch.as_tensor(plan.slots(), device=counts.device)
+    m = counts.reshape(*counts.shape[:-1], n, n)
+    return m.index_select(-2, idx).index_select(-1, idx)
 
 
 def reduce_matrix(subst: torch.Tensor, homol: torch.Tensor) -> None:

@@ -552,33 +552,51 @@ def test_config2_full_size(pb, oracle, ctx):
     assert np.array_equal(ctx.homology_counts(), want["hom_counts"].astype(np.uint64))
 
 
-def test_sharded_plumbing_on_one_gpu(pb, oracle):
-    """the multi-GPU C ABI (index export/import, row store slices, matrix tiles) with two
-    contexts on one device and plain copies in place of the NCCL collectives"""
+def _broadcast_stand_in(ctxs, ref):
+    """index built on context 0, copied into the others (stands in for the NCCL broadcast)"""
     import torch
 
     from phylonium_b200 import sharding
 
-    rng = np.random.default_rng(23)
-    r = datasets.random_dna(rng, 30000)
-    genomes = [r] + [datasets.mutate(rng, r, 0.004 * (k + 1)) for k in range(6)]
-    genomes[3] = datasets.revcomp(genomes[3])
-    total, world = len(genomes), 2
-    want = oracle.process(genomes, 0, 0, threads=4)
-    thr = pb.threshold_for(r)
-    ctxs = [pb.Context(), pb.Context()]
-    try:
-        plans = [sharding.make_plan(total, world, k) for k in range(world)]
-        ctxs[0].esa_build(r)
-        ctxs[1].esa_alloc(len(r))
-        a0, a1 = ctxs[0].esa_device_arrays(), ctxs[1].esa_device_arrays()
-        for name in a0:  # stands in for the broadcast
+    ctxs[0].esa_build(ref)
+    a0 = ctxs[0].esa_device_arrays()
+    for c in ctxs[1:]:
+        c.esa_alloc(len(ref))
+        a1 = c.esa_device_arrays()
+        for name in a0:
             src = sharding.DeviceBuffer(a0[name][0], a0[name][1], 0).tensor()
             dst = sharding.DeviceBuffer(a1[name][0], a1[name][1], 0).tensor()
             dst.copy_(src)
         torch.cuda.synchronize()
-        ctxs[1].esa_finish_import()
-        assert ctxs[1].stat("esa.gc_count") == ctxs[0].stat("esa.gc_count")
+        c.esa_finish_import()
+        assert c.stat("esa.gc_count") == ctxs[0].stat("esa.gc_count")
+
+
+def _sharded_family(seed=23, n=30000, count=7):
+    rng = np.random.default_rng(seed)
+    r = datasets.random_dna(rng, n)
+    genomes = [r] + [datasets.mutate(rng, r, 0.004 * (k + 1)) for k in range(count - 1)]
+    genomes[3] = datasets.revcomp(genomes[3])
+    return genomes
+
+
+@pytest.mark.parametrize("flags", [0, 4])
+def test_sharded_plumbing_on_one_gpu(pb, oracle, flags):
+    """the multi-GPU C ABI (index export/import, row store slices, matrix tiles) with two
+    contexts on one device and plain copies in place of the NCCL collectives; 7 genomes on 2
+    ranks leave a padding slot, which complete deletion (flags = 4) must not count as a genome"""
+    import torch
+
+    from phylonium_b200 import sharding
+
+    genomes = _sharded_family()
+    total, world = len(genomes), 2
+    want = oracle.process(genomes, 0, flags, threads=4)
+    thr = pb.threshold_for(genomes[0])
+    ctxs = [pb.Context(), pb.Context()]
+    try:
+        plans = [sharding.make_plan(total, world, k) for k in range(world)]
+        _broadcast_stand_in(ctxs, genomes[0])
         stores = []
         for k in range(world):
             p = plans[k]
@@ -596,15 +614,161 @@ def test_sharded_plumbing_on_one_gpu(pb, oracle):
         acc = torch.zeros(2, n * n, dtype=torch.int64, device="cuda")
         for k in range(world):  # stands in for the all-reduce
             part = torch.zeros(2, n * n, dtype=torch.int64, device="cuda")
-            ctxs[k].compare_tiles_dev(part[0].data_ptr(), part[1].data_ptr(), k, world)
+            ctxs[k].compare_tiles_dev(part[0].data_ptr(), part[1].data_ptr(), k, world, flags)
             acc += part
         subst = acc[0].cpu().numpy().reshape(n, n)[:total, :total].astype(np.uint64)
         homol = acc[1].cpu().numpy().reshape(n, n)[:total, :total].astype(np.uint64)
+        assert homol.any()
         assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
         assert not acc[1].cpu().numpy().reshape(n, n)[total:, :].any()  # padding rows stay empty
+        # a rank's share of the tiles is not a matrix to estimate distances from
+        with pytest.raises(pb.PhyloError):
+            ctxs[0].estimate(pb.DIST_JC, total=n)
     finally:
         for c in ctxs:
             c.close()
+
+
+@pytest.mark.parametrize("flags", [0, 4])
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_push_exchange_on_one_gpu(pb, oracle, world, flags):
+    """rows pushed into the peers' stores while the next batch is mapped (phylo_rows_set_peers,
+    the in-process form of the IPC exchange), genomes dealt round-robin to the ranks, the
+    slot-ordered matrix brought back into genome order: counts equal to the oracle's"""
+    import torch
+
+    from phylonium_b200 import sharding
+
+    genomes = _sharded_family(count=11)
+    total = len(genomes)
+    want = oracle.process(genomes, 0, flags, threads=4)
+    thr = pb.threshold_for(genomes[0])
+    ctxs = [pb.Context(map_batch_bytes=50000) for _ in range(world)]  # several batches per rank
+    try:
+        plans = [sharding.make_plan(total, world, k, "interleaved") for k in range(world)]
+        _broadcast_stand_in(ctxs, genomes[0])
+        for k in range(world):
+            ctxs[k].rows_configure(plans[k].padded_total, plans[k].first)
+        ptrs = [c.rows_device()[0] for c in ctxs]
+        for k in range(world):
+            ctxs[k].rows_set_peers(ptrs, k)
+        for k in range(world):
+            ctxs[k].map_queries([genomes[g] for g in plans[k].genomes()], thr)
+            assert ctxs[k].stat("map.batches") > 1
+        torch.cuda.synchronize()  # stands in for the barrier across ranks
+        n = plans[0].padded_total
+        acc = torch.zeros(2, n * n, dtype=torch.int64, device="cuda")
+        for k in range(world):
+            part = torch.zeros(2, n * n, dtype=torch.int64, device="cuda")
+            ctxs[k].compare_tiles_dev(part[0].data_ptr(), part[1].data_ptr(), k, world, flags)
+            acc += part
+        got = sharding.genome_order(acc, plans[0]).cpu().numpy().astype(np.uint64)
+        assert np.array_equal(got[0], want["subst"]) and np.array_equal(got[1], want["homologs"])
+        # switching the push off again: the context keeps its rows to itself
+        ctxs[0].rows_set_peers(None, 0)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def _ipc_worker(rank, world, port, genomes, thr, flags, results):
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    import phylonium_b200 as pb
+    from phylonium_b200 import sharding
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(0)
+        total = len(genomes)
+        plan = sharding.make_plan(total, world, rank, "interleaved")
+        with pb.Context(0, map_batch_bytes=60000) as ctx:
+            ctx.esa_build(genomes[0])  # index replicated
+            ctx.rows_configure(plan.padded_total, plan.first)
+            sharding.setup_push(ctx, rank, world)
+            ctx.map_queries([genomes[g] for g in plan.genomes()], thr)
+            torch.cuda.synchronize()
+            dist.barrier()  # every rank's pushes have landed
+            n = plan.padded_total
+            part = torch.zeros(2, n * n, dtype=torch.int64, device="cuda")
+            ctx.compare_tiles_dev(part[0].data_ptr(), part[1].data_ptr(), rank, world, flags)
+            part = part.cpu()
+            dist.all_reduce(part)
+            got = sharding.genome_order(part, plan).numpy().astype(np.uint64)
+            dist.barrier()  # nobody closes its row store while a peer still has it mapped
+            results[rank] = (got[0], got[1])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_exchange_across_processes(pb, oracle):
+    """two processes (ranks) on this one GPU: CUDA IPC handles of the row stores are exchanged
+    (sharding.setup_push) and every rank pushes its rows into the other's store"""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    genomes = _sharded_family(seed=5, count=9)
+    want = oracle.process(genomes, 0, 0, threads=4)
+    thr = pb.threshold_for(genomes[0])
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        results = mgr.dict()
+        mp.spawn(_ipc_worker, args=(2, port, genomes, thr, 0, results), nprocs=2, join=True)
+        got = dict(results)
+    for r in (0, 1):
+        assert np.array_equal(got[r][0], want["subst"]) and np.array_equal(got[r][1], want["homologs"])
+
+
+def test_second_pass_keeps_sequences_on_the_device(pb, oracle, ctx):
+    """--2pass (src/phylonium.cxx:289-296): process() again with another reference; the
+    sequences stay where the first pass put them"""
+    genomes = _sharded_family(seed=9, count=6)
+    first = ctx.process(genomes, 0, 0)
+    want0 = oracle.process(genomes, 0, 0, threads=4)
+    assert np.array_equal(first[0], want0["subst"]) and np.array_equal(first[1], want0["homologs"])
+    for ref in (4, 3, 0):  # genome 3 is a reverse complement
+        want = oracle.process(genomes, ref, 0, threads=4)
+        subst, homol = ctx.process_again(ref)
+        assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"]), ref
+        assert ctx.stat("process.h2d_bytes") == 0
+    with pytest.raises(pb.PhyloError):
+        ctx.process_again(len(genomes))
+    with pb.Context() as fresh, pytest.raises(pb.PhyloError):
+        fresh.process_again(0)
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+@pytest.mark.parametrize("flags", [0, 4])
+def test_batched_process_from_ordinary_memory(pb, oracle, threads, flags):
+    """phylo_process on plain (pageable) buffers with many batches: sequences staged through
+    the pinned rings by worker threads, tile columns compared as the batches get mapped;
+    40 genomes = three tile columns of 16"""
+    rng = np.random.default_rng(77)
+    r = datasets.random_dna(rng, 9000)
+    genomes = [r] + [datasets.mutate(rng, r, 0.002 * (k + 1)) for k in range(39)]
+    genomes[7] = datasets.revcomp(genomes[7])
+    genomes[21] = genomes[21][:4000] + b"!" + genomes[21][4000:]
+    want = oracle.process(genomes, 0, flags, threads=8)
+    with pb.Context(map_batch_bytes=9000 * 16, stage_threads=threads) as c:
+        subst, homol = c.process(genomes, 0, flags)
+        assert c.stat("process.pageable") == 1 and c.stat("map.batches") >= 3
+        assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
+        # same through pinned memory (the plain asynchronous copies)
+        import torch
+
+        pinned = [torch.frombuffer(bytearray(g), dtype=torch.uint8).pin_memory() for g in genomes]
+        out = c.process_ptrs([t.data_ptr() for t in pinned], [len(g) for g in genomes], 0, flags)
+        assert c.stat("process.pageable") == 0
+        assert np.array_equal(out[0], want["subst"]) and np.array_equal(out[1], want["homologs"])
 
 
 def test_properties_without_oracle(pb, ctx):

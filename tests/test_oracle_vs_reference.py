@@ -141,3 +141,22 @@ def test_simf_matches_reference_generator(libs, tmp_path):
     for i, w in enumerate(want):
         txt = (tmp_path / f"g{i}.fasta").read_text().split("\n", 1)[1].replace("\n", "")
         assert txt.encode() == w
+
+
+def test_saturated_and_empty_pairs_print_like_libm(libs):
+    """raw distance > 0.75: log() of a negative number; the reference prints what glibc hands
+    back ("-nan"), an uncovered pair prints "nan", raw == 0.75 prints "inf" — port, reference
+    and the host mirror (phylonium_b200.pipeline) must agree byte for byte"""
+    import phylonium_b200.pipeline as pl
+
+    p, r = libs
+    names = ["a", "b", "c", "d"]
+    subst = np.array([[0, 80, 75, 0], [80, 0, 10, 0], [75, 10, 0, 0], [0, 0, 0, 0]], np.uint64)
+    homol = np.array([[0, 100, 100, 0], [100, 0, 100, 0], [100, 100, 0, 0], [0, 0, 0, 0]], np.uint64)
+    for kind in (0, 1, 2):
+        want = r.format_matrix(names, subst, homol, kind)
+        assert p.format_matrix(names, subst, homol, kind) == want
+        mat = [pl.EvoModel(int(subst[i, j]), int(homol[i, j])) for i in range(4) for j in range(4)]
+        assert pl.format_matrix(names, mat, kind) == want
+    jc = r.format_matrix(names, subst, homol, 1)
+    assert "-nan" in jc and "inf" in jc

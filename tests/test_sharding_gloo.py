@@ -95,3 +95,32 @@ def test_plan_and_tiles_cover_everything():
                         seen.add(u)
                 side = (n + sharding.tile_side(n) - 1) // sharding.tile_side(n)
                 assert len(seen) == side * (side + 1) // 2 * chunks
+
+
+def test_interleaved_plan_and_genome_order():
+    """interleaved layout: genome g lives on rank g % world at slot rank * per_rank + g // world;
+    the slot-ordered matrix indexed with plan.slots() is the matrix in genome order"""
+    for total in (1, 2, 7, 8, 13, 100):
+        for world in (1, 2, 4, 8):
+            plans = [sharding.make_plan(total, world, r, "interleaved") for r in range(world)]
+            assert sum(p.count for p in plans) == total
+            owned = sorted(g for p in plans for g in p.genomes())
+            assert owned == list(range(total))
+            slots = plans[0].slots()
+            assert len(set(slots)) == total and max(slots) < plans[0].padded_total
+            for p in plans:
+                for k, g in enumerate(p.genomes()):
+                    assert p.slot_of(g) == p.first + k and sharding.owner_of(p, g) == p.rank
+                    assert p.first + k < p.first + p.per_rank
+            # a matrix whose cell (slot a, slot b) encodes the genomes that live there
+            n = plans[0].padded_total
+            genome_at = {s: g for g, s in enumerate(slots)}
+            m = torch.full((2, n * n), -1, dtype=torch.int64)
+            for a in range(n):
+                for b in range(n):
+                    if a in genome_at and b in genome_at:
+                        m[:, a * n + b] = genome_at[a] * 1000 + genome_at[b]
+            out = sharding.genome_order(m, plans[0])
+            assert out.shape == (2, total, total)
+            want = torch.arange(total)[:, None] * 1000 + torch.arange(total)[None, :]
+            assert bool((out[0] == want).all() and (out[1] == want).all())
