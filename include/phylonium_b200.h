@@ -182,6 +182,9 @@ int phylo_process_again(phylo_ctx *ctx, uint64_t ref_index, int flags, uint64_t 
 int phylo_esa_build_dev(phylo_ctx *ctx, const void *d_ref, uint64_t n);
 int phylo_map_queries_dev(phylo_ctx *ctx, const void *d_queries, const uint64_t *offs, const uint64_t *lens,
                           uint64_t N, uint64_t threshold);
+/* phylo_compare_all_dev / phylo_compare_tiles_dev return as soon as the work is queued on the
+ * context's stream (phylo_set_stream): the counts are there in stream order, so a collective
+ * or a copy queued on that stream next sees them without the host waiting in between. */
 int phylo_compare_all_dev(phylo_ctx *ctx, int flags, void *d_subst, void *d_homologs);
 
 /* Sharding across GPUs (one context per GPU, the exchange itself is the caller's

@@ -831,6 +831,54 @@ int po_process(const char *const *seqs, const int64_t *lens, int64_t N, int64_t 
 	return 0;
 }
 
+/* process() for a sample of the matrix: all sequences mapped (src/process.cxx:433-458), only
+ * the listed rows compared against every sequence (:524-549 for those i) */
+int po_process_rows(const char *const *seqs, const int64_t *lens, int64_t N, int64_t ref_index, int flags,
+                    int threads, const int64_t *rows, int64_t nrows, uint64_t *subst, uint64_t *homologs,
+                    double *timings)
+{
+	if (threads < 1) threads = 1;
+	std::vector<std::string> q((size_t)N);
+	for (int64_t g = 0; g < N; g++)
+		q[(size_t)g].assign(seqs[g], (size_t)lens[g]);
+	po_sa_seconds = 0;
+	double t0 = now();
+	esa_t *e = build_esa(q[(size_t)ref_index].c_str(), lens[ref_index]);
+	double t1 = now();
+	double gc = po_gc_content(q[(size_t)ref_index].c_str(), lens[ref_index]);
+	int64_t thr = po_min_anchor_length(0.025, gc, e->m);
+	std::vector<std::vector<hom>> H((size_t)N);
+#pragma omp parallel for num_threads(threads) schedule(dynamic)
+	for (int64_t g = 0; g < N; g++) {
+		auto hv = anchor_homologies(*e, thr, q[(size_t)g].c_str(), lens[g]);
+		sort_by_start(hv);
+		filter_overlaps_max(hv);
+		H[(size_t)g] = std::move(hv);
+	}
+	double t2 = now();
+	if (flags & 4) H = complete_delete(H);
+	double t3 = now();
+#pragma omp parallel for num_threads(threads) schedule(dynamic) collapse(2)
+	for (int64_t r = 0; r < nrows; r++) {
+		for (int64_t j = 0; j < N; j++) {
+			const int64_t i = rows[r];
+			counts c{0, 0};
+			if (j != i) c = compare_lists(q[(size_t)i].c_str(), H[(size_t)i], q[(size_t)j].c_str(), H[(size_t)j]);
+			subst[r * N + j] = c.subst;
+			homologs[r * N + j] = c.homologs;
+		}
+	}
+	double t4 = now();
+	if (timings) {
+		timings[0] = t1 - t0;
+		timings[1] = t2 - t1;
+		timings[2] = t4 - t3;
+		timings[3] = po_sa_seconds;
+	}
+	delete e;
+	return 0;
+}
+
 double po_estimate(uint64_t subst, uint64_t homologs, int kind)
 {
 	return estimate(subst, homologs, kind);

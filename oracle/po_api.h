@@ -66,6 +66,13 @@ int po_process(const char *const *seqs, const int64_t *lens, int64_t N, int64_t 
                int flags, int threads, uint64_t *subst, uint64_t *homologs, double *timings,
                int64_t *hom_counts);
 
+/* the same for a sample of the matrix: every sequence is mapped, rows[0..nrows) of the
+ * matrix are computed (subst/homologs: nrows*N, row r = sequence rows[r] against all);
+ * timings as above */
+int po_process_rows(const char *const *seqs, const int64_t *lens, int64_t N, int64_t ref_index,
+                    int flags, int threads, const int64_t *rows, int64_t nrows, uint64_t *subst,
+                    uint64_t *homologs, double *timings);
+
 /* distances and printing: src/evo_model.cxx:100-131, src/io.cxx:141-163.
  * kind 0 = raw, 1 = JC, 2 = ANI */
 double po_estimate(uint64_t subst, uint64_t homologs, int kind);

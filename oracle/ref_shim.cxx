@@ -307,6 +307,59 @@ int po_process(const char *const *seqs, const int64_t *lens, int64_t N, int64_t 
 	return 0;
 }
 
+/* process() for a sample of the matrix: every sequence is mapped like in process()
+ * (src/process.cxx:433-458), then only the listed rows are compared against all
+ * sequences (:524-549 for those i) — what a benchmark at 1000 genomes can afford. */
+int po_process_rows(const char *const *seqs, const int64_t *lens, int64_t N, int64_t ref_index, int flags_,
+                    int threads, const int64_t *rows, int64_t nrows, uint64_t *subst, uint64_t *homologs,
+                    double *timings)
+{
+	std::vector<sequence> queries;
+	for (int64_t g = 0; g < N; g++)
+		queries.emplace_back("g" + std::to_string(g), std::string(seqs[g], (size_t)lens[g]));
+	FLAGS = flags_ & flags::complete_deletion;
+	THREADS = threads > 0 ? threads : 1;
+	reference_index = (size_t)ref_index;
+	const sequence &subject = queries[(size_t)ref_index];
+	po_sa_seconds = 0;
+	double t0 = now();
+	auto ref = esa(subject);
+	double t1 = now();
+	auto gc = gc_content(subject.get_nucl());
+	size_t threshold = min_anchor_length(ANCHOR_P_VALUE, gc, ref.size());
+	auto homologies = std::vector<std::vector<homology>>((size_t)N);
+#pragma omp parallel for num_threads(THREADS) schedule(dynamic)
+	for (size_t j = 0; j < (size_t)N; j++) {
+		auto hvlocal = anchor_homologies(ref, threshold, queries[j]);
+		std::sort(begin(hvlocal), end(hvlocal), [](const homology &self, const homology &other) {
+			return self.starts_left_of(other);
+		});
+		filter_overlaps_max(hvlocal);
+		homologies[j] = std::move(hvlocal);
+	}
+	double t2 = now();
+	if (FLAGS & flags::complete_deletion) homologies = complete_delete(homologies);
+	double t3 = now();
+#pragma omp parallel for num_threads(THREADS) schedule(dynamic) collapse(2)
+	for (int64_t r = 0; r < nrows; r++) {
+		for (int64_t j = 0; j < N; j++) {
+			const size_t i = (size_t)rows[r];
+			evo_model em;
+			if ((size_t)j != i) em = compare(queries[i], homologies[i], queries[(size_t)j], homologies[(size_t)j]);
+			subst[r * N + j] = em.substitutions;
+			homologs[r * N + j] = em.homologs;
+		}
+	}
+	double t4 = now();
+	if (timings) {
+		timings[0] = t1 - t0;
+		timings[1] = t2 - t1;
+		timings[2] = t4 - t3;
+		timings[3] = po_sa_seconds;
+	}
+	return 0;
+}
+
 double po_estimate(uint64_t subst, uint64_t homologs, int kind)
 {
 	evo_model em;

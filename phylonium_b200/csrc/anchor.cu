@@ -402,13 +402,13 @@ __global__ void k_query_offsets(const int32_t *__restrict__ qids, const uint32_t
 // elements at all — every homology is kept (keep[] is preset to 1) and the DP is skipped.
 __global__ void k_filter(const int64_t *__restrict__ offs, int32_t nq, const int32_t *__restrict__ start,
                          const int32_t *__restrict__ len, int64_t *__restrict__ score, int32_t *__restrict__ pred,
-                         uint8_t *__restrict__ keep, const int32_t *__restrict__ overlap)
+                         uint8_t *__restrict__ keep, int32_t *__restrict__ heap, const int32_t *__restrict__ overlap)
 {
 	const int32_t q = blockIdx.x * blockDim.x + threadIdx.x;
 	if (q >= nq || !overlap[q]) return;
 	const int64_t o = offs[q];
 	const int32_t h = (int32_t)(offs[q + 1] - o);
-	filter_overlaps_max(start + o, len + o, h, score + o, pred + o, keep + o);
+	filter_overlaps_max(start + o, len + o, h, score + o, pred + o, keep + o, heap + o);
 }
 
 // ------------------------------------------------------------------ sort + filter, one block per query
@@ -426,7 +426,7 @@ constexpr int FIN_FLAG_TIES = 1, FIN_FLAG_BIG = 2;
 struct FinSmem {
 	uint64_t key[FIN_CAP]; // (start << 32) | push index; padding keys are all ones
 	int64_t score[FIN_CAP];
-	int32_t start[FIN_CAP], len[FIN_CAP], pred[FIN_CAP];
+	int32_t start[FIN_CAP], len[FIN_CAP], pred[FIN_CAP], heap[FIN_CAP];
 	uint8_t keep[FIN_CAP];
 	uint32_t scan_tmp[32];
 	int flags;
@@ -495,7 +495,7 @@ k_sort_filter(const int64_t *__restrict__ raw_offs, const Hom *__restrict__ raw,
 		return;
 	}
 	if (overlap) {
-		if (threadIdx.x == 0) filter_overlaps_max(sm.start, sm.len, h, sm.score, sm.pred, sm.keep);
+		if (threadIdx.x == 0) filter_overlaps_max(sm.start, sm.len, h, sm.score, sm.pred, sm.keep, sm.heap);
 		__syncthreads();
 	}
 	// survivors, in sorted order, to fin[lo ...]
@@ -531,14 +531,14 @@ void host_sort_filter(std::vector<Hom> &list)
 	// the very call of process.cxx:438-441: unstable, so equal starts keep libstdc++'s order
 	std::sort(list.begin(), list.end(), [](const Hom &a, const Hom &b) { return a.iproj < b.iproj; });
 	const int32_t h = (int32_t)list.size();
-	std::vector<int32_t> start(h), len(h), pred(h);
+	std::vector<int32_t> start(h), len(h), pred(h), heap(h);
 	std::vector<int64_t> score(h);
 	std::vector<uint8_t> keep(h);
 	for (int32_t k = 0; k < h; k++) {
 		start[k] = list[k].iproj;
 		len[k] = list[k].len;
 	}
-	filter_overlaps_max(start.data(), len.data(), h, score.data(), pred.data(), keep.data());
+	filter_overlaps_max(start.data(), len.data(), h, score.data(), pred.data(), keep.data(), heap.data());
 	size_t w = 0;
 	for (int32_t k = 0; k < h; k++)
 		if (keep[k]) list[w++] = list[k];
@@ -852,7 +852,7 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 			d_ties.get(), s);
 		const uint32_t ties = d2h_scalar(d_ties.get(), s);
 		if (!ties) {
-			DevBuf<int32_t> st(n_raw, s), ln(n_raw, s), pred(n_raw, s);
+			DevBuf<int32_t> st(n_raw, s), ln(n_raw, s), pred(n_raw, s), heap(n_raw, s);
 			DevBuf<int64_t> score(n_raw, s);
 			DevBuf<uint8_t> keep(n_raw, s);
 			DevBuf<int32_t> overlap(nq, s);
@@ -873,7 +873,7 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 				}, s);
 			}
 			k_filter<<<div_up(nq, 32), 32, 0, s>>>(d_raw_offs.get(), nq, st.get(), ln.get(), score.get(), pred.get(),
-			                                       keep.get(), overlap.get());
+			                                       keep.get(), heap.get(), overlap.get());
 			KERNEL_CHECK();
 			DevBuf<uint32_t> d_n(1, s);
 			const uint8_t *KP = keep.get();

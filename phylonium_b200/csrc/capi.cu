@@ -785,33 +785,6 @@ int phylo_esa_get_matches(phylo_ctx *c, const char *text, const uint64_t *offs, 
 	});
 }
 
-int phylo_map_queries(phylo_ctx *c, const char *const *queries, const uint64_t *lens, uint64_t N, uint64_t threshold)
-{
-	return guarded(c, [&] {
-		if (N && (!queries || !lens)) throw std::invalid_argument("NULL argument");
-		std::vector<uint64_t> offs((size_t)N);
-		uint64_t total = 0;
-		for (uint64_t k = 0; k < N; k++) {
-			if (!queries[k] && lens[k]) throw std::invalid_argument("NULL sequence");
-			offs[k] = total;
-			total = (total + lens[k] + 1 + 15) / 16 * 16; // >= 1 zero byte, 16-byte aligned starts
-		}
-		cudaStream_t s = c->stream;
-		CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
-		c->stager.drain();
-		c->q_resident = false;
-		c->q_own.alloc(total + 64, s);
-		c->q_own.zero();
-		for (uint64_t k = 0; k < N; k++)
-			if (lens[k])
-				CUDA_CHECK(cudaMemcpyAsync(c->q_own.get() + offs[k], queries[k], lens[k], cudaMemcpyHostToDevice, s));
-		do_map(c, c->q_own.get(), offs.data(), lens, N, threshold);
-		c->q_offs = offs;
-		c->q_lens.assign(lens, lens + N);
-		c->q_resident = true;
-	});
-}
-
 int phylo_map_queries_dev(phylo_ctx *c, const void *d_queries, const uint64_t *offs, const uint64_t *lens, uint64_t N,
                           uint64_t threshold)
 {
@@ -1014,64 +987,71 @@ void quiesce(phylo_ctx *c)
 
 } // namespace
 
-int phylo_process(phylo_ctx *c, const char *const *seqs, const uint64_t *lens, uint64_t N, uint64_t ref_index, int flags,
-                  uint64_t *subst, uint64_t *homologs)
+namespace
 {
-	if (!c) return fail(nullptr, PHYLO_ERR_INVALID, "context is NULL");
-	if (!seqs || !lens || !subst || !homologs || ref_index >= N)
-		return fail(c, PHYLO_ERR_INVALID, "bad arguments to phylo_process");
-	const int rc = guarded(c, [&] {
-		// one device buffer for all sequences; the reference goes first on the main stream,
-		// the other sequences follow on the copy stream while the index is being built
+
+// Lays the sequences out in one device buffer of the context (16-byte aligned starts, a zero
+// byte behind every sequence) and gets them on their way: sequence `first` (if < N) on the main
+// stream at once — phylo_process needs the reference for the index — the others batch by
+// batch next to whatever the main stream does meanwhile.  before_batch(b) puts the main stream
+// behind the bytes of batch b.
+struct Uploader {
+	phylo_ctx *c;
+	const char *const *seqs;
+	const uint64_t *lens;
+	uint64_t N, first;
+	std::vector<uint64_t> ends;
+	size_t queued = 0;
+	bool pageable = false;
+	static constexpr uint64_t COPY_QUEUE = 256;
+
+	Uploader(phylo_ctx *ctx, const char *const *seqs_, const uint64_t *lens_, uint64_t N_, uint64_t first_)
+		: c(ctx), seqs(seqs_), lens(lens_), N(N_), first(first_)
+	{
 		c->q_resident = false;
 		c->q_offs.assign((size_t)N, 0);
 		c->q_lens.assign(lens, lens + N);
-		uint64_t total = 0;
-		bool pageable = false;
+		uint64_t total = 0, bases = 0;
 		for (uint64_t k = 0; k < N; k++) {
 			if (!seqs[k] && lens[k]) throw std::invalid_argument("NULL sequence");
 			c->q_offs[k] = total;
-			total = (total + lens[k] + 1 + 15) / 16 * 16;
+			total = (total + lens[k] + 1 + 15) / 16 * 16; // >= 1 zero byte, 16-byte aligned starts
+			bases += lens[k];
 		}
 		// where do the sequences live?  one probe: callers do not mix pinned and ordinary memory
-		for (uint64_t k = 0; k < N && !pageable; k++)
-			if (k != ref_index && lens[k]) {
+		for (uint64_t k = 0; k < N; k++)
+			if (k != first && lens[k]) {
 				pageable = HostStager::is_pageable(seqs[k]);
 				break;
 			}
-		const uint64_t *offs = c->q_offs.data();
 		cudaStream_t s = c->stream;
 		CUDA_CHECK(cudaStreamSynchronize(c->copy_stream)); // nothing may still write into the old buffer
 		c->stager.drain();
 		c->q_own.alloc(total + 64, s);
 		c->q_own.zero();
 		uint8_t *dq = c->q_own.get();
-		if (lens[ref_index])
-			CUDA_CHECK(cudaMemcpyAsync(dq + offs[ref_index], seqs[ref_index], lens[ref_index], cudaMemcpyHostToDevice, s));
+		const uint64_t *offs = c->q_offs.data();
+		if (first < N && lens[first])
+			CUDA_CHECK(cudaMemcpyAsync(dq + offs[first], seqs[first], lens[first], cudaMemcpyHostToDevice, s));
 		CUDA_CHECK(cudaEventRecord(c->ev_main, s));
 		CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
-		const std::vector<uint64_t> ends = plan_batches(lens, N);
-		MapHooks hooks;
-		hooks.ends = &ends;
-		size_t queued = 0;
+		ends = plan_batches(lens, N);
 		if (pageable) {
 			// ordinary host memory: worker threads stage the pieces through pinned rings (staging.h)
 			uint64_t k = 0;
 			for (size_t b = 0; b < ends.size(); b++)
 				for (; k < ends[b]; k++)
-					if (k != ref_index && lens[k]) c->stager.add(dq + offs[k], seqs[k], lens[k], (int)b);
+					if (k != first && lens[k]) c->stager.add(dq + offs[k], seqs[k], lens[k], (int)b);
 			int threads = (int)c->opt_stage_threads;
 			if (threads <= 0) {
 				const unsigned hw = std::thread::hardware_concurrency();
 				threads = hw >= 16 ? 4 : hw >= 4 ? 2 : 1;
 			}
 			if (!c->stager.empty()) c->stager.start(c->device, (int)ends.size(), threads, c->ev_main);
-			hooks.before_batch = [&](size_t b) { c->stager.wait_batch((int)b, s); };
 		} else {
-			// pinned memory: plain asynchronous copies on the copy stream, batch by batch, with an
-			// event behind every batch: batch b is mapped while the later ones are still crossing
-			// PCIe.  At most COPY_QUEUE copies are queued ahead of the batch being mapped — a
-			// thousand queued copies fill the driver's queue and block the host until they have
+			// pinned memory: plain asynchronous copies on the copy stream with an event behind
+			// every batch.  At most COPY_QUEUE copies are queued ahead of the batch being mapped —
+			// a thousand queued copies fill the driver's queue and block the host until they have
 			// drained, with the index build not yet launched (measured: 1000 x 3 Mbp) — but never
 			// fewer than two batches.
 			while (c->batch_events.size() < ends.size()) {
@@ -1079,35 +1059,65 @@ int phylo_process(phylo_ctx *c, const char *const *seqs, const uint64_t *lens, u
 				CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 				c->batch_events.push_back(e);
 			}
-			constexpr uint64_t COPY_QUEUE = 256;
-			auto queue_copies = [&, dq, offs](size_t current) { // `current` = the batch about to be mapped
-				const uint64_t seq0 = current ? ends[current - 1] : 0;
-				size_t last = current + 2;
-				while (last + 1 < ends.size() && ends[last + 1] - seq0 <= COPY_QUEUE)
-					last++;
-				for (; queued <= last && queued < ends.size(); queued++) {
-					for (uint64_t k = queued ? ends[queued - 1] : 0; k < ends[queued]; k++)
-						if (k != ref_index && lens[k])
-							CUDA_CHECK(cudaMemcpyAsync(dq + offs[k], seqs[k], lens[k], cudaMemcpyHostToDevice, c->copy_stream));
-					CUDA_CHECK(cudaEventRecord(c->batch_events[queued], c->copy_stream));
-				}
-			};
 			queue_copies(0);
-			hooks.before_batch = [&, queue_copies](size_t b) mutable {
-				queue_copies(b);
-				CUDA_CHECK(cudaStreamWaitEvent(s, c->batch_events[b], 0));
-			};
 		}
 		c->stats["process.pageable"] = pageable ? 1 : 0;
-		{
-			uint64_t bases = 0;
-			for (uint64_t k = 0; k < N; k++)
-				bases += lens[k];
-			c->stats["process.h2d_bytes"] = (double)bases;
+		c->stats["process.h2d_bytes"] = (double)bases;
+	}
+
+	void queue_copies(size_t current) // `current` = the batch about to be mapped
+	{
+		uint8_t *dq = c->q_own.get();
+		const uint64_t *offs = c->q_offs.data();
+		const uint64_t seq0 = current ? ends[current - 1] : 0;
+		size_t last = current + 2;
+		while (last + 1 < ends.size() && ends[last + 1] - seq0 <= COPY_QUEUE)
+			last++;
+		for (; queued <= last && queued < ends.size(); queued++) {
+			for (uint64_t k = queued ? ends[queued - 1] : 0; k < ends[queued]; k++)
+				if (k != first && lens[k])
+					CUDA_CHECK(cudaMemcpyAsync(dq + offs[k], seqs[k], lens[k], cudaMemcpyHostToDevice, c->copy_stream));
+			CUDA_CHECK(cudaEventRecord(c->batch_events[queued], c->copy_stream));
 		}
-		process_resident(c, N, ref_index, flags, hooks, subst, homologs);
+	}
+
+	void before_batch(size_t b)
+	{
+		if (pageable) {
+			c->stager.wait_batch((int)b, c->stream);
+		} else {
+			queue_copies(b);
+			CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->batch_events[b], 0));
+		}
+	}
+
+	MapHooks hooks()
+	{
+		MapHooks h;
+		h.ends = &ends;
+		h.before_batch = [this](size_t b) { before_batch(b); };
+		return h;
+	}
+
+	void done()
+	{
 		c->stager.finish();
 		c->q_resident = true;
+	}
+};
+
+} // namespace
+
+int phylo_process(phylo_ctx *c, const char *const *seqs, const uint64_t *lens, uint64_t N, uint64_t ref_index, int flags,
+                  uint64_t *subst, uint64_t *homologs)
+{
+	if (!c) return fail(nullptr, PHYLO_ERR_INVALID, "context is NULL");
+	if (!seqs || !lens || !subst || !homologs || ref_index >= N)
+		return fail(c, PHYLO_ERR_INVALID, "bad arguments to phylo_process");
+	const int rc = guarded(c, [&] {
+		Uploader up(c, seqs, lens, N, ref_index);
+		process_resident(c, N, ref_index, flags, up.hooks(), subst, homologs);
+		up.done();
 	});
 	if (rc != PHYLO_OK) quiesce(c);
 	return rc;
@@ -1125,6 +1135,20 @@ int phylo_process_again(phylo_ctx *c, uint64_t ref_index, int flags, uint64_t *s
 		CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
 		process_resident(c, N, ref_index, flags, MapHooks(), subst, homologs);
 		c->stats["process.h2d_bytes"] = 0;
+	});
+	if (rc != PHYLO_OK) quiesce(c);
+	return rc;
+}
+
+int phylo_map_queries(phylo_ctx *c, const char *const *queries, const uint64_t *lens, uint64_t N, uint64_t threshold)
+{
+	if (!c) return fail(nullptr, PHYLO_ERR_INVALID, "context is NULL");
+	const int rc = guarded(c, [&] {
+		if (N && (!queries || !lens)) throw std::invalid_argument("NULL argument");
+		// batch b is mapped while the later ones are still crossing PCIe
+		Uploader up(c, queries, lens, N, N);
+		do_map(c, c->q_own.get(), c->q_offs.data(), lens, N, threshold, up.hooks());
+		up.done();
 	});
 	if (rc != PHYLO_OK) quiesce(c);
 	return rc;

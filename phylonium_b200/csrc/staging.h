@@ -49,16 +49,18 @@ class HostStager
 		const uint8_t *p = static_cast<const uint8_t *>(src);
 		for (uint64_t o = 0; o < len; o += SLOT_BYTES) {
 			const uint64_t l = len - o < SLOT_BYTES ? len - o : SLOT_BYTES;
-			pieces_.push_back(Piece{dst + o, p + o, (uint32_t)l, batch});
+			pending_.push_back(Piece{dst + o, p + o, (uint32_t)l, batch});
 		}
 	}
-	bool empty() const { return pieces_.empty(); }
+	bool empty() const { return pending_.empty(); }
 
 	// `after`: an event (of another stream) the copies must not overtake, e.g. the clearing of
 	// the destination buffer
 	void start(int device, int nbatches, int threads, cudaEvent_t after)
 	{
 		finish();
+		pieces_.swap(pending_);
+		pending_.clear();
 		if (threads < 1) threads = 1;
 		if ((size_t)threads > pieces_.size()) threads = (int)(pieces_.size() ? pieces_.size() : 1);
 		device_ = device;
@@ -105,10 +107,7 @@ class HostStager
 	// caller's buffers any more (the copies out of the pinned rings may still be in flight).
 	void finish(bool abort = false)
 	{
-		if (!running_) {
-			pieces_.clear();
-			return;
-		}
+		if (!running_) return;
 		if (abort) abort_ = true;
 		for (auto &w : workers_)
 			if (w.th.joinable()) w.th.join();
@@ -120,6 +119,7 @@ class HostStager
 	void drain()
 	{
 		finish(true);
+		pending_.clear();
 		for (auto &w : workers_)
 			if (w.stream) cudaStreamSynchronize(w.stream);
 	}
@@ -193,7 +193,8 @@ class HostStager
 		publish_up_to(nbatches_);
 	}
 
-	std::vector<Piece> pieces_;
+	std::vector<Piece> pending_; // added, not started yet
+	std::vector<Piece> pieces_;  // what the running workers read
 	std::vector<Worker> workers_;
 	std::mutex mu_;
 	std::condition_variable cv_;

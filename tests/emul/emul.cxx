@@ -291,8 +291,23 @@ int64_t emul_anchor(const uint8_t *S, const int64_t *SA, const int64_t *LCP, con
 int32_t emul_filter(const int32_t *start, const int32_t *len, int32_t h, uint8_t *keep)
 {
 	std::vector<int64_t> score((size_t)h + 1);
-	std::vector<int32_t> pred((size_t)h + 1);
-	return filter_overlaps_max(start, len, h, score.data(), pred.data(), keep);
+	std::vector<int32_t> pred((size_t)h + 1), heap((size_t)h + 1);
+	return filter_overlaps_max(start, len, h, score.data(), pred.data(), keep, heap.data());
+}
+
+// the two implementations behind filter_overlaps_max on their own: which = 0 clusters (with an
+// unlimited budget), 1 heap (O(h log h))
+int32_t emul_filter_variant(const int32_t *start, const int32_t *len, int32_t h, uint8_t *keep, int32_t which)
+{
+	std::vector<int64_t> score((size_t)h + 1);
+	std::vector<int32_t> pred((size_t)h + 1), heap((size_t)h + 1);
+	if (h < 2) {
+		for (int32_t k = 0; k < h; k++)
+			keep[k] = 1;
+		return h;
+	}
+	if (which == 0) return filter_overlaps_clusters(start, len, h, score.data(), pred.data(), keep, INT64_MAX);
+	return filter_overlaps_heap(start, len, h, score.data(), pred.data(), keep, heap.data());
 }
 
 } // extern "C"

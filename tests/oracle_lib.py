@@ -81,6 +81,11 @@ class OracleLib:
             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         ]
         L.po_process.restype = C.c_int
+        L.po_process_rows.argtypes = [
+            C.POINTER(C.c_char_p), _c_i64p, C.c_int64, C.c_int64, C.c_int, C.c_int,
+            C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+        ]
+        L.po_process_rows.restype = C.c_int
         L.po_estimate.argtypes = [C.c_uint64, C.c_uint64, C.c_int]
         L.po_estimate.restype = C.c_double
         L.po_format_matrix.argtypes = [C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_char_p, C.c_int64]
@@ -173,6 +178,27 @@ class OracleLib:
             res["timings"] = {"esa": timings[0], "anchor": timings[1], "compare": timings[2], "sa_sort": timings[3]}
             res["hom_counts"] = hcount
         return res
+
+    def process_rows(self, seqs, rows, ref_index: int = 0, flags: int = 0, threads: int = 1, lens=None):
+        """rows `rows` of process()'s matrix (every sequence is mapped, only those rows are
+        compared).  seqs: byte strings, or raw host addresses together with `lens`."""
+        if lens is None:
+            seqs = [_as_bytes(s) for s in seqs]
+            lens = [len(s) for s in seqs]
+            arr = (C.c_char_p * len(seqs))(*seqs)
+        else:
+            arr = (C.c_char_p * len(seqs))(*[C.c_char_p(int(p)) for p in seqs])
+        N = len(seqs)
+        lens = np.ascontiguousarray(lens, dtype=np.int64)
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        subst = np.zeros(len(rows) * N, dtype=np.uint64)
+        homol = np.zeros(len(rows) * N, dtype=np.uint64)
+        timings = np.zeros(4, dtype=np.float64)
+        rc = self.lib.po_process_rows(arr, lens.ctypes.data_as(_c_i64p), N, ref_index, flags, threads, rows.ctypes.data,
+                                      len(rows), subst.ctypes.data, homol.ctypes.data, timings.ctypes.data)
+        assert rc == 0
+        return {"subst": subst.reshape(len(rows), N), "homologs": homol.reshape(len(rows), N),
+                "timings": {"esa": timings[0], "anchor": timings[1], "compare": timings[2], "sa_sort": timings[3]}}
 
     def estimate(self, subst: int, homologs: int, kind: int = 1) -> float:
         return self.lib.po_estimate(int(subst), int(homologs), kind)

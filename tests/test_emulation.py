@@ -139,12 +139,17 @@ def test_low_thresholds(emul, oracle):
                 assert np.array_equal(got, want), (thr, CH, stats)
 
 
-def _filter_via_emul(emul, homs):
+def _filter_via_emul(emul, homs, variant=None):
+    """variant None: filter_overlaps_max as the kernels call it; 0: the cluster DP alone;
+    1: the O(h log h) heap version alone"""
     h = len(homs)
     start = np.ascontiguousarray(homs["index_reference_projected"], dtype=np.int32)
     ln = np.ascontiguousarray(homs["length"], dtype=np.int32)
     keep = np.zeros(max(h, 1), np.uint8)
-    emul.emul_filter(_ptr(start), _ptr(ln), C.c_int32(h), _ptr(keep))
+    if variant is None:
+        emul.emul_filter(_ptr(start), _ptr(ln), C.c_int32(h), _ptr(keep))
+    else:
+        emul.emul_filter_variant(_ptr(start), _ptr(ln), C.c_int32(h), _ptr(keep), C.c_int32(variant))
     return homs[keep[:h] != 0]
 
 
@@ -167,8 +172,9 @@ def test_filter_known_answers(emul, oracle):
         ),
     ]
     for pile, expected in cases:
-        got = _filter_via_emul(emul, _homs(pile))
-        assert np.array_equal(got, _homs(expected))
+        for variant in (None, 0, 1):
+            got = _filter_via_emul(emul, _homs(pile), variant)
+            assert np.array_equal(got, _homs(expected)), variant
         assert np.array_equal(oracle.sort_filter(_homs(pile), do_sort=False), _homs(expected))
 
 
@@ -183,5 +189,23 @@ def test_filter_random_lists(emul, oracle):
         lens = rng.integers(1, max(2, span // 6), size=len(starts))
         pile = _homs([(int(s), int(rng.integers(0, 10**6)), int(l)) for s, l in zip(starts, lens)])
         want = oracle.sort_filter(pile, do_sort=False)
-        got = _filter_via_emul(emul, pile)
-        assert np.array_equal(got, want), trial
+        for variant in (None, 0, 1):
+            got = _filter_via_emul(emul, pile, variant)
+            assert np.array_equal(got, want), (trial, variant)
+
+
+def test_filter_large_clusters_take_the_heap(emul, oracle):
+    """thousands of mutually overlapping homologies (one cluster): the cluster DP gives up
+    on its work budget and the O(h log h) version answers — same survivors as the reference's
+    O(h^2) loop, including its tie rules (equal scores, equal starts, equal ends)"""
+    rng = np.random.default_rng(12)
+    for trial, (h, span, maxlen) in enumerate([(1500, 3000, 2500), (3000, 4000, 60), (2000, 500, 400), (800, 100000, 90000)]):
+        starts = np.sort(rng.integers(0, span, size=h))
+        lens = rng.integers(1, maxlen, size=h)
+        if trial == 2:
+            lens[:] = rng.integers(1, 4, size=h) * 100  # many equal scores
+        pile = _homs([(int(s), int(rng.integers(0, 10**6)), int(l)) for s, l in zip(starts, lens)])
+        want = oracle.sort_filter(pile, do_sort=False)
+        for variant in (None, 0, 1):
+            got = _filter_via_emul(emul, pile, variant)
+            assert np.array_equal(got, want), (trial, variant)

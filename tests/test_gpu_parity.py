@@ -614,7 +614,9 @@ def test_sharded_plumbing_on_one_gpu(pb, oracle, flags):
         acc = torch.zeros(2, n * n, dtype=torch.int64, device="cuda")
         for k in range(world):  # stands in for the all-reduce
             part = torch.zeros(2, n * n, dtype=torch.int64, device="cuda")
+            torch.cuda.synchronize()  # torch's stream and the context's are not ordered
             ctxs[k].compare_tiles_dev(part[0].data_ptr(), part[1].data_ptr(), k, world, flags)
+            torch.cuda.synchronize()  # the call only queues the work on the context's stream
             acc += part
         subst = acc[0].cpu().numpy().reshape(n, n)[:total, :total].astype(np.uint64)
         homol = acc[1].cpu().numpy().reshape(n, n)[:total, :total].astype(np.uint64)
@@ -660,7 +662,9 @@ def test_sharded_push_exchange_on_one_gpu(pb, oracle, world, flags):
         acc = torch.zeros(2, n * n, dtype=torch.int64, device="cuda")
         for k in range(world):
             part = torch.zeros(2, n * n, dtype=torch.int64, device="cuda")
+            torch.cuda.synchronize()  # torch's stream and the context's are not ordered
             ctxs[k].compare_tiles_dev(part[0].data_ptr(), part[1].data_ptr(), k, world, flags)
+            torch.cuda.synchronize()  # the call only queues the work on the context's stream
             acc += part
         got = sharding.genome_order(acc, plans[0]).cpu().numpy().astype(np.uint64)
         assert np.array_equal(got[0], want["subst"]) and np.array_equal(got[1], want["homologs"])
@@ -696,7 +700,9 @@ def _ipc_worker(rank, world, port, genomes, thr, flags, results):
             dist.barrier()  # every rank's pushes have landed
             n = plan.padded_total
             part = torch.zeros(2, n * n, dtype=torch.int64, device="cuda")
+            torch.cuda.synchronize()  # torch's stream and the context's are not ordered
             ctx.compare_tiles_dev(part[0].data_ptr(), part[1].data_ptr(), rank, world, flags)
+            torch.cuda.synchronize()  # the call only queues the work on the context's stream
             part = part.cpu()
             dist.all_reduce(part)
             got = sharding.genome_order(part, plan).numpy().astype(np.uint64)

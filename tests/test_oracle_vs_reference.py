@@ -160,3 +160,18 @@ def test_saturated_and_empty_pairs_print_like_libm(libs):
         assert pl.format_matrix(names, mat, kind) == want
     jc = r.format_matrix(names, subst, homol, 1)
     assert "-nan" in jc and "inf" in jc
+
+
+@pytest.mark.parametrize("flags", [0, 4])
+def test_sampled_rows_equal_the_full_matrix(libs, flags):
+    """po_process_rows (what the benchmark's sampled check uses at 1000 genomes) against the
+    untouched process() call of the reference, and the port against both"""
+    p, r = libs
+    genomes = datasets.ALL_SETS["rearranged"]() if "rearranged" in datasets.ALL_SETS else datasets.divergent_set()
+    full = r.process(genomes, 0, flags, threads=2)
+    rows = [len(genomes) - 1, 0, 1]
+    for lib in (p, r):
+        got = lib.process_rows(genomes, rows, 0, flags, threads=2)
+        for k, i in enumerate(rows):
+            assert np.array_equal(got["subst"][k], full["subst"][i]), (lib.kind, i)
+            assert np.array_equal(got["homologs"][k], full["homologs"][i]), (lib.kind, i)
