@@ -169,6 +169,10 @@ class Context:
         ref = _b(ref)
         self._check(self.lib.phylo_esa_build(self.h, ref, len(ref)))
 
+    def esa_build_ptr(self, host_ptr: int, n: int):
+        """phylo_esa_build on caller-owned host memory (e.g. a pinned buffer)"""
+        self._check(self.lib.phylo_esa_build(self.h, C.c_char_p(int(host_ptr)), n))
+
     def esa_build_dev(self, d_ptr: int, n: int):
         self._check(self.lib.phylo_esa_build_dev(self.h, d_ptr, n))
 
@@ -201,6 +205,14 @@ class Context:
         N = len(qs)
         arr = (C.c_char_p * max(N, 1))(*qs)
         lens = np.array([len(q) for q in qs], dtype=np.uint64)
+        self._check(self.lib.phylo_map_queries(self.h, arr, lens.ctypes.data, N, threshold))
+        self.N = N
+
+    def map_queries_ptrs(self, ptrs, lens, threshold: int):
+        """phylo_map_queries on caller-owned host memory: ptrs are addresses"""
+        N = len(ptrs)
+        arr = (C.c_char_p * max(N, 1))(*[C.c_char_p(int(p)) for p in ptrs])
+        lens = np.ascontiguousarray(lens, dtype=np.uint64)
         self._check(self.lib.phylo_map_queries(self.h, arr, lens.ctypes.data, N, threshold))
         self.N = N
 
