@@ -296,6 +296,7 @@ class Pipeline:
         if args.kmer_k is not None:
             self.ctx.set_option("kmer_k", args.kmer_k)
         self.ctx.set_option("sort_path", args.sort_path)
+        self.ctx.set_option("stage_threads", max(1, min(16, host_threads(world))))  # the ranks share the host's cores
         if world > 1 and batch_bytes:
             # several batches per rank: the rows of one batch cross NVLink while the next is mapped
             self.ctx.set_option("map_batch_bytes", batch_bytes)
@@ -396,7 +397,12 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     mods = (torch, dist, pb, sharding)
-    stream = torch.cuda.current_stream()
+    # one explicit stream for everything: the library's kernels (phylo_set_stream), torch's own
+    # work, the NCCL collectives and the timing events.  (The default stream has the handle 0,
+    # which phylo_set_stream reads as "use the context's own stream" — events recorded on
+    # torch's stream would then not see the library's kernels.)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     threads = host_threads(world)
 
@@ -461,7 +467,6 @@ def run_b200(args):
     launches0 = ctx.stat("launches")
     step_ms = time_steps(pipe.step, args.steps, 0)
     launches = int(round((ctx.stat("launches") - launches0) / max(1, args.steps)))
-    clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(sum(step_ms) / len(step_ms))
     srt = sorted(step_ms)
     step_stats = {"min": srt[0], "median": srt[len(srt) // 2], "max": srt[-1]}
@@ -497,14 +502,17 @@ def run_b200(args):
                     and (torch.from_numpy(out[1].astype(np.int64)) == counts_dev[1].cpu()).all())
         e2e = {"value": bases_total / 1e6 / (e_ms / 1e3), "unit": "Mbp/s", "ms_per_step": e_ms,
                "h2d_bytes_per_step": int(bases_local), "d2h_bytes_per_step": int(2 * G * G * 8),
-               "same_counts_as_device_path": same, "call": "phylo_process (C ABI, pinned host pointers)"}
+               "same_counts_as_device_path": same, "call": "phylo_process (C ABI, pinned host pointers)",
+               "bus_bytes_per_step": int(ctx.stat("process.h2d_bytes")),
+               "note": "h2d_bytes_per_step counts the caller's buffers; the library packs the query sequences to 2 bits per "
+                       "base on the host, so bus_bytes_per_step cross PCIe"}
         # the same call on ordinary (pageable) memory, as the C++ host's std::string storage is
         pageable = [np.frombuffer((ctypes.c_char * L).from_address(p), dtype=np.uint8).copy() for p in shard.ptrs]
         pts = time_steps(lambda: ctx.process_ptrs([a.ctypes.data for a in pageable], shard.lens, 0, 0, out), e2e_steps, 1,
                          wall=True)
         p_ms = sum(pts) / len(pts)
         e2e["pageable"] = {"value": bases_total / 1e6 / (p_ms / 1e3), "ms_per_step": p_ms,
-                           "staged_by_library": ctx.stat("process.pageable") == 1,
+                           "seen_as_pageable": ctx.stat("process.pageable") == 1,
                            "same_counts": bool((torch.from_numpy(out[1].astype(np.int64)) == counts_dev[1].cpu()).all())}
         del pageable
     else:
@@ -525,6 +533,8 @@ def run_b200(args):
                "d2h_bytes_per_step": int(2 * total * total * 8), "same_counts_as_device_path": same,
                "call": "phylo_esa_build + phylo_map_queries on pinned host buffers per rank, rows pushed to the peers, "
                        "phylo_compare_tiles_dev + all-reduce, matrix read back on rank 0"}
+
+    clocks = sampler.stop() if rank == 0 else None  # sampled over the timed steps and the e2e steps
 
     # ---- profile pass: per-phase device times and the roofline of the dominant streaming kernel ---
     phases, roofline = None, None

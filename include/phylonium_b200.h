@@ -90,8 +90,10 @@ int phylo_set_stream(phylo_ctx *ctx, void *stream);
  *               the general sorter (3-bit codes, 64-bit keys)
  *   "sort_mode" radix sort scheme: 0 = by size (default), 1 = histogram+scan+scatter per
  *              pass, 2 = single-pass look-back ("onesweep")
- *   "stage_threads" worker threads that stage sequences from ordinary (pageable) host memory
- *               through pinned buffers in phylo_process; 0 = from the core count (default)
+ *   "stage_threads" worker threads that pack the sequences of phylo_process / phylo_map_queries
+ *               to 2 bits per base for the trip over PCIe; 0 = from the core count (default)
+ *   "upload_raw" 1 = send the bytes as they are (asynchronous from pinned memory, staged by the
+ *               driver otherwise) instead of packing them on the host; default 0
  *   "keep_raw" keep unsorted/unfiltered homology lists for phylo_get_homologies(raw=1)
  *   "timings"  record per-phase device times (adds synchronisation) */
 int phylo_set_option(phylo_ctx *ctx, const char *key, int64_t value);

@@ -345,6 +345,7 @@ void accumulate(AnchorStats &sum, const AnchorStats &st)
 struct MapHooks {
 	const std::vector<uint64_t> *ends = nullptr;
 	std::function<void(size_t)> before_batch, after_batch;
+	bool validated = false; // the alphabet was checked while the sequences were packed on the host
 };
 
 // copies rows [first, first + count) of this context's store into the peers' stores
@@ -416,34 +417,40 @@ void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_
 		DevBuf<QueryInfo> d_qi((size_t)cnt, s);
 		DevBuf<int> bad(1, s);
 		CUDA_CHECK(cudaMemcpyAsync(d_qi.get(), qi.data(), cnt * sizeof(QueryInfo), cudaMemcpyHostToDevice, s));
-		bad.zero();
-		// ... on a stream of its own, next to the walk
-		if (!c->check_stream) {
-			CUDA_CHECK(cudaStreamCreateWithFlags(&c->check_stream, cudaStreamNonBlocking));
-			CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_check_fork, cudaEventDisableTiming));
-			CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_check_done, cudaEventDisableTiming));
+		const bool validate = !hooks.validated; // sequences packed on the host were checked there
+		if (validate) {
+			bad.zero();
+			// ... on a stream of its own, next to the walk
+			if (!c->check_stream) {
+				CUDA_CHECK(cudaStreamCreateWithFlags(&c->check_stream, cudaStreamNonBlocking));
+				CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_check_fork, cudaEventDisableTiming));
+				CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_check_done, cudaEventDisableTiming));
+			}
+			CUDA_CHECK(cudaEventRecord(c->ev_check_fork, s));
+			CUDA_CHECK(cudaStreamWaitEvent(c->check_stream, c->ev_check_fork, 0));
+			for (uint64_t k0 = 0; k0 < cnt; k0 += 32768) {
+				const int32_t part = (int32_t)(cnt - k0 < 32768 ? cnt - k0 : 32768);
+				uint64_t longest = 0;
+				for (uint64_t k = k0; k < k0 + (uint64_t)part; k++)
+					longest = std::max<uint64_t>(longest, lens[b0 + k]);
+				dim3 grid((unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (longest / 16 + 256) / 256), 4096), part);
+				k_validate_queries<<<grid, 256, 0, c->check_stream>>>(dQ, d_qi.get() + k0, part, bad.get());
+				KERNEL_CHECK();
+			}
+			CUDA_CHECK(cudaEventRecord(c->ev_check_done, c->check_stream));
 		}
-		CUDA_CHECK(cudaEventRecord(c->ev_check_fork, s));
-		CUDA_CHECK(cudaStreamWaitEvent(c->check_stream, c->ev_check_fork, 0));
-		for (uint64_t k0 = 0; k0 < cnt; k0 += 32768) {
-			const int32_t part = (int32_t)(cnt - k0 < 32768 ? cnt - k0 : 32768);
-			uint64_t longest = 0;
-			for (uint64_t k = k0; k < k0 + (uint64_t)part; k++)
-				longest = std::max<uint64_t>(longest, lens[b0 + k]);
-			dim3 grid((unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (longest / 16 + 256) / 256), 4096), part);
-			k_validate_queries<<<grid, 256, 0, c->check_stream>>>(dQ, d_qi.get() + k0, part, bad.get());
-			KERNEL_CHECK();
-		}
-		CUDA_CHECK(cudaEventRecord(c->ev_check_done, c->check_stream));
-		opt.input_flags_ready = c->ev_check_done;
+		opt.input_flags_ready = validate ? c->ev_check_done : nullptr;
 		// whatever happens below, the mapping stream is behind the validation before d_qi and
 		// bad (declared above, released after this guard) can be handed out again
 		struct JoinGuard {
 			cudaStream_t s;
 			cudaEvent_t e;
-			~JoinGuard() { cudaStreamWaitEvent(s, e, 0); }
-		} join_guard{s, c->ev_check_done};
-		opt.input_flags = bad.get();
+			~JoinGuard()
+			{
+				if (e) cudaStreamWaitEvent(s, e, 0);
+			}
+		} join_guard{s, validate ? c->ev_check_done : nullptr};
+		opt.input_flags = validate ? bad.get() : nullptr;
 		AnchorStats st;
 		anchor_queries_device(c->esa, dQ, qi, (int32_t)thr, opt, s, B.res, &st);
 		if (st.input_flags & 1) throw std::invalid_argument("a sequence contains bytes outside {A,C,G,T,!}");
@@ -632,6 +639,8 @@ int phylo_set_option(phylo_ctx *c, const char *key, int64_t value)
 		} else if (k == "key_chars") {
 			if (value < 0 || value > 21) throw std::invalid_argument("key_chars must be in [0, 21]");
 			c->opt_key_chars = value;
+		} else if (k == "upload_raw") {
+			c->tuning.upload_raw = value != 0;
 		} else if (k == "stage_threads") {
 			if (value < 0 || value > 64) throw std::invalid_argument("stage_threads must be in [0, 64]");
 			c->opt_stage_threads = value;
@@ -1002,7 +1011,7 @@ struct Uploader {
 	uint64_t N, first;
 	std::vector<uint64_t> ends;
 	size_t queued = 0;
-	bool pageable = false;
+	bool pageable = false, packed = true;
 	static constexpr uint64_t COPY_QUEUE = 256;
 
 	Uploader(phylo_ctx *ctx, const char *const *seqs_, const uint64_t *lens_, uint64_t N_, uint64_t first_)
@@ -1036,8 +1045,10 @@ struct Uploader {
 		CUDA_CHECK(cudaEventRecord(c->ev_main, s));
 		CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
 		ends = plan_batches(lens, N);
-		if (pageable) {
-			// ordinary host memory: worker threads stage the pieces through pinned rings (staging.h)
+		packed = c->tuning.upload_raw == 0;
+		if (packed) {
+			// worker threads pack the pieces to 2 bits per base into pinned rings, a kernel unpacks
+			// them at their place (staging.h): a quarter of the bytes on the bus, pageable or pinned
 			uint64_t k = 0;
 			for (size_t b = 0; b < ends.size(); b++)
 				for (; k < ends[b]; k++)
@@ -1045,12 +1056,12 @@ struct Uploader {
 			int threads = (int)c->opt_stage_threads;
 			if (threads <= 0) {
 				const unsigned hw = std::thread::hardware_concurrency();
-				threads = hw >= 16 ? 4 : hw >= 4 ? 2 : 1;
+				threads = hw >= 16 ? 8 : hw >= 8 ? 4 : hw >= 4 ? 2 : 1;
 			}
 			if (!c->stager.empty()) c->stager.start(c->device, (int)ends.size(), threads, c->ev_main);
 		} else {
-			// pinned memory: plain asynchronous copies on the copy stream with an event behind
-			// every batch.  At most COPY_QUEUE copies are queued ahead of the batch being mapped —
+			// option "upload_raw": the bytes as they are, plain asynchronous copies on the copy
+			// stream (truly asynchronous only from pinned memory) with an event behind every batch.  At most COPY_QUEUE copies are queued ahead of the batch being mapped —
 			// a thousand queued copies fill the driver's queue and block the host until they have
 			// drained, with the index build not yet launched (measured: 1000 x 3 Mbp) — but never
 			// fewer than two batches.
@@ -1062,7 +1073,9 @@ struct Uploader {
 			queue_copies(0);
 		}
 		c->stats["process.pageable"] = pageable ? 1 : 0;
-		c->stats["process.h2d_bytes"] = (double)bases;
+		c->stats["process.packed"] = packed ? 1 : 0;
+		c->stats["process.h2d_bytes"] = packed ? (double)((bases - (first < N ? lens[first] : 0)) / 4 + (first < N ? lens[first] : 0))
+		                                       : (double)bases;
 	}
 
 	void queue_copies(size_t current) // `current` = the batch about to be mapped
@@ -1083,7 +1096,7 @@ struct Uploader {
 
 	void before_batch(size_t b)
 	{
-		if (pageable) {
+		if (packed) {
 			c->stager.wait_batch((int)b, c->stream);
 		} else {
 			queue_copies(b);
@@ -1096,6 +1109,9 @@ struct Uploader {
 		MapHooks h;
 		h.ends = &ends;
 		h.before_batch = [this](size_t b) { before_batch(b); };
+		// packed sequences were checked by the packer; the reference of phylo_process (copied as
+		// it is) by the text kernel of the index build
+		h.validated = packed;
 		return h;
 	}
 

@@ -1,14 +1,17 @@
-// Host-to-device copies from ordinary (pageable) host memory.
+// Host-to-device upload of the sequences, packed.
 //
 // phylo_process() receives the sequences where the caller keeps them — in the reference that
-// is the std::string inside a `sequence` (src/sequence.h), i.e. pageable memory.  A
-// cudaMemcpyAsync from pageable memory is staged by the driver on the calling thread, one
-// copy after the other, while that thread should be launching the index build and the
-// mapping.  Here a few worker threads copy pieces of the sequences into pinned ring buffers
-// and issue the asynchronous copies from there, each on a stream of its own; the mapping
-// waits, batch by batch, for an event behind the last piece of the batch.
+// is the std::string inside a `sequence` (src/sequence.h), i.e. ordinary pageable memory — and
+// for a thousand genomes the PCIe bus, not the GPU, bounds the call.  So the bytes do not
+// cross the bus as they are: a few worker threads pack pieces of the sequences to 2 bits per
+// base (host_pack.cpp; the alphabet check happens there too) into small pinned ring buffers,
+// copy the packed pieces over — a quarter of the bytes, and from pinned memory whatever the
+// caller's buffers are — and a kernel on the worker's stream unpacks each piece to bytes at
+// its final place.  The mapping waits, batch by batch, for an event behind the last piece of
+// the batch.  Pageable and pinned callers take the same path.
 #pragma once
 #include "common.cuh"
+#include "host_pack.h"
 
 #include <atomic>
 #include <condition_variable>
@@ -20,16 +23,52 @@
 namespace phy
 {
 
+// packed piece -> bytes; 16 bases (one 32-bit word of codes) per thread
+static __global__ void __launch_bounds__(256)
+k_unpack_2bit(const uint32_t *__restrict__ packed, uint8_t *__restrict__ dst, uint32_t n)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t i0 = t * 16;
+	if (i0 >= n) return;
+	const uint32_t w = packed[t];
+	uint32_t out[4];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		uint32_t x = 0;
+#pragma unroll
+		for (int b = 0; b < 4; b++) {
+			const uint32_t code = (w >> (8 * k + 2 * b)) & 3u;
+			x |= ((0x47544341u >> (8 * code)) & 0xffu) << (8 * b); // 0 A, 1 C, 2 T, 3 G
+		}
+		out[k] = x;
+	}
+	if (i0 + 16 <= n) {
+		*reinterpret_cast<uint4 *>(dst + i0) = make_uint4(out[0], out[1], out[2], out[3]); // dst is 16-byte aligned
+	} else {
+		for (uint32_t i = i0; i < n; i++)
+			dst[i] = (uint8_t)(out[(i - i0) >> 2] >> (8 * ((i - i0) & 3)));
+	}
+}
+
+static __global__ void k_put_bangs(uint8_t *__restrict__ dst, const uint32_t *__restrict__ pos, uint32_t count)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < count) dst[pos[t]] = (uint8_t)'!';
+}
+
 class HostStager
 {
   public:
 	struct Piece {
-		uint8_t *dst;       // device
-		const uint8_t *src; // host, pageable
-		uint32_t len;       // <= SLOT_BYTES
+		uint8_t *dst;       // device, 16-byte aligned
+		const uint8_t *src; // host
+		uint32_t len;       // <= PIECE_BYTES
 		int32_t batch;
 	};
-	static constexpr size_t SLOT_BYTES = 4u << 20;
+	static constexpr size_t PIECE_BYTES = 2u << 20;         // bases per piece
+	static constexpr size_t PACKED_BYTES = PIECE_BYTES / 4; // its packed form
+	static constexpr uint32_t BANG_CAP = 4096;              // '!' per piece listed with the packed form
+	static constexpr size_t SLOT_BYTES = PACKED_BYTES + BANG_CAP * sizeof(uint32_t);
 	static constexpr int SLOTS = 4;
 
 	// true if a cudaMemcpyAsync from p would be staged by the driver
@@ -43,12 +82,12 @@ class HostStager
 		return a.type == cudaMemoryTypeUnregistered;
 	}
 
-	// appends the pieces of one sequence (call in batch order, then start())
+	// appends the pieces of one sequence (call in batch order, then start()); dst 16-byte aligned
 	void add(uint8_t *dst, const void *src, uint64_t len, int batch)
 	{
 		const uint8_t *p = static_cast<const uint8_t *>(src);
-		for (uint64_t o = 0; o < len; o += SLOT_BYTES) {
-			const uint64_t l = len - o < SLOT_BYTES ? len - o : SLOT_BYTES;
+		for (uint64_t o = 0; o < len; o += PIECE_BYTES) {
+			const uint64_t l = len - o < PIECE_BYTES ? len - o : PIECE_BYTES;
 			pending_.push_back(Piece{dst + o, p + o, (uint32_t)l, batch});
 		}
 	}
@@ -67,12 +106,14 @@ class HostStager
 		nbatches_ = nbatches;
 		abort_ = false;
 		error_.clear();
+		bad_input_ = false;
 		if ((int)workers_.size() != threads) {
 			release_workers();
 			workers_.resize(threads);
 			for (auto &w : workers_) {
 				CUDA_CHECK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
 				CUDA_CHECK(cudaHostAlloc((void **)&w.ring, SLOT_BYTES * SLOTS, cudaHostAllocDefault));
+				CUDA_CHECK(cudaMalloc((void **)&w.dring, SLOT_BYTES * SLOTS));
 				for (auto &e : w.slot_ev)
 					CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 			}
@@ -91,13 +132,15 @@ class HostStager
 			workers_[t].th = std::thread([this, t] { run(t); });
 	}
 
-	// blocks until every worker has issued its copies of batch b, then puts `s` behind them
+	// blocks until every worker has issued its copies of batch b, then puts `s` behind them;
+	// throws std::invalid_argument if a byte outside the alphabet was met on the way
 	void wait_batch(int b, cudaStream_t s)
 	{
 		if (!running_) return;
 		std::unique_lock<std::mutex> lock(mu_);
 		for (auto &w : workers_) {
-			cv_.wait(lock, [&] { return w.issued > b || !error_.empty(); });
+			cv_.wait(lock, [&] { return w.issued > b || !error_.empty() || bad_input_; });
+			if (bad_input_) throw std::invalid_argument("a sequence contains bytes outside {A,C,G,T,!}");
 			if (!error_.empty()) throw CudaError("staging copy failed: " + error_);
 			CUDA_CHECK(cudaStreamWaitEvent(s, w.batch_ev[b], 0));
 		}
@@ -135,7 +178,8 @@ class HostStager
 	struct Worker {
 		std::thread th;
 		cudaStream_t stream = nullptr;
-		uint8_t *ring = nullptr;
+		uint8_t *ring = nullptr;  // pinned: SLOTS x (packed piece, '!' list)
+		uint8_t *dring = nullptr; // the same on the device
 		cudaEvent_t slot_ev[SLOTS] = {};
 		std::vector<cudaEvent_t> batch_ev;
 		int issued = 0; // batches whose events have been recorded (guarded by mu_)
@@ -149,6 +193,7 @@ class HostStager
 				cudaStreamDestroy(w.stream);
 			}
 			if (w.ring) cudaFreeHost(w.ring);
+			if (w.dring) cudaFree(w.dring);
 			for (auto e : w.slot_ev)
 				if (e) cudaEventDestroy(e);
 			for (auto e : w.batch_ev)
@@ -179,9 +224,38 @@ class HostStager
 			const int slot = (int)(used++ % SLOTS);
 			e = cudaEventSynchronize(w.slot_ev[slot]); // the copy that last used this slot has left it
 			if (e != cudaSuccess) break;
-			uint8_t *stage = w.ring + (size_t)slot * SLOT_BYTES;
-			std::memcpy(stage, p.src, p.len);
-			e = cudaMemcpyAsync(p.dst, stage, p.len, cudaMemcpyHostToDevice, w.stream);
+			uint8_t *hp = w.ring + (size_t)slot * SLOT_BYTES, *dp = w.dring + (size_t)slot * SLOT_BYTES;
+			uint32_t *hb = reinterpret_cast<uint32_t *>(hp + PACKED_BYTES);
+			uint32_t nb = 0;
+			if (pack_2bit(p.src, p.len, hp, hb, BANG_CAP, &nb)) {
+				std::lock_guard<std::mutex> lock(mu_);
+				bad_input_ = true;
+				abort_ = true;
+				cv_.notify_all();
+				break;
+			}
+			if (nb > BANG_CAP) {
+				// a piece that is mostly separators: as it is (the driver stages it if need be)
+				e = cudaMemcpyAsync(p.dst, p.src, p.len, cudaMemcpyHostToDevice, w.stream);
+			} else {
+				const size_t pbytes = ((size_t)p.len + 3) / 4;
+				e = cudaMemcpyAsync(dp, hp, (pbytes + 3) / 4 * 4, cudaMemcpyHostToDevice, w.stream);
+				if (e == cudaSuccess) {
+					k_unpack_2bit<<<(unsigned)((p.len + 16 * 256 - 1) / (16 * 256)), 256, 0, w.stream>>>(
+						reinterpret_cast<const uint32_t *>(dp), p.dst, p.len);
+					g_kernel_launches++;
+					e = cudaGetLastError();
+				}
+				if (e == cudaSuccess && nb) {
+					e = cudaMemcpyAsync(dp + PACKED_BYTES, hb, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, w.stream);
+					if (e == cudaSuccess) {
+						k_put_bangs<<<(nb + 255) / 256, 256, 0, w.stream>>>(
+							p.dst, reinterpret_cast<const uint32_t *>(dp + PACKED_BYTES), nb);
+						g_kernel_launches++;
+						e = cudaGetLastError();
+					}
+				}
+			}
 			if (e != cudaSuccess) break;
 			e = cudaEventRecord(w.slot_ev[slot], w.stream);
 		}
@@ -199,6 +273,7 @@ class HostStager
 	std::mutex mu_;
 	std::condition_variable cv_;
 	std::string error_;
+	bool bad_input_ = false; // guarded by mu_
 	std::atomic<bool> abort_{false};
 	bool running_ = false;
 	int device_ = 0, nbatches_ = 0;

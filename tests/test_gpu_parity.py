@@ -777,6 +777,32 @@ def test_batched_process_from_ordinary_memory(pb, oracle, threads, flags):
         assert np.array_equal(out[0], want["subst"]) and np.array_equal(out[1], want["homologs"])
 
 
+def test_upload_paths_agree(pb, oracle):
+    """sequences cross PCIe packed to 2 bits per base (default) or as bytes (upload_raw); a
+    piece with more separators than the packed form lists (4096) goes over as it is"""
+    rng = np.random.default_rng(31)
+    r = datasets.random_dna(rng, 120000)
+    shredded = b"!".join(r[k : k + 20] for k in range(0, 110000, 20))  # 5500 contigs of 20 bases
+    genomes = [r, datasets.mutate(rng, r, 0.01), shredded, datasets.revcomp(datasets.mutate(rng, r, 0.02))]
+    want = oracle.process(genomes, 0, 0, threads=4)
+    for raw in (0, 1):
+        with pb.Context(upload_raw=raw) as c:
+            subst, homol = c.process(genomes, 0, 0)
+            assert c.stat("process.packed") == 1 - raw
+            assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"]), raw
+            thr = pb.threshold_for(r)
+            c.esa_build(r)
+            c.map_queries(genomes, thr)
+            s2, h2 = c.compare_all()
+            assert np.array_equal(s2, want["subst"]) and np.array_equal(h2, want["homologs"]), raw
+            with pytest.raises(pb.PhyloError):
+                c.process([r, r[:5000] + b"N" + r[5000:]], 0, 0)
+            with pytest.raises(pb.PhyloError):
+                c.process([r, r[:70000] + b"a"], 0, 0)
+            subst, homol = c.process(genomes, 0, 0)  # still usable
+            assert np.array_equal(homol, want["homologs"])
+
+
 def test_properties_without_oracle(pb, ctx):
     """size-independent properties: symmetric matrix, zero diagonal, identical genomes have
     distance zero and full coverage, subst <= homologs <= min(lengths)"""
