@@ -92,6 +92,9 @@ int phylo_set_stream(phylo_ctx *ctx, void *stream);
  *              pass, 2 = single-pass look-back ("onesweep")
  *   "stage_threads" worker threads that pack the sequences of phylo_process / phylo_map_queries
  *               to 2 bits per base for the trip over PCIe; 0 = from the core count (default)
+ *   "compare_path" how the all-pairs kernel brings the row tiles into shared memory: 0 = tensor
+ *               copies (TMA) through a 3-stage transaction-barrier pipeline (default), 1 =
+ *               cp.async by all threads, double buffered (kept for comparison)
  *   "upload_raw" 1 = send the bytes as they are (asynchronous from pinned memory, staged by the
  *               driver otherwise) instead of packing them on the host; default 0
  *   "keep_raw" keep unsorted/unfiltered homology lists for phylo_get_homologies(raw=1)

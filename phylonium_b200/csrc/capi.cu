@@ -639,6 +639,9 @@ int phylo_set_option(phylo_ctx *c, const char *key, int64_t value)
 		} else if (k == "key_chars") {
 			if (value < 0 || value > 21) throw std::invalid_argument("key_chars must be in [0, 21]");
 			c->opt_key_chars = value;
+		} else if (k == "compare_path") {
+			if (value < 0 || value > 1) throw std::invalid_argument("compare_path must be 0 or 1");
+			c->tuning.compare_path = (int)value;
 		} else if (k == "upload_raw") {
 			c->tuning.upload_raw = value != 0;
 		} else if (k == "stage_threads") {
@@ -1055,8 +1058,10 @@ struct Uploader {
 					if (k != first && lens[k]) c->stager.add(dq + offs[k], seqs[k], lens[k], (int)b);
 			int threads = (int)c->opt_stage_threads;
 			if (threads <= 0) {
+				// packing runs at ~6 GB/s per core and has to keep up with 4 x the bus: all cores but
+				// two (the calling thread launches kernels meanwhile), at most 16
 				const unsigned hw = std::thread::hardware_concurrency();
-				threads = hw >= 16 ? 8 : hw >= 8 ? 4 : hw >= 4 ? 2 : 1;
+				threads = hw > 18 ? 16 : hw > 3 ? (int)hw - 2 : 1;
 			}
 			if (!c->stager.empty()) c->stager.start(c->device, (int)ends.size(), threads, c->ev_main);
 		} else {

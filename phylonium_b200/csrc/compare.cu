@@ -20,6 +20,8 @@
 #include "compare_device.h"
 #include "primitives.cuh"
 
+#include <cuda.h> // CUtensorMap (types only: the encoder is fetched through the runtime)
+
 namespace phy
 {
 
@@ -163,11 +165,11 @@ __host__ __device__ constexpr int cmp_threads(int CT)
 // words per lane and step: the 3-plane path adds up three words per pair with one carry-save
 // step before it counts bits; the 5-plane path (reverse strands, separators) goes word by word
 constexpr int CMP_WPL_FAST = 3, CMP_WPL_FULL = 1;
-__host__ __device__ constexpr size_t cmp_smem_bytes(int CT)
+__host__ __device__ constexpr size_t cmp_smem_bytes(int CT, int stages)
 {
-	// two buffers of 2 CT genomes x planes x (32 * words per lane) words; the larger of the two paths
-	const size_t fast = (size_t)2 * 2 * CT * 3 * 32 * CMP_WPL_FAST, full = (size_t)2 * 2 * CT * ROW_PLANES * 32 * CMP_WPL_FULL;
-	return (fast > full ? fast : full) * sizeof(uint32_t);
+	// `stages` buffers of 2 CT genomes x planes x (32 * words per lane) words; the larger of the two paths
+	const size_t fast = (size_t)2 * CT * 3 * 32 * CMP_WPL_FAST, full = (size_t)2 * CT * ROW_PLANES * 32 * CMP_WPL_FULL;
+	return (size_t)stages * (fast > full ? fast : full) * sizeof(uint32_t);
 }
 
 __device__ __forceinline__ void cmp_cp_async16(void *smem_dst, const void *gsrc, int src_bytes)
@@ -184,6 +186,53 @@ template <uint32_t K> __device__ __forceinline__ uint32_t cmp_mad(uint32_t x, ui
 	return r;
 }
 
+// ---- TMA + mbarrier plumbing (Blackwell tile movement: one thread issues a tensor copy per
+// tile side and step, the data lands in shared memory and completes a transaction barrier) ----
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	asm volatile("{\n"
+	             ".reg .pred p;\n"
+	             "CMP_WAIT:\n"
+	             "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	             "@p bra CMP_DONE;\n"
+	             "bra CMP_WAIT;\n"
+	             "CMP_DONE:\n"
+	             "}" ::"r"(smem_u32(bar)),
+	             "r"(parity)
+	             : "memory");
+}
+// box of the 3-d tensor (word, plane, genome) at (w, 0, g) -> shared memory, completes on bar
+__device__ __forceinline__ void tma_load_rows(void *smem_dst, const CUtensorMap *tm, int32_t w, int32_t g, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+	             :
+	             : "r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(w), "r"(0), "r"(g)
+	             : "memory");
+}
+
+constexpr int CMP_STAGES = 3; // shared-memory stages of the TMA pipeline
+
 // One (tile pair, chunk) unit.  P = planes to look at (3: V, C0, C1; 5: all), WPL = words per
 // lane and step.  Per pair and word: both = Va & Vb, diff = both & (codes differ [or, on the
 // same strand, '!' flags differ]).  The two counts of a pair share one register (homologous
@@ -195,11 +244,19 @@ template <uint32_t K> __device__ __forceinline__ uint32_t cmp_mad(uint32_t x, ui
 // With WPL = 3 the three words of a pair go through one full-adder step first,
 //     ones = x0 ^ x1 ^ x2,  twos = maj(x0, x1, x2),  count = popc(ones) + 2 popc(twos),
 // two POPC instead of three for two more LOP3: logic and XU pipes come out even.
-template <int P, int CT, int WPL>
-__device__ __forceinline__ void compare_tile(uint32_t *stage, const uint32_t *__restrict__ rows, int64_t genome_words,
-                                             int64_t W, int64_t N, int64_t gi0, int64_t gj0, int64_t w_begin, int64_t w_end,
-                                             const uint32_t *__restrict__ vall, unsigned long long *__restrict__ subst,
-                                             unsigned long long *__restrict__ homol)
+//
+// Tile movement, TMA = true: per step ONE thread issues two tensor copies (the I and the J
+// genomes' planes, a box of STEP words x P planes x CT genomes each; out-of-range genomes and
+// words arrive as zeros) into one of CMP_STAGES stages; the warps wait on the stage's "full"
+// transaction barrier, compute, and release the stage through its "empty" barrier — no block-
+// wide barrier in the loop, no per-thread address arithmetic.  TMA = false is the Ampere-style
+// path (cp.async by all threads, double buffered, one __syncthreads per step), kept for A/B
+// measurements (option "compare_path").
+template <int P, int CT, int WPL, bool TMA>
+__device__ __forceinline__ void compare_tile(uint32_t *stage, const uint32_t *__restrict__ rows, const CUtensorMap *tm,
+                                             int64_t genome_words, int64_t W, int64_t N, int64_t gi0, int64_t gj0,
+                                             int64_t w_begin, int64_t w_end, const uint32_t *__restrict__ vall,
+                                             unsigned long long *__restrict__ subst, unsigned long long *__restrict__ homol)
 {
 	constexpr int STEP = 32 * WPL;                  // words per genome plane and step
 	constexpr int SLOT_WORDS = P * STEP;            // stage[buf][slot][plane][STEP]: slots 0..CT-1 the I genomes, then J
@@ -210,19 +267,6 @@ __device__ __forceinline__ void compare_tile(uint32_t *stage, const uint32_t *__
 	constexpr int FLUSH_STEPS = 65535 / STEP; // a lane adds at most STEP per step to either half
 	static_assert(SUBS % WARPS == 0 && SPW >= 1, "sub-tiles per warp");
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-	auto prefetch = [&](int64_t w0, int buf) {
-		for (int piece = threadIdx.x; piece < PIECES; piece += THREADS) {
-			const int slot = piece / (P * (STEP / 4)), rem = piece % (P * (STEP / 4)), plane = rem / (STEP / 4),
-			          part = rem % (STEP / 4);
-			const int64_t g = slot < CT ? gi0 + slot : gj0 + (slot - CT);
-			const int64_t w = w0 + 4 * part;
-			const bool ok = g < N && w < w_end; // w_end and W are multiples of 4
-			const uint32_t *src = rows + (ok ? g * genome_words + plane * W + w : 0);
-			cmp_cp_async16(stage + buf * BUF_WORDS + slot * SLOT_WORDS + plane * STEP + 4 * part, src, ok ? 16 : 0);
-		}
-		asm volatile("cp.async.commit_group;\n" ::: "memory");
-	};
 
 	// sub-tiles of padding genomes, or below the diagonal of a diagonal tile, have nothing to count
 	bool active[SPW];
@@ -264,14 +308,9 @@ __device__ __forceinline__ void compare_tile(uint32_t *stage, const uint32_t *__
 			}
 		}
 	};
-
-	prefetch(w_begin, 0);
-	int buf = 0, steps = 0;
-	for (int64_t w0 = w_begin; w0 < w_end; w0 += STEP, buf ^= 1) {
-		asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-		__syncthreads(); // this step's words are in; everybody is done with the other buffer
-		if (w0 + STEP < w_end) prefetch(w0 + STEP, buf ^ 1);
-		const uint32_t *st = stage + buf * BUF_WORDS + lane;
+	// the 2 CT genomes' words [w0, w0 + STEP) sit in buf: count them into acc
+	auto compute = [&](const uint32_t *buf, int64_t w0) {
+		const uint32_t *st = buf + lane;
 		uint32_t mask[WPL];
 #pragma unroll
 		for (int k = 0; k < WPL; k++)
@@ -340,26 +379,98 @@ __device__ __forceinline__ void compare_tile(uint32_t *stage, const uint32_t *__
 				}
 			}
 		}
-		if (++steps == FLUSH_STEPS) {
-			flush();
-			steps = 0;
+	};
+
+	if constexpr (TMA) {
+		__shared__ __align__(8) uint64_t full_bar[CMP_STAGES], empty_bar[CMP_STAGES];
+		constexpr uint32_t STAGE_BYTES = BUF_WORDS * sizeof(uint32_t);
+		const int nsteps = (int)((w_end - w_begin + STEP - 1) / STEP);
+		if (threadIdx.x == 0) {
+#pragma unroll
+			for (int sidx = 0; sidx < CMP_STAGES; sidx++) {
+				mbar_init(&full_bar[sidx], 1);
+				mbar_init(&empty_bar[sidx], WARPS);
+			}
+			mbar_fence_init();
 		}
+		__syncthreads();
+		auto issue = [&](int n) { // thread 0: step n into stage n % CMP_STAGES
+			const int sidx = n % CMP_STAGES;
+			uint32_t *dst = stage + sidx * BUF_WORDS;
+			const int32_t w = (int32_t)(w_begin + (int64_t)n * STEP);
+			mbar_expect_tx(&full_bar[sidx], STAGE_BYTES);
+			tma_load_rows(dst, tm, w, (int32_t)gi0, &full_bar[sidx]);
+			tma_load_rows(dst + CT * SLOT_WORDS, tm, w, (int32_t)gj0, &full_bar[sidx]);
+		};
+		if (threadIdx.x == 0)
+			for (int n = 0; n < CMP_STAGES - 1 && n < nsteps; n++)
+				issue(n);
+		int steps = 0;
+		for (int it = 0; it < nsteps; it++) {
+			const int sidx = it % CMP_STAGES;
+			if (threadIdx.x == 0) {
+				// step it + STAGES - 1 goes into the stage step it - 1 used: once every warp has let go of it
+				const int nxt = it + CMP_STAGES - 1;
+				if (nxt < nsteps) {
+					if (it >= 1) mbar_wait(&empty_bar[nxt % CMP_STAGES], (uint32_t)(((it - 1) / CMP_STAGES) & 1));
+					issue(nxt);
+				}
+			}
+			__syncwarp();
+			mbar_wait(&full_bar[sidx], (uint32_t)((it / CMP_STAGES) & 1));
+			compute(stage + sidx * BUF_WORDS, w_begin + (int64_t)it * STEP);
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&empty_bar[sidx]);
+			if (++steps == FLUSH_STEPS) {
+				flush();
+				steps = 0;
+			}
+		}
+		flush();
+	} else {
+		auto prefetch = [&](int64_t w0, int buf) {
+			for (int piece = threadIdx.x; piece < PIECES; piece += THREADS) {
+				const int slot = piece / (P * (STEP / 4)), rem = piece % (P * (STEP / 4)), plane = rem / (STEP / 4),
+				          part = rem % (STEP / 4);
+				const int64_t g = slot < CT ? gi0 + slot : gj0 + (slot - CT);
+				const int64_t w = w0 + 4 * part;
+				const bool ok = g < N && w < w_end; // w_end and W are multiples of 4
+				const uint32_t *src = rows + (ok ? g * genome_words + plane * W + w : 0);
+				cmp_cp_async16(stage + buf * BUF_WORDS + slot * SLOT_WORDS + plane * STEP + 4 * part, src, ok ? 16 : 0);
+			}
+			asm volatile("cp.async.commit_group;\n" ::: "memory");
+		};
+		prefetch(w_begin, 0);
+		int buf = 0, steps = 0;
+		for (int64_t w0 = w_begin; w0 < w_end; w0 += STEP, buf ^= 1) {
+			asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+			__syncthreads(); // this step's words are in; everybody is done with the other buffer
+			if (w0 + STEP < w_end) prefetch(w0 + STEP, buf ^ 1);
+			compute(stage + buf * BUF_WORDS, w0);
+			if (++steps == FLUSH_STEPS) {
+				flush();
+				steps = 0;
+			}
+		}
+		flush();
 	}
-	flush();
 }
 
 // Work units are (tile pair, chunk of columns).  Tile pairs (ti <= tj) are numbered column by
 // column, tp = tj (tj + 1) / 2 + ti, so that "all pairs whose later tile is in [tj0, tj1)" —
 // what becomes computable when another batch of genomes has been mapped — is one range of
 // tp.  Unit u of this launch is tile pair tp_begin + (u * tile_world + tile_rank) / chunks.
-template <int CT>
+// tm_fast / tm_full: tensor maps of the row store with the boxes of the 3-plane and the
+// 5-plane path (TMA = true).
+template <int CT, bool TMA>
 __global__ void __launch_bounds__(cmp_threads(CT), CT == 16 ? 2 : 4)
-k_compare_tiles(const uint32_t *__restrict__ rows, int64_t genome_words, int64_t W, int64_t N, int64_t tp_begin,
+k_compare_tiles(const __grid_constant__ CUtensorMap tm_fast, const __grid_constant__ CUtensorMap tm_full,
+                const uint32_t *__restrict__ rows, int64_t genome_words, int64_t W, int64_t N, int64_t tp_begin,
                 int64_t units, int32_t chunks, int64_t chunk_words, int tile_rank, int tile_world,
                 const uint32_t *__restrict__ vall, unsigned long long *__restrict__ subst,
                 unsigned long long *__restrict__ homol)
 {
-	extern __shared__ __align__(16) uint32_t cmp_stage[];
+	extern __shared__ __align__(128) uint32_t cmp_stage[];
 	__shared__ uint32_t tile_flags;
 	const int64_t unit = (int64_t)blockIdx.x * tile_world + tile_rank; // units are dealt round-robin
 	if (unit >= units) return;
@@ -387,9 +498,11 @@ k_compare_tiles(const uint32_t *__restrict__ rows, int64_t genome_words, int64_t
 	}
 	__syncthreads();
 	if (tile_flags)
-		compare_tile<5, CT, CMP_WPL_FULL>(cmp_stage, rows, genome_words, W, N, gi0, gj0, w_begin, w_end, vall, subst, homol);
+		compare_tile<5, CT, CMP_WPL_FULL, TMA>(cmp_stage, rows, &tm_full, genome_words, W, N, gi0, gj0, w_begin, w_end, vall,
+		                                       subst, homol);
 	else
-		compare_tile<3, CT, CMP_WPL_FAST>(cmp_stage, rows, genome_words, W, N, gi0, gj0, w_begin, w_end, vall, subst, homol);
+		compare_tile<3, CT, CMP_WPL_FAST, TMA>(cmp_stage, rows, &tm_fast, genome_words, W, N, gi0, gj0, w_begin, w_end, vall,
+		                                       subst, homol);
 }
 
 // seg[w] = core columns where some genome differs from genome 0 (process.cxx:484-490:
@@ -497,6 +610,36 @@ void rows_build(RowStore &rs, int64_t first_row, const uint8_t *d_Q, const Query
 	}
 }
 
+namespace
+{
+// Tensor map of the row store as a 3-d tensor of 32-bit words (word, plane, genome) whose box
+// is what one tile side needs per step: step_words x planes x CT.  Words past W and genomes
+// past the store read as zeros.  cuTensorMapEncodeTiled is a driver entry point; it is fetched
+// through the runtime so that the library does not link against libcuda.
+void rows_tensor_map(const RowStore &rs, int step_words, int planes, int CT, CUtensorMap *out)
+{
+	using Encode = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+	                            const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+	                            CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+	static Encode encode = nullptr;
+	if (!encode) {
+		void *fn = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+		if (q != cudaDriverEntryPointSuccess || !fn) throw CudaError("cuTensorMapEncodeTiled is not available in this driver");
+		encode = (Encode)fn;
+	}
+	const cuuint64_t dims[3] = {(cuuint64_t)rs.W, (cuuint64_t)ROW_PLANES, (cuuint64_t)rs.genomes};
+	const cuuint64_t strides[2] = {(cuuint64_t)rs.W * sizeof(uint32_t), (cuuint64_t)rs.genome_words() * sizeof(uint32_t)};
+	const cuuint32_t box[3] = {(cuuint32_t)step_words, (cuuint32_t)planes, (cuuint32_t)CT};
+	const cuuint32_t elem[3] = {1, 1, 1};
+	const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, rs.data.get(), dims, strides, box, elem,
+	                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+	                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed for the row store (code " + std::to_string((int)r) + ")");
+}
+} // namespace
+
 int compare_tile_side(int64_t N)
 {
 	return N <= 24 ? 8 : 16; // sharding.py mirrors this choice
@@ -535,27 +678,46 @@ void compare_all_device(const RowStore &rs, int64_t N, bool complete_deletion, i
 		if (chunks > max_chunks) chunks = max_chunks;
 		if (chunks < 1) chunks = 1;
 		int64_t chunk_words = (rs.W + chunks - 1) / chunks;
-		chunk_words = (chunk_words + 31) / 32 * 32;
+		chunk_words = (chunk_words + 95) / 96 * 96; // whole steps of both paths (96 and 32 words): a tensor copy never straddles a chunk end
 		chunks = (rs.W + chunk_words - 1) / chunk_words;
 		const int64_t units = n_tile_pairs * chunks;
 		const int64_t my_units = (units - tile_rank + tile_world - 1) / tile_world;
+		const bool tma = g_tuning.compare_path == 0;
+		const int stages = tma ? CMP_STAGES : 2;
 		static PerDeviceOnce once;
 		if (once.first()) {
-			CUDA_CHECK(cudaFuncSetAttribute(k_compare_tiles<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-			                                (int)cmp_smem_bytes(16)));
-			CUDA_CHECK(cudaFuncSetAttribute(k_compare_tiles<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-			                                (int)cmp_smem_bytes(8)));
+			CUDA_CHECK(cudaFuncSetAttribute(k_compare_tiles<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                                (int)cmp_smem_bytes(16, CMP_STAGES)));
+			CUDA_CHECK(cudaFuncSetAttribute(k_compare_tiles<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                                (int)cmp_smem_bytes(8, CMP_STAGES)));
+			CUDA_CHECK(cudaFuncSetAttribute(k_compare_tiles<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                                (int)cmp_smem_bytes(16, 2)));
+			CUDA_CHECK(cudaFuncSetAttribute(k_compare_tiles<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                                (int)cmp_smem_bytes(8, 2)));
 		}
 		if (my_units > 0x7fffffffll) throw std::invalid_argument("too many tile pairs for one launch");
 		if (my_units > 0) {
-			if (CT == 16)
-				k_compare_tiles<16><<<(unsigned)my_units, cmp_threads(16), cmp_smem_bytes(16), s>>>(
-					rs.data.get(), rs.genome_words(), rs.W, N, tp_begin, units, (int32_t)chunks, chunk_words, tile_rank,
-					tile_world, vall.get(), d_subst, d_homologs);
+			CUtensorMap tm_fast, tm_full;
+			memset(&tm_fast, 0, sizeof tm_fast);
+			memset(&tm_full, 0, sizeof tm_full);
+			if (tma) {
+				rows_tensor_map(rs, 32 * CMP_WPL_FAST, 3, CT, &tm_fast);
+				rows_tensor_map(rs, 32 * CMP_WPL_FULL, ROW_PLANES, CT, &tm_full);
+			}
+			const size_t smem = cmp_smem_bytes(CT, stages);
+#define PHY_LAUNCH_COMPARE(CTV, TMAV)                                                                                    \
+	k_compare_tiles<CTV, TMAV><<<(unsigned)my_units, cmp_threads(CTV), smem, s>>>(                                       \
+		tm_fast, tm_full, rs.data.get(), rs.genome_words(), rs.W, N, tp_begin, units, (int32_t)chunks, chunk_words,      \
+		tile_rank, tile_world, vall.get(), d_subst, d_homologs)
+			if (CT == 16 && tma)
+				PHY_LAUNCH_COMPARE(16, true);
+			else if (CT == 16)
+				PHY_LAUNCH_COMPARE(16, false);
+			else if (tma)
+				PHY_LAUNCH_COMPARE(8, true);
 			else
-				k_compare_tiles<8><<<(unsigned)my_units, cmp_threads(8), cmp_smem_bytes(8), s>>>(
-					rs.data.get(), rs.genome_words(), rs.W, N, tp_begin, units, (int32_t)chunks, chunk_words, tile_rank,
-					tile_world, vall.get(), d_subst, d_homologs);
+				PHY_LAUNCH_COMPARE(8, false);
+#undef PHY_LAUNCH_COMPARE
 			KERNEL_CHECK();
 		}
 	}

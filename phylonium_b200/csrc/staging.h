@@ -94,14 +94,14 @@ class HostStager
 	bool empty() const { return pending_.empty(); }
 
 	// `after`: an event (of another stream) the copies must not overtake, e.g. the clearing of
-	// the destination buffer
+	// the destination buffer.  The worker threads live as long as the stager (a call of
+	// phylo_process on 8 x 5 Mbp takes 2 ms: creating threads per call would show).
 	void start(int device, int nbatches, int threads, cudaEvent_t after)
 	{
 		finish();
 		pieces_.swap(pending_);
 		pending_.clear();
 		if (threads < 1) threads = 1;
-		if ((size_t)threads > pieces_.size()) threads = (int)(pieces_.size() ? pieces_.size() : 1);
 		device_ = device;
 		nbatches_ = nbatches;
 		abort_ = false;
@@ -117,6 +117,9 @@ class HostStager
 				for (auto &e : w.slot_ev)
 					CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 			}
+			quit_ = false;
+			for (int t = 0; t < threads; t++)
+				workers_[t].th = std::thread([this, t, g = generation_] { thread_main(t, g); }); // jobs posted from now on
 		}
 		for (auto &w : workers_) {
 			while ((int)w.batch_ev.size() < nbatches) {
@@ -124,12 +127,17 @@ class HostStager
 				CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 				w.batch_ev.push_back(e);
 			}
-			w.issued = 0;
 			if (after) CUDA_CHECK(cudaStreamWaitEvent(w.stream, after, 0));
 		}
-		running_ = true;
-		for (int t = 0; t < threads; t++)
-			workers_[t].th = std::thread([this, t] { run(t); });
+		{
+			std::lock_guard<std::mutex> lock(mu_);
+			for (auto &w : workers_)
+				w.issued = 0;
+			done_ = 0;
+			generation_++;
+			running_ = true;
+		}
+		cv_job_.notify_all();
 	}
 
 	// blocks until every worker has issued its copies of batch b, then puts `s` behind them;
@@ -146,14 +154,15 @@ class HostStager
 		}
 	}
 
-	// joins the workers; with abort they stop at the next piece.  Afterwards nothing reads the
-	// caller's buffers any more (the copies out of the pinned rings may still be in flight).
+	// waits until the workers are through with the job; with abort they stop at the next piece.
+	// Afterwards nothing reads the caller's buffers any more (the copies out of the pinned
+	// rings may still be in flight).
 	void finish(bool abort = false)
 	{
 		if (!running_) return;
 		if (abort) abort_ = true;
-		for (auto &w : workers_)
-			if (w.th.joinable()) w.th.join();
+		std::unique_lock<std::mutex> lock(mu_);
+		cv_.wait(lock, [&] { return done_ == (int)workers_.size(); });
 		running_ = false;
 		pieces_.clear();
 	}
@@ -187,6 +196,13 @@ class HostStager
 
 	void release_workers()
 	{
+		{
+			std::lock_guard<std::mutex> lock(mu_);
+			quit_ = true;
+		}
+		cv_job_.notify_all();
+		for (auto &w : workers_)
+			if (w.th.joinable()) w.th.join();
 		for (auto &w : workers_) {
 			if (w.stream) {
 				cudaStreamSynchronize(w.stream);
@@ -200,6 +216,24 @@ class HostStager
 				cudaEventDestroy(e);
 		}
 		workers_.clear();
+	}
+
+	void thread_main(int t, uint64_t seen)
+	{
+		for (;;) {
+			{
+				std::unique_lock<std::mutex> lock(mu_);
+				cv_job_.wait(lock, [&] { return quit_ || generation_ != seen; });
+				if (quit_) return;
+				seen = generation_;
+			}
+			run(t);
+			{
+				std::lock_guard<std::mutex> lock(mu_);
+				done_++;
+			}
+			cv_.notify_all();
+		}
 	}
 
 	void run(int t)
@@ -271,7 +305,10 @@ class HostStager
 	std::vector<Piece> pieces_;  // what the running workers read
 	std::vector<Worker> workers_;
 	std::mutex mu_;
-	std::condition_variable cv_;
+	std::condition_variable cv_, cv_job_;
+	uint64_t generation_ = 0; // guarded by mu_: bumped per job
+	int done_ = 0;            // workers through with the current job
+	bool quit_ = false;
 	std::string error_;
 	bool bad_input_ = false; // guarded by mu_
 	std::atomic<bool> abort_{false};
