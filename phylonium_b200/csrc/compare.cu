@@ -123,11 +123,12 @@ __global__ void k_build_rows(uint32_t *__restrict__ rows, int64_t genome_words, 
 		}
 	}
 	uint32_t *row = rows + (first_row + k) * genome_words;
-	row[PL_V * W + w] = pv;
-	row[PL_C0 * W + w] = p0;
-	row[PL_C1 * W + w] = p1;
-	row[PL_D * W + w] = pd;
-	row[PL_B * W + w] = pb;
+	uint32_t *at = row + row_word(0, w); // the five planes of a block are ROW_BLK words apart
+	at[PL_V * ROW_BLK] = pv;
+	at[PL_C0 * ROW_BLK] = p0;
+	at[PL_C1 * ROW_BLK] = p1;
+	at[PL_D * ROW_BLK] = pd;
+	at[PL_B * ROW_BLK] = pb;
 	// flag words behind the planes: does this genome use the D / B planes at all?  The second
 	// word marks the row as written (the padding rows of a sharded store never are).
 	const uint32_t f = (pd ? ROW_FLAG_D : 0u) | (pb ? ROW_FLAG_B : 0u);
@@ -149,7 +150,7 @@ __global__ void k_and_valid(const uint32_t *__restrict__ rows, int64_t genome_wo
 	uint32_t v = 0xffffffffu;
 	for (int64_t g = 0; g < N; g++) {
 		const uint32_t *row = rows + g * genome_words;
-		if (row[ROW_PLANES * W + ROW_WORD_REAL]) v &= row[PL_V * W + w];
+		if (row[ROW_PLANES * W + ROW_WORD_REAL]) v &= row[row_word(PL_V, w)];
 	}
 	vall[w] = v;
 }
@@ -165,11 +166,12 @@ __host__ __device__ constexpr int cmp_threads(int CT)
 // words per lane and step: the 3-plane path adds up three words per pair with one carry-save
 // step before it counts bits; the 5-plane path (reverse strands, separators) goes word by word
 constexpr int CMP_WPL_FAST = 3, CMP_WPL_FULL = 1;
-__host__ __device__ constexpr size_t cmp_smem_bytes(int CT, int stages)
+__host__ __device__ constexpr size_t cmp_smem_bytes(int CT, int fast_stages)
 {
-	// `stages` buffers of 2 CT genomes x planes x (32 * words per lane) words; the larger of the two paths
-	const size_t fast = (size_t)2 * CT * 3 * 32 * CMP_WPL_FAST, full = (size_t)2 * CT * ROW_PLANES * 32 * CMP_WPL_FULL;
-	return (size_t)stages * (fast > full ? fast : full) * sizeof(uint32_t);
+	// buffers of 2 CT genomes x planes x (32 * words per lane) words: `fast_stages` of the 3-plane
+	// path, two of the 5-plane path; the larger of the two
+	const size_t fast = (size_t)fast_stages * 2 * CT * 3 * 32 * CMP_WPL_FAST, full = (size_t)2 * 2 * CT * ROW_PLANES * 32 * CMP_WPL_FULL;
+	return (fast > full ? fast : full) * sizeof(uint32_t);
 }
 
 __device__ __forceinline__ void cmp_cp_async16(void *smem_dst, const void *gsrc, int src_bytes)
@@ -222,12 +224,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 	             "r"(parity)
 	             : "memory");
 }
-// box of the 3-d tensor (word, plane, genome) at (w, 0, g) -> shared memory, completes on bar
-__device__ __forceinline__ void tma_load_rows(void *smem_dst, const CUtensorMap *tm, int32_t w, int32_t g, uint64_t *bar)
+// box of the 3-d tensor (word of a block, block, genome) at (0, blk, g) -> shared memory,
+// completes on bar
+__device__ __forceinline__ void tma_load_rows(void *smem_dst, const CUtensorMap *tm, int32_t blk, int32_t g, uint64_t *bar)
 {
 	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
 	             :
-	             : "r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(w), "r"(0), "r"(g)
+	             : "r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(0), "r"(blk), "r"(g)
 	             : "memory");
 }
 
@@ -245,9 +248,9 @@ constexpr int CMP_STAGES = 3; // shared-memory stages of the TMA pipeline
 //     ones = x0 ^ x1 ^ x2,  twos = maj(x0, x1, x2),  count = popc(ones) + 2 popc(twos),
 // two POPC instead of three for two more LOP3: logic and XU pipes come out even.
 //
-// Tile movement, TMA = true: per step ONE thread issues two tensor copies (the I and the J
-// genomes' planes, a box of STEP words x P planes x CT genomes each; out-of-range genomes and
-// words arrive as zeros) into one of CMP_STAGES stages; the warps wait on the stage's "full"
+// Tile movement, TMA = true (3-plane path): per step ONE thread issues two tensor copies (the I
+// and the J genomes: CT runs of 1152 contiguous bytes each, thanks to the interleaved row
+// layout; out-of-range genomes and blocks arrive as zeros) into one of CMP_STAGES stages; the warps wait on the stage's "full"
 // transaction barrier, compute, and release the stage through its "empty" barrier — no block-
 // wide barrier in the loop, no per-thread address arithmetic.  TMA = false is the Ampere-style
 // path (cp.async by all threads, double buffered, one __syncthreads per step), kept for A/B
@@ -394,13 +397,14 @@ __device__ __forceinline__ void compare_tile(uint32_t *stage, const uint32_t *__
 			mbar_fence_init();
 		}
 		__syncthreads();
+		static_assert(STEP == ROW_BLK && P == 3, "the tensor map's box is one block of the first three planes");
 		auto issue = [&](int n) { // thread 0: step n into stage n % CMP_STAGES
 			const int sidx = n % CMP_STAGES;
 			uint32_t *dst = stage + sidx * BUF_WORDS;
-			const int32_t w = (int32_t)(w_begin + (int64_t)n * STEP);
+			const int32_t blk = (int32_t)((w_begin + (int64_t)n * STEP) / ROW_BLK); // chunks start on block borders
 			mbar_expect_tx(&full_bar[sidx], STAGE_BYTES);
-			tma_load_rows(dst, tm, w, (int32_t)gi0, &full_bar[sidx]);
-			tma_load_rows(dst + CT * SLOT_WORDS, tm, w, (int32_t)gj0, &full_bar[sidx]);
+			tma_load_rows(dst, tm, blk, (int32_t)gi0, &full_bar[sidx]);
+			tma_load_rows(dst + CT * SLOT_WORDS, tm, blk, (int32_t)gj0, &full_bar[sidx]);
 		};
 		if (threadIdx.x == 0)
 			for (int n = 0; n < CMP_STAGES - 1 && n < nsteps; n++)
@@ -435,7 +439,7 @@ __device__ __forceinline__ void compare_tile(uint32_t *stage, const uint32_t *__
 				const int64_t g = slot < CT ? gi0 + slot : gj0 + (slot - CT);
 				const int64_t w = w0 + 4 * part;
 				const bool ok = g < N && w < w_end; // w_end and W are multiples of 4
-				const uint32_t *src = rows + (ok ? g * genome_words + plane * W + w : 0);
+				const uint32_t *src = rows + (ok ? g * genome_words + row_word(plane, w) : 0); // a step never straddles a block
 				cmp_cp_async16(stage + buf * BUF_WORDS + slot * SLOT_WORDS + plane * STEP + 4 * part, src, ok ? 16 : 0);
 			}
 			asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -460,12 +464,13 @@ __device__ __forceinline__ void compare_tile(uint32_t *stage, const uint32_t *__
 // column, tp = tj (tj + 1) / 2 + ti, so that "all pairs whose later tile is in [tj0, tj1)" —
 // what becomes computable when another batch of genomes has been mapped — is one range of
 // tp.  Unit u of this launch is tile pair tp_begin + (u * tile_world + tile_rank) / chunks.
-// tm_fast / tm_full: tensor maps of the row store with the boxes of the 3-plane and the
-// 5-plane path (TMA = true).
+// tm_fast: tensor map of the row store for the 3-plane path (TMA = true).  Tiles that need all
+// five planes (reverse strands, separators) go word by word and fetch their five 128-byte
+// pieces per genome and step with cp.async: that many short runs are not what the tensor copy
+// engine is good at.
 template <int CT, bool TMA>
 __global__ void __launch_bounds__(cmp_threads(CT), CT == 16 ? 2 : 4)
-k_compare_tiles(const __grid_constant__ CUtensorMap tm_fast, const __grid_constant__ CUtensorMap tm_full,
-                const uint32_t *__restrict__ rows, int64_t genome_words, int64_t W, int64_t N, int64_t tp_begin,
+k_compare_tiles(const __grid_constant__ CUtensorMap tm_fast, const uint32_t *__restrict__ rows, int64_t genome_words, int64_t W, int64_t N, int64_t tp_begin,
                 int64_t units, int32_t chunks, int64_t chunk_words, int tile_rank, int tile_world,
                 const uint32_t *__restrict__ vall, unsigned long long *__restrict__ subst,
                 unsigned long long *__restrict__ homol)
@@ -498,8 +503,8 @@ k_compare_tiles(const __grid_constant__ CUtensorMap tm_fast, const __grid_consta
 	}
 	__syncthreads();
 	if (tile_flags)
-		compare_tile<5, CT, CMP_WPL_FULL, TMA>(cmp_stage, rows, &tm_full, genome_words, W, N, gi0, gj0, w_begin, w_end, vall,
-		                                       subst, homol);
+		compare_tile<5, CT, CMP_WPL_FULL, false>(cmp_stage, rows, nullptr, genome_words, W, N, gi0, gj0, w_begin, w_end, vall,
+		                                         subst, homol);
 	else
 		compare_tile<3, CT, CMP_WPL_FAST, TMA>(cmp_stage, rows, &tm_fast, genome_words, W, N, gi0, gj0, w_begin, w_end, vall,
 		                                       subst, homol);
@@ -512,12 +517,13 @@ __global__ void k_seg_sites(const uint32_t *__restrict__ rows, int64_t genome_wo
 {
 	const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (w >= W) return;
-	const uint32_t *r0 = rows + w;
-	const uint32_t a0 = r0[PL_C0 * W], a1 = r0[PL_C1 * W], ad = r0[PL_D * W], ab = r0[PL_B * W];
+	const int64_t at = row_word(0, w);
+	const uint32_t *r0 = rows + at;
+	const uint32_t a0 = r0[PL_C0 * ROW_BLK], a1 = r0[PL_C1 * ROW_BLK], ad = r0[PL_D * ROW_BLK], ab = r0[PL_B * ROW_BLK];
 	uint32_t any = 0;
 	for (int64_t g = 1; g < N; g++) {
-		const uint32_t *r = rows + g * genome_words + w;
-		any |= (a0 ^ r[PL_C0 * W]) | (a1 ^ r[PL_C1 * W]) | (~(ad ^ r[PL_D * W]) & (ab ^ r[PL_B * W]));
+		const uint32_t *r = rows + g * genome_words + at;
+		any |= (a0 ^ r[PL_C0 * ROW_BLK]) | (a1 ^ r[PL_C1 * ROW_BLK]) | (~(ad ^ r[PL_D * ROW_BLK]) & (ab ^ r[PL_B * ROW_BLK]));
 	}
 	seg[w] = any & core[w];
 }
@@ -580,7 +586,7 @@ __global__ void k_estimate(const unsigned long long *__restrict__ subst, const u
 void rows_alloc(RowStore &rs, int64_t genomes, int32_t n, cudaStream_t s)
 {
 	rs.n = n;
-	rs.W = (((int64_t)n + 31) / 32 + 3) / 4 * 4;
+	rs.W = (((int64_t)n + 31) / 32 + ROW_BLK - 1) / ROW_BLK * ROW_BLK;
 	rs.genomes = genomes;
 	rs.data.alloc((size_t)(genomes * rs.genome_words()), s);
 	rs.data.zero(); // rows never written (padding genomes of a sharded run) are all-invalid
@@ -612,11 +618,13 @@ void rows_build(RowStore &rs, int64_t first_row, const uint8_t *d_Q, const Query
 
 namespace
 {
-// Tensor map of the row store as a 3-d tensor of 32-bit words (word, plane, genome) whose box
-// is what one tile side needs per step: step_words x planes x CT.  Words past W and genomes
-// past the store read as zeros.  cuTensorMapEncodeTiled is a driver entry point; it is fetched
-// through the runtime so that the library does not link against libcuda.
-void rows_tensor_map(const RowStore &rs, int step_words, int planes, int CT, CUtensorMap *out)
+// Tensor map of the row store for the 3-plane path: a 3-d tensor of 64-bit elements (element
+// of a block's first three planes, block, genome) whose box is one block of one tile side:
+// 144 elements (= 3 planes x ROW_BLK words, 1152 contiguous bytes) x 1 block x CT genomes.
+// (64-bit elements because a box dimension may not exceed 256 elements.)  Blocks past the row
+// and genomes past the store read as zeros.  cuTensorMapEncodeTiled is a driver entry point; it
+// is fetched through the runtime so that the library does not link against libcuda.
+void rows_tensor_map(const RowStore &rs, int CT, CUtensorMap *out)
 {
 	using Encode = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
 	                            const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -629,11 +637,13 @@ void rows_tensor_map(const RowStore &rs, int step_words, int planes, int CT, CUt
 		if (q != cudaDriverEntryPointSuccess || !fn) throw CudaError("cuTensorMapEncodeTiled is not available in this driver");
 		encode = (Encode)fn;
 	}
-	const cuuint64_t dims[3] = {(cuuint64_t)rs.W, (cuuint64_t)ROW_PLANES, (cuuint64_t)rs.genomes};
-	const cuuint64_t strides[2] = {(cuuint64_t)rs.W * sizeof(uint32_t), (cuuint64_t)rs.genome_words() * sizeof(uint32_t)};
-	const cuuint32_t box[3] = {(cuuint32_t)step_words, (cuuint32_t)planes, (cuuint32_t)CT};
+	constexpr cuuint32_t RUN = 3 * ROW_BLK / 2; // 64-bit elements of the three planes of a block
+	const cuuint64_t dims[3] = {RUN, (cuuint64_t)(rs.W / ROW_BLK), (cuuint64_t)rs.genomes};
+	const cuuint64_t strides[2] = {(cuuint64_t)ROW_PLANES * ROW_BLK * sizeof(uint32_t),
+	                               (cuuint64_t)rs.genome_words() * sizeof(uint32_t)};
+	const cuuint32_t box[3] = {RUN, 1, (cuuint32_t)CT};
 	const cuuint32_t elem[3] = {1, 1, 1};
-	const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, rs.data.get(), dims, strides, box, elem,
+	const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, rs.data.get(), dims, strides, box, elem,
 	                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
 	                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed for the row store (code " + std::to_string((int)r) + ")");
@@ -697,17 +707,13 @@ void compare_all_device(const RowStore &rs, int64_t N, bool complete_deletion, i
 		}
 		if (my_units > 0x7fffffffll) throw std::invalid_argument("too many tile pairs for one launch");
 		if (my_units > 0) {
-			CUtensorMap tm_fast, tm_full;
+			CUtensorMap tm_fast;
 			memset(&tm_fast, 0, sizeof tm_fast);
-			memset(&tm_full, 0, sizeof tm_full);
-			if (tma) {
-				rows_tensor_map(rs, 32 * CMP_WPL_FAST, 3, CT, &tm_fast);
-				rows_tensor_map(rs, 32 * CMP_WPL_FULL, ROW_PLANES, CT, &tm_full);
-			}
+			if (tma) rows_tensor_map(rs, CT, &tm_fast);
 			const size_t smem = cmp_smem_bytes(CT, stages);
 #define PHY_LAUNCH_COMPARE(CTV, TMAV)                                                                                    \
 	k_compare_tiles<CTV, TMAV><<<(unsigned)my_units, cmp_threads(CTV), smem, s>>>(                                       \
-		tm_fast, tm_full, rs.data.get(), rs.genome_words(), rs.W, N, tp_begin, units, (int32_t)chunks, chunk_words,      \
+		tm_fast, rs.data.get(), rs.genome_words(), rs.W, N, tp_begin, units, (int32_t)chunks, chunk_words,      \
 		tile_rank, tile_world, vall.get(), d_subst, d_homologs)
 			if (CT == 16 && tma)
 				PHY_LAUNCH_COMPARE(16, true);

@@ -21,16 +21,29 @@ namespace phy
 // the D / B planes is set (genomes without reverse-strand homologies and separators, the
 // common case, let the all-pairs kernel skip those planes).  The flags travel with the rows
 // in the all-gather of a sharded run.
+// In memory the planes of a genome are interleaved in blocks of ROW_BLK words:
+//   [block 0: V C0 C1 D B, ROW_BLK words each][block 1: ...] ... [flag words]
+// so that what the all-pairs kernel needs of one genome per step — ROW_BLK words of its first
+// three planes — is ONE contiguous run of 1152 bytes (a tensor copy then moves 16 such runs per
+// tile side; with whole planes back to back it had to fetch 48 runs of 384 bytes and the copy
+// engine, not the arithmetic, set the pace).  row_word() gives the place of a word.
 constexpr int ROW_PLANES = 5;
+constexpr int ROW_BLK = 96;
 constexpr int ROW_FLAG_WORDS = 4;
 enum : int { PL_V = 0, PL_C0 = 1, PL_C1 = 2, PL_D = 3, PL_B = 4 };
 enum : uint32_t { ROW_FLAG_D = 1, ROW_FLAG_B = 2 };
 enum : int { ROW_WORD_FLAGS = 0, ROW_WORD_REAL = 1 }; // flag words: D/B use; "this row was written"
 
+// index of word w of plane `plane` inside a genome's row
+__host__ __device__ inline int64_t row_word(int plane, int64_t w)
+{
+	return (w / ROW_BLK) * (ROW_PLANES * ROW_BLK) + plane * ROW_BLK + (w % ROW_BLK);
+}
+
 struct RowStore {
 	DevBuf<uint32_t> data; // genomes * (ROW_PLANES * W + ROW_FLAG_WORDS)
 	int64_t genomes = 0;   // capacity in genomes
-	int64_t W = 0;         // words per plane, multiple of 4
+	int64_t W = 0;         // words per plane, multiple of ROW_BLK
 	int32_t n = 0;         // reference length (columns)
 	uint32_t *row(int64_t g) const { return data.get() + g * genome_words(); }
 	int64_t genome_words() const { return ROW_PLANES * W + ROW_FLAG_WORDS; }

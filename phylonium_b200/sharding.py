@@ -74,7 +74,7 @@ def owner_of(plan: ShardPlan, genome: int) -> int:
 
 
 NUM_SMS = 148
-STEP_WORDS = 32  # words per step (compare.cu: CMP_STEP)
+STEP_WORDS = 96  # chunk granularity in words (compare.cu: whole steps of both paths, ROW_BLK)
 
 
 def tile_side(n_genomes: int) -> int:
