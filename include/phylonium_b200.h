@@ -178,6 +178,18 @@ int phylo_process(phylo_ctx *ctx, const char *const *seqs, const uint64_t *lens,
  * (or phylo_map_queries) call are still in device memory; nothing crosses the bus again. */
 int phylo_process_again(phylo_ctx *ctx, uint64_t ref_index, int flags, uint64_t *subst, uint64_t *homologs);
 
+/* Ingest pipelined with the upload (the reference reads all FASTA files, src/io.cxx:66-104 with
+ * libs/pfasta.c, before process() sees a byte): the host announces N sequences with an upper
+ * bound of each one's length (the file size will do), then hands every sequence over as soon
+ * as its parser is done with it — from any thread, in any order.  phylo_ingest_put packs the
+ * sequence to 2 bits per base, checks the alphabet, sends it and returns; the bytes are not
+ * referenced afterwards.  `lanes` = how many puts can be in flight at once (one stream and one
+ * small pinned ring each).  After phylo_ingest_end the sequences are resident:
+ * phylo_process_again(ctx, ref_index, ...) is process() on them. */
+int phylo_ingest_begin(phylo_ctx *ctx, uint64_t N, const uint64_t *max_lens, int lanes);
+int phylo_ingest_put(phylo_ctx *ctx, uint64_t index, const char *seq, uint64_t len);
+int phylo_ingest_end(phylo_ctx *ctx);
+
 /* ---- device-resident variants (benchmarks, multi-GPU plumbing) --------------------------- */
 
 /* Same stages with inputs/outputs already in device memory of ctx's device.

@@ -52,6 +52,9 @@ SIGNATURES = {
     "phylo_estimate": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "phylo_process": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]),
     "phylo_process_again": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]),
+    "phylo_ingest_begin": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]),
+    "phylo_ingest_put": (C.c_int, [C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64]),
+    "phylo_ingest_end": (C.c_int, [C.c_void_p]),
     "phylo_esa_build_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "phylo_map_queries_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "phylo_compare_all_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -286,6 +289,20 @@ class Context:
         self._check(self.lib.phylo_process(self.h, arr, lens.ctypes.data, N, ref_index, flags, out[0].ctypes.data, out[1].ctypes.data))
         self.N = N
         return out
+
+    def ingest(self, seqs, max_lens=None, lanes: int = 4, threads: int = 4):
+        """phylo_ingest_begin / _put (from `threads` Python threads, ctypes drops the GIL) / _end;
+        afterwards process_again(ref) is process() on the sequences"""
+        from concurrent.futures import ThreadPoolExecutor
+
+        qs = [_b(q) for q in seqs]
+        caps = np.array(max_lens if max_lens is not None else [len(q) for q in qs], dtype=np.uint64)
+        self._check(self.lib.phylo_ingest_begin(self.h, len(qs), caps.ctypes.data, lanes))
+        with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:
+            rcs = list(ex.map(lambda k: self.lib.phylo_ingest_put(self.h, k, qs[k], len(qs[k])), range(len(qs))))
+        self._check(self.lib.phylo_ingest_end(self.h))
+        assert all(rc == 0 for rc in rcs)
+        self.N = len(qs)
 
     def process_again(self, ref_index: int, flags: int = 0, out=None):
         """second pass of --2pass: same sequences (still on the device), another reference"""

@@ -66,7 +66,20 @@ struct phylo_ctx {
 	// sequences of the last phylo_process / phylo_map_queries, still in q_own (phylo_process_again)
 	std::vector<uint64_t> q_offs, q_lens;
 	bool q_resident = false;
-	HostStager stager; // pageable host buffers go through pinned bounce rings (staging.h)
+	HostStager stager; // sequences cross PCIe packed to 2 bits per base (staging.h)
+
+	// phylo_ingest_*: sequences handed over one by one, from any thread, as a parser gets
+	// them ready; each call packs and uploads its sequence at once
+	struct Ingest {
+		bool active = false;
+		std::vector<uint64_t> caps;
+		std::vector<uint8_t> got;
+		std::vector<UploadLane> lanes;
+		std::vector<uint8_t> lane_busy;
+		std::mutex mu;
+		std::condition_variable cv;
+		std::string err; // first failure of a put (guarded by mu)
+	} ingest;
 
 	DevBuf<unsigned long long> d_subst, d_hom;
 	uint64_t matN = 0;
@@ -568,6 +581,9 @@ void phylo_ctx_destroy(phylo_ctx *c)
 		cudaEventDestroy(c->ev_check_done);
 	}
 	c->stager.release();
+	for (auto &l : c->ingest.lanes)
+		l.destroy();
+	c->ingest.lanes.clear();
 	clear_peers(c);
 	if (c->push_stream) {
 		cudaStreamSynchronize(c->push_stream);
@@ -1139,6 +1155,118 @@ int phylo_process(phylo_ctx *c, const char *const *seqs, const uint64_t *lens, u
 		Uploader up(c, seqs, lens, N, ref_index);
 		process_resident(c, N, ref_index, flags, up.hooks(), subst, homologs);
 		up.done();
+	});
+	if (rc != PHYLO_OK) quiesce(c);
+	return rc;
+}
+
+int phylo_ingest_begin(phylo_ctx *c, uint64_t N, const uint64_t *max_lens, int lanes)
+{
+	const int rc = guarded(c, [&] {
+		if (!N || !max_lens) throw std::invalid_argument("NULL argument");
+		if (lanes < 1) lanes = 1;
+		if (lanes > 64) lanes = 64;
+		auto &in = c->ingest;
+		cudaStream_t s = c->stream;
+		CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
+		c->stager.drain();
+		c->q_resident = false;
+		c->mapped = false;
+		c->q_offs.assign((size_t)N, 0);
+		c->q_lens.assign((size_t)N, 0);
+		in.caps.assign(max_lens, max_lens + N);
+		in.got.assign((size_t)N, 0);
+		in.err.clear();
+		uint64_t total = 0;
+		for (uint64_t k = 0; k < N; k++) {
+			if (max_lens[k] > 0x7fffff00ull) throw std::invalid_argument("sequence too long for 32-bit indices");
+			c->q_offs[k] = total;
+			total = (total + max_lens[k] + 1 + 15) / 16 * 16;
+		}
+		c->q_own.alloc(total + 64, s);
+		c->q_own.zero();
+		CUDA_CHECK(cudaEventRecord(c->ev_main, s));
+		while ((int)in.lanes.size() < lanes) {
+			in.lanes.emplace_back();
+			in.lanes.back().create();
+		}
+		in.lane_busy.assign(in.lanes.size(), 0);
+		for (auto &l : in.lanes)
+			CUDA_CHECK(cudaStreamWaitEvent(l.stream, c->ev_main, 0)); // not before the buffer is cleared
+		in.active = true;
+	});
+	return rc;
+}
+
+int phylo_ingest_put(phylo_ctx *c, uint64_t index, const char *seq, uint64_t len)
+{
+	if (!c) return PHYLO_ERR_INVALID;
+	auto &in = c->ingest;
+	auto failed = [&](int code, const std::string &msg) {
+		std::lock_guard<std::mutex> lock(in.mu);
+		if (in.err.empty()) in.err = msg;
+		return code;
+	};
+	if (!in.active) return failed(PHYLO_ERR_INVALID, "phylo_ingest_begin has not been called");
+	if (index >= in.caps.size() || (!seq && len)) return failed(PHYLO_ERR_INVALID, "bad arguments to phylo_ingest_put");
+	if (len > in.caps[index]) return failed(PHYLO_ERR_INVALID, "sequence longer than announced to phylo_ingest_begin");
+	if (cudaSetDevice(c->device) != cudaSuccess) return failed(PHYLO_ERR_CUDA, "cudaSetDevice failed");
+	int lane = -1;
+	{
+		std::unique_lock<std::mutex> lock(in.mu);
+		if (in.got[index]) {
+			if (in.err.empty()) in.err = "sequence handed over twice";
+			return PHYLO_ERR_INVALID;
+		}
+		in.got[index] = 1;
+		in.cv.wait(lock, [&] {
+			for (size_t l = 0; l < in.lane_busy.size(); l++)
+				if (!in.lane_busy[l]) {
+					lane = (int)l;
+					return true;
+				}
+			return false;
+		});
+		in.lane_busy[lane] = 1;
+	}
+	UploadLane &L = in.lanes[lane];
+	uint8_t *dst = c->q_own.get() + c->q_offs[index];
+	const uint8_t *src = reinterpret_cast<const uint8_t *>(seq);
+	int rc = PHYLO_OK;
+	for (uint64_t o = 0; o < len && rc == PHYLO_OK; o += UploadLane::PIECE_BYTES) {
+		const uint32_t l = (uint32_t)(len - o < UploadLane::PIECE_BYTES ? len - o : UploadLane::PIECE_BYTES);
+		int bad = 0;
+		const cudaError_t e = L.upload_piece(dst + o, src + o, l, &bad);
+		if (bad) rc = failed(PHYLO_ERR_INVALID, "a sequence contains bytes outside {A,C,G,T,!}");
+		else if (e != cudaSuccess) rc = failed(PHYLO_ERR_CUDA, std::string("upload failed: ") + cudaGetErrorString(e));
+	}
+	c->q_lens[index] = len; // one writer per index
+	{
+		std::lock_guard<std::mutex> lock(in.mu);
+		in.lane_busy[lane] = 0;
+	}
+	in.cv.notify_one();
+	return rc;
+}
+
+int phylo_ingest_end(phylo_ctx *c)
+{
+	const int rc = guarded(c, [&] {
+		auto &in = c->ingest;
+		if (!in.active) throw std::invalid_argument("phylo_ingest_begin has not been called");
+		in.active = false;
+		for (auto &l : in.lanes)
+			CUDA_CHECK(cudaStreamSynchronize(l.stream));
+		if (!in.err.empty()) throw std::invalid_argument(in.err);
+		for (size_t k = 0; k < in.got.size(); k++)
+			if (!in.got[k]) throw std::invalid_argument("phylo_ingest_end: not every sequence was handed over");
+		c->N = in.got.size();
+		c->q_resident = true;
+		uint64_t bases = 0;
+		for (uint64_t l : c->q_lens)
+			bases += l;
+		c->stats["process.h2d_bytes"] = (double)(bases / 4);
+		c->stats["process.packed"] = 1;
 	});
 	if (rc != PHYLO_OK) quiesce(c);
 	return rc;

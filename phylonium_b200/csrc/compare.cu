@@ -159,9 +159,19 @@ constexpr int PT = 4; // genomes per side of a warp's sub-tile
 // CT = genomes per side of a block's tile: 16, or 8 when there are so few genomes that 16 x 16
 // tiles would be mostly padding.  A tile has (CT / PT)^2 sub-tiles of 4 x 4 pairs; a block of 8
 // warps takes two sub-tiles per warp (CT = 16), a block of 4 warps one (CT = 8).
+// (geometry switchable at compile time for A/B runs: warps per 16 x 16 tile, resident blocks)
+#ifndef CMP_TILE_WARPS
+#define CMP_TILE_WARPS 8
+#endif
+#ifndef CMP_MIN_BLOCKS
+#define CMP_MIN_BLOCKS 2
+#endif
+#ifndef CMP_STAGES_N
+#define CMP_STAGES_N 3
+#endif
 __host__ __device__ constexpr int cmp_threads(int CT)
 {
-	return CT == 16 ? 256 : 128;
+	return CT == 16 ? 32 * CMP_TILE_WARPS : 128;
 }
 // words per lane and step: the 3-plane path adds up three words per pair with one carry-save
 // step before it counts bits; the 5-plane path (reverse strands, separators) goes word by word
@@ -234,7 +244,7 @@ __device__ __forceinline__ void tma_load_rows(void *smem_dst, const CUtensorMap 
 	             : "memory");
 }
 
-constexpr int CMP_STAGES = 3; // shared-memory stages of the TMA pipeline
+constexpr int CMP_STAGES = CMP_STAGES_N; // shared-memory stages of the TMA pipeline
 
 // One (tile pair, chunk) unit.  P = planes to look at (3: V, C0, C1; 5: all), WPL = words per
 // lane and step.  Per pair and word: both = Va & Vb, diff = both & (codes differ [or, on the
@@ -469,7 +479,7 @@ __device__ __forceinline__ void compare_tile(uint32_t *stage, const uint32_t *__
 // pieces per genome and step with cp.async: that many short runs are not what the tensor copy
 // engine is good at.
 template <int CT, bool TMA>
-__global__ void __launch_bounds__(cmp_threads(CT), CT == 16 ? 2 : 4)
+__global__ void __launch_bounds__(cmp_threads(CT), CT == 16 ? CMP_MIN_BLOCKS : 4)
 k_compare_tiles(const __grid_constant__ CUtensorMap tm_fast, const uint32_t *__restrict__ rows, int64_t genome_words, int64_t W, int64_t N, int64_t tp_begin,
                 int64_t units, int32_t chunks, int64_t chunk_words, int tile_rank, int tile_world,
                 const uint32_t *__restrict__ vall, unsigned long long *__restrict__ subst,

@@ -56,6 +56,81 @@ static __global__ void k_put_bangs(uint8_t *__restrict__ dst, const uint32_t *__
 	if (t < count) dst[pos[t]] = (uint8_t)'!';
 }
 
+// resources of one upload lane: a stream, a pinned ring of packed pieces and its twin on the device
+struct UploadLane {
+	static constexpr size_t PIECE_BYTES = 2u << 20;         // bases per piece
+	static constexpr size_t PACKED_BYTES = PIECE_BYTES / 4; // its packed form
+	static constexpr uint32_t BANG_CAP = 4096;              // '!' per piece listed with the packed form
+	static constexpr size_t SLOT_BYTES = PACKED_BYTES + BANG_CAP * sizeof(uint32_t);
+	static constexpr int SLOTS = 4;
+	cudaStream_t stream = nullptr;
+	uint8_t *ring = nullptr;  // pinned: SLOTS x (packed piece, '!' list)
+	uint8_t *dring = nullptr; // the same on the device
+	cudaEvent_t slot_ev[SLOTS] = {};
+	size_t used = 0;
+
+	void create()
+	{
+		CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+		CUDA_CHECK(cudaHostAlloc((void **)&ring, SLOT_BYTES * SLOTS, cudaHostAllocDefault));
+		CUDA_CHECK(cudaMalloc((void **)&dring, SLOT_BYTES * SLOTS));
+		for (auto &e : slot_ev)
+			CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	}
+	void destroy()
+	{
+		if (stream) {
+			cudaStreamSynchronize(stream);
+			cudaStreamDestroy(stream);
+		}
+		if (ring) cudaFreeHost(ring);
+		if (dring) cudaFree(dring);
+		for (auto e : slot_ev)
+			if (e) cudaEventDestroy(e);
+		stream = nullptr;
+		ring = dring = nullptr;
+		for (auto &e : slot_ev)
+			e = nullptr;
+	}
+	// packs src[0, len), len <= PIECE_BYTES, sends it and unpacks it at dst (16-byte aligned).
+	// *bad = 1: a byte outside the alphabet (nothing sent).  The host bytes are not needed any
+	// more when this returns.
+	cudaError_t upload_piece(uint8_t *dst, const uint8_t *src, uint32_t len, int *bad)
+	{
+		const int slot = (int)(used++ % SLOTS);
+		cudaError_t e = cudaEventSynchronize(slot_ev[slot]); // the copy that last used this slot has left it
+		if (e != cudaSuccess) return e;
+		uint8_t *hp = ring + (size_t)slot * SLOT_BYTES, *dp = dring + (size_t)slot * SLOT_BYTES;
+		uint32_t *hb = reinterpret_cast<uint32_t *>(hp + PACKED_BYTES);
+		uint32_t nb = 0;
+		*bad = pack_2bit(src, len, hp, hb, BANG_CAP, &nb);
+		if (*bad) return cudaSuccess;
+		if (nb > BANG_CAP) {
+			// a piece that is mostly separators: as it is, through the driver's own staging, and
+			// done before we return (the caller may reuse src)
+			e = cudaMemcpyAsync(dst, src, len, cudaMemcpyHostToDevice, stream);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+			return e;
+		}
+		const size_t pbytes = ((size_t)len + 3) / 4;
+		e = cudaMemcpyAsync(dp, hp, (pbytes + 3) / 4 * 4, cudaMemcpyHostToDevice, stream);
+		if (e != cudaSuccess) return e;
+		k_unpack_2bit<<<(unsigned)((len + 16 * 256 - 1) / (16 * 256)), 256, 0, stream>>>(
+			reinterpret_cast<const uint32_t *>(dp), dst, len);
+		g_kernel_launches++;
+		e = cudaGetLastError();
+		if (e == cudaSuccess && nb) {
+			e = cudaMemcpyAsync(dp + PACKED_BYTES, hb, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, stream);
+			if (e != cudaSuccess) return e;
+			k_put_bangs<<<(nb + 255) / 256, 256, 0, stream>>>(dst, reinterpret_cast<const uint32_t *>(dp + PACKED_BYTES), nb);
+			g_kernel_launches++;
+			e = cudaGetLastError();
+		}
+		if (e != cudaSuccess) return e;
+		return cudaEventRecord(slot_ev[slot], stream);
+	}
+};
+
 class HostStager
 {
   public:
@@ -65,11 +140,7 @@ class HostStager
 		uint32_t len;       // <= PIECE_BYTES
 		int32_t batch;
 	};
-	static constexpr size_t PIECE_BYTES = 2u << 20;         // bases per piece
-	static constexpr size_t PACKED_BYTES = PIECE_BYTES / 4; // its packed form
-	static constexpr uint32_t BANG_CAP = 4096;              // '!' per piece listed with the packed form
-	static constexpr size_t SLOT_BYTES = PACKED_BYTES + BANG_CAP * sizeof(uint32_t);
-	static constexpr int SLOTS = 4;
+	static constexpr size_t PIECE_BYTES = UploadLane::PIECE_BYTES;
 
 	// true if a cudaMemcpyAsync from p would be staged by the driver
 	static bool is_pageable(const void *p)
@@ -110,13 +181,8 @@ class HostStager
 		if ((int)workers_.size() != threads) {
 			release_workers();
 			workers_.resize(threads);
-			for (auto &w : workers_) {
-				CUDA_CHECK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
-				CUDA_CHECK(cudaHostAlloc((void **)&w.ring, SLOT_BYTES * SLOTS, cudaHostAllocDefault));
-				CUDA_CHECK(cudaMalloc((void **)&w.dring, SLOT_BYTES * SLOTS));
-				for (auto &e : w.slot_ev)
-					CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-			}
+			for (auto &w : workers_)
+				w.lane.create();
 			quit_ = false;
 			for (int t = 0; t < threads; t++)
 				workers_[t].th = std::thread([this, t, g = generation_] { thread_main(t, g); }); // jobs posted from now on
@@ -127,7 +193,7 @@ class HostStager
 				CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 				w.batch_ev.push_back(e);
 			}
-			if (after) CUDA_CHECK(cudaStreamWaitEvent(w.stream, after, 0));
+			if (after) CUDA_CHECK(cudaStreamWaitEvent(w.lane.stream, after, 0));
 		}
 		{
 			std::lock_guard<std::mutex> lock(mu_);
@@ -173,7 +239,7 @@ class HostStager
 		finish(true);
 		pending_.clear();
 		for (auto &w : workers_)
-			if (w.stream) cudaStreamSynchronize(w.stream);
+			if (w.lane.stream) cudaStreamSynchronize(w.lane.stream);
 	}
 
 	void release()
@@ -186,10 +252,7 @@ class HostStager
   private:
 	struct Worker {
 		std::thread th;
-		cudaStream_t stream = nullptr;
-		uint8_t *ring = nullptr;  // pinned: SLOTS x (packed piece, '!' list)
-		uint8_t *dring = nullptr; // the same on the device
-		cudaEvent_t slot_ev[SLOTS] = {};
+		UploadLane lane;
 		std::vector<cudaEvent_t> batch_ev;
 		int issued = 0; // batches whose events have been recorded (guarded by mu_)
 	};
@@ -204,14 +267,7 @@ class HostStager
 		for (auto &w : workers_)
 			if (w.th.joinable()) w.th.join();
 		for (auto &w : workers_) {
-			if (w.stream) {
-				cudaStreamSynchronize(w.stream);
-				cudaStreamDestroy(w.stream);
-			}
-			if (w.ring) cudaFreeHost(w.ring);
-			if (w.dring) cudaFree(w.dring);
-			for (auto e : w.slot_ev)
-				if (e) cudaEventDestroy(e);
+			w.lane.destroy();
 			for (auto e : w.batch_ev)
 				cudaEventDestroy(e);
 		}
@@ -243,7 +299,7 @@ class HostStager
 		int batch = 0;
 		auto publish_up_to = [&](int upto) { // events of batches [batch, upto)
 			for (; batch < upto; batch++) {
-				const cudaError_t e = cudaEventRecord(w.batch_ev[batch], w.stream);
+				const cudaError_t e = cudaEventRecord(w.batch_ev[batch], w.lane.stream);
 				std::lock_guard<std::mutex> lock(mu_);
 				if (e != cudaSuccess && error_.empty()) error_ = cudaGetErrorString(e);
 				w.issued = batch + 1;
@@ -251,47 +307,18 @@ class HostStager
 			}
 		};
 		cudaError_t e = cudaSetDevice(device_);
-		size_t used = 0;
 		for (size_t i = t; e == cudaSuccess && i < pieces_.size() && !abort_; i += T) {
 			const Piece &p = pieces_[i];
 			publish_up_to(p.batch);
-			const int slot = (int)(used++ % SLOTS);
-			e = cudaEventSynchronize(w.slot_ev[slot]); // the copy that last used this slot has left it
-			if (e != cudaSuccess) break;
-			uint8_t *hp = w.ring + (size_t)slot * SLOT_BYTES, *dp = w.dring + (size_t)slot * SLOT_BYTES;
-			uint32_t *hb = reinterpret_cast<uint32_t *>(hp + PACKED_BYTES);
-			uint32_t nb = 0;
-			if (pack_2bit(p.src, p.len, hp, hb, BANG_CAP, &nb)) {
+			int bad = 0;
+			e = w.lane.upload_piece(p.dst, p.src, p.len, &bad);
+			if (bad) {
 				std::lock_guard<std::mutex> lock(mu_);
 				bad_input_ = true;
 				abort_ = true;
 				cv_.notify_all();
 				break;
 			}
-			if (nb > BANG_CAP) {
-				// a piece that is mostly separators: as it is (the driver stages it if need be)
-				e = cudaMemcpyAsync(p.dst, p.src, p.len, cudaMemcpyHostToDevice, w.stream);
-			} else {
-				const size_t pbytes = ((size_t)p.len + 3) / 4;
-				e = cudaMemcpyAsync(dp, hp, (pbytes + 3) / 4 * 4, cudaMemcpyHostToDevice, w.stream);
-				if (e == cudaSuccess) {
-					k_unpack_2bit<<<(unsigned)((p.len + 16 * 256 - 1) / (16 * 256)), 256, 0, w.stream>>>(
-						reinterpret_cast<const uint32_t *>(dp), p.dst, p.len);
-					g_kernel_launches++;
-					e = cudaGetLastError();
-				}
-				if (e == cudaSuccess && nb) {
-					e = cudaMemcpyAsync(dp + PACKED_BYTES, hb, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, w.stream);
-					if (e == cudaSuccess) {
-						k_put_bangs<<<(nb + 255) / 256, 256, 0, w.stream>>>(
-							p.dst, reinterpret_cast<const uint32_t *>(dp + PACKED_BYTES), nb);
-						g_kernel_launches++;
-						e = cudaGetLastError();
-					}
-				}
-			}
-			if (e != cudaSuccess) break;
-			e = cudaEventRecord(w.slot_ev[slot], w.stream);
 		}
 		if (e != cudaSuccess) {
 			std::lock_guard<std::mutex> lock(mu_);

@@ -18,8 +18,11 @@
 #include <getopt.h>
 #include <iostream>
 #include <limits>
+#include <atomic>
 #include <numeric>
 #include <random>
+#include <sys/stat.h>
+#include <thread>
 
 #include "../../include/phylonium_b200.h"
 
@@ -144,6 +147,19 @@ static void write_reference_positions(phylo_ctx *ctx, const sequence &subject)
 
 // ------------------------------------------------------------------ the seam
 
+// one context for the life of the program (the second pass of --2pass reuses it)
+static phylo_ctx *context()
+{
+	static phylo_ctx *ctx = nullptr;
+	if (!ctx && phylo_ctx_create(-1, &ctx) != PHYLO_OK) errx(1, "%s", phylo_last_error(nullptr));
+	return ctx;
+}
+
+// the strings whose bytes the context already holds on the device (handed over while the
+// files were being read, or by the previous process() call)
+static std::vector<const char *> resident_ptr;
+static std::vector<uint64_t> resident_len;
+
 std::vector<evo_model> process(const sequence &subject, const std::vector<sequence> &queries)
 {
 	const size_t N = queries.size();
@@ -152,8 +168,7 @@ std::vector<evo_model> process(const sequence &subject, const std::vector<sequen
 		ref = std::find(queries.begin(), queries.end(), subject) - queries.begin();
 		if (ref == N) errx(1, "process(): the subject is not one of the queries");
 	}
-	static phylo_ctx *ctx = nullptr; // one context for the life of the program (2-pass reuses it)
-	if (!ctx && phylo_ctx_create(-1, &ctx) != PHYLO_OK) errx(1, "%s", phylo_last_error(nullptr));
+	phylo_ctx *ctx = context();
 
 	std::vector<const char *> ptr(N);
 	std::vector<uint64_t> len(N);
@@ -163,10 +178,9 @@ std::vector<evo_model> process(const sequence &subject, const std::vector<sequen
 	}
 	if (FLAGS & flags::verbose) std::cerr << "ref: " << subject.get_name() << std::endl;
 	std::vector<uint64_t> subst(N * N), homol(N * N);
-	// The second call of --2pass (src/phylonium.cxx:289-296) hands over the very same strings:
-	// they are still on the device, only the index and the mapping are redone.
-	static std::vector<const char *> resident_ptr;
-	static std::vector<uint64_t> resident_len;
+	// Strings the device already holds — uploaded while the files were read (read_and_upload),
+	// or by the first call of --2pass (src/phylonium.cxx:289-296) — are not sent again: only the
+	// index and the mapping are done.
 	int rc;
 	if (ptr == resident_ptr && len == resident_len) {
 		rc = phylo_process_again(ctx, ref, FLAGS & flags::complete_deletion, subst.data(), homol.data());
@@ -226,6 +240,46 @@ genome read_genome(const std::string &file_name)
 	flush();
 	if (contigs.empty()) errx(1, "%s: no sequence found", file_name.c_str());
 	return genome(genome_name(file_name), std::move(contigs));
+}
+
+// Reads all files with a pool of threads; every genome goes to the device (packed, see
+// phylo_ingest_put) the moment its file is parsed, while the other files are still being read
+// — the reference parses everything first (src/phylonium.cxx:255-270, src/io.cxx:66-104).
+static std::vector<sequence> read_and_upload(const std::vector<std::string> &files)
+{
+	const size_t N = files.size();
+	std::vector<sequence> queries(N);
+	std::vector<uint64_t> caps(N);
+	for (size_t i = 0; i < N; i++) {
+		struct stat st;
+		if (stat(files[i].c_str(), &st) != 0) err(1, "%s", files[i].c_str());
+		caps[i] = (uint64_t)st.st_size; // a sequence is never longer than its file
+	}
+	const unsigned hw = std::thread::hardware_concurrency();
+	const size_t threads = std::max<size_t>(1, std::min<size_t>({(size_t)(hw ? hw : 1), N, (size_t)16}));
+	phylo_ctx *ctx = context();
+	if (phylo_ingest_begin(ctx, N, caps.data(), (int)threads) != PHYLO_OK) errx(1, "%s", phylo_last_error(ctx));
+	std::atomic<size_t> next{0};
+	auto worker = [&] {
+		for (size_t i = next++; i < N; i = next++) {
+			queries[i] = join(read_genome(files[i]));
+			phylo_ingest_put(ctx, i, queries[i].c_str(), queries[i].size()); // failures surface in phylo_ingest_end
+		}
+	};
+	std::vector<std::thread> pool;
+	for (size_t t = 1; t < threads; t++)
+		pool.emplace_back(worker);
+	worker();
+	for (auto &t : pool)
+		t.join();
+	if (phylo_ingest_end(ctx) != PHYLO_OK) errx(1, "%s", phylo_last_error(ctx));
+	resident_ptr.resize(N);
+	resident_len.resize(N);
+	for (size_t i = 0; i < N; i++) {
+		resident_ptr[i] = queries[i].c_str();
+		resident_len[i] = queries[i].size();
+	}
+	return queries;
 }
 
 static void soft_warnx(const char *fmt, const char *a, const char *b, double x = 0, double y = 0)
@@ -440,9 +494,7 @@ int main(int argc, char *argv[])
 	}
 	if (files.size() < 2) usage(EXIT_FAILURE);
 
-	std::vector<sequence> queries(files.size());
-	for (size_t i = 0; i < files.size(); i++)
-		queries[i] = join(read_genome(files[i]));
+	std::vector<sequence> queries = read_and_upload(files);
 
 	if (reference_name.empty())
 		pick_first_pass(queries);

@@ -777,6 +777,36 @@ def test_batched_process_from_ordinary_memory(pb, oracle, threads, flags):
         assert np.array_equal(out[0], want["subst"]) and np.array_equal(out[1], want["homologs"])
 
 
+def test_ingest_pipelined_with_the_upload(pb, oracle):
+    """phylo_ingest_*: sequences handed over one by one from several threads (as a FASTA
+    parser would), each packed and uploaded at once; then process() on what is resident"""
+    genomes = _sharded_family(seed=41, n=250000, count=9)  # several pieces of 2 MB? no: one each; plus a long one
+    rng = np.random.default_rng(8)
+    genomes.append(datasets.mutate(rng, genomes[0] * 10, 0.01))  # 2.5 Mbp: two pieces
+    genomes[5] = genomes[5][:100000] + b"!" + genomes[5][100000:]
+    want = oracle.process(genomes, 0, 0, threads=8)
+    with pb.Context() as c:
+        c.ingest(genomes, max_lens=[len(g) + 1000 for g in genomes], lanes=3, threads=4)
+        subst, homol = c.process_again(0)
+        assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
+        want4 = oracle.process(genomes, 4, 4, threads=8)
+        subst, homol = c.process_again(4, flags=4)
+        assert np.array_equal(subst, want4["subst"]) and np.array_equal(homol, want4["homologs"])
+        # a byte outside the alphabet, a sequence longer than announced, a missing sequence
+        with pytest.raises(pb.PhyloError):
+            c.ingest([genomes[0], genomes[1][:500] + b"n" + genomes[1][500:]])
+        with pytest.raises(pb.PhyloError):
+            c.ingest([genomes[0], genomes[1]], max_lens=[len(genomes[0]), 10])
+        lens = np.array([len(genomes[0]), len(genomes[1])], dtype=np.uint64)
+        assert c.lib.phylo_ingest_begin(c.h, 2, lens.ctypes.data, 2) == 0
+        assert c.lib.phylo_ingest_put(c.h, 0, genomes[0], len(genomes[0])) == 0
+        assert c.lib.phylo_ingest_end(c.h) != 0
+        with pytest.raises(pb.PhyloError):
+            c.process_again(0)  # nothing resident after a failed ingest
+        subst, homol = c.process(genomes, 0, 0)  # the context is still usable
+        assert np.array_equal(homol, want["homologs"])
+
+
 def test_upload_paths_agree(pb, oracle):
     """sequences cross PCIe packed to 2 bits per base (default) or as bytes (upload_raw); a
     piece with more separators than the packed form lists (4096) goes over as it is"""
