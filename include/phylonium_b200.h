@@ -95,8 +95,9 @@ int phylo_set_stream(phylo_ctx *ctx, void *stream);
  *   "compare_path" how the all-pairs kernel brings the row tiles into shared memory: 0 = tensor
  *               copies (TMA) through a 3-stage transaction-barrier pipeline (default), 1 =
  *               cp.async by all threads, double buffered (kept for comparison)
- *   "upload_raw" 1 = send the bytes as they are (asynchronous from pinned memory, staged by the
- *               driver otherwise) instead of packing them on the host; default 0
+ *   "upload_raw" 0 (default) = pack on the host unless the input is pinned and under 128 MiB
+ *               (then the plain asynchronous copies are hidden behind the index build anyway),
+ *               1 = always send the bytes as they are, -1 = always pack
  *   "keep_raw" keep unsorted/unfiltered homology lists for phylo_get_homologies(raw=1)
  *   "timings"  record per-phase device times (adds synchronisation) */
 int phylo_set_option(phylo_ctx *ctx, const char *key, int64_t value);

@@ -659,7 +659,8 @@ int phylo_set_option(phylo_ctx *c, const char *key, int64_t value)
 			if (value < 0 || value > 1) throw std::invalid_argument("compare_path must be 0 or 1");
 			c->tuning.compare_path = (int)value;
 		} else if (k == "upload_raw") {
-			c->tuning.upload_raw = value != 0;
+			if (value < -1 || value > 1) throw std::invalid_argument("upload_raw must be -1, 0 or 1");
+			c->tuning.upload_raw = (int)value;
 		} else if (k == "stage_threads") {
 			if (value < 0 || value > 64) throw std::invalid_argument("stage_threads must be in [0, 64]");
 			c->opt_stage_threads = value;
@@ -1064,7 +1065,10 @@ struct Uploader {
 		CUDA_CHECK(cudaEventRecord(c->ev_main, s));
 		CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
 		ends = plan_batches(lens, N);
-		packed = c->tuning.upload_raw == 0;
+		// Packing pays when the bus is the bottleneck or the memory is pageable (the driver would
+		// stage it on this thread).  A small pinned input (measured: 8 x 5 Mbp) is over the bus
+		// before the index is built either way, and plain asynchronous copies cost no host work.
+		packed = c->tuning.upload_raw == 0 && (pageable || bases >= (128ull << 20) || c->tuning.upload_raw < 0);
 		if (packed) {
 			// worker threads pack the pieces to 2 bits per base into pinned rings, a kernel unpacks
 			// them at their place (staging.h): a quarter of the bytes on the bus, pageable or pinned
