@@ -454,8 +454,8 @@ def run_b200(args):
     else:
         ref_host = torch.zeros(L, dtype=torch.uint8).pin_memory()
         simgen.simf(SIMF_SEED, SIMF_SEED, L, 0.0, out=ref_host.data_ptr())
-    pipe = Pipeline(mods, args, dev, local_rank, rank, world, plan, shard, ref_host, L, args.index, args.exchange,
-                    batch_bytes=2 * L)
+    # (8 genomes per rank are one batch: their rows, 25 MB, are pushed in one go behind the mapping)
+    pipe = Pipeline(mods, args, dev, local_rank, rank, world, plan, shard, ref_host, L, args.index, args.exchange)
     ctx = pipe.ctx
     bases_local, bases_total = shard.bases, G * L * world
 

@@ -92,6 +92,9 @@ int phylo_set_stream(phylo_ctx *ctx, void *stream);
  *              pass, 2 = single-pass look-back ("onesweep")
  *   "stage_threads" worker threads that pack the sequences of phylo_process / phylo_map_queries
  *               to 2 bits per base for the trip over PCIe; 0 = from the core count (default)
+ *   "esa_speculative" 1 (default) = the index build makes no host round trip until its end and
+ *               is redone step by step if what it took for granted (valid input, few separators,
+ *               no repeats beyond the direct comparisons) turns out wrong; 0 = always step by step
  *   "compare_path" how the all-pairs kernel brings the row tiles into shared memory: 0 = tensor
  *               copies (TMA) through a 3-stage transaction-barrier pipeline (default), 1 =
  *               cp.async by all threads, double buffered (kept for comparison)

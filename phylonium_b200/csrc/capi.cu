@@ -655,6 +655,8 @@ int phylo_set_option(phylo_ctx *c, const char *key, int64_t value)
 		} else if (k == "key_chars") {
 			if (value < 0 || value > 21) throw std::invalid_argument("key_chars must be in [0, 21]");
 			c->opt_key_chars = value;
+		} else if (k == "esa_speculative") {
+			c->tuning.esa_speculative = value != 0;
 		} else if (k == "compare_path") {
 			if (value < 0 || value > 1) throw std::invalid_argument("compare_path must be 0 or 1");
 			c->tuning.compare_path = (int)value;
@@ -1066,9 +1068,17 @@ struct Uploader {
 		CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
 		ends = plan_batches(lens, N);
 		// Packing pays when the bus is the bottleneck or the memory is pageable (the driver would
-		// stage it on this thread).  A small pinned input (measured: 8 x 5 Mbp) is over the bus
-		// before the index is built either way, and plain asynchronous copies cost no host work.
-		packed = c->tuning.upload_raw == 0 && (pageable || bases >= (128ull << 20) || c->tuning.upload_raw < 0);
+		// stage it on this thread), and when there are cores to do it: at ~6 GB/s per core it takes
+		// eight of them to outrun the plain copy of pinned memory (55 GB/s).  A small pinned input
+		// (measured: 8 x 5 Mbp) is over the bus before the index is built either way, and several
+		// ranks that share one host's cores are better off with the copy engines.
+		int threads = (int)c->opt_stage_threads;
+		if (threads <= 0) {
+			const unsigned hw = std::thread::hardware_concurrency();
+			threads = hw > 18 ? 16 : hw > 3 ? (int)hw - 2 : 1;
+		}
+		packed = c->tuning.upload_raw < 0 ||
+		         (c->tuning.upload_raw == 0 && (pageable || (bases >= (128ull << 20) && threads >= 8)));
 		if (packed) {
 			// worker threads pack the pieces to 2 bits per base into pinned rings, a kernel unpacks
 			// them at their place (staging.h): a quarter of the bytes on the bus, pageable or pinned
@@ -1076,13 +1086,6 @@ struct Uploader {
 			for (size_t b = 0; b < ends.size(); b++)
 				for (; k < ends[b]; k++)
 					if (k != first && lens[k]) c->stager.add(dq + offs[k], seqs[k], lens[k], (int)b);
-			int threads = (int)c->opt_stage_threads;
-			if (threads <= 0) {
-				// packing runs at ~6 GB/s per core and has to keep up with 4 x the bus: all cores but
-				// two (the calling thread launches kernels meanwhile), at most 16
-				const unsigned hw = std::thread::hardware_concurrency();
-				threads = hw > 18 ? 16 : hw > 3 ? (int)hw - 2 : 1;
-			}
 			if (!c->stager.empty()) c->stager.start(c->device, (int)ends.size(), threads, c->ev_main);
 		} else {
 			// option "upload_raw": the bytes as they are, plain asynchronous copies on the copy

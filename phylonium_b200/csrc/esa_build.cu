@@ -386,9 +386,11 @@ struct CldTable {
 // that no separate packing pass re-reads the arrays.
 __global__ void __launch_bounds__(CLD_THREADS)
 k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ long_list, uint32_t *__restrict__ long_count,
-      const int32_t *__restrict__ SA, const uint8_t *__restrict__ FVC, EsaNode *__restrict__ node)
+      const int32_t *__restrict__ SA, const uint8_t *__restrict__ FVC, EsaNode *__restrict__ node,
+      const int *__restrict__ skip)
 {
 	__shared__ CldTable T;
+	if (skip && *skip) return; // the speculative build found out that LCP is not final yet
 	const int32_t *__restrict__ LCP = py.level[0];
 	const int64_t tile0 = (int64_t)blockIdx.x * CLD_TILE;
 	const int64_t lo = tile0 - CLD_HALO; // global index of window position 0
@@ -530,8 +532,9 @@ __device__ __forceinline__ int32_t coop_range_min(const Pyramid &py, int32_t a, 
 // entries whose scans are long: one warp each, 32 positions per step
 __global__ void __launch_bounds__(256)
 k_cld_long(Pyramid py, const int32_t *__restrict__ long_list, const uint32_t *__restrict__ long_count,
-           int32_t *__restrict__ CLD, EsaNode *__restrict__ node)
+           int32_t *__restrict__ CLD, EsaNode *__restrict__ node, const int *__restrict__ skip)
 {
+	if (skip && *skip) return;
 	const uint32_t count = *long_count;
 	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
 	const int32_t *__restrict__ LCP = py.level[0];
@@ -562,8 +565,9 @@ k_cld_long(Pyramid py, const int32_t *__restrict__ long_list, const uint32_t *__
 
 // ---------------------------------------------------------------- table
 
-__global__ void k_table(EsaView e, int32_t K, Interval *__restrict__ table)
+__global__ void k_table(EsaView e, int32_t K, Interval *__restrict__ table, const int *__restrict__ skip)
 {
+	if (skip && *skip) return;
 	const uint32_t code = blockIdx.x * blockDim.x + threadIdx.x;
 	if (code >= (1u << (2 * K))) return;
 	table[code] = esa_table_entry(e, code, K);
@@ -663,6 +667,17 @@ struct Timer {
 
 } // namespace
 
+namespace
+{
+// fail[0] = 1 if what the speculative build took for granted does not hold: valid input, the
+// dirty suffixes fit their list and were put in place, no tie group left for the doubling rounds
+__global__ void k_spec_check(const int *__restrict__ text_flags, const uint32_t *__restrict__ counters,
+                             const uint32_t *__restrict__ dirty_ctl, uint32_t dirty_cap, int *__restrict__ fail)
+{
+	*fail = (text_flags[0] != 0 || counters[1] != 0 || (dirty_ctl && (dirty_ctl[0] > dirty_cap || dirty_ctl[1] != 0))) ? 1 : 0;
+}
+} // namespace
+
 int esa_default_k(int32_t m)
 {
 	// about one table record per 4..16 suffixes; 4^K records of 16 bytes.  One level more
@@ -691,7 +706,7 @@ __global__ void k_pack_nodes(const int32_t *__restrict__ SA, const int32_t *__re
 }
 } // namespace
 
-void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t s, bool nodes_ready)
+void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t s, bool nodes_ready, const int *skip)
 {
 	// the descent reads interleaved records; the build writes them with the child table, an
 	// imported index packs them here (13 B read, 16 B written per suffix)
@@ -715,9 +730,10 @@ void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t s, bool nodes_read
 		// entries are the same cache lines, so this is as fast as or faster than the level-wise
 		// build with its extra launches (measured on B200: 0.097 vs 0.193 ms at K = 10, 0.262 vs
 		// 0.265 ms at K = 11; a head + one-launch tail variant: 0.149 / 0.302); same table
-		k_table<<<div_up(entries, 128), 128, 0, s>>>(v, K, esa.table.get());
+		k_table<<<div_up(entries, 128), 128, 0, s>>>(v, K, esa.table.get(), skip);
 		KERNEL_CHECK();
 	} else {
+		if (skip) throw std::invalid_argument("the level-wise table build does not run speculatively");
 		const int32_t k0 = K < TABLE_HEAD_LEVELS ? K : TABLE_HEAD_LEVELS;
 		// level L lives in buf[L & 1]; the largest stored level is K - 1
 		const size_t big = (size_t)1 << (2 * (K > 0 ? K - 1 : 0)), small = K > 1 ? big / 4 : 1;
@@ -758,8 +774,33 @@ int esa_default_packed_chars(int32_t m)
 	return c;
 }
 
+namespace
+{
+bool esa_build_impl(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k, int key_chars, cudaStream_t s,
+                    EsaTimings *tm, bool spec);
+}
+
+// The build normally runs without a single host round trip until its end ("speculative"): it
+// takes for granted that the input is valid, that the few suffixes next to separators fit
+// their list, and that no group of suffixes ties beyond what the direct comparisons settle —
+// true for every genome that is not highly repetitive — and the kernels downstream of those
+// assumptions skip their work if a device-side check says otherwise.  One read-back at the end
+// tells; if an assumption failed the index is built again the careful way, deciding on the host
+// after each stage like before.
 void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k, int key_chars, cudaStream_t s,
                       EsaTimings *tm)
+{
+	const bool timed = tm && tm->enabled; // per-phase timers synchronise anyway
+	const bool spec = !timed && g_tuning.esa_speculative && g_tuning.table_direct != 2;
+	if (spec && esa_build_impl(esa, d_ref, n, kmer_k, key_chars, s, tm, true)) return;
+	esa_build_impl(esa, d_ref, n, kmer_k, key_chars, s, tm, false);
+}
+
+namespace
+{
+// returns false (speculative mode only) if the index has to be built again without assumptions
+bool esa_build_impl(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k, int key_chars, cudaStream_t s,
+                    EsaTimings *tm, bool spec)
 {
 	if (n < 1) throw std::invalid_argument("reference is empty");
 	if ((int64_t)n * 2 + 1 > 0x7fffffffll - 128) throw std::invalid_argument("reference too long for 32-bit indices");
@@ -788,7 +829,7 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 	k_build_text<<<NUM_SMS_B200 * 8, 256, 0, s>>>(d_ref, n, esa.S.get(), padded, bad.get());
 	KERNEL_CHECK();
 	int64_t bangs = 0;
-	{
+	if (!spec) {
 		int h_flags[3];
 		CUDA_CHECK(cudaMemcpyAsync(h_flags, bad.get(), sizeof h_flags, cudaMemcpyDeviceToHost, s));
 		CUDA_CHECK(cudaStreamSynchronize(s));
@@ -797,11 +838,16 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 		bangs = h_flags[2];
 	}
 	T.text_ms = lap.lap();
+	DevBuf<int> spec_fail(1, s); // speculative mode: set by k_spec_check, read by the kernels after it
+	const int *skip = spec ? spec_fail.get() : nullptr;
+	DevBuf<uint32_t> spec_counters(4, s); // copies of {groups, hard groups, dirty suffixes, dirty error} for the final read-back
+	if (spec) spec_counters.zero();
 
 	// Which sorter: packed words (2-bit codes, <= 16 characters, suffix_sort.cuh) unless the
 	// caller asks for longer keys, the text has so many separators that ordering the dirty
 	// suffixes pairwise would cost more than it saves, or 16 characters are hopelessly few.
-	const int64_t dirty_bound = 16 * (2 * bangs + 2); // 16 suffixes in front of every byte below 'A'
+	// 16 suffixes in front of every byte below 'A'; not known yet when speculating: room for ~1000 contigs
+	const int64_t dirty_bound = spec ? PK_DIRTY_CAP : 16 * (2 * bangs + 2);
 	const bool packed = g_tuning.sort_path != 1 && key_chars <= PK_MAX_CHARS && dirty_bound <= PK_DIRTY_CAP && m <= (1 << 30);
 	int kc;
 	if (packed) {
@@ -837,10 +883,11 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 					T.scatter_ms_avg = prof.scatter_ms / prof.passes;
 				}
 			}
-			k_dirty_rank<<<div_up(cap, 8), 256, 0, s>>>(dirty_list.get(), dirty_ctl.get(), esa.S.get(), dirty_sorted.get());
+			const int dirty_blocks = std::min(div_up(cap, 8), 64); // a warp per dirty suffix, grid-stride
+			k_dirty_rank<<<dirty_blocks, 256, 0, s>>>(dirty_list.get(), dirty_ctl.get(), cap, esa.S.get(), dirty_sorted.get());
 			KERNEL_CHECK();
-			k_dirty_fix<<<div_up(cap, 8), 256, 0, s>>>(dirty_sorted.get(), dirty_ctl.get(), esa.S.get(), m, kc, W,
-			                                           (int *)(dirty_ctl.get() + 1));
+			k_dirty_fix<<<dirty_blocks, 256, 0, s>>>(dirty_sorted.get(), dirty_ctl.get(), cap, esa.S.get(), m, kc, W,
+			                                         (int *)(dirty_ctl.get() + 1));
 			KERNEL_CHECK();
 			K1 = W;
 			T.sort_ms = lap.lap();
@@ -887,14 +934,26 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 				k_small_groups<false><<<NUM_SMS_B200 * 4, 128, 0, s>>>(heads.get(), counters.get(), K1, esa.S.get(), m,
 				                                                      esa.SA.get(), esa.LCP.get(), esa.FVC.get(), kc);
 			KERNEL_CHECK();
-			uint32_t h_dirty[2] = {0, 0};
-			if (packed) CUDA_CHECK(cudaMemcpyAsync(h_dirty, dirty_ctl.get(), sizeof h_dirty, cudaMemcpyDeviceToHost, s));
-			CUDA_CHECK(cudaMemcpyAsync(h_counters, counters.get(), sizeof h_counters, cudaMemcpyDeviceToHost, s));
-			CUDA_CHECK(cudaStreamSynchronize(s));
-			T.tie_groups = h_counters[0];
-			T.dirty = h_dirty[0];
-			if (h_dirty[1] || h_dirty[0] > (uint64_t)dirty_bound)
-				throw std::runtime_error("suffix sort: dirty suffixes inconsistent with their key groups");
+			if (spec) {
+				// no read-back: a device-side check decides whether the kernels below may run, the
+				// host learns about it at the very end (counters travel with the other flags)
+				k_spec_check<<<1, 1, 0, s>>>(bad.get(), counters.get(), packed ? dirty_ctl.get() : nullptr, (uint32_t)dirty_bound,
+				                             spec_fail.get());
+				KERNEL_CHECK();
+				CUDA_CHECK(cudaMemcpyAsync(spec_counters.get(), counters.get(), 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+				if (packed)
+					CUDA_CHECK(cudaMemcpyAsync(spec_counters.get() + 2, dirty_ctl.get(), 2 * sizeof(uint32_t),
+					                           cudaMemcpyDeviceToDevice, s));
+			} else {
+				uint32_t h_dirty[2] = {0, 0};
+				if (packed) CUDA_CHECK(cudaMemcpyAsync(h_dirty, dirty_ctl.get(), sizeof h_dirty, cudaMemcpyDeviceToHost, s));
+				CUDA_CHECK(cudaMemcpyAsync(h_counters, counters.get(), sizeof h_counters, cudaMemcpyDeviceToHost, s));
+				CUDA_CHECK(cudaStreamSynchronize(s));
+				T.tie_groups = h_counters[0];
+				T.dirty = h_dirty[0];
+				if (h_dirty[1] || h_dirty[0] > (uint64_t)dirty_bound)
+					throw std::runtime_error("suffix sort: dirty suffixes inconsistent with their key groups");
+			}
 		}
 
 		// 5b. refinement of the tie groups that are left (repeats): prefix doubling
@@ -1054,18 +1113,37 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 		esa.node.alloc((size_t)m + 1, s);
 		k_cld<<<div_up((int64_t)m + 1, CLD_TILE), CLD_THREADS, 0, s>>>(py, m, esa.CLD.get(), long_list.get(),
 		                                                               long_count.get(), esa.SA.get(), esa.FVC.get(),
-		                                                               esa.node.get());
+		                                                               esa.node.get(), skip);
 		KERNEL_CHECK();
 		CUDA_CHECK(cudaStreamWaitEvent(s, ev_join, 0));
-		k_cld_long<<<NUM_SMS_B200 * 8, 256, 0, s>>>(py, long_list.get(), long_count.get(), esa.CLD.get(), esa.node.get());
+		k_cld_long<<<NUM_SMS_B200 * 8, 256, 0, s>>>(py, long_list.get(), long_count.get(), esa.CLD.get(), esa.node.get(), skip);
 		KERNEL_CHECK();
 		T.cld_ms = lap.lap();
 	}
 
 	// 8. K-mer table
-	esa_build_table(esa, kmer_k, s, true);
+	esa_build_table(esa, kmer_k, s, true, skip);
 	T.table_ms = lap.lap();
 	T.total_ms = total.lap();
+	if (spec) {
+		// the one read-back of the speculative build
+		struct {
+			int text[3];
+			int fail;
+			uint32_t cnt[4];
+		} h;
+		CUDA_CHECK(cudaMemcpyAsync(h.text, bad.get(), sizeof h.text, cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaMemcpyAsync(&h.fail, spec_fail.get(), sizeof h.fail, cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaMemcpyAsync(h.cnt, spec_counters.get(), sizeof h.cnt, cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaStreamSynchronize(s));
+		if (h.text[0]) throw std::invalid_argument("reference contains bytes outside {A,C,G,T,!}");
+		esa.gc_count = h.text[1];
+		T.tie_groups = h.cnt[0];
+		T.dirty = h.cnt[2];
+		if (h.fail) return false; // separators beyond the list, or repeats: once more, step by step
+	}
+	return true;
 }
+} // namespace
 
 } // namespace phy

@@ -80,7 +80,8 @@ void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_
 
 // builds only the table (used after importing S/SA/LCP/CLD/FVC from another GPU)
 // nodes_ready: esa.node already holds the interleaved records
-void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t stream, bool nodes_ready = false);
+// skip: device flag; if set when the kernel starts, it does nothing (speculative build)
+void esa_build_table(EsaDevice &esa, int kmer_k, cudaStream_t stream, bool nodes_ready = false, const int *skip = nullptr);
 
 int esa_default_k(int32_t m);
 

@@ -558,81 +558,84 @@ __device__ __forceinline__ bool pk_suffix_less(const uint8_t *__restrict__ S, ui
 
 // exact order of the dirty suffixes: one warp per suffix counts the smaller ones
 static __global__ void __launch_bounds__(256)
-k_dirty_rank(const uint32_t *__restrict__ list, const uint32_t *__restrict__ count, const uint8_t *__restrict__ S,
-             uint32_t *__restrict__ sorted)
+k_dirty_rank(const uint32_t *__restrict__ list, const uint32_t *__restrict__ count, uint32_t cap,
+             const uint8_t *__restrict__ S, uint32_t *__restrict__ sorted)
 {
-	const uint32_t D = *count;
-	const uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t D = *count < cap ? *count : cap; // more than cap: the caller falls back to the general sorter
+	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
 	const int lane = threadIdx.x & 31;
-	if (x >= D) return;
-	const uint32_t me = list[x];
-	uint32_t smaller = 0;
-	for (uint32_t y = lane; y < D; y += 32) {
-		const uint32_t other = list[y];
-		if (other != me && pk_suffix_less(S, other, me)) smaller++;
-	}
+	for (uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; x < D; x += nwarps) {
+		const uint32_t me = list[x];
+		uint32_t smaller = 0;
+		for (uint32_t y = lane; y < D; y += 32) {
+			const uint32_t other = list[y];
+			if (other != me && pk_suffix_less(S, other, me)) smaller++;
+		}
 #pragma unroll
-	for (int d = 16; d > 0; d >>= 1)
-		smaller += __shfl_xor_sync(0xffffffffu, smaller, d);
-	if (lane == 0) sorted[smaller] = me;
+		for (int d = 16; d > 0; d >>= 1)
+			smaller += __shfl_xor_sync(0xffffffffu, smaller, d);
+		if (lane == 0) sorted[smaller] = me;
+	}
 }
 
 // One warp per run of dirty suffixes with the same key: inside that key's group of the
 // sorted words the clean members move up (stable) and the dirty ones take the front, in
 // their exact order.  err[0] is set if the group does not hold exactly the run's suffixes.
 static __global__ void __launch_bounds__(256)
-k_dirty_fix(const uint32_t *__restrict__ sorted, const uint32_t *__restrict__ count, const uint8_t *__restrict__ S,
-            int32_t m, int kc, uint64_t *__restrict__ words, int *__restrict__ err)
+k_dirty_fix(const uint32_t *__restrict__ sorted, const uint32_t *__restrict__ count, uint32_t cap,
+            const uint8_t *__restrict__ S, int32_t m, int kc, uint64_t *__restrict__ words, int *__restrict__ err)
 {
+	if (*count > cap) return; // the list is incomplete: nothing here can be trusted, the caller starts over
 	const uint32_t D = *count;
-	const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
 	const int lane = threadIdx.x & 31;
-	if (r >= D) return;
-	const uint32_t key = pk_key_scalar(S, sorted[r], kc);
-	if (r > 0 && pk_key_scalar(S, sorted[r - 1], kc) == key) return; // not the first of its run
-	uint32_t cnt = 1;
-	while (r + cnt < D && pk_key_scalar(S, sorted[r + cnt], kc) == key)
-		cnt++;
-	// [a, b): the words with this key.  32 probes per round, one per lane.
-	int64_t bound[2];
+	for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < D; r += nwarps) {
+		const uint32_t key = pk_key_scalar(S, sorted[r], kc);
+		if (r > 0 && pk_key_scalar(S, sorted[r - 1], kc) == key) continue; // not the first of its run
+		uint32_t cnt = 1;
+		while (r + cnt < D && pk_key_scalar(S, sorted[r + cnt], kc) == key)
+			cnt++;
+		// [a, b): the words with this key.  32 probes per round, one per lane.
+		int64_t bound[2];
 #pragma unroll
-	for (int upper = 0; upper < 2; upper++) {
-		int64_t lo = upper ? bound[0] : 0, hi = m; // the answer is in [lo, hi]
-		while (lo < hi) {
-			const int64_t step = (hi - lo) / 32 + 1;
-			const int64_t pos = lo + lane * step;
-			bool before = false; // words[pos] sorts before the bound
-			if (pos < hi) {
-				const uint32_t k = (uint32_t)(words[pos] >> 32);
-				before = upper ? k <= key : k < key;
+		for (int upper = 0; upper < 2; upper++) {
+			int64_t lo = upper ? bound[0] : 0, hi = m; // the answer is in [lo, hi]
+			while (lo < hi) {
+				const int64_t step = (hi - lo) / 32 + 1;
+				const int64_t pos = lo + lane * step;
+				bool before = false; // words[pos] sorts before the bound
+				if (pos < hi) {
+					const uint32_t k = (uint32_t)(words[pos] >> 32);
+					before = upper ? k <= key : k < key;
+				}
+				const int nb = __popc(__ballot_sync(0xffffffffu, before)); // the predicate is monotone
+				const int64_t new_lo = nb ? lo + (nb - 1) * step + 1 : lo;
+				const int64_t new_hi = nb < 32 && lo + nb * step < hi ? lo + nb * step : hi;
+				lo = new_lo;
+				hi = new_hi;
 			}
-			const int nb = __popc(__ballot_sync(0xffffffffu, before)); // the predicate is monotone
-			const int64_t new_lo = nb ? lo + (nb - 1) * step + 1 : lo;
-			const int64_t new_hi = nb < 32 && lo + nb * step < hi ? lo + nb * step : hi;
-			lo = new_lo;
-			hi = new_hi;
+			bound[upper] = lo;
 		}
-		bound[upper] = lo;
+		const int64_t a = bound[0], b = bound[1];
+		// clean members to the right end, from the right (writes never pass the reads)
+		int64_t w = b;
+		for (int64_t top = b; top > a; top -= 32) {
+			const int64_t j = top - 1 - lane;
+			const uint64_t e = j >= a ? words[j] : 0;
+			const bool clean = j >= a && !((uint32_t)e & PK_DIRTY);
+			const uint32_t bal = __ballot_sync(0xffffffffu, clean);
+			__syncwarp();
+			if (clean) words[w - 1 - __popc(bal & ((1u << lane) - 1))] = e;
+			w -= __popc(bal);
+			__syncwarp();
+		}
+		if (w - a != (int64_t)cnt) {
+			if (lane == 0) atomicExch(err, 1);
+			continue;
+		}
+		for (uint32_t t = lane; t < cnt; t += 32)
+			words[a + t] = ((uint64_t)key << 32) | PK_DIRTY | sorted[r + t];
 	}
-	const int64_t a = bound[0], b = bound[1];
-	// clean members to the right end, from the right (writes never pass the reads)
-	int64_t w = b;
-	for (int64_t top = b; top > a; top -= 32) {
-		const int64_t j = top - 1 - lane;
-		const uint64_t e = j >= a ? words[j] : 0;
-		const bool clean = j >= a && !((uint32_t)e & PK_DIRTY);
-		const uint32_t bal = __ballot_sync(0xffffffffu, clean);
-		__syncwarp();
-		if (clean) words[w - 1 - __popc(bal & ((1u << lane) - 1))] = e;
-		w -= __popc(bal);
-		__syncwarp();
-	}
-	if (w - a != (int64_t)cnt) {
-		if (lane == 0) atomicExch(err, 1);
-		return;
-	}
-	for (uint32_t t = lane; t < cnt; t += 32)
-		words[a + t] = ((uint64_t)key << 32) | PK_DIRTY | sorted[r + t];
 }
 
 inline size_t pk_padded_words(int32_t m)

@@ -44,6 +44,19 @@ def test_esa_arrays(ctx, oracle, name):
         assert np.array_equal(got[k], want[k]), k
 
 
+@pytest.mark.parametrize("name", SETS)
+def test_esa_arrays_built_step_by_step(pb, oracle, name):
+    """the careful build (a host decision after every stage) that the speculative one falls
+    back to gives the same index; the speculative one is what every other test runs"""
+    ref = datasets.ALL_SETS[name]()[0]
+    with pb.Context(esa_speculative=0) as c:
+        c.esa_build(ref)
+        got = c.esa_arrays()
+    want = oracle.esa(ref).arrays()
+    for k in ("S", "SA", "LCP", "CLD", "FVC"):
+        assert np.array_equal(got[k], want[k]), k
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 31, 1023, 1024, 2047, 2048, 2049, 4095, 4096, 4097, 70001])
 def test_esa_sizes_across_tile_boundaries(ctx, oracle, n):
     rng = np.random.default_rng(n)
