@@ -69,6 +69,57 @@ struct PerDeviceOnce {
 	}
 };
 
+// ---- transaction barriers and bulk copies (Blackwell tile movement) -------------------------
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	asm volatile("{\n"
+	             ".reg .pred p;\n"
+	             "MBAR_WAIT:\n"
+	             "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	             "@p bra MBAR_DONE;\n"
+	             "bra MBAR_WAIT;\n"
+	             "MBAR_DONE:\n"
+	             "}" ::"r"(smem_u32(bar)),
+	             "r"(parity)
+	             : "memory");
+}
+// orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy
+// ones (a bulk copy into a buffer the threads have just been reading and writing)
+__device__ __forceinline__ void fence_proxy_async()
+{
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// bytes (multiple of 16, 16-byte aligned on both sides) global -> shared, completes on bar
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :
+	             : "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+	             : "memory");
+}
+#endif
+
 inline int div_up(int64_t a, int64_t b)
 {
 	return (int)((a + b - 1) / b);

@@ -201,39 +201,6 @@ template <uint32_t K> __device__ __forceinline__ uint32_t cmp_mad(uint32_t x, ui
 // ---- TMA + mbarrier plumbing (Blackwell tile movement: one thread issues a tensor copy per
 // tile side and step, the data lands in shared memory and completes a transaction barrier) ----
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-	return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init()
-{
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-	asm volatile("{\n"
-	             ".reg .pred p;\n"
-	             "CMP_WAIT:\n"
-	             "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-	             "@p bra CMP_DONE;\n"
-	             "bra CMP_WAIT;\n"
-	             "CMP_DONE:\n"
-	             "}" ::"r"(smem_u32(bar)),
-	             "r"(parity)
-	             : "memory");
-}
 // box of the 3-d tensor (word of a block, block, genome) at (0, blk, g) -> shared memory,
 // completes on bar
 __device__ __forceinline__ void tma_load_rows(void *smem_dst, const CUtensorMap *tm, int32_t blk, int32_t g, uint64_t *bar)

@@ -361,13 +361,16 @@ template <bool FROM_TEXT> struct PkSmem {
 	uint4 raw[FROM_TEXT ? 2 : 1][FROM_TEXT ? PK_RAW_CHUNKS : 1]; // text of this and the next tile
 	uint32_t codes[FROM_TEXT ? PK_WORDS + 2 : 1];
 	uint32_t spec[FROM_TEXT ? PK_WORDS + 2 : 1];
+	uint64_t full[2]; // transaction barriers of the two word buffers (bulk copies)
 };
 
 // One stable radix pass over packed words, persistent blocks: block b takes tiles b,
 // b + gridDim.x, ...; the input of the next tile (and its 256 offsets) is on its way while
 // the current one is ranked, exchanged through shared memory and written out so that every
-// digit's run leaves as one contiguous store.  offsets[tile * 256 + d] and totals[d] from
-// pk_scan_counts.  FROM_TEXT: the words are made here from the text (all ones from index n
+// digit's run leaves as one contiguous store.  A tile of words (32 KB) comes in as ONE bulk
+// copy issued by one thread (cp.async.bulk, completion on a transaction barrier) instead of
+// sixteen cp.async per thread; the text of the first pass, with its ragged end, stays with
+// cp.async.  offsets[tile * 256 + d] and totals[d] from pk_scan_counts.  FROM_TEXT: the words are made here from the text (all ones from index n
 // on), and the index of every dirty suffix is appended to dirty_list.
 // Five block barriers per tile; the kernel is bound by the logic pipe and by shared-memory
 // latency, not by HBM (profiles/), so the count of both is what was tuned.
@@ -391,12 +394,11 @@ pk_scatter(const uint64_t *__restrict__ in, const uint8_t *__restrict__ S, int32
 				const bool ok = o + 16 <= padded;
 				pk_cp_async16(&sm.raw[slot][c], S + (ok ? o : 0), ok ? 16 : 0);
 			}
-		} else {
-			const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(in) + (size_t)tile * (PK_TILE / 2) + threadIdx.x;
-			ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(sm.buf[slot]) + threadIdx.x;
-#pragma unroll
-			for (int r = 0; r < PKS_ITEMS / 2; r++)
-				pk_cp_async16(dst + r * PKS_THREADS, src + r * PKS_THREADS, 16);
+		} else if (threadIdx.x == 0) {
+			// the buffer was read and written by everybody a moment ago (before the last barrier)
+			fence_proxy_async();
+			mbar_expect_tx(&sm.full[slot], PK_TILE * (uint32_t)sizeof(uint64_t));
+			bulk_load(sm.buf[slot], in + (size_t)tile * PK_TILE, PK_TILE * (uint32_t)sizeof(uint64_t), &sm.full[slot]);
 		}
 	};
 	auto zero_counters = [&] {
@@ -406,6 +408,14 @@ pk_scatter(const uint64_t *__restrict__ in, const uint8_t *__restrict__ S, int32
 
 	int tile = blockIdx.x;
 	uint32_t my_offset = 0;
+	if (!FROM_TEXT) {
+		if (threadIdx.x == 0) {
+			mbar_init(&sm.full[0], 1);
+			mbar_init(&sm.full[1], 1);
+			mbar_fence_init();
+		}
+		__syncthreads();
+	}
 	if (tile < ntiles) {
 		prefetch(tile, 0);
 		if (threadIdx.x < RS_BINS) my_offset = offsets[(size_t)tile * RS_BINS + threadIdx.x];
@@ -438,8 +448,11 @@ pk_scatter(const uint64_t *__restrict__ in, const uint8_t *__restrict__ S, int32
 		const uint32_t tile_base = (uint32_t)tile * PK_TILE;
 		uint64_t *const buf = sm.buf[slot];
 
-		pk_cp_async_wait<0>(); // this tile's copies have landed
-		__syncthreads();       // (1) ... for everybody; the previous tile has left; the counters are zero
+		if (FROM_TEXT)
+			pk_cp_async_wait<0>(); // this tile's copies have landed
+		else
+			mbar_wait(&sm.full[slot], (uint32_t)((it >> 1) & 1)); // use it / 2 of this buffer
+		__syncthreads(); // (1) ... for everybody; the previous tile has left; the counters are zero
 		// the next tile starts to arrive
 		const int next = tile + gridDim.x;
 		const uint32_t offset_now = my_offset;
