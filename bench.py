@@ -669,7 +669,7 @@ def run_north_star(mods, args, dev, local_rank, rank, world, name, seed, ntot, l
         simgen.simf(seed, seed, length, 0.0, out=ref_host.data_ptr())
     gen_s = time.perf_counter() - t0
     pipe = Pipeline(mods, args, dev, local_rank, rank, world, plan, shard, ref_host, length, args.index, args.exchange,
-                    batch_bytes=max(16 * length, (shard.bases + 5) // 6))
+                    batch_bytes=max(16 * length, (shard.bases + 2) // 3))  # three batches per rank
     ctx = pipe.ctx
     bases_total = ntot * length
     steps = max(1, args.ns_steps)

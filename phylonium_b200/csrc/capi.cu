@@ -60,8 +60,9 @@ struct phylo_ctx {
 	std::vector<uint32_t *> peer_rows;
 	std::vector<void *> peer_ipc; // what cudaIpcOpenMemHandle returned (closed with the context)
 	int peer_rank = 0;
-	cudaStream_t push_stream = nullptr;
-	cudaEvent_t ev_rows = nullptr, ev_pushed = nullptr;
+	std::vector<cudaStream_t> push_streams; // one per peer: the copies to different peers run side by side
+	std::vector<cudaEvent_t> ev_pushed;
+	cudaEvent_t ev_rows = nullptr;
 
 	// sequences of the last phylo_process / phylo_map_queries, still in q_own (phylo_process_again)
 	std::vector<uint64_t> q_offs, q_lens;
@@ -122,7 +123,8 @@ void trim_scratch_if_large(phylo_ctx *ctx)
 
 void clear_peers(phylo_ctx *c)
 {
-	if (c->push_stream) cudaStreamSynchronize(c->push_stream);
+	for (cudaStream_t st : c->push_streams)
+		cudaStreamSynchronize(st);
 	for (void *p : c->peer_ipc)
 		if (p) cudaIpcCloseMemHandle(p);
 	c->peer_ipc.clear();
@@ -361,22 +363,37 @@ struct MapHooks {
 	bool validated = false; // the alphabet was checked while the sequences were packed on the host
 };
 
-// copies rows [first, first + count) of this context's store into the peers' stores
+// copies rows [first, first + count) of this context's store into the peers' stores, every peer
+// on a stream of its own (NVSwitch gives each pair of GPUs its full bandwidth at the same time)
 void push_rows(phylo_ctx *c, uint64_t first, uint64_t count)
 {
 	if (c->peer_rows.empty() || !count) return;
-	if (!c->push_stream) {
-		CUDA_CHECK(cudaStreamCreateWithFlags(&c->push_stream, cudaStreamNonBlocking));
-		CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_rows, cudaEventDisableTiming));
-		CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_pushed, cudaEventDisableTiming));
+	if (!c->ev_rows) CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_rows, cudaEventDisableTiming));
+	while (c->push_streams.size() < c->peer_rows.size()) {
+		cudaStream_t st;
+		cudaEvent_t ev;
+		CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+		CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+		c->push_streams.push_back(st);
+		c->ev_pushed.push_back(ev);
 	}
 	CUDA_CHECK(cudaEventRecord(c->ev_rows, c->stream));
-	CUDA_CHECK(cudaStreamWaitEvent(c->push_stream, c->ev_rows, 0));
 	const size_t off = (size_t)first * (size_t)c->rows.genome_words();
 	const size_t bytes = (size_t)count * (size_t)c->rows.genome_words() * sizeof(uint32_t);
 	for (size_t p = 0; p < c->peer_rows.size(); p++) {
 		if ((int)p == c->peer_rank || !c->peer_rows[p]) continue;
-		CUDA_CHECK(cudaMemcpyAsync(c->peer_rows[p] + off, c->rows.data.get() + off, bytes, cudaMemcpyDefault, c->push_stream));
+		CUDA_CHECK(cudaStreamWaitEvent(c->push_streams[p], c->ev_rows, 0));
+		CUDA_CHECK(cudaMemcpyAsync(c->peer_rows[p] + off, c->rows.data.get() + off, bytes, cudaMemcpyDefault, c->push_streams[p]));
+	}
+}
+
+// whatever the caller puts on the stream next (its barrier across ranks) is behind our pushes
+void join_pushes(phylo_ctx *c)
+{
+	for (size_t p = 0; p < c->push_streams.size() && p < c->peer_rows.size(); p++) {
+		if ((int)p == c->peer_rank || !c->peer_rows[p]) continue;
+		CUDA_CHECK(cudaEventRecord(c->ev_pushed[p], c->push_streams[p]));
+		CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_pushed[p], 0));
 	}
 }
 
@@ -480,11 +497,7 @@ void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_
 		if (hooks.after_batch) hooks.after_batch(b);
 		b0 = b1;
 	}
-	if (!c->peer_rows.empty() && c->push_stream) {
-		// whatever the caller puts on the stream next (its barrier across ranks) is behind our pushes
-		CUDA_CHECK(cudaEventRecord(c->ev_pushed, c->push_stream));
-		CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_pushed, 0));
-	}
+	if (!c->peer_rows.empty()) join_pushes(c);
 	record_anchor_stats(c, sum);
 	c->stats["rows.ms"] = rows_ms;
 	c->stats["map.batches"] = (double)ends.size();
@@ -585,12 +598,13 @@ void phylo_ctx_destroy(phylo_ctx *c)
 		l.destroy();
 	c->ingest.lanes.clear();
 	clear_peers(c);
-	if (c->push_stream) {
-		cudaStreamSynchronize(c->push_stream);
-		cudaStreamDestroy(c->push_stream);
-		cudaEventDestroy(c->ev_rows);
-		cudaEventDestroy(c->ev_pushed);
+	for (cudaStream_t st : c->push_streams) {
+		cudaStreamSynchronize(st);
+		cudaStreamDestroy(st);
 	}
+	for (cudaEvent_t ev : c->ev_pushed)
+		cudaEventDestroy(ev);
+	if (c->ev_rows) cudaEventDestroy(c->ev_rows);
 	c->q_own.release();
 	c->batches.clear();
 	for (cudaEvent_t e : c->batch_events)
@@ -1012,7 +1026,8 @@ void quiesce(phylo_ctx *c)
 	c->stager.drain();
 	cudaStreamSynchronize(c->copy_stream);
 	cudaStreamSynchronize(c->stream);
-	if (c->push_stream) cudaStreamSynchronize(c->push_stream);
+	for (cudaStream_t st : c->push_streams)
+		cudaStreamSynchronize(st);
 	cudaGetLastError();
 }
 
