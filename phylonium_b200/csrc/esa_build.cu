@@ -565,12 +565,21 @@ k_cld_long(Pyramid py, const int32_t *__restrict__ long_list, const uint32_t *__
 
 // ---------------------------------------------------------------- table
 
-__global__ void k_table(EsaView e, int32_t K, Interval *__restrict__ table, const int *__restrict__ skip)
+__device__ __forceinline__ void table_put(TableRec *dst, const TableRec &r)
+{
+	int4 *d = reinterpret_cast<int4 *>(dst);
+	d[0] = make_int4(r.ij.l, r.ij.i, r.ij.j, r.ij.m);
+	d[1] = make_int4(r.ni.sa, r.ni.lcp, r.ni.cld, r.ni.fvc);
+	d[2] = make_int4(r.nm.sa, r.nm.lcp, r.nm.cld, r.nm.fvc);
+	d[3] = make_int4(r.np.sa, r.np.lcp, r.np.cld, r.np.fvc);
+}
+
+__global__ void k_table(EsaView e, int32_t K, TableRec *__restrict__ table, const int *__restrict__ skip)
 {
 	if (skip && *skip) return;
 	const uint32_t code = blockIdx.x * blockDim.x + threadIdx.x;
 	if (code >= (1u << (2 * K))) return;
-	table[code] = esa_table_entry(e, code, K);
+	table_put(table + code, esa_table_record(e, esa_table_entry(e, code, K)));
 }
 
 // The table level by level (esa_search.h, esa_table_extend).  Levels 0 .. k0 are small and
@@ -594,7 +603,7 @@ __device__ __forceinline__ void table_store(TableBuild *p, const TableBuild &t)
 }
 
 __global__ void __launch_bounds__(1024)
-k_table_head(EsaView e, int32_t k0, TableBuild *buf0, TableBuild *buf1, Interval *__restrict__ final_out)
+k_table_head(EsaView e, int32_t k0, TableBuild *buf0, TableBuild *buf1, TableRec *__restrict__ final_out)
 {
 	TableBuild *buf[2] = {buf0, buf1};
 	if (threadIdx.x == 0) buf[0][0] = esa_table_root(e);
@@ -606,24 +615,24 @@ k_table_head(EsaView e, int32_t k0, TableBuild *buf0, TableBuild *buf1, Interval
 		for (uint32_t code = threadIdx.x; code < entries; code += blockDim.x) {
 			const TableBuild r = esa_table_extend(e, prev[code >> 2], k, (uint8_t)(0x54474341u >> (8 * (code & 3))));
 			if (final_out && k + 1 == k0)
-				final_out[code] = r.cur;
+				table_put(final_out + code, esa_table_record(e, r.cur));
 			else
 				next[code] = r;
 		}
 		__syncthreads(); // one block: the level is visible to all its threads
 	}
-	if (k0 == 0 && final_out && threadIdx.x == 0) final_out[0] = buf[0][0].cur;
+	if (k0 == 0 && final_out && threadIdx.x == 0) table_put(final_out, esa_table_record(e, buf[0][0].cur));
 }
 
 __global__ void __launch_bounds__(256)
 k_table_level(EsaView e, int32_t k, const TableBuild *__restrict__ prev, TableBuild *__restrict__ next,
-              Interval *__restrict__ final_out)
+              TableRec *__restrict__ final_out)
 {
 	const uint32_t code = blockIdx.x * blockDim.x + threadIdx.x;
 	if (code >= (1u << (2 * (k + 1)))) return;
 	const TableBuild r = esa_table_extend(e, table_load(prev + (code >> 2)), k, (uint8_t)(0x54474341u >> (8 * (code & 3))));
 	if (final_out)
-		reinterpret_cast<int4 *>(final_out)[code] = make_int4(r.cur.l, r.cur.i, r.cur.j, r.cur.m);
+		table_put(final_out + code, esa_table_record(e, r.cur));
 	else
 		table_store(next + code, r);
 }

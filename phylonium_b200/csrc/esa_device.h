@@ -31,7 +31,7 @@ struct EsaDevice {
 	DevBuf<int32_t> LCP; // m + 1
 	DevBuf<int32_t> CLD; // m + 1
 	DevBuf<EsaNode> node;   // m + 1: SA/LCP/CLD/FVC interleaved for the descent (esa_search.h)
-	DevBuf<Interval> table; // 4^K
+	DevBuf<TableRec> table; // 4^K
 	// side stream of the build (min-pyramid next to the child-table kernel), made on first use
 	cudaStream_t side = nullptr;
 	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

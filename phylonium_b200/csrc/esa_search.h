@@ -47,26 +47,17 @@ PHY_HD bool interval_empty(const Interval &ij)
 	return ij.i == -1 && ij.j == -1;
 }
 
-// src/esa.cxx:361-427 — child interval of ij whose suffixes continue with character a.
-// sa receives SA[result.i] (undefined for an empty result).
-PHY_HD Interval esa_get_interval(const EsaView &e, Interval ij, uint8_t a, int32_t &sa)
+// src/esa.cxx:361-427 — child interval of ij (i < j) whose suffixes continue with character a,
+// given the records of i (ni), of the first l-index m (nm) and of m - 1 (np) and the text byte
+// c0 = S[SA[i] + l].  sa receives SA[result.i] (undefined for an empty result).
+PHY_HD Interval esa_get_interval_core(const EsaView &e, Interval ij, uint8_t a, int32_t &sa, EsaNode ni, EsaNode nm,
+                                      EsaNode np, uint8_t c0)
 {
 	int32_t i = ij.i;
 	const int32_t j = ij.j;
-	EsaNode ni = esa_node(e, i);
 	sa = ni.sa;
-	if (i == j) {
-		if (e.S[ni.sa + ij.l] != a) ij.i = ij.j = -1;
-		return ij;
-	}
 	int32_t m = ij.m;
 	const int32_t l = ij.l;
-	// the record of the next l-index m and, speculatively, of m - 1 (whose CLD and hint give the
-	// child [i, m - 1] if that is the one we are after): both are independent of the text load
-	// below and of each other, so a step down costs two round trips to memory instead of four
-	EsaNode nm = esa_node(e, m);
-	EsaNode np = esa_node(e, m - 1);
-	const uint8_t c0 = e.S[ni.sa + l];
 	uint8_t c = c0;
 	for (;;) {
 		if (c == a) {
@@ -93,6 +84,25 @@ PHY_HD Interval esa_get_interval(const EsaView &e, Interval ij, uint8_t a, int32
 	ij.l = nm.lcp; // LCP[m]; for i == j == m this is LCP[i] like in the reference
 	ij.m = m;
 	return ij;
+}
+
+// src/esa.cxx:361-427 — child interval of ij whose suffixes continue with character a.
+// sa receives SA[result.i] (undefined for an empty result).
+PHY_HD Interval esa_get_interval(const EsaView &e, Interval ij, uint8_t a, int32_t &sa)
+{
+	const EsaNode ni = esa_node(e, ij.i);
+	sa = ni.sa;
+	if (ij.i == ij.j) {
+		if (e.S[ni.sa + ij.l] != a) ij.i = ij.j = -1;
+		return ij;
+	}
+	// the record of the next l-index m and, speculatively, of m - 1 (whose CLD and hint give the
+	// child [i, m - 1] if that is the one we are after): both are independent of the text load
+	// below and of each other, so a step down costs two round trips to memory instead of four
+	const EsaNode nm = esa_node(e, ij.m);
+	const EsaNode np = esa_node(e, ij.m - 1);
+	const uint8_t c0 = e.S[ni.sa + ij.l];
+	return esa_get_interval_core(e, ij, a, sa, ni, nm, np, c0);
 }
 
 // Lane groups.  A walker of anchor.cu is run by COOP consecutive lanes of a warp (32, 16 or
@@ -208,8 +218,11 @@ PHY_HD Match esa_extend_singleton(const EsaView &e, const uint8_t *q, int32_t ql
 
 // src/esa.cxx:446-513 — continue a match of q[0..k) that sits in the proper interval ij
 // (i < j, k == ij.l).
+// pre: a table record whose ij is this very interval; its ni / nm / np / text byte serve the
+// first step (no loads), later steps fetch their own
 template <int COOP = 0>
-PHY_HD Match esa_match_from(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t k, Interval ij, int32_t cap)
+PHY_HD Match esa_match_from(const EsaView &e, const uint8_t *q, int32_t qlen, int32_t k, Interval ij, int32_t cap,
+                            const TableRec *pre = nullptr)
 {
 	Match res;
 	res.i = ij.i;
@@ -218,7 +231,12 @@ PHY_HD Match esa_match_from(const EsaView &e, const uint8_t *q, int32_t qlen, in
 	res.sa = -1;
 	do {
 		int32_t sa;
-		ij = esa_get_interval(e, ij, q[k], sa);
+		if (pre) {
+			ij = esa_get_interval_core(e, ij, q[k], sa, pre->ni, pre->nm, pre->np, (uint8_t)pre->np.sa);
+			pre = nullptr;
+		} else {
+			ij = esa_get_interval(e, ij, q[k], sa);
+		}
 		if (interval_empty(ij)) {
 			res.l = k;
 			return res;
@@ -282,22 +300,45 @@ template <int COOP = 0> PHY_HD Match esa_match(const EsaView &e, const uint8_t *
 			code = (code << 2) | (uint32_t)c;
 		}
 	}
+	TableRec rec;
 #if defined(__CUDA_ARCH__)
-	const int4 tv = __ldg(reinterpret_cast<const int4 *>(e.table) + code);
-	Interval ij{tv.x, tv.y, tv.z, tv.w};
+	{
+		const int4 *src = reinterpret_cast<const int4 *>(e.table + code);
+		const int4 t0 = __ldg(src), t1 = __ldg(src + 1), t2 = __ldg(src + 2), t3 = __ldg(src + 3);
+		rec.ij = Interval{t0.x, t0.y, t0.z, t0.w};
+		rec.ni = EsaNode{t1.x, t1.y, t1.z, t1.w};
+		rec.nm = EsaNode{t2.x, t2.y, t2.z, t2.w};
+		rec.np = EsaNode{t3.x, t3.y, t3.z, t3.w};
+	}
 #else
-	Interval ij = e.table[code];
+	rec = e.table[code];
 #endif
+	const Interval ij = rec.ij;
 	if (ij.i == ij.j) return esa_extend_singleton<COOP>(e, q, qlen, ij.l, ij.i, ij.m, cap);
 	int32_t k = ij.l;
 	if (k > K) {
 		// the table verified K characters of this deep interval; finish its label
 		const int32_t l = ij.l < qlen ? ij.l : qlen;
-		k = match_run<COOP>(e.S + esa_node(e, ij.i).sa, q, K, l);
+		k = match_run<COOP>(e.S + rec.ni.sa, q, K, l);
 		if (k < l) return Match{k, ij.i, ij.j, 0, -1};
 		if (k >= qlen) return Match{qlen, ij.i, ij.j, 0, -1};
 	}
-	return esa_match_from<COOP>(e, q, qlen, k, ij, cap);
+	return esa_match_from<COOP>(e, q, qlen, k, ij, cap, &rec);
+}
+
+// The table record of an interval: the interval and what the first step down from it needs.
+PHY_HD TableRec esa_table_record(const EsaView &e, const Interval &ij)
+{
+	TableRec r;
+	r.ij = ij;
+	r.ni = r.nm = r.np = EsaNode{0, 0, 0, 0};
+	if (ij.i != ij.j && ij.i >= 0) {
+		r.ni = esa_node(e, ij.i);
+		r.nm = esa_node(e, ij.m);
+		r.np = esa_node(e, ij.m - 1);
+		r.np.sa = (int32_t)e.S[r.ni.sa + ij.l];
+	}
+	return r;
 }
 
 // One record of the K-mer table: descend on the K characters of `code`, stop before a

@@ -39,6 +39,16 @@ PHY_HD int32_t esa_pack_fvc(uint8_t fvc, int32_t lcp_of_cld)
 	return (int32_t)((uint32_t)fvc | (hint << 8));
 }
 
+// One record of the K-mer table: the descent state for the K-mer (see Interval) and, for a
+// proper interval, everything the NEXT step of the descent would have to fetch first — the
+// records of index i, of the first l-index m and of m - 1, and the text byte S[SA[i] + l] (kept
+// in np.sa, which the descent never reads) — so that a search that starts from the table takes
+// its first step down without a single dependent load.  64 bytes, one or two sectors.
+struct alignas(64) TableRec {
+	Interval ij;
+	EsaNode ni, nm, np;
+};
+
 struct EsaView {
 	const uint8_t *S;   // m bytes, followed by >= 64 zero bytes
 	const int32_t *SA;  // m
@@ -46,7 +56,7 @@ struct EsaView {
 	const int32_t *CLD; // m + 1
 	const uint8_t *FVC; // m
 	const EsaNode *node; // m + 1: the four arrays above interleaved (used by the descent)
-	const Interval *table; // 4^K records, the GPU counterpart of the 6-mer cache (src/esa.cxx:90-228)
+	const TableRec *table; // 4^K records, the GPU counterpart of the 6-mer cache (src/esa.cxx:90-228)
 	int32_t K;
 	int32_t m; // 2n + 1
 	int32_t n; // reference length == index of '#'

@@ -27,7 +27,7 @@ namespace
 struct HostEsa {
 	std::vector<uint8_t> S, FVC;
 	std::vector<int32_t> SA, LCP, CLD;
-	std::vector<Interval> table;
+	std::vector<TableRec> table;
 	std::vector<EsaNode> node;
 	EsaView view;
 };
@@ -65,7 +65,7 @@ HostEsa make_esa(const uint8_t *S, const int64_t *SA, const int64_t *LCP, const 
 	if (K > 0) {
 		e.table.resize((size_t)1 << (2 * K));
 		for (uint32_t code = 0; code < e.table.size(); code++)
-			e.table[code] = esa_table_entry(e.view, code, K);
+			e.table[code] = esa_table_record(e.view, esa_table_entry(e.view, code, K));
 		// the level-by-level construction of esa_build.cu must give the very same records
 		std::vector<TableBuild> level(1, esa_table_root(e.view));
 		for (int32_t k = 0; k < K; k++) {
@@ -75,7 +75,7 @@ HostEsa make_esa(const uint8_t *S, const int64_t *SA, const int64_t *LCP, const 
 			level.swap(next);
 		}
 		for (uint32_t code = 0; code < e.table.size(); code++) {
-			const Interval a = e.table[code], b = level[code].cur;
+			const Interval a = e.table[code].ij, b = level[code].cur;
 			if (a.l != b.l || a.i != b.i || a.j != b.j || a.m != b.m) {
 				fprintf(stderr, "emul: hierarchical table differs at K=%d code=%u: (%d %d %d %d) vs (%d %d %d %d)\n", K, code,
 				        a.l, a.i, a.j, a.m, b.l, b.i, b.j, b.m);
