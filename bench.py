@@ -371,9 +371,9 @@ class Pipeline:
 
     def counts(self):
         """(2, total, total) int64 in genome order"""
-        if self.world > 1:
+        if self.world > 1 and (self.plan.layout != "block" or self.plan.padded_total != self.plan.total):
             return self.sharding.genome_order(self.d_counts, self.plan)
-        return self.d_counts.reshape(2, self.n, self.n)
+        return self.d_counts.reshape(2, self.n, self.n)  # slot order is genome order
 
     def close(self):
         self.ctx.close()
