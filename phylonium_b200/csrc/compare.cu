@@ -157,17 +157,21 @@ __global__ void k_and_valid(const uint32_t *__restrict__ rows, int64_t genome_wo
 
 constexpr int PT = 4; // genomes per side of a warp's sub-tile
 // CT = genomes per side of a block's tile: 16, or 8 when there are so few genomes that 16 x 16
-// tiles would be mostly padding.  A tile has (CT / PT)^2 sub-tiles of 4 x 4 pairs; a block of 8
-// warps takes two sub-tiles per warp (CT = 16), a block of 4 warps one (CT = 8).
+// tiles would be mostly padding.  A tile has (CT / PT)^2 sub-tiles of 4 x 4 pairs, one per warp
+// (two with CMP_TILE_WARPS = 8).
 // (geometry switchable at compile time for A/B runs: warps per 16 x 16 tile, resident blocks)
+// Measured on B200, 1000 x 3 Mbp: 8 warps x 2 blocks per SM x 3 stages 31.4 ms; 16 warps x 1
+// block x 6 (or 5) stages 25.7 ms — the same 16 warps per SM, but one deep pipeline instead of
+// two shallow ones: the warps that run ahead find their tiles there; 16 warps x 2 blocks (64
+// registers) and 8 warps x 3 blocks (80 registers) spill and take 43 / 41 ms.
 #ifndef CMP_TILE_WARPS
-#define CMP_TILE_WARPS 8
+#define CMP_TILE_WARPS 16
 #endif
 #ifndef CMP_MIN_BLOCKS
-#define CMP_MIN_BLOCKS 2
+#define CMP_MIN_BLOCKS 1
 #endif
 #ifndef CMP_STAGES_N
-#define CMP_STAGES_N 3
+#define CMP_STAGES_N 6
 #endif
 __host__ __device__ constexpr int cmp_threads(int CT)
 {
