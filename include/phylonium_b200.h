@@ -92,6 +92,9 @@ int phylo_set_stream(phylo_ctx *ctx, void *stream);
  *              pass, 2 = single-pass look-back ("onesweep")
  *   "stage_threads" worker threads that pack the sequences of phylo_process / phylo_map_queries
  *               to 2 bits per base for the trip over PCIe; 0 = from the core count (default)
+ *   "push_kernel" sharded runs, rows of the last batch of a mapping: 1 (default) = written into
+ *               the peers' stores by a kernel (stores over NVLink, three planes where enough),
+ *               0 = copy engines like the earlier batches
  *   "esa_speculative" 1 (default) = the index build makes no host round trip until its end and
  *               is redone step by step if what it took for granted (valid input, few separators,
  *               no repeats beyond the direct comparisons) turns out wrong; 0 = always step by step

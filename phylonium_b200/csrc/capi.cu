@@ -60,6 +60,9 @@ struct phylo_ctx {
 	std::vector<uint32_t *> peer_rows;
 	std::vector<void *> peer_ipc; // what cudaIpcOpenMemHandle returned (closed with the context)
 	int peer_rank = 0;
+	DevBuf<int> db_sent; // device flag of rows_push_kernel
+	bool db_sent_host = false;
+	bool pushed_async = false; // copy-engine pushes in flight that the mapping stream has not joined yet // ... and what the copy-engine pushes (always all planes) imply
 	std::vector<cudaStream_t> push_streams; // one per peer: the copies to different peers run side by side
 	std::vector<cudaEvent_t> ev_pushed;
 	cudaEvent_t ev_rows = nullptr;
@@ -129,6 +132,8 @@ void clear_peers(phylo_ctx *c)
 		if (p) cudaIpcCloseMemHandle(p);
 	c->peer_ipc.clear();
 	c->peer_rows.clear();
+	c->db_sent.release(); // new peers (or a new store): nothing has been sent to them yet
+	c->db_sent_host = false;
 }
 
 template <typename F> int guarded(phylo_ctx *ctx, F &&f)
@@ -363,11 +368,32 @@ struct MapHooks {
 	bool validated = false; // the alphabet was checked while the sequences were packed on the host
 };
 
-// copies rows [first, first + count) of this context's store into the peers' stores, every peer
-// on a stream of its own (NVSwitch gives each pair of GPUs its full bandwidth at the same time)
-void push_rows(phylo_ctx *c, uint64_t first, uint64_t count)
+// copies rows [first, first + count) of this context's store into the peers' stores.
+// A batch that is followed by another one goes through the copy engines, every peer on a stream
+// of its own (NVSwitch gives each pair of GPUs its full bandwidth at the same time), next to the
+// mapping of the next batch.  The last batch — the only one nothing can hide — is pushed by a
+// kernel on the mapping stream itself: all SMs feed the links, three of five planes where that
+// is enough, no extra streams and events to wait for.
+void push_rows(phylo_ctx *c, uint64_t first, uint64_t count, bool last)
 {
 	if (c->peer_rows.empty() || !count) return;
+	if (c->peer_rows.size() > 16) throw std::invalid_argument("at most 16 ranks can exchange rows");
+	if (!c->db_sent.get()) {
+		c->db_sent.alloc(1, c->stream);
+		c->db_sent.zero();
+	}
+	if (last && c->tuning.push_kernel) {
+		RowPeers peers;
+		peers.n = (int)c->peer_rows.size();
+		for (int p = 0; p < 16; p++)
+			peers.ptr[p] = (p < peers.n && p != c->peer_rank) ? c->peer_rows[p] : nullptr;
+		if (c->db_sent_host) { // a copy-engine push has sent D / B planes before: tell the kernel
+			const int one = 1;
+			CUDA_CHECK(cudaMemcpyAsync(c->db_sent.get(), &one, sizeof one, cudaMemcpyHostToDevice, c->stream));
+		}
+		rows_push_kernel(c->rows, peers, (int64_t)first, (int32_t)count, c->db_sent.get(), c->stream);
+		return;
+	}
 	if (!c->ev_rows) CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_rows, cudaEventDisableTiming));
 	while (c->push_streams.size() < c->peer_rows.size()) {
 		cudaStream_t st;
@@ -385,11 +411,15 @@ void push_rows(phylo_ctx *c, uint64_t first, uint64_t count)
 		CUDA_CHECK(cudaStreamWaitEvent(c->push_streams[p], c->ev_rows, 0));
 		CUDA_CHECK(cudaMemcpyAsync(c->peer_rows[p] + off, c->rows.data.get() + off, bytes, cudaMemcpyDefault, c->push_streams[p]));
 	}
+	c->db_sent_host = true; // whole rows went over: D / B planes included
+	c->pushed_async = true;
 }
 
 // whatever the caller puts on the stream next (its barrier across ranks) is behind our pushes
 void join_pushes(phylo_ctx *c)
 {
+	if (!c->pushed_async) return;
+	c->pushed_async = false;
 	for (size_t p = 0; p < c->push_streams.size() && p < c->peer_rows.size(); p++) {
 		if ((int)p == c->peer_rank || !c->peer_rows[p]) continue;
 		CUDA_CHECK(cudaEventRecord(c->ev_pushed[p], c->push_streams[p]));
@@ -493,7 +523,7 @@ void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_
 		rows_build(c->rows, (int64_t)(first_row + b0), dQ, d_qi.get(), (int32_t)cnt, B.res.homs.get(), B.res.d_begin.get(),
 		           B.res.d_count.get(), s);
 		rows_ms += wt.stop();
-		push_rows(c, first_row + b0, cnt);
+		push_rows(c, first_row + b0, cnt, b + 1 == ends.size());
 		if (hooks.after_batch) hooks.after_batch(b);
 		b0 = b1;
 	}
@@ -669,6 +699,8 @@ int phylo_set_option(phylo_ctx *c, const char *key, int64_t value)
 		} else if (k == "key_chars") {
 			if (value < 0 || value > 21) throw std::invalid_argument("key_chars must be in [0, 21]");
 			c->opt_key_chars = value;
+		} else if (k == "push_kernel") {
+			c->tuning.push_kernel = value != 0;
 		} else if (k == "esa_speculative") {
 			c->tuning.esa_speculative = value != 0;
 		} else if (k == "compare_path") {

@@ -50,6 +50,7 @@ struct Tuning {
 	int sort_path = 0;         // "sort_path": 0 pick, 1 always the general sorter (3-bit codes, 64-bit keys)
 	int table_direct = 0;      // "table_direct": 0 / 1 entry by entry from the root, 2 level by level
 	uint64_t map_batch_bytes = 512ull << 20; // "map_batch_bytes"
+	int push_kernel = 1;       // "push_kernel": 1 = the last batch of rows goes to the peers by a kernel, 0 = copy engines
 	int esa_speculative = 1;   // "esa_speculative": 1 = index build without host round trips (checked at its end)
 	int compare_path = 0;      // "compare_path": 0 = TMA + mbarrier pipeline, 1 = cp.async double buffering
 	int upload_raw = 0;        // "upload_raw": 1 = sequences cross PCIe as bytes instead of packed to 2 bits

@@ -599,6 +599,34 @@ void rows_build(RowStore &rs, int64_t first_row, const uint8_t *d_Q, const Query
 
 namespace
 {
+// Rows [first, first + count) of this GPU's store written into the peers' stores with plain
+// stores over NVLink (peer memory mapped into this process): the exchange of a sharded run as
+// a kernel, for the batch nothing else can hide — 16 bytes per thread and peer, every SM
+// feeding the links.  A genome that uses no D / B plane sends only its first three planes
+// (1152 of every 1920 bytes), unless D / B planes have ever been sent from this store
+// (*db_sent): then the peers may hold stale ones and zeros have to go over as well.
+__global__ void __launch_bounds__(256)
+k_push_rows(const uint32_t *__restrict__ rows, RowPeers peers, int64_t genome_words, int64_t W, int64_t first,
+            int *__restrict__ db_sent)
+{
+	const int64_t g = first + blockIdx.y;
+	const uint32_t *row = rows + g * genome_words;
+	const uint32_t flags = row[ROW_PLANES * W + ROW_WORD_FLAGS];
+	const bool all_planes = flags != 0 || *db_sent != 0;
+	if (flags != 0 && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(db_sent, 1);
+	constexpr int UNITS_PER_BLK = ROW_PLANES * ROW_BLK / 4, UNITS_3 = 3 * ROW_BLK / 4; // 16-byte units
+	const int64_t units = (W / ROW_BLK) * UNITS_PER_BLK + ROW_FLAG_WORDS / 4;          // + the flag words
+	const uint4 *src = reinterpret_cast<const uint4 *>(row);
+	for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (int64_t)gridDim.x * blockDim.x) {
+		if (!all_planes && u < units - 1 && (u % UNITS_PER_BLK) >= UNITS_3) continue;
+		const uint4 v = src[u];
+		const int64_t at = g * (genome_words / 4) + u;
+#pragma unroll 4
+		for (int p = 0; p < peers.n; p++)
+			if (peers.ptr[p]) reinterpret_cast<uint4 *>(peers.ptr[p])[at] = v;
+	}
+}
+
 // Tensor map of the row store for the 3-plane path: a 3-d tensor of 64-bit elements (element
 // of a block's first three planes, block, genome) whose box is one block of one tile side:
 // 144 elements (= 3 planes x ROW_BLK words, 1152 contiguous bytes) x 1 block x CT genomes.
@@ -630,6 +658,20 @@ void rows_tensor_map(const RowStore &rs, int CT, CUtensorMap *out)
 	if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed for the row store (code " + std::to_string((int)r) + ")");
 }
 } // namespace
+
+void rows_push_kernel(const RowStore &rs, const RowPeers &peers, int64_t first, int32_t count, int *d_db_sent,
+                      cudaStream_t s)
+{
+	if (count <= 0 || peers.n <= 0) return;
+	const int64_t units = (rs.W / ROW_BLK) * (ROW_PLANES * ROW_BLK / 4) + 1;
+	int bx = div_up(units, 256 * 4); // four 16-byte units per thread
+	if (bx > 2048) bx = 2048;
+	for (int32_t k0 = 0; k0 < count; k0 += 32768) {
+		const int32_t c = count - k0 < 32768 ? count - k0 : 32768;
+		k_push_rows<<<dim3(bx, c), 256, 0, s>>>(rs.data.get(), peers, rs.genome_words(), rs.W, first + k0, d_db_sent);
+		KERNEL_CHECK();
+	}
+}
 
 int compare_tile_side(int64_t N)
 {

@@ -49,6 +49,17 @@ struct RowStore {
 	int64_t genome_words() const { return ROW_PLANES * W + ROW_FLAG_WORDS; }
 };
 
+// the row stores of the other ranks of a sharded run, as mapped into this process (nullptr
+// for this rank itself)
+struct RowPeers {
+	uint32_t *ptr[16];
+	int n = 0;
+};
+// copies rows [first, first + count) into the peers' stores with a kernel (stores over NVLink);
+// d_db_sent: device flag "D / B planes have been sent from this store before"
+void rows_push_kernel(const RowStore &rs, const RowPeers &peers, int64_t first, int32_t count, int *d_db_sent,
+                      cudaStream_t s);
+
 void rows_alloc(RowStore &rs, int64_t genomes, int32_t n, cudaStream_t s);
 // marks every slot as "not written" (and without D / B planes)
 void rows_clear_flags(RowStore &rs, cudaStream_t s);
