@@ -49,7 +49,8 @@ def make_family(rng, big=False):
             ref = ref[:b] + b"!" + ref[b:]
     flat = ref.replace(b"!", b"") or b"A"
     genomes = [ref]
-    for _ in range(int(rng.integers(1, 9))):
+    many = rng.random() < 0.12 and n < 6000  # enough genomes for 16 x 16 tiles and several tile columns
+    for _ in range(int(rng.integers(25, 45)) if many else int(rng.integers(1, 9))):
         r = rng.random()
         q = datasets.mutate(rng, flat, float(rng.choice([0.0, 0.001, 0.01, 0.03, 0.08, 0.2])))
         if r < 0.15:
@@ -100,13 +101,22 @@ def main():
                 kmer_k=int(rng.choice([-1, 0, 1, 5, 9])), key_chars=int(rng.choice([0, 0, 2, 7, 16, 21])),
                 sort_path=int(rng.choice([0, 0, 1])), scan_mode=int(rng.choice([1, 1, 0])),
                 map_batch_bytes=int(rng.choice([1, 5000, 512 << 20])), table_direct=int(rng.choice([0, 2])), keep_raw=1,
+                upload_raw=int(rng.choice([0, 0, 1, -1])), compare_path=int(rng.choice([0, 0, 1])),
+                esa_speculative=int(rng.choice([1, 1, 0])), stage_threads=int(rng.choice([0, 1, 3])),
             )
+            via_ingest = rng.random() < 0.25
             flags = int(rng.choice([0, 0, 4]))
-            recipe = f"seed={args.seed} round={rounds} ref_index={ref_index} flags={flags} opts={opts} lens={[len(g) for g in genomes]}"
+            recipe = (f"seed={args.seed} round={rounds} ref_index={ref_index} flags={flags} opts={opts} "
+                      f"lens={[len(g) for g in genomes]}")
             want = oracle.process(genomes, ref_index, flags, threads=4)
             print_recipe_on_error = recipe
             with pb.Context(**opts) as ctx:
-                subst, homol = ctx.process(genomes, ref_index, flags)
+                if via_ingest:  # sequences handed over one by one, then process() on what is resident
+                    ctx.ingest(genomes, max_lens=[len(g) + int(rng.integers(0, 50)) for g in genomes],
+                               lanes=int(rng.integers(1, 4)), threads=int(rng.integers(1, 4)))
+                    subst, homol = ctx.process_again(ref_index, flags)
+                else:
+                    subst, homol = ctx.process(genomes, ref_index, flags)
                 if not (np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])):
                     print("COUNTS DIFFER:", recipe)
                     return 1
