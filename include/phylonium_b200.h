@@ -119,6 +119,13 @@ double phylo_gc_content(const char *seq, uint64_t n);
  * as min_anchor_length(ANCHOR_P_VALUE = 0.025, gc, 2n + 1) (:416-417) */
 uint64_t phylo_min_anchor_length(double p, double gc, uint64_t l);
 
+/* The packing the library applies to sequences before they cross PCIe (host code, no GPU
+ * needed; exported for tests): n bytes over {A,C,G,T,!} -> (n + 3) / 4 bytes, base k of a
+ * group of four in bits 2k, 2k + 1, code (c >> 1) & 3 (A 0, C 1, T 2, G 3); '!' packs as 0 and
+ * its position goes to bangs (at most cap entries are written, *nbangs counts all).  Returns 1
+ * if a byte outside the alphabet was met, else 0. */
+int phylo_host_pack_2bit(const char *seq, uint64_t n, uint8_t *packed, uint32_t *bangs, uint32_t cap, uint32_t *nbangs);
+
 /* ---- stage 1: index ---------------------------------------------------------------- */
 
 /* esa::esa(const sequence &), src/esa.cxx:69-81: S = ref '#' revcomp(ref), suffix array

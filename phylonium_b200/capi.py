@@ -41,6 +41,7 @@ SIGNATURES = {
     "phylo_get_stat": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double)]),
     "phylo_gc_content": (C.c_double, [C.c_char_p, C.c_uint64]),
     "phylo_min_anchor_length": (C.c_uint64, [C.c_double, C.c_double, C.c_uint64]),
+    "phylo_host_pack_2bit": (C.c_int, [C.c_char_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "phylo_esa_build": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64]),
     "phylo_esa_size": (C.c_int, [C.c_void_p, _u64p]),
     "phylo_esa_get_arrays": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5),

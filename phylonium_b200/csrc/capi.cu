@@ -777,6 +777,14 @@ double shuprop(uint64_t x, double p, uint64_t l)
 }
 } // namespace
 
+int phylo_host_pack_2bit(const char *seq, uint64_t n, uint8_t *packed, uint32_t *bangs, uint32_t cap, uint32_t *nbangs)
+{
+	uint32_t nb = 0;
+	const int bad = pack_2bit(reinterpret_cast<const uint8_t *>(seq), (size_t)n, packed, bangs, cap, &nb);
+	if (nbangs) *nbangs = nb;
+	return bad;
+}
+
 uint64_t phylo_min_anchor_length(double p, double gc, uint64_t l)
 {
 	uint64_t x = 1;
