@@ -356,6 +356,7 @@ constexpr int CLD_TILE = CLD_THREADS * CLD_ITEMS; // entries per block
 constexpr int CLD_HALO = 128;
 constexpr int CLD_LEVELS = 8;                     // windows of 1 .. 128 entries
 constexpr int CLD_SPAN = CLD_TILE + 2 * CLD_HALO + 1;
+constexpr int CLD_NEAR = 4; // neighbours looked at directly before the sparse table is asked
 
 struct CldTable {
 	int32_t st[CLD_LEVELS][CLD_SPAN];
@@ -405,11 +406,81 @@ k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ lo
 			T.st[k][t] = (t + 2 * half <= CLD_SPAN) ? min(T.st[k - 1][t], T.st[k - 1][t + half]) : 0x7fffffff;
 	}
 	__syncthreads();
+	// Three out of four answers lie within CLD_NEAR positions (LCP values of neighbouring suffixes
+	// are small and close): those are found by looking at the neighbours directly.  The others
+	// are queued in shared memory and go through the sparse table afterwards, densely packed —
+	// a warp in which one lane needs the 8-level gallops would otherwise make all 32 pay for them.
+	__shared__ uint16_t hard[CLD_TILE];
+	__shared__ int nhard;
+	if (threadIdx.x == 0) nhard = 0;
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	auto emit = [&](int64_t i, int32_t a, int res) { // res: window position of the answer, or -1 = far
+		const int32_t cld = res >= 0 ? (int32_t)(lo + res) : 0; // far entries: k_cld_long fills it in
+		if (res >= 0) CLD[i] = cld;
+		const int32_t lcp_of_cld = res >= 0 ? T.st[0][res] : 0x7ffffff0; // far: no hint yet
+		reinterpret_cast<int4 *>(node)[i] = make_int4(SA[i], a, cld, esa_pack_fvc(FVC[i], lcp_of_cld));
+	};
 #pragma unroll
 	for (int r = 0; r < CLD_ITEMS; r++) {
 		const int64_t i = tile0 + r * CLD_THREADS + threadIdx.x;
-		int res = -1;
+		bool is_hard = false;
 		if (i < m) {
+			const int t = (int)(i - lo);
+			const int32_t a = T.st[0][t], b = T.st[0][t + 1];
+			const bool up = b < a;
+			// up: last position left of t with LCP <= b; down: first position right of t with LCP <= a
+			const int32_t v = up ? b : a;
+			const int dir = up ? -1 : 1;
+			int x = -1;
+#pragma unroll
+			for (int k = CLD_NEAR; k >= 1; k--)
+				if (T.st[0][t + dir * k] <= v) x = t + dir * k; // the nearest one wins (k counts down)
+			if (x >= 0) {
+				int res;
+				if (!up && T.st[0][x] == a) {
+					res = x; // the next l-index
+				} else {
+					// leftmost minimum of (x, t] (up) or (t, x) (down): at most CLD_NEAR entries
+					const int from = up ? x + 1 : t + 1, to = up ? t : x - 1;
+					res = from;
+					int32_t best = T.st[0][from];
+#pragma unroll
+					for (int k = 1; k < CLD_NEAR; k++) {
+						const int q = from + k;
+						if (q <= to) {
+							const int32_t val = T.st[0][q];
+							if (val < best) {
+								best = val;
+								res = q;
+							}
+						}
+					}
+				}
+				emit(i, a, res);
+			} else {
+				is_hard = true;
+			}
+		} else if (i == m) {
+			CLD[i] = 0;
+			reinterpret_cast<int4 *>(node)[i] = make_int4(0, LCP[m], 0, esa_pack_fvc(0, LCP[0]));
+		}
+		const uint32_t bal = __ballot_sync(0xffffffffu, is_hard);
+		if (bal) {
+			int base = 0;
+			if (lane == __ffs(bal) - 1) base = atomicAdd(&nhard, __popc(bal));
+			base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+			if (is_hard) hard[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)(i - tile0);
+		}
+	}
+	__syncthreads();
+	const int n_hard = nhard;
+	for (int q0 = 0; q0 < n_hard; q0 += CLD_THREADS) {
+		const int q = q0 + threadIdx.x;
+		bool far = false;
+		int64_t i = 0;
+		if (q < n_hard) {
+			i = tile0 + hard[q];
 			const int t = (int)(i - lo);
 			const int32_t a = T.st[0][t], b = T.st[0][t + 1];
 			// One code path for both cases (lanes of a warp are a mix of them, and divergent
@@ -418,6 +489,7 @@ k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ lo
 			// of i with LCP <= a; then the leftmost minimum of (p, i] or (i, s) — unless LCP[s] == a,
 			// when s itself is the next l-index.
 			const bool up = b < a;
+			int res = -1;
 			const int x = T.gallop(up ? t - 1 : t + 1, up ? b : a, up);
 			if (x >= 0) {
 				if (!up && T.st[0][x] == a) {
@@ -427,19 +499,12 @@ k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ lo
 					res = T.gallop(from, T.range_min(from, to), false);
 				}
 			}
-			const int32_t cld = res >= 0 ? (int32_t)(lo + res) : 0; // far entries: k_cld_long fills it in
-			if (res >= 0) CLD[i] = cld;
-			const int32_t lcp_of_cld = res >= 0 ? T.st[0][res] : 0x7ffffff0; // far: no hint yet
-			reinterpret_cast<int4 *>(node)[i] = make_int4(SA[i], a, cld, esa_pack_fvc(FVC[i], lcp_of_cld));
-		} else if (i == m) {
-			CLD[i] = 0;
-			reinterpret_cast<int4 *>(node)[i] = make_int4(0, LCP[m], 0, esa_pack_fvc(0, LCP[0]));
+			emit(i, a, res);
+			far = res < 0;
 		}
 		// far away: queue the entry for the warp-cooperative kernel (one atomic per warp)
-		const bool far = i < m && res < 0;
 		const uint32_t bal = __ballot_sync(0xffffffffu, far);
 		if (bal) {
-			const int lane = threadIdx.x & 31;
 			uint32_t base = 0;
 			if (lane == __ffs(bal) - 1) base = atomicAdd(long_count, (uint32_t)__popc(bal));
 			base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
