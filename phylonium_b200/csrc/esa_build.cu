@@ -354,32 +354,85 @@ constexpr int CLD_THREADS = 256;
 constexpr int CLD_ITEMS = 4;
 constexpr int CLD_TILE = CLD_THREADS * CLD_ITEMS; // entries per block
 constexpr int CLD_HALO = 128;
-constexpr int CLD_LEVELS = 8;                     // windows of 1 .. 128 entries
 constexpr int CLD_SPAN = CLD_TILE + 2 * CLD_HALO + 1;
 constexpr int CLD_NEAR = 4; // neighbours looked at directly before the sparse table is asked
 
-struct CldTable {
-	int32_t st[CLD_LEVELS][CLD_SPAN];
+// Range structure over the staged stretch of LCP for the entries whose answer is not next door:
+// minima of blocks of CLD_BLK positions and a sparse table over those (windows of 1 .. 32
+// blocks).  Searching in steps of blocks and finishing inside one block costs a few probes more
+// per query than a sparse table over all positions, but building it costs a quarter — and the
+// build, not the queries, was what this kernel spent its time on (profiles/).
+constexpr int CLD_BLK = 4;
+constexpr int CLD_NB = (CLD_SPAN + CLD_BLK - 1) / CLD_BLK;
+constexpr int CLD_BLEVELS = 6;
+struct alignas(16) CldTable {
+	int32_t v[CLD_NB * CLD_BLK];        // the values; positions outside [0, m] hold INT_MAX
+	int32_t st[CLD_BLEVELS][CLD_NB + 1]; // st[k][b] = min of blocks b .. b + 2^k - 1
 
 	// first position >= from (left == false) or last position <= from (left == true) with
-	// value <= v, or -1 if it is not within reach: both directions in one instruction stream
-	__device__ __forceinline__ int gallop(int from, int32_t v, bool left) const
+	// value <= val, or -1 if it is not within reach
+	__device__ __forceinline__ int gallop(int from, int32_t val, bool left) const
 	{
+		if (from < 0 || from >= CLD_SPAN) return -1;
 		int pos = from;
-		const int neg = left ? -1 : 0;
+		if (!left) {
+			// the rest of from's block, then whole blocks, then inside the block that has it
 #pragma unroll
-		for (int k = CLD_LEVELS - 1; k >= 0; k--) {
-			const int w = pos - (neg & ((1 << k) - 1)); // first entry of the window of 2^k that starts/ends at pos
-			if (w >= 0 && w + (1 << k) <= CLD_SPAN && st[k][w] > v) pos += left ? -(1 << k) : (1 << k);
+			for (int k = 0; k < CLD_BLK - 1; k++) {
+				if ((pos & (CLD_BLK - 1)) == 0) break;
+				if (v[pos] <= val) return pos;
+				pos++;
+			}
+			int b = pos / CLD_BLK;
+#pragma unroll
+			for (int k = CLD_BLEVELS - 1; k >= 0; k--)
+				if (b + (1 << k) <= CLD_NB && st[k][b] > val) b += 1 << k;
+			if (b >= CLD_NB || st[0][b] > val) return -1;
+			pos = b * CLD_BLK;
+#pragma unroll
+			for (int k = 0; k < CLD_BLK - 1; k++)
+				if (v[pos] > val) pos++;
+			return pos < CLD_SPAN ? pos : -1;
 		}
-		return (pos >= 0 && pos < CLD_SPAN && st[0][pos] <= v) ? pos : -1;
+#pragma unroll
+		for (int k = 0; k < CLD_BLK - 1; k++) {
+			if ((pos & (CLD_BLK - 1)) == CLD_BLK - 1) break;
+			if (v[pos] <= val) return pos;
+			if (--pos < 0) return -1;
+		}
+		int b = pos / CLD_BLK; // blocks b, b - 1, ... lie wholly at or left of `from`
+#pragma unroll
+		for (int k = CLD_BLEVELS - 1; k >= 0; k--)
+			if (b - (1 << k) + 1 >= 0 && st[k][b - (1 << k) + 1] > val) b -= 1 << k;
+		if (b < 0 || st[0][b] > val) return -1;
+		pos = b * CLD_BLK + CLD_BLK - 1;
+#pragma unroll
+		for (int k = 0; k < CLD_BLK - 1; k++)
+			if (v[pos] > val) pos--;
+		return pos;
 	}
-	// minimum over [a, b], 1 <= b - a + 1 <= 256 (two windows of 128 still cover 256)
+	// minimum over [a, b], 1 <= b - a + 1 <= 256 + CLD_BLK
 	__device__ __forceinline__ int32_t range_min(int a, int b) const
 	{
-		int k = 31 - __clz(b - a + 1);
-		if (k > CLD_LEVELS - 1) k = CLD_LEVELS - 1;
-		return min(st[k][a], st[k][b - (1 << k) + 1]);
+		const int ba = (a + CLD_BLK - 1) / CLD_BLK, bb = (b + 1) / CLD_BLK - 1; // whole blocks inside
+		int32_t mn = 0x7fffffff;
+		if (ba > bb) {
+			for (int q = a; q <= b; q++) // fewer than two blocks' worth
+				mn = min(mn, v[q]);
+			return mn;
+		}
+		for (int q = a; q < ba * CLD_BLK; q++)
+			mn = min(mn, v[q]);
+		for (int q = (bb + 1) * CLD_BLK; q <= b; q++)
+			mn = min(mn, v[q]);
+		int k = 31 - __clz(bb - ba + 1);
+		if (k > CLD_BLEVELS - 1) k = CLD_BLEVELS - 1;
+		// two windows of 2^k blocks cover up to 2^(k+1) of them; longer ranges (k capped) take more
+		for (int w = ba; w <= bb; w += 1 << k) {
+			const int at = w + (1 << k) - 1 <= bb ? w : bb - (1 << k) + 1;
+			mn = min(mn, st[k][at]);
+		}
+		return mn;
 	}
 };
 
@@ -395,15 +448,20 @@ k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ lo
 	const int32_t *__restrict__ LCP = py.level[0];
 	const int64_t tile0 = (int64_t)blockIdx.x * CLD_TILE;
 	const int64_t lo = tile0 - CLD_HALO; // global index of window position 0
-	for (int t = threadIdx.x; t < CLD_SPAN; t += CLD_THREADS) {
+	for (int t = threadIdx.x; t < CLD_NB * CLD_BLK; t += CLD_THREADS) {
 		const int64_t g = lo + t;
-		T.st[0][t] = (g >= 0 && g <= m) ? LCP[g] : 0x7fffffff;
+		T.v[t] = (t < CLD_SPAN && g >= 0 && g <= m) ? LCP[g] : 0x7fffffff;
 	}
-	for (int k = 1; k < CLD_LEVELS; k++) {
+	__syncthreads();
+	for (int b = threadIdx.x; b < CLD_NB; b += CLD_THREADS) {
+		const int4 q = *reinterpret_cast<const int4 *>(&T.v[b * CLD_BLK]);
+		T.st[0][b] = min(min(q.x, q.y), min(q.z, q.w));
+	}
+	for (int k = 1; k < CLD_BLEVELS; k++) {
 		__syncthreads();
 		const int half = 1 << (k - 1);
-		for (int t = threadIdx.x; t < CLD_SPAN; t += CLD_THREADS)
-			T.st[k][t] = (t + 2 * half <= CLD_SPAN) ? min(T.st[k - 1][t], T.st[k - 1][t + half]) : 0x7fffffff;
+		for (int b = threadIdx.x; b < CLD_NB; b += CLD_THREADS)
+			T.st[k][b] = (b + 2 * half <= CLD_NB) ? min(T.st[k - 1][b], T.st[k - 1][b + half]) : 0x7fffffff;
 	}
 	__syncthreads();
 	// Three out of four answers lie within CLD_NEAR positions (LCP values of neighbouring suffixes
@@ -418,16 +476,16 @@ k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ lo
 	auto emit = [&](int64_t i, int32_t a, int res) { // res: window position of the answer, or -1 = far
 		const int32_t cld = res >= 0 ? (int32_t)(lo + res) : 0; // far entries: k_cld_long fills it in
 		if (res >= 0) CLD[i] = cld;
-		const int32_t lcp_of_cld = res >= 0 ? T.st[0][res] : 0x7ffffff0; // far: no hint yet
+		const int32_t lcp_of_cld = res >= 0 ? T.v[res] : 0x7ffffff0; // far: no hint yet
 		reinterpret_cast<int4 *>(node)[i] = make_int4(SA[i], a, cld, esa_pack_fvc(FVC[i], lcp_of_cld));
 	};
+	uint32_t my_hard = 0; // bit r: item r of this thread needs the sparse table
 #pragma unroll
 	for (int r = 0; r < CLD_ITEMS; r++) {
 		const int64_t i = tile0 + r * CLD_THREADS + threadIdx.x;
-		bool is_hard = false;
 		if (i < m) {
 			const int t = (int)(i - lo);
-			const int32_t a = T.st[0][t], b = T.st[0][t + 1];
+			const int32_t a = T.v[t], b = T.v[t + 1];
 			const bool up = b < a;
 			// up: last position left of t with LCP <= b; down: first position right of t with LCP <= a
 			const int32_t v = up ? b : a;
@@ -435,21 +493,21 @@ k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ lo
 			int x = -1;
 #pragma unroll
 			for (int k = CLD_NEAR; k >= 1; k--)
-				if (T.st[0][t + dir * k] <= v) x = t + dir * k; // the nearest one wins (k counts down)
+				if (T.v[t + dir * k] <= v) x = t + dir * k; // the nearest one wins (k counts down)
 			if (x >= 0) {
 				int res;
-				if (!up && T.st[0][x] == a) {
+				if (!up && T.v[x] == a) {
 					res = x; // the next l-index
 				} else {
 					// leftmost minimum of (x, t] (up) or (t, x) (down): at most CLD_NEAR entries
 					const int from = up ? x + 1 : t + 1, to = up ? t : x - 1;
 					res = from;
-					int32_t best = T.st[0][from];
+					int32_t best = T.v[from];
 #pragma unroll
 					for (int k = 1; k < CLD_NEAR; k++) {
 						const int q = from + k;
 						if (q <= to) {
-							const int32_t val = T.st[0][q];
+							const int32_t val = T.v[q];
 							if (val < best) {
 								best = val;
 								res = q;
@@ -459,19 +517,18 @@ k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ lo
 				}
 				emit(i, a, res);
 			} else {
-				is_hard = true;
+				my_hard |= 1u << r;
 			}
 		} else if (i == m) {
 			CLD[i] = 0;
 			reinterpret_cast<int4 *>(node)[i] = make_int4(0, LCP[m], 0, esa_pack_fvc(0, LCP[0]));
 		}
-		const uint32_t bal = __ballot_sync(0xffffffffu, is_hard);
-		if (bal) {
-			int base = 0;
-			if (lane == __ffs(bal) - 1) base = atomicAdd(&nhard, __popc(bal));
-			base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-			if (is_hard) hard[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)(i - tile0);
-		}
+	}
+	if (my_hard) { // one shared-memory atomic per thread reserves room in the queue
+		int at = atomicAdd(&nhard, __popc(my_hard));
+#pragma unroll
+		for (int r = 0; r < CLD_ITEMS; r++)
+			if (my_hard & (1u << r)) hard[at++] = (uint16_t)(r * CLD_THREADS + threadIdx.x);
 	}
 	__syncthreads();
 	const int n_hard = nhard;
@@ -482,7 +539,7 @@ k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ lo
 		if (q < n_hard) {
 			i = tile0 + hard[q];
 			const int t = (int)(i - lo);
-			const int32_t a = T.st[0][t], b = T.st[0][t + 1];
+			const int32_t a = T.v[t], b = T.v[t + 1];
 			// One code path for both cases (lanes of a warp are a mix of them, and divergent
 			// branches would run one after the other): a gallop to the left for p = last position
 			// left of i with LCP <= b ("up", b < a), or to the right for s = first position right
@@ -492,7 +549,7 @@ k_cld(Pyramid py, int32_t m, int32_t *__restrict__ CLD, int32_t *__restrict__ lo
 			int res = -1;
 			const int x = T.gallop(up ? t - 1 : t + 1, up ? b : a, up);
 			if (x >= 0) {
-				if (!up && T.st[0][x] == a) {
+				if (!up && T.v[x] == a) {
 					res = x;
 				} else {
 					const int from = up ? x + 1 : t + 1, to = up ? t : x - 1;
