@@ -35,6 +35,14 @@ namespace phy
 #ifndef PKS_MIN_BLOCKS
 #define PKS_MIN_BLOCKS 3
 #endif
+// how a lane learns which lanes of its warp hold the same digit: 0 = eight votes (registers
+// only), 1 = one OR into a per-warp table of 256 lane masks in shared memory.  The votes are 44 %
+// of the kernel's instructions, the table needs five; measured on B200 (tools/sortbench.cu,
+// m = 10^7 / 10^8): votes 49.0 / 400 us, table 55.3 / 467 us — the shared-memory pipe, already
+// busy with the conflicts of the exchange, is the scarcer resource.
+#ifndef PK_PEERS_SMEM
+#define PK_PEERS_SMEM 0
+#endif
 constexpr int PK_THREADS = 256; // histogram and scan kernels
 constexpr int PK_ITEMS = 16;
 constexpr int PK_TILE = PK_THREADS * PK_ITEMS; // suffixes per tile
@@ -495,13 +503,36 @@ pk_scatter(const uint64_t *__restrict__ in, const uint8_t *__restrict__ S, int32
 			}
 		}
 		// stable rank of every item among the items of its warp with the same digit
+#if PK_PEERS_SMEM
+		// The warp's stretch of the word buffer is free once its 16 words sit in registers: its
+		// first KB serves as a table of lane masks, one per digit.  Every lane ORs its bit into
+		// the entry of its digit; what it reads back is the set of lanes with that digit.  The
+		// lowest of them bumps the digit's counter and clears the entry for the next row.
+		uint32_t *const tbl = reinterpret_cast<uint32_t *>(buf + warp_base);
+		__syncwarp();
+#pragma unroll
+		for (int k = 0; k < RS_BINS / 32; k++)
+			tbl[k * 32 + lane] = 0;
+		__syncwarp();
+#endif
 #pragma unroll
 		for (int r = 0; r < PKS_ITEMS; r++) {
 			const uint32_t d = pk_digit(e[r], shift);
+#if PK_PEERS_SMEM
+			atomicOr(&tbl[d], 1u << lane);
+			__syncwarp();
+			const uint32_t peers = tbl[d];
+#else
 			const uint32_t peers = pk_warp_peers(d);
+#endif
 			const uint32_t before = my_cnt[d];
 			__syncwarp();
-			if ((peers & lanes_below) == 0) my_cnt[d] = (uint16_t)(before + __popc(peers)); // lowest peer
+			if ((peers & lanes_below) == 0) { // lowest peer
+				my_cnt[d] = (uint16_t)(before + __popc(peers));
+#if PK_PEERS_SMEM
+				tbl[d] = 0;
+#endif
+			}
 			__syncwarp();
 			const uint32_t rk = before + __popc(peers & lanes_below);
 			if (r & 1)
