@@ -504,6 +504,8 @@ def run_b200(args):
                "h2d_bytes_per_step": int(bases_local), "d2h_bytes_per_step": int(2 * G * G * 8),
                "same_counts_as_device_path": same, "call": "phylo_process (C ABI, pinned host pointers)",
                "bus_bytes_per_step": int(ctx.stat("process.h2d_bytes")),
+               "host_timeline_ms": {"index_done": ctx.stat("process.host_index_done_ms"), "map_done": ctx.stat("process.host_map_done_ms"),
+                                    "done": ctx.stat("process.host_done_ms")},
                "note": "h2d_bytes_per_step counts the caller's buffers; the library packs the query sequences to 2 bits per "
                        "base on the host, so bus_bytes_per_step cross PCIe"}
         # the same call on ordinary (pageable) memory, as the C++ host's std::string storage is

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <functional>
 #include <cstring>
@@ -1011,6 +1012,10 @@ namespace
 void process_resident(phylo_ctx *c, uint64_t N, uint64_t ref_index, int flags, MapHooks hooks, uint64_t *subst,
                       uint64_t *homologs)
 {
+	const auto t_enter = std::chrono::steady_clock::now();
+	auto since = [&](const char *key) { // host clock since the call began, as a statistic
+		c->stats[key] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
+	};
 	const uint8_t *dq = c->q_own.get();
 	const uint64_t *offs = c->q_offs.data(), *lens = c->q_lens.data();
 	cudaStream_t s = c->stream;
@@ -1023,6 +1028,7 @@ void process_resident(phylo_ctx *c, uint64_t N, uint64_t ref_index, int flags, M
 	const double gc = (double)c->esa.gc_count / (double)lens[ref_index];
 	const uint64_t thr = phylo_min_anchor_length(0.025, gc, 2 * lens[ref_index] + 1);
 	c->stats["threshold"] = (double)thr;
+	since("process.host_index_done_ms");
 
 	const uint64_t tot = c->rows_total ? c->rows_total : N;
 	ensure_matrix(c, tot);
@@ -1045,6 +1051,7 @@ void process_resident(phylo_ctx *c, uint64_t N, uint64_t ref_index, int flags, M
 		tiles_done = ready;
 	};
 	do_map(c, dq, offs, lens, N, thr, hooks);
+	since("process.host_map_done_ms");
 	{
 		WallTimer wt(s, c->timings);
 		compare_all_device(c->rows, (int64_t)tot, complete_deletion, 0, 1, c->d_subst.get(), c->d_hom.get(), s, tiles_done,
@@ -1058,6 +1065,7 @@ void process_resident(phylo_ctx *c, uint64_t N, uint64_t ref_index, int flags, M
 	CUDA_CHECK(cudaMemcpyAsync(subst, c->d_subst.get(), bytes, cudaMemcpyDeviceToHost, s));
 	CUDA_CHECK(cudaMemcpyAsync(homologs, c->d_hom.get(), bytes, cudaMemcpyDeviceToHost, s));
 	CUDA_CHECK(cudaStreamSynchronize(s));
+	since("process.host_done_ms");
 }
 
 // after a failed call nothing of ours may still be reading the caller's buffers

@@ -180,11 +180,11 @@ __host__ __device__ constexpr int cmp_threads(int CT)
 // words per lane and step: the 3-plane path adds up three words per pair with one carry-save
 // step before it counts bits; the 5-plane path (reverse strands, separators) goes word by word
 constexpr int CMP_WPL_FAST = 3, CMP_WPL_FULL = 1;
-__host__ __device__ constexpr size_t cmp_smem_bytes(int CT, int fast_stages)
+__host__ __device__ constexpr size_t cmp_smem_bytes(int CT, bool tma)
 {
-	// buffers of 2 CT genomes x planes x (32 * words per lane) words: `fast_stages` of the 3-plane
-	// path, two of the 5-plane path; the larger of the two
-	const size_t fast = (size_t)fast_stages * 2 * CT * 3 * 32 * CMP_WPL_FAST, full = (size_t)2 * 2 * CT * ROW_PLANES * 32 * CMP_WPL_FULL;
+	// buffers of 2 CT genomes x planes x (32 * words per lane) words; the larger of the two paths
+	const size_t fast = (size_t)(tma ? CMP_STAGES_N : 2) * 2 * CT * 3 * 32 * CMP_WPL_FAST;
+	const size_t full = tma ? (size_t)3 * 2 * CT * ROW_PLANES * 32 * CMP_WPL_FAST : (size_t)2 * 2 * CT * ROW_PLANES * 32 * CMP_WPL_FULL;
 	return (fast > full ? fast : full) * sizeof(uint32_t);
 }
 
@@ -215,7 +215,8 @@ __device__ __forceinline__ void tma_load_rows(void *smem_dst, const CUtensorMap 
 	             : "memory");
 }
 
-constexpr int CMP_STAGES = CMP_STAGES_N; // shared-memory stages of the TMA pipeline
+constexpr int CMP_STAGES_FAST = CMP_STAGES_N; // shared-memory stages of the TMA pipeline, 3-plane path
+constexpr int CMP_STAGES_FULL = 3;            // ... 5-plane path
 
 // One (tile pair, chunk) unit.  P = planes to look at (3: V, C0, C1; 5: all), WPL = words per
 // lane and step.  Per pair and word: both = Va & Vb, diff = both & (codes differ [or, on the
@@ -366,6 +367,8 @@ __device__ __forceinline__ void compare_tile(uint32_t *stage, const uint32_t *__
 	};
 
 	if constexpr (TMA) {
+		// 36 KB per stage with three planes, 60 KB with five: six or three stages fit one SM
+		constexpr int CMP_STAGES = P == 3 ? CMP_STAGES_FAST : CMP_STAGES_FULL;
 		__shared__ __align__(8) uint64_t full_bar[CMP_STAGES], empty_bar[CMP_STAGES];
 		constexpr uint32_t STAGE_BYTES = BUF_WORDS * sizeof(uint32_t);
 		const int nsteps = (int)((w_end - w_begin + STEP - 1) / STEP);
@@ -378,7 +381,7 @@ __device__ __forceinline__ void compare_tile(uint32_t *stage, const uint32_t *__
 			mbar_fence_init();
 		}
 		__syncthreads();
-		static_assert(STEP == ROW_BLK && P == 3, "the tensor map's box is one block of the first three planes");
+		static_assert(STEP == ROW_BLK, "the tensor map's box is one block of the first P planes");
 		auto issue = [&](int n) { // thread 0: step n into stage n % CMP_STAGES
 			const int sidx = n % CMP_STAGES;
 			uint32_t *dst = stage + sidx * BUF_WORDS;
@@ -445,13 +448,14 @@ __device__ __forceinline__ void compare_tile(uint32_t *stage, const uint32_t *__
 // column, tp = tj (tj + 1) / 2 + ti, so that "all pairs whose later tile is in [tj0, tj1)" —
 // what becomes computable when another batch of genomes has been mapped — is one range of
 // tp.  Unit u of this launch is tile pair tp_begin + (u * tile_world + tile_rank) / chunks.
-// tm_fast: tensor map of the row store for the 3-plane path (TMA = true).  Tiles that need all
-// five planes (reverse strands, separators) go word by word and fetch their five 128-byte
-// pieces per genome and step with cp.async: that many short runs are not what the tensor copy
-// engine is good at.
+// tm_fast / tm_full: tensor maps of the row store whose boxes are one block of the first three
+// / of all five planes per genome (TMA = true).  Tiles in which some genome uses the D / B
+// planes (reverse strands, separators) take the 5-plane path: same structure, 1920 instead of
+// 1152 bytes per genome and step, three stages instead of six.
 template <int CT, bool TMA>
 __global__ void __launch_bounds__(cmp_threads(CT), CT == 16 ? CMP_MIN_BLOCKS : 4)
-k_compare_tiles(const __grid_constant__ CUtensorMap tm_fast, const uint32_t *__restrict__ rows, int64_t genome_words, int64_t W, int64_t N, int64_t tp_begin,
+k_compare_tiles(const __grid_constant__ CUtensorMap tm_fast, const __grid_constant__ CUtensorMap tm_full,
+                const uint32_t *__restrict__ rows, int64_t genome_words, int64_t W, int64_t N, int64_t tp_begin,
                 int64_t units, int32_t chunks, int64_t chunk_words, int tile_rank, int tile_world,
                 const uint32_t *__restrict__ vall, unsigned long long *__restrict__ subst,
                 unsigned long long *__restrict__ homol)
@@ -484,8 +488,8 @@ k_compare_tiles(const __grid_constant__ CUtensorMap tm_fast, const uint32_t *__r
 	}
 	__syncthreads();
 	if (tile_flags)
-		compare_tile<5, CT, CMP_WPL_FULL, false>(cmp_stage, rows, nullptr, genome_words, W, N, gi0, gj0, w_begin, w_end, vall,
-		                                         subst, homol);
+		compare_tile<5, CT, TMA ? CMP_WPL_FAST : CMP_WPL_FULL, TMA>(cmp_stage, rows, &tm_full, genome_words, W, N, gi0, gj0,
+		                                                            w_begin, w_end, vall, subst, homol);
 	else
 		compare_tile<3, CT, CMP_WPL_FAST, TMA>(cmp_stage, rows, &tm_fast, genome_words, W, N, gi0, gj0, w_begin, w_end, vall,
 		                                       subst, homol);
@@ -627,13 +631,14 @@ k_push_rows(const uint32_t *__restrict__ rows, RowPeers peers, int64_t genome_wo
 	}
 }
 
-// Tensor map of the row store for the 3-plane path: a 3-d tensor of 64-bit elements (element
-// of a block's first three planes, block, genome) whose box is one block of one tile side:
-// 144 elements (= 3 planes x ROW_BLK words, 1152 contiguous bytes) x 1 block x CT genomes.
+// Tensor map of the row store: a 3-d tensor of 64-bit elements (element of a block's first
+// `planes` planes, block, genome) whose box is one block of one tile side: 144 elements (= 3
+// planes x ROW_BLK words, 1152 contiguous bytes; 240 elements for all five planes) x 1 block x
+// CT genomes.
 // (64-bit elements because a box dimension may not exceed 256 elements.)  Blocks past the row
 // and genomes past the store read as zeros.  cuTensorMapEncodeTiled is a driver entry point; it
 // is fetched through the runtime so that the library does not link against libcuda.
-void rows_tensor_map(const RowStore &rs, int CT, CUtensorMap *out)
+void rows_tensor_map(const RowStore &rs, int planes, int CT, CUtensorMap *out)
 {
 	using Encode = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
 	                            const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -646,7 +651,7 @@ void rows_tensor_map(const RowStore &rs, int CT, CUtensorMap *out)
 		if (q != cudaDriverEntryPointSuccess || !fn) throw CudaError("cuTensorMapEncodeTiled is not available in this driver");
 		encode = (Encode)fn;
 	}
-	constexpr cuuint32_t RUN = 3 * ROW_BLK / 2; // 64-bit elements of the three planes of a block
+	const cuuint32_t RUN = (cuuint32_t)planes * ROW_BLK / 2; // 64-bit elements of the first `planes` planes of a block
 	const cuuint64_t dims[3] = {RUN, (cuuint64_t)(rs.W / ROW_BLK), (cuuint64_t)rs.genomes};
 	const cuuint64_t strides[2] = {(cuuint64_t)ROW_PLANES * ROW_BLK * sizeof(uint32_t),
 	                               (cuuint64_t)rs.genome_words() * sizeof(uint32_t)};
@@ -716,27 +721,30 @@ void compare_all_device(const RowStore &rs, int64_t N, bool complete_deletion, i
 		const int64_t units = n_tile_pairs * chunks;
 		const int64_t my_units = (units - tile_rank + tile_world - 1) / tile_world;
 		const bool tma = g_tuning.compare_path == 0;
-		const int stages = tma ? CMP_STAGES : 2;
 		static PerDeviceOnce once;
 		if (once.first()) {
 			CUDA_CHECK(cudaFuncSetAttribute(k_compare_tiles<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-			                                (int)cmp_smem_bytes(16, CMP_STAGES)));
+			                                (int)cmp_smem_bytes(16, true)));
 			CUDA_CHECK(cudaFuncSetAttribute(k_compare_tiles<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-			                                (int)cmp_smem_bytes(8, CMP_STAGES)));
+			                                (int)cmp_smem_bytes(8, true)));
 			CUDA_CHECK(cudaFuncSetAttribute(k_compare_tiles<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-			                                (int)cmp_smem_bytes(16, 2)));
+			                                (int)cmp_smem_bytes(16, false)));
 			CUDA_CHECK(cudaFuncSetAttribute(k_compare_tiles<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-			                                (int)cmp_smem_bytes(8, 2)));
+			                                (int)cmp_smem_bytes(8, false)));
 		}
 		if (my_units > 0x7fffffffll) throw std::invalid_argument("too many tile pairs for one launch");
 		if (my_units > 0) {
-			CUtensorMap tm_fast;
+			CUtensorMap tm_fast, tm_full;
 			memset(&tm_fast, 0, sizeof tm_fast);
-			if (tma) rows_tensor_map(rs, CT, &tm_fast);
-			const size_t smem = cmp_smem_bytes(CT, stages);
+			memset(&tm_full, 0, sizeof tm_full);
+			if (tma) {
+				rows_tensor_map(rs, 3, CT, &tm_fast);
+				rows_tensor_map(rs, ROW_PLANES, CT, &tm_full);
+			}
+			const size_t smem = cmp_smem_bytes(CT, tma);
 #define PHY_LAUNCH_COMPARE(CTV, TMAV)                                                                                    \
 	k_compare_tiles<CTV, TMAV><<<(unsigned)my_units, cmp_threads(CTV), smem, s>>>(                                       \
-		tm_fast, rs.data.get(), rs.genome_words(), rs.W, N, tp_begin, units, (int32_t)chunks, chunk_words,      \
+		tm_fast, tm_full, rs.data.get(), rs.genome_words(), rs.W, N, tp_begin, units, (int32_t)chunks, chunk_words,      \
 		tile_rank, tile_world, vall.get(), d_subst, d_homologs)
 			if (CT == 16 && tma)
 				PHY_LAUNCH_COMPARE(16, true);
