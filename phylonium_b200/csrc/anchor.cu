@@ -93,6 +93,7 @@ __device__ __forceinline__ int32_t next_walker(int *counter)
 // ctl[0]: any open match, ctl[3]: the work counter (zero at launch)
 __global__ void __launch_bounds__(WALK_THREADS, WALK_MIN_BLOCKS) k_walk_chunks(WalkParams P, int *__restrict__ ctl)
 {
+	if (P.skip && *P.skip) return; // (ctl[0] stays 0: the kernels of phase 2 do nothing either)
 	for (;;) {
 		const int32_t w = next_walker(ctl + 3);
 		if (w >= P.total_chunks) return;
@@ -271,6 +272,7 @@ __global__ void k_apply_open(WalkParams P, const int *__restrict__ any_open, con
 
 __global__ void __launch_bounds__(WALK_THREADS) k_bridge(WalkParams P, int *__restrict__ counter)
 {
+	if (P.skip && *P.skip) return;
 	for (;;) {
 		const int32_t w = next_walker(counter); // one walker per lane group, pulled from a counter
 		if (w >= P.total_chunks) return;
@@ -293,7 +295,7 @@ k_resolve_path(WalkParams P, int32_t *__restrict__ jump_a, int32_t *__restrict__
 	const int32_t qid = blockIdx.x;
 	const QueryInfo qi = P.qi[qid];
 	const int32_t base = qi.chunk_base, nc = qi.nchunks;
-	if (nc == 0) {
+	if (nc == 0 || (P.skip && *P.skip)) {
 		if (threadIdx.x == 0) status[qid] = -1;
 		return;
 	}
@@ -383,10 +385,11 @@ __device__ __forceinline__ bool ev_is_right(const Event *ev, const int32_t *evq,
 
 // offsets of each query's list inside an array sorted by query id
 __global__ void k_query_offsets(const int32_t *__restrict__ qids, const uint32_t *__restrict__ n_ptr, int32_t nq,
-                                int64_t *__restrict__ offs)
+                                int64_t *__restrict__ offs, int32_t *__restrict__ total_out = nullptr)
 {
 	const int32_t q = blockIdx.x * blockDim.x + threadIdx.x;
 	if (q > nq) return;
+	if (q == 0 && total_out) *total_out = (int32_t)*n_ptr; // next to the per-query results the host reads back
 	int64_t lo = 0, hi = *n_ptr;
 	while (lo < hi) {
 		const int64_t mid = (lo + hi) >> 1;
@@ -446,6 +449,8 @@ k_sort_filter(const int64_t *__restrict__ raw_offs, const Hom *__restrict__ raw,
 		if (threadIdx.x == 0) {
 			fin_count[q] = 0;
 			fin_flags[q] = FIN_FLAG_BIG;
+			d_begin[q] = lo; // an empty list, in case the rows are built before the host has looked
+			d_count[q] = 0;
 		}
 		return;
 	}
@@ -491,6 +496,8 @@ k_sort_filter(const int64_t *__restrict__ raw_offs, const Hom *__restrict__ raw,
 		if (threadIdx.x == 0) {
 			fin_count[q] = 0;
 			fin_flags[q] = FIN_FLAG_TIES;
+			d_begin[q] = lo;
+			d_count[q] = 0;
 		}
 		return;
 	}
@@ -572,23 +579,29 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	if (total_chunks64 > 0x3fffffff) throw std::invalid_argument("too many chunks in one batch");
 	const int32_t total_chunks = (int32_t)total_chunks64;
 	ST.chunks = total_chunks;
-	std::vector<int32_t> chunk_query((size_t)total_chunks);
+	// (pinned: a copy from ordinary memory would make the host wait for everything queued on the
+	// stream before — the index build — and for the copy itself)
+	PinnedArena::Scope pinned_scope(g_pinned);
+	int32_t *const chunk_query = g_pinned.take<int32_t>((size_t)total_chunks + 1);
 	for (int32_t k = 0; k < nq; k++)
-		std::fill(chunk_query.begin() + qi[k].chunk_base, chunk_query.begin() + qi[k].chunk_base + qi[k].nchunks, k);
+		std::fill(chunk_query + qi[k].chunk_base, chunk_query + qi[k].chunk_base + qi[k].nchunks, k);
+	QueryInfo *const h_qi = g_pinned.take<QueryInfo>((size_t)nq + 1);
+	std::copy(qi.begin(), qi.end(), h_qi);
 
 	out.offs.assign((size_t)nq + 1, 0);
 	out.raw_offs.assign((size_t)nq + 1, 0);
 	out.homs.release();
 	out.raw.release();
 	out.d_offs.alloc((size_t)nq + 1, s);
-	out.d_offs.zero();
 	out.begin.assign((size_t)nq, 0);
 	out.count.assign((size_t)nq, 0);
 	out.d_begin.alloc((size_t)nq, s);
 	out.d_count.alloc((size_t)nq, s);
-	out.d_begin.zero();
-	out.d_count.zero();
 	if (total_chunks == 0) {
+		// (otherwise k_sort_filter or the general path write every entry)
+		out.d_offs.zero();
+		out.d_begin.zero();
+		out.d_count.zero();
 		if (opt.input_flags) {
 			if (opt.input_flags_ready) CUDA_CHECK(cudaStreamWaitEvent(s, opt.input_flags_ready, 0));
 			ST.input_flags = d2h_scalar(opt.input_flags, s);
@@ -599,15 +612,22 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	const int32_t cap_ev = CH / (thr + 1) + 2;
 	DevBuf<QueryInfo> d_qi(nq, s);
 	DevBuf<int32_t> d_cq(total_chunks, s);
-	CUDA_CHECK(cudaMemcpyAsync(d_qi.get(), qi.data(), nq * sizeof(QueryInfo), cudaMemcpyHostToDevice, s));
-	CUDA_CHECK(cudaMemcpyAsync(d_cq.get(), chunk_query.data(), (size_t)total_chunks * sizeof(int32_t),
-	                           cudaMemcpyHostToDevice, s));
+	CUDA_CHECK(cudaMemcpyAsync(d_qi.get(), h_qi, nq * sizeof(QueryInfo), cudaMemcpyHostToDevice, s));
+	CUDA_CHECK(cudaMemcpyAsync(d_cq.get(), chunk_query, (size_t)total_chunks * sizeof(int32_t), cudaMemcpyHostToDevice, s));
 	DevBuf<Event> ev((size_t)total_chunks * cap_ev, s), bev((size_t)total_chunks * cap_ev, s);
 	DevBuf<uint32_t> dead((size_t)total_chunks * (CH / 32), s);
 	dead.zero();
 	DevBuf<ChunkRec> rec(total_chunks, s);
-	DevBuf<int> flags(8, s); // [0] any_open, [1] error, [2] open chunks, [3] / [4] work counters of walk / bridge
-	flags.zero();
+	// Everything the host reads back at its first stop, in one block (one copy to pinned memory):
+	// ctl[0] any_open, [1] error, [2] open chunks, [3] / [4] work counters of walk / bridge,
+	// [8] number of true events, [9] copy of *opt.input_flags, [10] number of raw homologies;
+	// from [CTL_INTS] on the path status of every query.
+	constexpr int CTL_INTS = 16, CTL_EVENTS = 8, CTL_INPUT = 9, CTL_RAW = 10;
+	DevBuf<int> ctl((size_t)CTL_INTS + nq, s);
+	CUDA_CHECK(cudaMemsetAsync(ctl.get(), 0, CTL_INTS * sizeof(int), s));
+	int *const flags = ctl.get();
+	int32_t *const status = ctl.get() + CTL_INTS;
+	int *const h_ctl = g_pinned.take<int>((size_t)CTL_INTS + nq);
 
 	WalkParams P;
 	P.esa = esa.view();
@@ -639,10 +659,11 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	P.dead = dead.get();
 	P.rec = rec.get();
 	P.chunk_query = d_cq.get();
+	P.skip = opt.index_skip;
 
 	// 1. cold walks
 	const int walk_blocks = std::min(div_up(total_chunks, WALKERS_PER_BLOCK), NUM_SMS_B200 * WALK_MIN_BLOCKS);
-	k_walk_chunks<<<walk_blocks, WALK_THREADS, 0, s>>>(P, flags.get());
+	k_walk_chunks<<<walk_blocks, WALK_THREADS, 0, s>>>(P, flags);
 	KERNEL_CHECK();
 	ST.walk_ms = lap.lap();
 
@@ -650,42 +671,44 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	{
 		DevBuf<int32_t> lnk_a(total_chunks, s), end_a(total_chunks, s), lnk_b(total_chunks, s), end_b(total_chunks, s);
 		DevBuf<int32_t> open_list(total_chunks, s);
-		k_resolve_open<<<div_up((int64_t)total_chunks * 32, 256), 256, 0, s>>>(P, flags.get(), lnk_a.get(), end_a.get(),
+		k_resolve_open<<<div_up((int64_t)total_chunks * 32, 256), 256, 0, s>>>(P, flags, lnk_a.get(), end_a.get(),
 		                                                                       open_list.get());
 		KERNEL_CHECK();
 		CUDA_CHECK(cudaFuncSetAttribute(k_open_jump, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		                                2 * OPEN_SMEM * (int)sizeof(int32_t)));
-		k_open_jump<<<1, 1024, 2 * OPEN_SMEM * sizeof(int32_t), s>>>(flags.get(), open_list.get(), lnk_a.get(), end_a.get(),
+		k_open_jump<<<1, 1024, 2 * OPEN_SMEM * sizeof(int32_t), s>>>(flags, open_list.get(), lnk_a.get(), end_a.get(),
 		                                                             lnk_b.get(), end_b.get(), rounds_for(total_chunks));
 		KERNEL_CHECK();
-		k_apply_open<<<div_up(total_chunks, 256), 256, 0, s>>>(P, flags.get(), lnk_a.get(), end_a.get(), flags.get() + 1);
+		k_apply_open<<<div_up(total_chunks, 256), 256, 0, s>>>(P, flags, lnk_a.get(), end_a.get(), flags + 1);
 		KERNEL_CHECK();
 	}
 	ST.open_ms = lap.lap();
 
 	// 3. bridges
-	k_bridge<<<walk_blocks, WALK_THREADS, 0, s>>>(P, flags.get() + 4);
+	k_bridge<<<walk_blocks, WALK_THREADS, 0, s>>>(P, flags + 4);
 	KERNEL_CHECK();
 	ST.bridge_ms = lap.lap();
 
 	// 4. true path, with exact continuation of give-ups that lie on it
-	DevBuf<int32_t> jump_a(total_chunks, s), jump_b(total_chunks, s), from(total_chunks, s), status(nq, s);
+	DevBuf<int32_t> jump_a(total_chunks, s), jump_b(total_chunks, s), from(total_chunks, s);
 	DevBuf<uint8_t> reach(total_chunks, s);
 	std::vector<DevBuf<Event>> overflow;
-	std::vector<int32_t> h_status((size_t)nq);
 	// number of true events per (walker, bridge), scanned right after every path resolution so
 	// that its total comes back with the same synchronisation as the path status
 	DevBuf<uint32_t> cnt((size_t)2 * total_chunks + 1, s);
 	uint32_t n_events = 0;
 	for (int iter = 0;; iter++) {
-		k_resolve_path<<<nq, 1024, 0, s>>>(P, jump_a.get(), jump_b.get(), reach.get(), from.get(), status.get());
+		k_resolve_path<<<nq, 1024, 0, s>>>(P, jump_a.get(), jump_b.get(), reach.get(), from.get(), status);
 		KERNEL_CHECK();
+		if (opt.input_flags && opt.input_flags_ready && iter == 0) CUDA_CHECK(cudaStreamWaitEvent(s, opt.input_flags_ready, 0));
 		{
 			uint32_t *c = cnt.get();
 			const ChunkRec *rc = rec.get();
 			const uint8_t *rh = reach.get();
 			const int32_t *fr = from.get();
 			const int64_t n2 = 2 * (int64_t)total_chunks;
+			int *report = flags;
+			const int *input_flags = opt.input_flags;
 			device_scan<uint32_t>(
 				n2 + 1,
 				[rc, rh, fr, n2] __device__(int64_t i) -> uint32_t {
@@ -694,23 +717,26 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 					if (!rh[g]) return 0u;
 					return (i & 1) ? (uint32_t)rc[g].n_bridge : (uint32_t)(rc[g].n_events - fr[g]);
 				},
-				[c] __device__(int64_t i, uint32_t v) { c[i] = v; }, OpSum(), 0u, false, s);
+				[c, n2, report, input_flags] __device__(int64_t i, uint32_t v) {
+					c[i] = v;
+					if (i == n2) { // the total, and the verdict of the input validation next to it
+						report[CTL_EVENTS] = (int)v;
+						report[CTL_INPUT] = input_flags ? *input_flags : 0;
+					}
+				},
+				OpSum(), 0u, false, s);
 		}
-		CUDA_CHECK(cudaMemcpyAsync(h_status.data(), status.get(), nq * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-		int h_flags[4];
-		CUDA_CHECK(cudaMemcpyAsync(h_flags, flags.get(), sizeof h_flags, cudaMemcpyDeviceToHost, s));
-		CUDA_CHECK(cudaMemcpyAsync(&n_events, cnt.get() + 2 * (int64_t)total_chunks, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-		if (opt.input_flags) {
-			if (opt.input_flags_ready && iter == 0) CUDA_CHECK(cudaStreamWaitEvent(s, opt.input_flags_ready, 0));
-			CUDA_CHECK(cudaMemcpyAsync(&ST.input_flags, opt.input_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
-		}
+		CUDA_CHECK(cudaMemcpyAsync(h_ctl, ctl.get(), ((size_t)CTL_INTS + nq) * sizeof(int), cudaMemcpyDeviceToHost, s));
 		CUDA_CHECK(cudaStreamSynchronize(s));
+		if (iter == 0 && opt.index_verdict_host && *opt.index_verdict_host) throw IndexNotBuilt();
+		ST.input_flags = h_ctl[CTL_INPUT];
+		n_events = (uint32_t)h_ctl[CTL_EVENTS];
 		if (ST.input_flags) return; // the caller reports what is wrong with the input
-		if (h_flags[1]) throw std::runtime_error("internal error: open match left unresolved");
-		ST.open_events += (iter == 0 && h_flags[0]) ? 1 : 0;
+		if (h_ctl[1]) throw std::runtime_error("internal error: open match left unresolved");
+		ST.open_events += (iter == 0 && h_ctl[0]) ? 1 : 0;
 		std::vector<int32_t> stuck;
 		for (int32_t q = 0; q < nq; q++)
-			if (h_status[q] >= 0) stuck.push_back(h_status[q]);
+			if (h_ctl[CTL_INTS + q] >= 0) stuck.push_back(h_ctl[CTL_INTS + q]);
 		if (stuck.empty()) break;
 		if (iter > total_chunks + 2) throw std::runtime_error("internal error: path resolution does not terminate");
 		ST.unresolved += (int64_t)stuck.size();
@@ -741,8 +767,7 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 
 	DevBuf<Hom> raw;
 	DevBuf<int32_t> raw_q;
-	DevBuf<uint32_t> d_n_raw(1, s);
-	d_n_raw.zero();
+	uint32_t *const d_n_raw = reinterpret_cast<uint32_t *>(ctl.get() + CTL_RAW); // zero so far
 	uint32_t n_raw = 0;
 	if (n_events) {
 		DevBuf<Event> tev(n_events, s);
@@ -794,28 +819,35 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 					R[w] = h;
 					RQ[w] = EQ[t];
 				},
-				d_n_raw.get(), s);
+				d_n_raw, s);
 		}
 	}
 	ST.assemble_ms = lap.lap();
 
-	// per-query ranges of the raw lists, then the per-query sort + filter in shared memory
-	DevBuf<int64_t> d_raw_offs((size_t)nq + 1, s);
+	// per-query ranges of the raw lists, then the per-query sort + filter in shared memory.
+	// What the host wants to see of it sits in one block: raw_offs (nq + 1 int64), then as
+	// int32 the survivors per query, the per-query flags and the number of raw homologies.
+	DevBuf<int64_t> finrep((size_t)nq + 1 + ((size_t)2 * nq + 1 + 1) / 2, s);
+	int64_t *const d_raw_offs = finrep.get();
+	int32_t *const fin_count = reinterpret_cast<int32_t *>(finrep.get() + nq + 1);
+	int32_t *const fin_flags = fin_count + nq;
 	DevBuf<Hom> fin(n_events, s);
-	DevBuf<int32_t> fin_count(nq, s), fin_flags(nq, s);
-	k_query_offsets<<<div_up(nq + 1, 128), 128, 0, s>>>(raw_q.get(), d_n_raw.get(), nq, d_raw_offs.get());
+	k_query_offsets<<<div_up(nq + 1, 128), 128, 0, s>>>(raw_q.get(), d_n_raw, nq, d_raw_offs, fin_flags + nq);
 	KERNEL_CHECK();
 	CUDA_CHECK(cudaFuncSetAttribute(k_sort_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmem)));
-	k_sort_filter<<<nq, FIN_THREADS, sizeof(FinSmem), s>>>(d_raw_offs.get(), raw.get(), fin.get(), fin_count.get(),
-	                                                       fin_flags.get(), out.d_begin.get(), out.d_count.get());
+	k_sort_filter<<<nq, FIN_THREADS, sizeof(FinSmem), s>>>(d_raw_offs, raw.get(), fin.get(), fin_count, fin_flags,
+	                                                       out.d_begin.get(), out.d_count.get());
 	KERNEL_CHECK();
-	std::vector<int32_t> h_fin_count((size_t)nq), h_fin_flags((size_t)nq);
-	CUDA_CHECK(cudaMemcpyAsync(out.raw_offs.data(), d_raw_offs.get(), ((size_t)nq + 1) * sizeof(int64_t),
-	                           cudaMemcpyDeviceToHost, s));
-	CUDA_CHECK(cudaMemcpyAsync(h_fin_count.data(), fin_count.get(), (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-	CUDA_CHECK(cudaMemcpyAsync(h_fin_flags.data(), fin_flags.get(), (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-	CUDA_CHECK(cudaMemcpyAsync(&n_raw, d_n_raw.get(), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+	int64_t *const h_finrep = g_pinned.take<int64_t>(finrep.size());
+	CUDA_CHECK(cudaMemcpyAsync(h_finrep, finrep.get(), finrep.bytes(), cudaMemcpyDeviceToHost, s));
+	// the lists are final unless a query needs the general path (rare): let the caller queue
+	// its next step behind them while the host waits for the verdict
+	if (opt.on_filtered && !opt.keep_raw) opt.on_filtered(fin.get(), out.d_begin.get(), out.d_count.get());
 	CUDA_CHECK(cudaStreamSynchronize(s));
+	const int32_t *const h_fin_count = reinterpret_cast<const int32_t *>(h_finrep + nq + 1);
+	const int32_t *const h_fin_flags = h_fin_count + nq;
+	std::copy(h_finrep, h_finrep + nq + 1, out.raw_offs.begin());
+	n_raw = (uint32_t)h_fin_flags[nq];
 	bool general_path = false;
 	for (int32_t q = 0; q < nq; q++)
 		general_path = general_path || h_fin_flags[q] != 0;
@@ -872,7 +904,7 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 					}
 				}, s);
 			}
-			k_filter<<<div_up(nq, 32), 32, 0, s>>>(d_raw_offs.get(), nq, st.get(), ln.get(), score.get(), pred.get(),
+			k_filter<<<div_up(nq, 32), 32, 0, s>>>(d_raw_offs, nq, st.get(), ln.get(), score.get(), pred.get(),
 			                                       keep.get(), heap.get(), overlap.get());
 			KERNEL_CHECK();
 			DevBuf<uint32_t> d_n(1, s);

@@ -2,6 +2,8 @@
 // /root/reference/src/process.cxx:433-458 — anchor_homologies() + std::sort +
 // filter_overlaps_max() for every query.
 #pragma once
+#include <functional>
+#include <stdexcept>
 #include <vector>
 
 #include "common.cuh"
@@ -33,6 +35,21 @@ struct AnchorOptions {
 	// if set: recorded (on another stream) behind the validation kernel; the mapping stream
 	// waits for it only right before it reads input_flags, so the validation runs next to the walk
 	cudaEvent_t input_flags_ready = nullptr;
+	// An index whose build has not been looked at yet (EsaDevice::pending): the device flag that
+	// makes the kernels do nothing if the build failed, and where the host finds the verdict once
+	// the stream has been synchronised (pinned).  The mapping throws IndexNotBuilt then.
+	const int *index_skip = nullptr;
+	const int *index_verdict_host = nullptr;
+	// Called once the filtered lists of the batch are queued (device pointers: lists, per-query
+	// begin and count) and before the host waits for them: whatever the caller queues here (the
+	// row builder) runs while the host is still looking at the counts.  If the lists turn out to
+	// need the general path (AnchorStats::general_path), the final ones replace them and the
+	// caller has to redo that work.
+	std::function<void(const Hom *, const int64_t *, const int64_t *)> on_filtered;
+};
+
+struct IndexNotBuilt : std::runtime_error {
+	IndexNotBuilt() : std::runtime_error("the speculative index build failed: build it again step by step") {}
 };
 
 struct AnchorResult {

@@ -35,6 +35,7 @@ struct phylo_ctx {
 
 	EsaDevice esa;
 	bool esa_ready = false;
+	EsaTimings esa_t; // of the last build (completed by finish_index when the build was lazy)
 
 	DevBuf<uint8_t> q_own;       // queries uploaded by phylo_map_queries
 	const uint8_t *dQ = nullptr; // q_own or the caller's device buffer
@@ -51,6 +52,7 @@ struct phylo_ctx {
 	cudaStream_t check_stream = nullptr;   // input validation next to the walk
 	cudaEvent_t ev_check_fork = nullptr, ev_check_done = nullptr;
 	bool mapped = false;
+	bool last_general_path = false; // the last batch's lists went through the global sort (do_map)
 
 	RowStore rows;
 	uint64_t rows_total = 0; // 0: follow N
@@ -316,9 +318,23 @@ void do_esa_build(phylo_ctx *c, const uint8_t *d_ref, uint64_t n, uint64_t query
 		kmer = esa_default_k((int32_t)(2 * n + 1)) + 1;
 		if (kmer > 12) kmer = 12;
 	}
-	esa_build_device(c->esa, d_ref, (int32_t)n, kmer, (int)c->opt_key_chars, c->stream, &t);
+	// lazy: the call returns with the build queued (and the reference's alphabet checked); whoever
+	// uses the index next either queues its work behind the build (do_map) or waits (finish_index)
+	esa_build_device(c->esa, d_ref, (int32_t)n, kmer, (int)c->opt_key_chars, c->stream, &t, true);
+	c->esa_t = t;
 	record_esa_stats(c, t);
 	c->esa_ready = true;
+}
+
+// Waits for a lazily built index; if what the build took for granted did not hold, the index is
+// built again step by step.  Returns true in that case: work queued behind the build with
+// EsaDevice::skip() has done nothing and must be queued again.
+bool finish_index(phylo_ctx *c)
+{
+	if (!c->esa.pending) return false;
+	const bool rebuilt = esa_finish(c->esa, c->stream, &c->esa_t);
+	record_esa_stats(c, c->esa_t);
+	return rebuilt;
 }
 
 // batch b = sequences [ends[b - 1], ends[b]).  With many short sequences a batch ends on a
@@ -366,6 +382,9 @@ void accumulate(AnchorStats &sum, const AnchorStats &st)
 struct MapHooks {
 	const std::vector<uint64_t> *ends = nullptr;
 	std::function<void(size_t)> before_batch, after_batch;
+	// after_batch(b) may have run on lists that turned out not to be final (do_map queues it
+	// before the host has seen the mapping's last read-back): forget what it did, it is called again
+	std::function<void()> redo;
 	bool validated = false; // the alphabet was checked while the sequences were packed on the host
 };
 
@@ -477,7 +496,10 @@ void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_
 		// verdict is read back with the first synchronisation of the mapping
 		DevBuf<QueryInfo> d_qi((size_t)cnt, s);
 		DevBuf<int> bad(1, s);
-		CUDA_CHECK(cudaMemcpyAsync(d_qi.get(), qi.data(), cnt * sizeof(QueryInfo), cudaMemcpyHostToDevice, s));
+		PinnedArena::Scope pinned_scope(g_pinned); // (copies from ordinary memory would wait for the stream)
+		QueryInfo *const h_qi = g_pinned.take<QueryInfo>((size_t)cnt + 1);
+		std::copy(qi.begin(), qi.end(), h_qi);
+		CUDA_CHECK(cudaMemcpyAsync(d_qi.get(), h_qi, cnt * sizeof(QueryInfo), cudaMemcpyHostToDevice, s));
 		const bool validate = !hooks.validated; // sequences packed on the host were checked there
 		if (validate) {
 			bad.zero();
@@ -512,20 +534,52 @@ void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_
 			}
 		} join_guard{s, validate ? c->ev_check_done : nullptr};
 		opt.input_flags = validate ? bad.get() : nullptr;
+		// reference-coordinate rows for the all-pairs stage, their way to the peers and whatever
+		// the caller does with a finished batch: queued as soon as the filtered lists are, while
+		// the host still waits for the mapping's last read-back
+		bool batch_done = false;
+		const bool last_batch = b + 1 == ends.size();
+		auto finish_batch = [&](const Hom *homs, const int64_t *begin, const int64_t *count) {
+			WallTimer wt(s, c->timings);
+			rows_build(c->rows, (int64_t)(first_row + b0), dQ, d_qi.get(), (int32_t)cnt, homs, begin, count, s);
+			rows_ms += wt.stop();
+			push_rows(c, first_row + b0, cnt, last_batch);
+			if (hooks.after_batch) hooks.after_batch(b);
+			batch_done = true;
+		};
+		// (timed runs keep the phases apart; after a batch that needed the general path the next
+		// one probably does too: no point in building its rows twice)
+		if (!c->timings && !c->last_general_path)
+			opt.on_filtered = finish_batch;
+		else
+			opt.on_filtered = nullptr;
 		AnchorStats st;
-		anchor_queries_device(c->esa, dQ, qi, (int32_t)thr, opt, s, B.res, &st);
+		for (;;) {
+			// the first batch may find the index still being built: its kernels are queued behind
+			// the build and skip their work should the build's assumptions fail
+			opt.index_skip = c->esa.skip();
+			opt.index_verdict_host = c->esa.host_verdict();
+			batch_done = false;
+			try {
+				anchor_queries_device(c->esa, dQ, qi, (int32_t)thr, opt, s, B.res, &st);
+			} catch (const IndexNotBuilt &) {
+				if (!finish_index(c)) throw std::runtime_error("internal error: index verdict inconsistent");
+				continue;
+			}
+			if (finish_index(c)) { // (a batch without a single base does not look at the verdict)
+				if (batch_done && hooks.redo) hooks.redo();
+				continue;
+			}
+			break;
+		}
 		if (st.input_flags & 1) throw std::invalid_argument("a sequence contains bytes outside {A,C,G,T,!}");
 		if (st.input_flags & 2) throw std::invalid_argument("a sequence is not followed by a zero byte in the device buffer");
 		accumulate(sum, st);
-
-		// reference-coordinate rows for the all-pairs stage
-		WallTimer wt(s, c->timings);
-		CUDA_CHECK(cudaMemcpyAsync(d_qi.get(), qi.data(), cnt * sizeof(QueryInfo), cudaMemcpyHostToDevice, s));
-		rows_build(c->rows, (int64_t)(first_row + b0), dQ, d_qi.get(), (int32_t)cnt, B.res.homs.get(), B.res.d_begin.get(),
-		           B.res.d_count.get(), s);
-		rows_ms += wt.stop();
-		push_rows(c, first_row + b0, cnt, b + 1 == ends.size());
-		if (hooks.after_batch) hooks.after_batch(b);
+		c->last_general_path = st.general_path != 0;
+		if (!batch_done || st.general_path) {
+			if (batch_done && hooks.redo) hooks.redo();
+			finish_batch(B.res.homs.get(), B.res.d_begin.get(), B.res.d_count.get());
+		}
 		b0 = b1;
 	}
 	if (!c->peer_rows.empty()) join_pushes(c);
@@ -647,8 +701,12 @@ void phylo_ctx_destroy(phylo_ctx *c)
 	cudaStreamSynchronize(c->stream);
 	cudaStreamSynchronize(c->copy_stream);
 	// blocks cached for this context's streams go back to the driver
+	g_scan_states.drop(c->device, c->own_stream);
 	g_block_cache.trim(c->device, c->own_stream);
-	if (c->stream != c->own_stream) g_block_cache.trim(c->device, c->stream);
+	if (c->stream != c->own_stream) {
+		g_scan_states.drop(c->device, c->stream);
+		g_block_cache.trim(c->device, c->stream);
+	}
 	cudaStreamDestroy(c->copy_stream);
 	cudaEventDestroy(c->ev_main);
 	cudaEventDestroy(c->ev_copy);
@@ -660,7 +718,10 @@ int phylo_set_stream(phylo_ctx *c, void *stream)
 {
 	return guarded(c, [&] {
 		CUDA_CHECK(cudaStreamSynchronize(c->stream));
-		if (c->stream != c->own_stream) g_block_cache.trim(c->device, c->stream);
+		if (c->stream != c->own_stream) {
+			g_scan_states.drop(c->device, c->stream);
+			g_block_cache.trim(c->device, c->stream);
+		}
 		c->stream = stream ? (cudaStream_t)stream : c->own_stream;
 	});
 }
@@ -729,6 +790,12 @@ int phylo_get_stat(const phylo_ctx *c, const char *key, double *out)
 	if (std::string(key) == "launches") {
 		*out = (double)g_kernel_launches.load(); // process-wide count of kernel launches so far
 		return PHYLO_OK;
+	}
+	if (c->esa.pending && !strncmp(key, "esa.", 4) && strcmp(key, "esa.gc_count") && strcmp(key, "esa.kmer_k")) {
+		// figures the build itself produces: wait for it (gc_count is known as soon as the build is queued)
+		auto *m = const_cast<phylo_ctx *>(c);
+		const int rc = guarded(m, [&] { finish_index(m); });
+		if (rc != PHYLO_OK) return rc;
 	}
 	auto it = c->stats.find(key);
 	*out = it == c->stats.end() ? -1.0 : it->second;
@@ -825,6 +892,7 @@ int phylo_esa_get_arrays(const phylo_ctx *cc, int64_t *SA, int64_t *LCP, int64_t
 	auto *c = const_cast<phylo_ctx *>(cc);
 	return guarded(c, [&] {
 		if (!c->esa_ready) throw std::invalid_argument("no index");
+		finish_index(c);
 		const size_t m = (size_t)c->esa.m;
 		cudaStream_t s = c->stream;
 		std::vector<int32_t> tmp(m + 1);
@@ -848,6 +916,7 @@ int phylo_esa_get_matches(phylo_ctx *c, const char *text, const uint64_t *offs, 
 {
 	return guarded(c, [&] {
 		if (!c->esa_ready) throw std::invalid_argument("no index");
+		finish_index(c);
 		if (!count) return;
 		if (!text || !offs || !lens || !out) throw std::invalid_argument("NULL argument");
 		uint64_t extent = 0;
@@ -1050,6 +1119,7 @@ void process_resident(phylo_ctx *c, uint64_t N, uint64_t ref_index, int flags, M
 		compare_ms += wt.stop();
 		tiles_done = ready;
 	};
+	hooks.redo = [&] { tiles_done = 0; }; // (the next comparison starts over: it clears the matrix first)
 	do_map(c, dq, offs, lens, N, thr, hooks);
 	since("process.host_map_done_ms");
 	{
@@ -1062,9 +1132,21 @@ void process_resident(phylo_ctx *c, uint64_t N, uint64_t ref_index, int flags, M
 	c->stats["compare.increments"] = (double)ends.size();
 	c->matN = tot;
 	const size_t bytes = (size_t)(tot * tot) * sizeof(uint64_t);
-	CUDA_CHECK(cudaMemcpyAsync(subst, c->d_subst.get(), bytes, cudaMemcpyDeviceToHost, s));
-	CUDA_CHECK(cudaMemcpyAsync(homologs, c->d_hom.get(), bytes, cudaMemcpyDeviceToHost, s));
-	CUDA_CHECK(cudaStreamSynchronize(s));
+	if (bytes <= (512u << 10)) {
+		// small matrices through pinned memory: two queued copies and one wait instead of two
+		// copies that each block the host
+		PinnedArena::Scope pinned_scope(g_pinned);
+		uint64_t *h = g_pinned.take<uint64_t>((size_t)(2 * tot * tot));
+		CUDA_CHECK(cudaMemcpyAsync(h, c->d_subst.get(), bytes, cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaMemcpyAsync(h + tot * tot, c->d_hom.get(), bytes, cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaStreamSynchronize(s));
+		memcpy(subst, h, bytes);
+		memcpy(homologs, h + tot * tot, bytes);
+	} else {
+		CUDA_CHECK(cudaMemcpyAsync(subst, c->d_subst.get(), bytes, cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaMemcpyAsync(homologs, c->d_hom.get(), bytes, cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaStreamSynchronize(s));
+	}
 	since("process.host_done_ms");
 }
 
@@ -1399,6 +1481,11 @@ int phylo_esa_device_arrays(const phylo_ctx *c, void **S, uint64_t *S_bytes, voi
                             void **FVC)
 {
 	if (!c || !c->esa.m) return PHYLO_ERR_INVALID;
+	if (c->esa.pending) { // the arrays are about to leave the library: the build must be over (and good)
+		auto *m = const_cast<phylo_ctx *>(c);
+		const int rc = guarded(m, [&] { finish_index(m); });
+		if (rc != PHYLO_OK) return rc;
+	}
 	if (S) *S = c->esa.S.get();
 	if (S_bytes) *S_bytes = c->esa.S.size();
 	if (SA) *SA = c->esa.SA.get();

@@ -574,6 +574,7 @@ void rows_alloc(RowStore &rs, int64_t genomes, int32_t n, cudaStream_t s)
 	rs.W = (((int64_t)n + 31) / 32 + ROW_BLK - 1) / ROW_BLK * ROW_BLK;
 	rs.genomes = genomes;
 	rs.data.alloc((size_t)(genomes * rs.genome_words()), s);
+	rs.maps.base = nullptr; // the tensor maps describe the old geometry
 	rs.data.zero(); // rows never written (padding genomes of a sharded run) are all-invalid
 }
 
@@ -734,12 +735,22 @@ void compare_all_device(const RowStore &rs, int64_t N, bool complete_deletion, i
 		}
 		if (my_units > 0x7fffffffll) throw std::invalid_argument("too many tile pairs for one launch");
 		if (my_units > 0) {
+			static_assert(sizeof(CUtensorMap) == 128, "RowStore::MapCache holds two tensor maps");
 			CUtensorMap tm_fast, tm_full;
 			memset(&tm_fast, 0, sizeof tm_fast);
 			memset(&tm_full, 0, sizeof tm_full);
 			if (tma) {
-				rows_tensor_map(rs, 3, CT, &tm_fast);
-				rows_tensor_map(rs, ROW_PLANES, CT, &tm_full);
+				if (rs.maps.base != rs.data.get() || rs.maps.ct != CT) { // (a new allocation or another tile side)
+					rows_tensor_map(rs, 3, CT, &tm_fast);
+					rows_tensor_map(rs, ROW_PLANES, CT, &tm_full);
+					memcpy(rs.maps.bytes[0], &tm_fast, 128);
+					memcpy(rs.maps.bytes[1], &tm_full, 128);
+					rs.maps.base = rs.data.get();
+					rs.maps.ct = CT;
+				} else {
+					memcpy(&tm_fast, rs.maps.bytes[0], 128);
+					memcpy(&tm_full, rs.maps.bytes[1], 128);
+				}
 			}
 			const size_t smem = cmp_smem_bytes(CT, tma);
 #define PHY_LAUNCH_COMPARE(CTV, TMAV)                                                                                    \

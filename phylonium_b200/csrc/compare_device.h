@@ -45,6 +45,14 @@ struct RowStore {
 	int64_t genomes = 0;   // capacity in genomes
 	int64_t W = 0;         // words per plane, multiple of ROW_BLK
 	int32_t n = 0;         // reference length (columns)
+	// tensor maps of the store (compare.cu: rows_tensor_map), encoded once per allocation and tile
+	// side: [0] three planes, [1] all five; 128 opaque bytes each (a CUtensorMap)
+	struct alignas(64) MapCache {
+		unsigned char bytes[2][128];
+		const void *base = nullptr;
+		int ct = 0;
+	};
+	mutable MapCache maps;
 	uint32_t *row(int64_t g) const { return data.get() + g * genome_words(); }
 	int64_t genome_words() const { return ROW_PLANES * W + ROW_FLAG_WORDS; }
 };

@@ -803,9 +803,14 @@ namespace
 // fail[0] = 1 if what the speculative build took for granted does not hold: valid input, the
 // dirty suffixes fit their list and were put in place, no tie group left for the doubling rounds
 __global__ void k_spec_check(const int *__restrict__ text_flags, const uint32_t *__restrict__ counters,
-                             const uint32_t *__restrict__ dirty_ctl, uint32_t dirty_cap, int *__restrict__ fail)
+                             const uint32_t *__restrict__ dirty_ctl, uint32_t dirty_cap, int *__restrict__ fail,
+                             uint32_t *__restrict__ counters_out)
 {
 	*fail = (text_flags[0] != 0 || counters[1] != 0 || (dirty_ctl && (dirty_ctl[0] > dirty_cap || dirty_ctl[1] != 0))) ? 1 : 0;
+	counters_out[0] = counters[0];
+	counters_out[1] = counters[1];
+	counters_out[2] = dirty_ctl ? dirty_ctl[0] : 0u;
+	counters_out[3] = dirty_ctl ? dirty_ctl[1] : 0u;
 }
 } // namespace
 
@@ -919,12 +924,41 @@ bool esa_build_impl(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k,
 // tells; if an assumption failed the index is built again the careful way, deciding on the host
 // after each stage like before.
 void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k, int key_chars, cudaStream_t s,
-                      EsaTimings *tm)
+                      EsaTimings *tm, bool lazy)
 {
 	const bool timed = tm && tm->enabled; // per-phase timers synchronise anyway
 	const bool spec = !timed && g_tuning.esa_speculative && g_tuning.table_direct != 2;
-	if (spec && esa_build_impl(esa, d_ref, n, kmer_k, key_chars, s, tm, true)) return;
+	if (spec) {
+		esa_build_impl(esa, d_ref, n, kmer_k, key_chars, s, tm, true);
+		// the first kernel's verdict has long arrived (the host was busy queueing the rest)
+		CUDA_CHECK(cudaEventSynchronize(esa.ev_early));
+		if (esa.h_report[0]) {
+			esa.pending = false;
+			throw std::invalid_argument("reference contains bytes outside {A,C,G,T,!}");
+		}
+		esa.gc_count = esa.h_report[1];
+		if (!lazy) esa_finish(esa, s, tm);
+		return;
+	}
 	esa_build_impl(esa, d_ref, n, kmer_k, key_chars, s, tm, false);
+}
+
+bool esa_finish(EsaDevice &esa, cudaStream_t s, EsaTimings *tm)
+{
+	if (!esa.pending) return false;
+	CUDA_CHECK(cudaEventSynchronize(esa.ev_done));
+	esa.pending = false;
+	const int *h = esa.h_report + 8;
+	if (tm) {
+		tm->tie_groups = (uint32_t)h[4];
+		tm->dirty = (uint32_t)h[6];
+	}
+	if (!h[3]) return false;
+	// separators beyond the list, or repeats: once more, step by step.  The reference is the
+	// first n bytes of the text that the failed build has left behind.
+	DevBuf<uint8_t> text = std::move(esa.S);
+	esa_build_impl(esa, text.get(), esa.n, esa.pend_kmer_k, esa.pend_key_chars, s, tm, false);
+	return true;
 }
 
 namespace
@@ -954,25 +988,46 @@ bool esa_build_impl(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k,
 	esa.CLD.alloc((size_t)m + 1, s);
 	esa.FVC.alloc(m, s);
 
+	if (!esa.side) {
+		CUDA_CHECK(cudaStreamCreateWithFlags(&esa.side, cudaStreamNonBlocking));
+		CUDA_CHECK(cudaEventCreateWithFlags(&esa.ev_fork, cudaEventDisableTiming));
+		CUDA_CHECK(cudaEventCreateWithFlags(&esa.ev_join, cudaEventDisableTiming));
+	}
+	if (!esa.h_report) {
+		CUDA_CHECK(cudaHostAlloc((void **)&esa.h_report, 16 * sizeof(int), cudaHostAllocPortable));
+		CUDA_CHECK(cudaEventCreateWithFlags(&esa.ev_text, cudaEventDisableTiming));
+		CUDA_CHECK(cudaEventCreateWithFlags(&esa.ev_early, cudaEventDisableTiming));
+		CUDA_CHECK(cudaEventCreateWithFlags(&esa.ev_done, cudaEventDisableTiming));
+	}
+
 	// 1. text
-	DevBuf<int> bad(3, s);
-	bad.zero();
-	k_build_text<<<NUM_SMS_B200 * 8, 256, 0, s>>>(d_ref, n, esa.S.get(), padded, bad.get());
+	// 8 report words (EsaDevice::report) and, cleared by the same memset, the build's counters:
+	// [8,9] dirty_ctl, [10,11] tie-group counters, [12] length of k_cld's list of long entries
+	esa.report.alloc(16, s);
+	esa.report.zero();
+	int *bad = esa.report.get(); // [0..2], see EsaDevice::report
+	k_build_text<<<NUM_SMS_B200 * 8, 256, 0, s>>>(d_ref, n, esa.S.get(), padded, bad);
 	KERNEL_CHECK();
 	int64_t bangs = 0;
 	if (!spec) {
-		int h_flags[3];
-		CUDA_CHECK(cudaMemcpyAsync(h_flags, bad.get(), sizeof h_flags, cudaMemcpyDeviceToHost, s));
+		PinnedArena::Scope scope(g_pinned);
+		int *h_flags = g_pinned.take<int>(3);
+		CUDA_CHECK(cudaMemcpyAsync(h_flags, bad, 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
 		CUDA_CHECK(cudaStreamSynchronize(s));
 		if (h_flags[0]) throw std::invalid_argument("reference contains bytes outside {A,C,G,T,!}");
 		esa.gc_count = h_flags[1];
 		bangs = h_flags[2];
+	} else {
+		// the verdict on the input and the G/C count go to the host right away, next to the sort
+		CUDA_CHECK(cudaEventRecord(esa.ev_text, s));
+		CUDA_CHECK(cudaStreamWaitEvent(esa.side, esa.ev_text, 0));
+		CUDA_CHECK(cudaMemcpyAsync(esa.h_report, bad, 3 * sizeof(int), cudaMemcpyDeviceToHost, esa.side));
+		CUDA_CHECK(cudaEventRecord(esa.ev_early, esa.side));
 	}
 	T.text_ms = lap.lap();
-	DevBuf<int> spec_fail(1, s); // speculative mode: set by k_spec_check, read by the kernels after it
-	const int *skip = spec ? spec_fail.get() : nullptr;
-	DevBuf<uint32_t> spec_counters(4, s); // copies of {groups, hard groups, dirty suffixes, dirty error} for the final read-back
-	if (spec) spec_counters.zero();
+	int *spec_fail = esa.report.get() + 3; // speculative mode: set by k_spec_check, read by the kernels after it
+	const int *skip = spec ? spec_fail : nullptr;
+	uint32_t *spec_counters = reinterpret_cast<uint32_t *>(esa.report.get() + 4); // copies of {groups, hard groups, dirty suffixes, dirty error}
 
 	// Which sorter: packed words (2-bit codes, <= 16 characters, suffix_sort.cuh) unless the
 	// caller asks for longer keys, the text has so many separators that ordering the dirty
@@ -994,17 +1049,16 @@ bool esa_build_impl(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k,
 		// 2. keys, 3. sort
 		const size_t key_words = packed ? pk_padded_words(m) : (size_t)m;
 		DevBuf<uint64_t> keys(key_words, s), keys_alt(key_words, s);
-		DevBuf<uint32_t> vals, vals_alt, dirty_list, dirty_sorted, dirty_ctl;
+		DevBuf<uint32_t> vals, vals_alt, dirty_list, dirty_sorted;
+		uint32_t *const dirty_ctl = reinterpret_cast<uint32_t *>(esa.report.get() + 8); // [0] number of dirty suffixes, [1] error flag of k_dirty_fix
 		const uint64_t *K1 = nullptr;
 		if (packed) {
 			const uint32_t cap = (uint32_t)dirty_bound;
 			dirty_list.alloc(cap, s);
 			dirty_sorted.alloc(cap, s);
-			dirty_ctl.alloc(2, s); // [0] number of dirty suffixes, [1] error flag of k_dirty_fix
-			dirty_ctl.zero();
 			PkProfile prof;
 			uint64_t *W = suffix_sort_packed(esa.S.get(), m, padded, kc, keys.get(), keys_alt.get(), dirty_list.get(),
-			                                 dirty_ctl.get(), cap, s, timed ? &prof : nullptr);
+			                                 dirty_ctl, cap, s, timed ? &prof : nullptr);
 			if (timed) {
 				T.first_pass_ms = prof.first_ms;
 				if (prof.passes) {
@@ -1015,10 +1069,10 @@ bool esa_build_impl(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k,
 				}
 			}
 			const int dirty_blocks = std::min(div_up(cap, 8), 64); // a warp per dirty suffix, grid-stride
-			k_dirty_rank<<<dirty_blocks, 256, 0, s>>>(dirty_list.get(), dirty_ctl.get(), cap, esa.S.get(), dirty_sorted.get());
+			k_dirty_rank<<<dirty_blocks, 256, 0, s>>>(dirty_list.get(), dirty_ctl, cap, esa.S.get(), dirty_sorted.get());
 			KERNEL_CHECK();
-			k_dirty_fix<<<dirty_blocks, 256, 0, s>>>(dirty_sorted.get(), dirty_ctl.get(), cap, esa.S.get(), m, kc, W,
-			                                         (int *)(dirty_ctl.get() + 1));
+			k_dirty_fix<<<dirty_blocks, 256, 0, s>>>(dirty_sorted.get(), dirty_ctl, cap, esa.S.get(), m, kc, W,
+			                                         (int *)(dirty_ctl + 1));
 			KERNEL_CHECK();
 			K1 = W;
 			T.sort_ms = lap.lap();
@@ -1043,15 +1097,14 @@ bool esa_build_impl(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k,
 
 		// 4. LCP/FVC from neighbouring keys; SA in its final place for all untied suffixes
 		DevBuf<int32_t> heads((size_t)m / 2 + 1, s);
-		DevBuf<uint32_t> counters(2, s);
-		counters.zero();
+		uint32_t *const counters = reinterpret_cast<uint32_t *>(esa.report.get() + 10);
 		if (packed) {
 			k_words_to_lcp<<<div_up(m, 256), 256, 0, s>>>(K1, esa.S.get(), m, esa.SA.get(), esa.LCP.get(), esa.FVC.get(),
-			                                              heads.get(), counters.get());
+			                                              heads.get(), counters);
 		} else {
 			const uint32_t *V1 = K1 == keys.get() ? vals.get() : vals_alt.get();
 			k_keys_to_lcp<<<div_up(m, 256), 256, 0, s>>>(K1, V1, esa.S.get(), m, esa.SA.get(), esa.LCP.get(),
-			                                             esa.FVC.get(), kc, heads.get(), counters.get());
+			                                             esa.FVC.get(), kc, heads.get(), counters);
 		}
 		KERNEL_CHECK();
 
@@ -1059,27 +1112,29 @@ bool esa_build_impl(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k,
 		uint32_t h_counters[2] = {0, 0};
 		{
 			if (packed)
-				k_small_groups<true><<<NUM_SMS_B200 * 4, 128, 0, s>>>(heads.get(), counters.get(), K1, esa.S.get(), m,
+				k_small_groups<true><<<NUM_SMS_B200 * 4, 128, 0, s>>>(heads.get(), counters, K1, esa.S.get(), m,
 				                                                     esa.SA.get(), esa.LCP.get(), esa.FVC.get(), kc);
 			else
-				k_small_groups<false><<<NUM_SMS_B200 * 4, 128, 0, s>>>(heads.get(), counters.get(), K1, esa.S.get(), m,
+				k_small_groups<false><<<NUM_SMS_B200 * 4, 128, 0, s>>>(heads.get(), counters, K1, esa.S.get(), m,
 				                                                      esa.SA.get(), esa.LCP.get(), esa.FVC.get(), kc);
 			KERNEL_CHECK();
 			if (spec) {
 				// no read-back: a device-side check decides whether the kernels below may run, the
 				// host learns about it at the very end (counters travel with the other flags)
-				k_spec_check<<<1, 1, 0, s>>>(bad.get(), counters.get(), packed ? dirty_ctl.get() : nullptr, (uint32_t)dirty_bound,
-				                             spec_fail.get());
+				// (it also copies the counters next to the flags for the read-back)
+				k_spec_check<<<1, 1, 0, s>>>(bad, counters, packed ? dirty_ctl : nullptr, (uint32_t)dirty_bound,
+				                             spec_fail, spec_counters);
 				KERNEL_CHECK();
-				CUDA_CHECK(cudaMemcpyAsync(spec_counters.get(), counters.get(), 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-				if (packed)
-					CUDA_CHECK(cudaMemcpyAsync(spec_counters.get() + 2, dirty_ctl.get(), 2 * sizeof(uint32_t),
-					                           cudaMemcpyDeviceToDevice, s));
 			} else {
-				uint32_t h_dirty[2] = {0, 0};
-				if (packed) CUDA_CHECK(cudaMemcpyAsync(h_dirty, dirty_ctl.get(), sizeof h_dirty, cudaMemcpyDeviceToHost, s));
-				CUDA_CHECK(cudaMemcpyAsync(h_counters, counters.get(), sizeof h_counters, cudaMemcpyDeviceToHost, s));
+				PinnedArena::Scope scope(g_pinned);
+				uint32_t *hp = g_pinned.take<uint32_t>(4);
+				uint32_t *h_dirty = hp + 2;
+				h_dirty[0] = h_dirty[1] = 0;
+				if (packed) CUDA_CHECK(cudaMemcpyAsync(h_dirty, dirty_ctl, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+				CUDA_CHECK(cudaMemcpyAsync(hp, counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 				CUDA_CHECK(cudaStreamSynchronize(s));
+				h_counters[0] = hp[0];
+				h_counters[1] = hp[1];
 				T.tie_groups = h_counters[0];
 				T.dirty = h_dirty[0];
 				if (h_dirty[1] || h_dirty[0] > (uint64_t)dirty_bound)
@@ -1200,11 +1255,6 @@ bool esa_build_impl(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k,
 	// 7. child table.  The min-pyramid is only read by k_cld_long (the entries whose scans are
 	// long): it is built on a side stream while k_cld works through the bulk of the entries.
 	{
-		if (!esa.side) {
-			CUDA_CHECK(cudaStreamCreateWithFlags(&esa.side, cudaStreamNonBlocking));
-			CUDA_CHECK(cudaEventCreateWithFlags(&esa.ev_fork, cudaEventDisableTiming));
-			CUDA_CHECK(cudaEventCreateWithFlags(&esa.ev_join, cudaEventDisableTiming));
-		}
 		cudaStream_t side = esa.side;
 		cudaEvent_t ev_fork = esa.ev_fork, ev_join = esa.ev_join;
 		Pyramid py;
@@ -1239,15 +1289,14 @@ bool esa_build_impl(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k,
 		}
 		CUDA_CHECK(cudaEventRecord(ev_join, side));
 		DevBuf<int32_t> long_list((size_t)m + 1, s);
-		DevBuf<uint32_t> long_count(1, s);
-		long_count.zero();
+		uint32_t *const long_count = reinterpret_cast<uint32_t *>(esa.report.get() + 12);
 		esa.node.alloc((size_t)m + 1, s);
 		k_cld<<<div_up((int64_t)m + 1, CLD_TILE), CLD_THREADS, 0, s>>>(py, m, esa.CLD.get(), long_list.get(),
-		                                                               long_count.get(), esa.SA.get(), esa.FVC.get(),
+		                                                               long_count, esa.SA.get(), esa.FVC.get(),
 		                                                               esa.node.get(), skip);
 		KERNEL_CHECK();
 		CUDA_CHECK(cudaStreamWaitEvent(s, ev_join, 0));
-		k_cld_long<<<NUM_SMS_B200 * 8, 256, 0, s>>>(py, long_list.get(), long_count.get(), esa.CLD.get(), esa.node.get(), skip);
+		k_cld_long<<<NUM_SMS_B200 * 8, 256, 0, s>>>(py, long_list.get(), long_count, esa.CLD.get(), esa.node.get(), skip);
 		KERNEL_CHECK();
 		T.cld_ms = lap.lap();
 	}
@@ -1257,21 +1306,12 @@ bool esa_build_impl(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k,
 	T.table_ms = lap.lap();
 	T.total_ms = total.lap();
 	if (spec) {
-		// the one read-back of the speculative build
-		struct {
-			int text[3];
-			int fail;
-			uint32_t cnt[4];
-		} h;
-		CUDA_CHECK(cudaMemcpyAsync(h.text, bad.get(), sizeof h.text, cudaMemcpyDeviceToHost, s));
-		CUDA_CHECK(cudaMemcpyAsync(&h.fail, spec_fail.get(), sizeof h.fail, cudaMemcpyDeviceToHost, s));
-		CUDA_CHECK(cudaMemcpyAsync(h.cnt, spec_counters.get(), sizeof h.cnt, cudaMemcpyDeviceToHost, s));
-		CUDA_CHECK(cudaStreamSynchronize(s));
-		if (h.text[0]) throw std::invalid_argument("reference contains bytes outside {A,C,G,T,!}");
-		esa.gc_count = h.text[1];
-		T.tie_groups = h.cnt[0];
-		T.dirty = h.cnt[2];
-		if (h.fail) return false; // separators beyond the list, or repeats: once more, step by step
+		// the one read-back of the speculative build: queued here, looked at by esa_finish()
+		CUDA_CHECK(cudaMemcpyAsync(esa.h_report + 8, esa.report.get(), 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaEventRecord(esa.ev_done, s));
+		esa.pending = true;
+		esa.pend_kmer_k = kmer_k;
+		esa.pend_key_chars = key_chars;
 	}
 	return true;
 }

@@ -35,8 +35,33 @@ struct EsaDevice {
 	// side stream of the build (min-pyramid next to the child-table kernel), made on first use
 	cudaStream_t side = nullptr;
 	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	// Verdicts of the speculative build (esa_build.cu).  report (device, 8 ints): [0] bytes outside
+	// the alphabet, [1] G/C count, [2] separators — written by the first kernel —, [3] != 0: an
+	// assumption of the build failed and the kernels behind the check did nothing, [4..7]
+	// {tie groups, hard groups, dirty suffixes, dirty error}.  h_report (pinned, 16 ints): [0..2]
+	// arrive early (ev_text: right behind the first kernel, on the side stream), [8..15] = report at
+	// the end of the build (ev_done, on the build's stream).  While `pending` the host has not
+	// looked at the second half yet: esa_finish() does, and what is queued behind the build in the
+	// meantime takes `skip()` along.
+	DevBuf<int> report;
+	int *h_report = nullptr;
+	cudaEvent_t ev_text = nullptr, ev_early = nullptr, ev_done = nullptr;
+	bool pending = false;
+	int pend_kmer_k = -1, pend_key_chars = 0;
+	const int *skip() const { return pending ? report.get() + 3 : nullptr; }
+	const int *host_verdict() const { return pending ? h_report + 8 + 3 : nullptr; }
 	void destroy_side()
 	{
+		if (h_report) {
+			cudaFreeHost(h_report);
+			h_report = nullptr;
+		}
+		if (ev_text) {
+			cudaEventDestroy(ev_text);
+			cudaEventDestroy(ev_early);
+			cudaEventDestroy(ev_done);
+			ev_text = nullptr;
+		}
 		if (!side) return;
 		cudaStreamSynchronize(side);
 		cudaStreamDestroy(side);
@@ -69,14 +94,23 @@ struct EsaDevice {
 		node.release();
 		table.release();
 		n = m = K = 0;
+		pending = false; // (report stays: kernels of an abandoned build may still be reading it)
 	}
 };
 
 // d_ref: n reference bytes over {A,C,G,T,!} already on the device. Throws CudaError /
 // std::invalid_argument. kmer_k < 0 picks K from m.
 // key_chars <= 0 picks the number of characters per sort key from m.
+// lazy: return as soon as everything is queued and the first kernel's verdict (alphabet, G/C
+// count) is in; esa.pending then says that esa_finish() has not been called yet.
 void esa_build_device(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k, int key_chars, cudaStream_t stream,
-                      EsaTimings *timings);
+                      EsaTimings *timings, bool lazy = false);
+
+// Waits for a lazily built index and looks at its verdict; if an assumption of the speculative
+// build did not hold, the index is built again step by step (from the text already on the
+// device).  Returns true if that happened: work queued behind the build with esa.skip() did
+// nothing and has to be queued again.  No-op (false) unless esa.pending.
+bool esa_finish(EsaDevice &esa, cudaStream_t stream, EsaTimings *timings);
 
 // builds only the table (used after importing S/SA/LCP/CLD/FVC from another GPU)
 // nodes_ready: esa.node already holds the interleaved records

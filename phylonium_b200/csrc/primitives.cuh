@@ -11,6 +11,7 @@
 #pragma once
 #include "common.cuh"
 
+#include <algorithm>
 #include <vector>
 
 namespace phy
@@ -114,22 +115,29 @@ template <typename T> struct ScanPtrOut {
 // One launch instead of reduce + scan + apply: a block takes the next tile from an atomic
 // counter, publishes the tile's aggregate, then adds up its predecessors' status words — a
 // warp looks at 32 of them at a time — until it meets one that already holds an inclusive
-// prefix.  status[t] = flag << 32 | value (32-bit T only); the status array and the counter
-// are zeroed by one memset before the launch.
-constexpr unsigned long long SP_AGGREGATE = 1ull << 32, SP_INCLUSIVE = 2ull << 32;
+// prefix.  status[t] = epoch << 34 | flag << 32 | value (32-bit T only).  The status array
+// belongs to the stream and is never cleared between scans: every launch has its own epoch and
+// a word of another epoch reads as "not there yet"; the block that draws the last tile puts
+// the tile counter back to zero.  (A memset per scan was a launch of its own: ~4 us each.)
+constexpr unsigned long long SP_AGGREGATE = 1ull, SP_INCLUSIVE = 2ull;
 
 template <typename T, typename InF, typename OutF, typename Op>
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_single_pass_kernel(int64_t n, InF in, OutF out, Op op, T identity, bool inclusive, unsigned long long *status,
-                        uint32_t *tile_counter)
+                        uint32_t *tile_counter, uint32_t epoch)
 {
 	static_assert(sizeof(T) == 4, "status words carry 32-bit values");
 	__shared__ T smem[32];
 	__shared__ uint32_t s_tile;
 	__shared__ T s_prefix;
-	if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+	if (threadIdx.x == 0) {
+		s_tile = atomicAdd(tile_counter, 1u);
+		if (s_tile == gridDim.x - 1) atomicExch(tile_counter, 0u); // every block has drawn: ready for the next scan
+	}
 	__syncthreads();
 	const uint32_t tile = s_tile;
+	const unsigned long long tag_agg = ((unsigned long long)epoch << 2) | SP_AGGREGATE;
+	const unsigned long long tag_inc = ((unsigned long long)epoch << 2) | SP_INCLUSIVE;
 	const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
 	T v[SCAN_ITEMS];
 	T acc = identity;
@@ -145,22 +153,24 @@ scan_single_pass_kernel(int64_t n, InF in, OutF out, Op op, T identity, bool inc
 		const int lane = threadIdx.x;
 		T prefix = identity;
 		if (tile == 0) {
-			if (lane == 0) atomicExch(status, SP_INCLUSIVE | (unsigned long long)(uint32_t)total);
+			if (lane == 0) atomicExch(status, (tag_inc << 32) | (unsigned long long)(uint32_t)total);
 		} else {
-			if (lane == 0) atomicExch(status + tile, SP_AGGREGATE | (unsigned long long)(uint32_t)total);
+			if (lane == 0) atomicExch(status + tile, (tag_agg << 32) | (unsigned long long)(uint32_t)total);
 			// windows of 32 predecessors, nearest first: lane l looks at tile - 1 - l
 			int64_t top = (int64_t)tile - 1;
 			for (;;) {
 				const int64_t t = top - lane;
-				unsigned long long w = SP_INCLUSIVE; // before tile 0: an inclusive prefix of `identity`
+				unsigned long long tag = tag_inc; // before tile 0: an inclusive prefix of `identity`
 				T val = identity;
 				if (t >= 0) {
+					unsigned long long w;
 					do {
 						w = *(volatile unsigned long long *)(status + t);
-					} while ((w >> 32) == 0);
+						tag = w >> 32;
+					} while (tag != tag_agg && tag != tag_inc);
 					val = (T)(uint32_t)w;
 				}
-				const uint32_t incl = __ballot_sync(0xffffffffu, (w >> 32) == 2);
+				const uint32_t incl = __ballot_sync(0xffffffffu, tag == tag_inc);
 				// lanes up to and including the nearest inclusive one contribute
 				const int stop = incl ? __ffs(incl) - 1 : 31;
 				T part = lane <= stop ? val : identity;
@@ -175,7 +185,7 @@ scan_single_pass_kernel(int64_t n, InF in, OutF out, Op op, T identity, bool inc
 				if (incl) break;
 				top -= 32;
 			}
-			if (lane == 0) atomicExch(status + tile, SP_INCLUSIVE | (unsigned long long)(uint32_t)op(prefix, total));
+			if (lane == 0) atomicExch(status + tile, (tag_inc << 32) | (unsigned long long)(uint32_t)op(prefix, total));
 		}
 		if (lane == 0) s_prefix = prefix;
 	}
@@ -190,6 +200,43 @@ scan_single_pass_kernel(int64_t n, InF in, OutF out, Op op, T identity, bool inc
 	}
 }
 
+// status words of the single-pass scans of one stream (scans on a stream run one after the other)
+struct ScanState {
+	DevBuf<unsigned long long> status; // [tiles] + the tile counter
+	uint32_t epoch = 0;
+};
+class ScanStates
+{
+	std::mutex mu_;
+	std::map<std::pair<int, cudaStream_t>, ScanState> states_;
+
+  public:
+	// status array for a scan of nblocks tiles on stream s, and the epoch of that scan
+	unsigned long long *get(int nblocks, cudaStream_t s, uint32_t *epoch)
+	{
+		int dev = 0;
+		CUDA_CHECK(cudaGetDevice(&dev));
+		std::lock_guard<std::mutex> lock(mu_);
+		ScanState &st = states_[{dev, s}];
+		if (st.status.size() < (size_t)nblocks + 1 || st.epoch >= (1u << 30) - 1) {
+			size_t cap = std::max<size_t>(st.status.size(), 4096);
+			while (cap < (size_t)nblocks + 1)
+				cap *= 2;
+			st.status.alloc(cap, s); // (the old array goes back to this stream's cache: ordered behind its last scan)
+			st.status.zero();
+			st.epoch = 0;
+		}
+		*epoch = ++st.epoch;
+		return st.status.get();
+	}
+	void drop(int device, cudaStream_t s)
+	{
+		std::lock_guard<std::mutex> lock(mu_);
+		states_.erase({device, s});
+	}
+};
+inline ScanStates g_scan_states;
+
 // out(i, scan value); exclusive: value before element i, inclusive: including it.
 template <typename T, typename InF, typename OutF, typename Op>
 void device_scan(int64_t n, InF in, OutF out, Op op, T identity, bool inclusive, cudaStream_t s)
@@ -202,10 +249,10 @@ void device_scan(int64_t n, InF in, OutF out, Op op, T identity, bool inclusive,
 		return;
 	}
 	if (g_tuning.scan_single_pass) {
-		DevBuf<unsigned long long> status((size_t)nblocks + 1, s); // [nblocks]: the tile counter
-		status.zero();
-		scan_single_pass_kernel<T><<<nblocks, SCAN_THREADS, 0, s>>>(n, in, out, op, identity, inclusive, status.get(),
-		                                                            reinterpret_cast<uint32_t *>(status.get() + nblocks));
+		uint32_t epoch = 0;
+		unsigned long long *status = g_scan_states.get(nblocks, s, &epoch); // [0]: the tile counter, tiles from [1]
+		scan_single_pass_kernel<T><<<nblocks, SCAN_THREADS, 0, s>>>(n, in, out, op, identity, inclusive, status + 1,
+		                                                            reinterpret_cast<uint32_t *>(status), epoch);
 		KERNEL_CHECK();
 		return;
 	}

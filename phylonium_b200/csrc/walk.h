@@ -145,6 +145,7 @@ struct WalkParams {
 	uint32_t *dead;     // total_chunks * CH / 32 bitmap words, zero-initialised
 	ChunkRec *rec;      // total_chunks
 	int32_t *chunk_query; // total_chunks: owning query
+	const int *skip = nullptr; // device flag of a lazily built index (EsaDevice::skip): != 0, the index is not there
 };
 
 // ---------------------------------------------------------------------------------

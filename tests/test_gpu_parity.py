@@ -383,6 +383,63 @@ def test_equal_starts_take_the_host_sort(pb, oracle):
     assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
 
 
+def _general_path_genomes():
+    """genome 2 and 3 carry more homologies than the per-query sort holds"""
+    rng = np.random.default_rng(43)
+    blocks = [datasets.random_dna(rng, 150) for _ in range(2600)]
+    r = b"".join(blocks)
+    order = rng.permutation(len(blocks))
+    q1 = b"".join(blocks[i] for i in order)
+    q2 = b"".join(datasets.revcomp(blocks[i]) if i % 3 == 0 else blocks[i] for i in order[::-1])
+    return [r, datasets.mutate(rng, r, 0.02), q1, q2, datasets.mutate(rng, r, 0.01), datasets.mutate(rng, r, 0.03)]
+
+
+@pytest.mark.parametrize("batch_bytes", [0, 300_000, 700_000])
+@pytest.mark.parametrize("flags", [0, 4])
+def test_process_redoes_a_batch_whose_lists_were_not_final(pb, oracle, batch_bytes, flags):
+    """phylo_process queues the rows (and the comparison) of a batch before the host has seen
+    whether its filtered lists are final; a batch that needs the global sort after all is
+    done again — in the first, a middle or the only batch"""
+    genomes = _general_path_genomes()
+    with pb.Context() as ctx:
+        if batch_bytes:
+            ctx.set_option("map_batch_bytes", batch_bytes)
+        subst, homol = ctx.process(genomes, 0, flags)
+        assert ctx.stat("anchor.general_path") >= 1
+        assert ctx.stat("map.batches") == {0: 1, 300_000: 6, 700_000: 3}[batch_bytes]  # 390 kbp per genome
+        again = ctx.process_again(0, flags)
+    want = oracle.process(genomes, 0, flags, threads=2)
+    assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
+    assert np.array_equal(again[0], want["subst"]) and np.array_equal(again[1], want["homologs"])
+
+
+@pytest.mark.parametrize("kind", ["contigs", "repeats"])
+def test_process_on_an_index_the_speculative_build_gives_up_on(pb, oracle, kind):
+    """the mapping is queued behind the index build; when the build's assumptions fail (too
+    many contigs for the packed sorter's list, repeats that need the doubling rounds) its kernels
+    do nothing, the index is built again step by step and the batch is mapped again"""
+    rng = np.random.default_rng(47)
+    if kind == "contigs":
+        r = b"!".join(datasets.random_dna(rng, 40 + (k % 7)) for k in range(3000))
+    else:
+        unit = datasets.random_dna(rng, 700)
+        r = unit * 6 + datasets.random_dna(rng, 3000) + unit * 3
+    genomes = [r, datasets.mutate(rng, r, 0.02), datasets.mutate(rng, r, 0.05), datasets.random_dna(rng, 5000)]
+    with pb.Context() as ctx:
+        subst, homol = ctx.process(genomes, 0, 0)
+        if kind == "contigs":
+            assert ctx.stat("esa.packed") == 0
+        else:
+            assert ctx.stat("esa.refine_rounds") >= 1
+        # ... and through the stage calls: the build returns early, the mapping finds out
+        ctx.esa_build(r)
+        ctx.map_queries(genomes, oracle.threshold(r))
+        s2, h2 = ctx.compare_all()
+    want = oracle.process(genomes, 0, 0, threads=2)
+    assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
+    assert np.array_equal(s2, want["subst"]) and np.array_equal(h2, want["homologs"])
+
+
 def test_thousands_of_homologies_take_the_global_sort(pb, oracle):
     """more homologies in one list than the per-query shared-memory sort holds"""
     rng = np.random.default_rng(43)
