@@ -27,6 +27,7 @@ struct phylo_ctx {
 	cudaStream_t own_stream = nullptr; // created with the context
 	cudaStream_t copy_stream = nullptr; // host-to-device copies that overlap the index build
 	cudaEvent_t ev_main = nullptr, ev_copy = nullptr;
+	cudaEvent_t ev_mark[4] = {nullptr, nullptr, nullptr, nullptr}; // device timeline of process(): start, index, mapped, done
 	std::string err;
 
 	int64_t opt_chunk = 2048, opt_cap = 0, opt_kmer = -1, opt_key_chars = 0, opt_stage_threads = 0;
@@ -211,6 +212,8 @@ void record_esa_stats(phylo_ctx *c, const EsaTimings &t)
 	s["esa.tie_groups"] = (double)t.tie_groups;
 	s["esa.kmer_k"] = c->esa.K;
 	s["esa.gc_count"] = (double)c->esa.gc_count;
+	s["esa.graph_instantiated"] = (double)c->esa.build_graph.instantiated;
+	s["esa.graph_updated"] = (double)c->esa.build_graph.updated;
 }
 
 void record_anchor_stats(phylo_ctx *c, const AnchorStats &t)
@@ -710,6 +713,8 @@ void phylo_ctx_destroy(phylo_ctx *c)
 	cudaStreamDestroy(c->copy_stream);
 	cudaEventDestroy(c->ev_main);
 	cudaEventDestroy(c->ev_copy);
+	for (cudaEvent_t e : c->ev_mark)
+		if (e) cudaEventDestroy(e);
 	cudaStreamDestroy(c->own_stream);
 	delete c;
 }
@@ -765,6 +770,8 @@ int phylo_set_option(phylo_ctx *c, const char *key, int64_t value)
 			c->tuning.push_kernel = value != 0;
 		} else if (k == "esa_speculative") {
 			c->tuning.esa_speculative = value != 0;
+		} else if (k == "esa_graph") {
+			c->tuning.esa_graph = value != 0;
 		} else if (k == "compare_path") {
 			if (value < 0 || value > 1) throw std::invalid_argument("compare_path must be 0 or 1");
 			c->tuning.compare_path = (int)value;
@@ -1091,7 +1098,12 @@ void process_resident(phylo_ctx *c, uint64_t N, uint64_t ref_index, int flags, M
 	uint64_t query_bases = 0;
 	for (uint64_t k = 0; k < N; k++)
 		query_bases += lens[k];
+	if (!c->ev_mark[0])
+		for (auto &e : c->ev_mark)
+			CUDA_CHECK(cudaEventCreate(&e));
+	CUDA_CHECK(cudaEventRecord(c->ev_mark[0], s));
 	do_esa_build(c, dq + offs[ref_index], lens[ref_index], query_bases);
+	CUDA_CHECK(cudaEventRecord(c->ev_mark[1], s));
 	// process.cxx:416-417; the G/C count comes out of the text kernel, the division and the
 	// threshold search are the reference's double arithmetic on the host
 	const double gc = (double)c->esa.gc_count / (double)lens[ref_index];
@@ -1109,20 +1121,26 @@ void process_resident(phylo_ctx *c, uint64_t N, uint64_t ref_index, int flags, M
 	const int64_t tiles_side = ((int64_t)tot + CT - 1) / CT;
 	int64_t tiles_done = 0;
 	float compare_ms = 0;
+	bool mirrored = false;
 	hooks.after_batch = [&](size_t b) {
 		if (!incremental) return;
-		const int64_t ready = b + 1 == ends.size() ? tiles_side : (int64_t)ends[b] / CT;
-		if (ready <= tiles_done) return;
+		const bool final = b + 1 == ends.size(); // the last batch also mirrors the triangle
+		const int64_t ready = final ? tiles_side : (int64_t)ends[b] / CT;
+		if (ready <= tiles_done && !final) return;
 		WallTimer wt(s, c->timings);
 		compare_all_device(c->rows, (int64_t)tot, false, 0, 1, c->d_subst.get(), c->d_hom.get(), s, tiles_done, ready,
-		                   tiles_done == 0, false);
+		                   tiles_done == 0, final);
 		compare_ms += wt.stop();
 		tiles_done = ready;
+		mirrored = final;
 	};
-	hooks.redo = [&] { tiles_done = 0; }; // (the next comparison starts over: it clears the matrix first)
+	hooks.redo = [&] { // (the next comparison starts over: it clears the matrix first)
+		tiles_done = 0;
+		mirrored = false;
+	};
 	do_map(c, dq, offs, lens, N, thr, hooks);
 	since("process.host_map_done_ms");
-	{
+	if (!mirrored) { // (complete deletion, a sharded row store, or no sequence at all)
 		WallTimer wt(s, c->timings);
 		compare_all_device(c->rows, (int64_t)tot, complete_deletion, 0, 1, c->d_subst.get(), c->d_hom.get(), s, tiles_done,
 		                   -1, tiles_done == 0, true);
@@ -1131,6 +1149,7 @@ void process_resident(phylo_ctx *c, uint64_t N, uint64_t ref_index, int flags, M
 	c->stats["compare.ms"] = compare_ms;
 	c->stats["compare.increments"] = (double)ends.size();
 	c->matN = tot;
+	CUDA_CHECK(cudaEventRecord(c->ev_mark[2], s));
 	const size_t bytes = (size_t)(tot * tot) * sizeof(uint64_t);
 	if (bytes <= (512u << 10)) {
 		// small matrices through pinned memory: two queued copies and one wait instead of two
@@ -1148,6 +1167,16 @@ void process_resident(phylo_ctx *c, uint64_t N, uint64_t ref_index, int flags, M
 		CUDA_CHECK(cudaStreamSynchronize(s));
 	}
 	since("process.host_done_ms");
+	// the same on the device's clock: when the index was built, when everything was compared
+	CUDA_CHECK(cudaEventRecord(c->ev_mark[3], s));
+	CUDA_CHECK(cudaEventSynchronize(c->ev_mark[3]));
+	float ms = 0;
+	CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev_mark[0], c->ev_mark[1]));
+	c->stats["process.gpu_index_ms"] = ms;
+	CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev_mark[0], c->ev_mark[2]));
+	c->stats["process.gpu_compared_ms"] = ms;
+	CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev_mark[0], c->ev_mark[3]));
+	c->stats["process.gpu_done_ms"] = ms;
 }
 
 // after a failed call nothing of ours may still be reading the caller's buffers

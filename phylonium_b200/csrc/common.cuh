@@ -55,6 +55,7 @@ struct Tuning {
 	int esa_speculative = 1;   // "esa_speculative": 1 = index build without host round trips (checked at its end)
 	int compare_path = 0;      // "compare_path": 0 = TMA + mbarrier pipeline, 1 = cp.async double buffering
 	int upload_raw = 0;        // "upload_raw": 1 = sequences cross PCIe as bytes instead of packed to 2 bits
+	int esa_graph = 1;         // "esa_graph": 1 = the speculative index build is replayed as a CUDA graph
 };
 inline thread_local Tuning g_tuning;
 
@@ -345,6 +346,69 @@ class PinnedArena
 };
 
 inline thread_local PinnedArena g_pinned;
+
+// A launch sequence submitted as ONE CUDA graph.  Every call captures the sequence anew (the
+// host code runs as usual, its launches are recorded instead of submitted), brings the
+// instantiated graph of the previous call up to date — same kernels, new parameters — and
+// launches that.  Measured on B200 for 30 kernels: capture 10 us + update 7 us + launch 27 us of
+// host time against 122 us for 30 launches; on the device 0.7 us from kernel to kernel instead of
+// 2.6 us, and no 4..6 us more per kernel while a host-to-device copy is in flight (the GPU fetches
+// every launch from host memory over the same bus).  A sequence whose shape changed (other
+// kernels, another number of them) is instantiated again (~160 us).
+struct GraphSegment {
+	cudaGraphExec_t exec = nullptr;
+	cudaStream_t capturing = nullptr;
+	uint64_t instantiated = 0, updated = 0;
+	void begin(cudaStream_t s)
+	{
+		// relaxed: the block cache may have to call cudaMalloc while the capture is on
+		CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+		capturing = s;
+	}
+	// ends the capture and submits what was captured
+	void launch()
+	{
+		cudaStream_t s = capturing;
+		capturing = nullptr;
+		cudaGraph_t g = nullptr;
+		CUDA_CHECK(cudaStreamEndCapture(s, &g));
+		struct Drop {
+			cudaGraph_t g;
+			~Drop() { cudaGraphDestroy(g); }
+		} drop{g};
+		if (exec) {
+			cudaGraphExecUpdateResultInfo info;
+			if (cudaGraphExecUpdate(exec, g, &info) == cudaSuccess) {
+				updated++;
+			} else {
+				cudaGetLastError();
+				cudaGraphExecDestroy(exec);
+				exec = nullptr;
+			}
+		}
+		if (!exec) {
+			CUDA_CHECK(cudaGraphInstantiate(&exec, g, 0));
+			instantiated++;
+		}
+		CUDA_CHECK(cudaGraphLaunch(exec, s));
+	}
+	// something threw while capturing: leave the stream usable
+	void abandon()
+	{
+		if (!capturing) return;
+		cudaGraph_t g = nullptr;
+		cudaStreamEndCapture(capturing, &g);
+		if (g) cudaGraphDestroy(g);
+		cudaGetLastError();
+		capturing = nullptr;
+	}
+	void destroy()
+	{
+		abandon();
+		if (exec) cudaGraphExecDestroy(exec);
+		exec = nullptr;
+	}
+};
 
 template <typename T> inline T d2h_scalar(const T *dptr, cudaStream_t s)
 {

@@ -1025,6 +1025,16 @@ bool esa_build_impl(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k,
 		CUDA_CHECK(cudaEventRecord(esa.ev_early, esa.side));
 	}
 	T.text_ms = lap.lap();
+	// Speculative builds have no host decision left in them: everything behind the first radix pass
+	// is recorded and submitted as one graph (GraphSegment, common.cuh).
+	GraphSegment *const graph = (spec && g_tuning.esa_graph && g_tuning.sort_path != 1) ? &esa.build_graph : nullptr;
+	struct GraphGuard {
+		GraphSegment *g;
+		~GraphGuard()
+		{
+			if (g) g->abandon();
+		}
+	} graph_guard{graph};
 	int *spec_fail = esa.report.get() + 3; // speculative mode: set by k_spec_check, read by the kernels after it
 	const int *skip = spec ? spec_fail : nullptr;
 	uint32_t *spec_counters = reinterpret_cast<uint32_t *>(esa.report.get() + 4); // copies of {groups, hard groups, dirty suffixes, dirty error}
@@ -1058,7 +1068,7 @@ bool esa_build_impl(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k,
 			dirty_sorted.alloc(cap, s);
 			PkProfile prof;
 			uint64_t *W = suffix_sort_packed(esa.S.get(), m, padded, kc, keys.get(), keys_alt.get(), dirty_list.get(),
-			                                 dirty_ctl, cap, s, timed ? &prof : nullptr);
+			                                 dirty_ctl, cap, s, timed ? &prof : nullptr, graph);
 			if (timed) {
 				T.first_pass_ms = prof.first_ms;
 				if (prof.passes) {
@@ -1308,6 +1318,7 @@ bool esa_build_impl(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k,
 	if (spec) {
 		// the one read-back of the speculative build: queued here, looked at by esa_finish()
 		CUDA_CHECK(cudaMemcpyAsync(esa.h_report + 8, esa.report.get(), 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+		if (graph && graph->capturing) graph->launch();
 		CUDA_CHECK(cudaEventRecord(esa.ev_done, s));
 		esa.pending = true;
 		esa.pend_kmer_k = kmer_k;

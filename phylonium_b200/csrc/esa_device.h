@@ -47,11 +47,13 @@ struct EsaDevice {
 	int *h_report = nullptr;
 	cudaEvent_t ev_text = nullptr, ev_early = nullptr, ev_done = nullptr;
 	bool pending = false;
+	GraphSegment build_graph; // the speculative build behind its first radix pass, as one graph
 	int pend_kmer_k = -1, pend_key_chars = 0;
 	const int *skip() const { return pending ? report.get() + 3 : nullptr; }
 	const int *host_verdict() const { return pending ? h_report + 8 + 3 : nullptr; }
 	void destroy_side()
 	{
+		build_graph.destroy();
 		if (h_report) {
 			cudaFreeHost(h_report);
 			h_report = nullptr;

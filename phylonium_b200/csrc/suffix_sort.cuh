@@ -718,7 +718,7 @@ template <bool FROM_TEXT> inline int pk_scatter_grid(int ntiles)
 
 inline uint64_t *suffix_sort_packed(const uint8_t *S, int32_t m, int32_t padded, int kc, uint64_t *buf_a,
                                     uint64_t *buf_b, uint32_t *dirty_list, uint32_t *dirty_count, uint32_t dirty_cap,
-                                    cudaStream_t s, PkProfile *prof)
+                                    cudaStream_t s, PkProfile *prof, GraphSegment *graph_after_first_pass = nullptr)
 {
 	const PkMasks mk = pk_masks(kc);
 	const int ntiles = div_up(m, PK_TILE);
@@ -758,6 +758,8 @@ inline uint64_t *suffix_sort_packed(const uint8_t *S, int32_t m, int32_t padded,
 		mark();
 		in = out;
 		out = (out == buf_a) ? buf_b : buf_a;
+		// the first pass keeps the GPU busy while the host records everything behind it
+		if (p == 0 && graph_after_first_pass) graph_after_first_pass->begin(s);
 	}
 	if (prof) {
 		CUDA_CHECK(cudaStreamSynchronize(s));
