@@ -1207,7 +1207,7 @@ struct Uploader {
 	uint64_t N, first;
 	std::vector<uint64_t> ends;
 	size_t queued = 0;
-	bool pageable = false, packed = true;
+	bool pageable = false, packed = true, ref_staged = false;
 	static constexpr uint64_t COPY_QUEUE = 256;
 
 	Uploader(phylo_ctx *ctx, const char *const *seqs_, const uint64_t *lens_, uint64_t N_, uint64_t first_)
@@ -1236,10 +1236,6 @@ struct Uploader {
 		c->q_own.zero();
 		uint8_t *dq = c->q_own.get();
 		const uint64_t *offs = c->q_offs.data();
-		if (first < N && lens[first])
-			CUDA_CHECK(cudaMemcpyAsync(dq + offs[first], seqs[first], lens[first], cudaMemcpyHostToDevice, s));
-		CUDA_CHECK(cudaEventRecord(c->ev_main, s));
-		CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
 		ends = plan_batches(lens, N);
 		// Packing pays when the bus is the bottleneck or the memory is pageable (the driver would
 		// stage it on this thread), and when there are cores to do it: at ~6 GB/s per core it takes
@@ -1253,14 +1249,30 @@ struct Uploader {
 		}
 		packed = c->tuning.upload_raw < 0 ||
 		         (c->tuning.upload_raw == 0 && (pageable || (bases >= (128ull << 20) && threads >= 8)));
+		// The reference is what everything waits for.  From pinned memory it goes over as it is;
+		// from ordinary memory the driver would stage it on this thread at a fraction of the bus
+		// rate (measured: ~0.5 ms for 5 Mbp), so the workers take it first, in pieces small
+		// enough that each of them gets one.
+		ref_staged = packed && first < N && lens[first] && HostStager::is_pageable(seqs[first]);
+		if (first < N && lens[first] && !ref_staged)
+			CUDA_CHECK(cudaMemcpyAsync(dq + offs[first], seqs[first], lens[first], cudaMemcpyHostToDevice, s));
+		CUDA_CHECK(cudaEventRecord(c->ev_main, s));
+		CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
 		if (packed) {
 			// worker threads pack the pieces to 2 bits per base into pinned rings, a kernel unpacks
 			// them at their place (staging.h): a quarter of the bytes on the bus, pageable or pinned
+			const int shift = ref_staged ? 1 : 0; // the reference's pieces are batch 0 of the stager then
+			if (ref_staged) {
+				uint64_t piece = (lens[first] + threads - 1) / threads;
+				piece = std::max<uint64_t>(64u << 10, (piece + 63) / 64 * 64);
+				c->stager.add(dq + offs[first], seqs[first], lens[first], 0, piece);
+			}
 			uint64_t k = 0;
 			for (size_t b = 0; b < ends.size(); b++)
 				for (; k < ends[b]; k++)
-					if (k != first && lens[k]) c->stager.add(dq + offs[k], seqs[k], lens[k], (int)b);
-			if (!c->stager.empty()) c->stager.start(c->device, (int)ends.size(), threads, c->ev_main);
+					if (k != first && lens[k]) c->stager.add(dq + offs[k], seqs[k], lens[k], (int)b + shift);
+			if (!c->stager.empty()) c->stager.start(c->device, (int)ends.size() + shift, threads, c->ev_main);
+			if (ref_staged) c->stager.wait_batch(0, s); // the index build is queued behind the reference's pieces
 		} else {
 			// option "upload_raw": the bytes as they are, plain asynchronous copies on the copy
 			// stream (truly asynchronous only from pinned memory) with an event behind every batch.  At most COPY_QUEUE copies are queued ahead of the batch being mapped —
@@ -1276,8 +1288,8 @@ struct Uploader {
 		}
 		c->stats["process.pageable"] = pageable ? 1 : 0;
 		c->stats["process.packed"] = packed ? 1 : 0;
-		c->stats["process.h2d_bytes"] = packed ? (double)((bases - (first < N ? lens[first] : 0)) / 4 + (first < N ? lens[first] : 0))
-		                                       : (double)bases;
+		const uint64_t ref_bytes = first < N ? lens[first] : 0;
+		c->stats["process.h2d_bytes"] = packed ? (double)((bases - ref_bytes) / 4 + (ref_staged ? ref_bytes / 4 : ref_bytes)) : (double)bases;
 	}
 
 	void queue_copies(size_t current) // `current` = the batch about to be mapped
@@ -1299,7 +1311,7 @@ struct Uploader {
 	void before_batch(size_t b)
 	{
 		if (packed) {
-			c->stager.wait_batch((int)b, c->stream);
+			c->stager.wait_batch((int)b + (ref_staged ? 1 : 0), c->stream);
 		} else {
 			queue_copies(b);
 			CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->batch_events[b], 0));

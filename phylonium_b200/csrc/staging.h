@@ -153,12 +153,15 @@ class HostStager
 		return a.type == cudaMemoryTypeUnregistered;
 	}
 
-	// appends the pieces of one sequence (call in batch order, then start()); dst 16-byte aligned
-	void add(uint8_t *dst, const void *src, uint64_t len, int batch)
+	// appends the pieces of one sequence (call in batch order, then start()); dst 16-byte aligned.
+	// piece: bases per piece, a multiple of 64, at most PIECE_BYTES (smaller pieces spread one
+	// sequence that everything waits for — the reference — over all workers)
+	void add(uint8_t *dst, const void *src, uint64_t len, int batch, uint64_t piece = PIECE_BYTES)
 	{
+		if (piece > PIECE_BYTES || piece < 64 || piece % 64) piece = PIECE_BYTES;
 		const uint8_t *p = static_cast<const uint8_t *>(src);
-		for (uint64_t o = 0; o < len; o += PIECE_BYTES) {
-			const uint64_t l = len - o < PIECE_BYTES ? len - o : PIECE_BYTES;
+		for (uint64_t o = 0; o < len; o += piece) {
+			const uint64_t l = len - o < piece ? len - o : piece;
 			pending_.push_back(Piece{dst + o, p + o, (uint32_t)l, batch});
 		}
 	}

@@ -41,7 +41,11 @@ def main():
     out = (np.zeros((G, G), np.uint64), np.zeros((G, G), np.uint64))
     keys = ("process.gpu_index_ms", "process.gpu_compared_ms", "process.gpu_done_ms", "process.host_index_done_ms",
             "process.host_map_done_ms", "process.host_done_ms", "process.h2d_bytes")
-    for name, opts, again in (("raw", {"upload_raw": 1}, False), ("packed", {"upload_raw": -1}, False), ("resident", {}, True)):
+    import ctypes
+    pageable = [np.frombuffer((ctypes.c_char * L).from_address(p), dtype=np.uint8).copy() for p in shard.ptrs]
+    pptrs = [x.ctypes.data for x in pageable]
+    for name, opts, again in (("raw", {"upload_raw": 1}, False), ("packed", {"upload_raw": -1}, False), ("resident", {}, True),
+                              ("pageable", {}, False), ("pageable", {}, False)):
         ctx = pb.Context(0)
         ctx.set_stream(stream.cuda_stream)
         for kv in filter(None, a.options.split(",")):
@@ -49,8 +53,9 @@ def main():
             ctx.set_option(k, int(v))
         for k, v in opts.items():
             ctx.set_option(k, v)
-        fn = (lambda: ctx.process_again(0, 0, out)) if again else (lambda: ctx.process_ptrs(shard.ptrs, shard.lens, 0, 0, out))
-        ctx.process_ptrs(shard.ptrs, shard.lens, 0, 0, out)
+        ptrs = pptrs if name == "pageable" else shard.ptrs
+        fn = (lambda: ctx.process_again(0, 0, out)) if again else (lambda: ctx.process_ptrs(ptrs, shard.lens, 0, 0, out))
+        ctx.process_ptrs(ptrs, shard.lens, 0, 0, out)
         for _ in range(3):
             fn()
         acc = {k: 0.0 for k in keys}
