@@ -107,6 +107,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 	             "r"(parity)
 	             : "memory");
 }
+// has the phase with this parity completed?  (does not wait)
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
+{
+	uint32_t ok;
+	asm volatile("{\n"
+	             ".reg .pred p;\n"
+	             "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+	             "selp.u32 %0, 1, 0, p;\n"
+	             "}"
+	             : "=r"(ok)
+	             : "r"(smem_u32(bar)), "r"(parity)
+	             : "memory");
+	return ok != 0;
+}
 // orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy
 // ones (a bulk copy into a buffer the threads have just been reading and writing)
 __device__ __forceinline__ void fence_proxy_async()

@@ -18,6 +18,7 @@
 // planes to load and half the logic per pair.  Work units (tile pair, chunk) are dealt
 // round-robin to the ranks of a sharded run.
 #include "compare_device.h"
+#include "tile_order.h"
 #include "primitives.cuh"
 
 #include <cuda.h> // CUtensorMap (types only: the encoder is fetched through the runtime)
@@ -390,6 +391,13 @@ __device__ __forceinline__ void compare_tile(uint32_t *stage, const uint32_t *__
 			tma_load_rows(dst, tm, blk, (int32_t)gi0, &full_bar[sidx]);
 			tma_load_rows(dst + CT * SLOT_WORDS, tm, blk, (int32_t)gj0, &full_bar[sidx]);
 		};
+		// Thread 0 refills the stages: at the top of step it, once every warp has let go of the stage
+		// step it - 1 used, step it + STAGES - 1 goes there.  (Tried: refilling without waiting —
+		// whatever stage mbarrier.test_wait finds free at the top of a step, blocking only for the
+		// step the warp itself needs.  Warp 0 then no longer trails the others, but the copies are
+		// issued up to a step later and the latency of L2 under this load, 4.4 TB/s, is several
+		// steps: 11.8 ms instead of 7.0 ms at 1000 x 0.9 Mbp, waits on the full barrier 37 % of the
+		// stall samples.  Depth of the pipeline is what counts here.)
 		if (threadIdx.x == 0)
 			for (int n = 0; n < CMP_STAGES - 1 && n < nsteps; n++)
 				issue(n);
@@ -397,7 +405,6 @@ __device__ __forceinline__ void compare_tile(uint32_t *stage, const uint32_t *__
 		for (int it = 0; it < nsteps; it++) {
 			const int sidx = it % CMP_STAGES;
 			if (threadIdx.x == 0) {
-				// step it + STAGES - 1 goes into the stage step it - 1 used: once every warp has let go of it
 				const int nxt = it + CMP_STAGES - 1;
 				if (nxt < nsteps) {
 					if (it >= 1) mbar_wait(&empty_bar[nxt % CMP_STAGES], (uint32_t)(((it - 1) / CMP_STAGES) & 1));
@@ -455,25 +462,19 @@ __device__ __forceinline__ void compare_tile(uint32_t *stage, const uint32_t *__
 template <int CT, bool TMA>
 __global__ void __launch_bounds__(cmp_threads(CT), CT == 16 ? CMP_MIN_BLOCKS : 4)
 k_compare_tiles(const __grid_constant__ CUtensorMap tm_fast, const __grid_constant__ CUtensorMap tm_full,
-                const uint32_t *__restrict__ rows, int64_t genome_words, int64_t W, int64_t N, int64_t tp_begin,
-                int64_t units, int32_t chunks, int64_t chunk_words, int tile_rank, int tile_world,
+                const uint32_t *__restrict__ rows, int64_t genome_words, int64_t W, int64_t N, int32_t tile_begin,
+                int32_t tile_end, int64_t units, int64_t unit0, int32_t chunks, int64_t chunk_words,
                 const uint32_t *__restrict__ vall, unsigned long long *__restrict__ subst,
                 unsigned long long *__restrict__ homol)
 {
 	extern __shared__ __align__(128) uint32_t cmp_stage[];
 	__shared__ uint32_t tile_flags;
-	const int64_t unit = (int64_t)blockIdx.x * tile_world + tile_rank; // units are dealt round-robin
+	const int64_t unit = unit0 + blockIdx.x; // this rank's units are one contiguous range
 	if (unit >= units) return;
-	const int64_t tp = tp_begin + unit / chunks;
 	const int32_t chunk = (int32_t)(unit % chunks);
-	// unrank tp -> (ti <= tj): column tj holds tj + 1 pairs
-	int64_t tj = (int64_t)((sqrt(8.0 * (double)tp + 1.0) - 1.0) * 0.5);
-	while (tj * (tj + 1) / 2 > tp)
-		tj--;
-	while ((tj + 1) * (tj + 2) / 2 <= tp)
-		tj++;
-	const int64_t ti = tp - tj * (tj + 1) / 2;
-	const int64_t gi0 = ti * CT, gj0 = tj * CT;
+	int32_t ti, tj;
+	cmp_unrank_pair(unit / chunks, tile_begin, tile_end, ti, tj);
+	const int64_t gi0 = (int64_t)ti * CT, gj0 = (int64_t)tj * CT;
 	const int64_t w_begin = (int64_t)chunk * chunk_words;
 	const int64_t w_end = w_begin + chunk_words < W ? w_begin + chunk_words : W;
 
@@ -707,8 +708,7 @@ void compare_all_device(const RowStore &rs, int64_t N, bool complete_deletion, i
 		KERNEL_CHECK();
 	}
 	// tile pairs (ti <= tj) with tj in [tile_begin, tile_end), numbered column by column
-	const int64_t tp_begin = tile_begin * (tile_begin + 1) / 2;
-	const int64_t n_tile_pairs = tile_end * (tile_end + 1) / 2 - tp_begin;
+	const int64_t n_tile_pairs = tile_end * (tile_end + 1) / 2 - tile_begin * (tile_begin + 1) / 2;
 	if (n_tile_pairs > 0) {
 		// enough blocks to fill the machine a few times over, chunks of at least 256 words
 		const int64_t want_blocks = (int64_t)NUM_SMS_B200 * 8 * tile_world;
@@ -720,7 +720,10 @@ void compare_all_device(const RowStore &rs, int64_t N, bool complete_deletion, i
 		chunk_words = (chunk_words + 95) / 96 * 96; // whole steps of both paths (96 and 32 words): a tensor copy never straddles a chunk end
 		chunks = (rs.W + chunk_words - 1) / chunk_words;
 		const int64_t units = n_tile_pairs * chunks;
-		const int64_t my_units = (units - tile_rank + tile_world - 1) / tile_world;
+		// every rank takes one contiguous range of the units (its blocks share rows in L2)
+		const int64_t per_rank = (units + tile_world - 1) / tile_world;
+		const int64_t unit0 = per_rank * tile_rank;
+		const int64_t my_units = unit0 >= units ? 0 : (units - unit0 < per_rank ? units - unit0 : per_rank);
 		const bool tma = g_tuning.compare_path == 0;
 		static PerDeviceOnce once;
 		if (once.first()) {
@@ -755,8 +758,8 @@ void compare_all_device(const RowStore &rs, int64_t N, bool complete_deletion, i
 			const size_t smem = cmp_smem_bytes(CT, tma);
 #define PHY_LAUNCH_COMPARE(CTV, TMAV)                                                                                    \
 	k_compare_tiles<CTV, TMAV><<<(unsigned)my_units, cmp_threads(CTV), smem, s>>>(                                       \
-		tm_fast, tm_full, rs.data.get(), rs.genome_words(), rs.W, N, tp_begin, units, (int32_t)chunks, chunk_words,      \
-		tile_rank, tile_world, vall.get(), d_subst, d_homologs)
+		tm_fast, tm_full, rs.data.get(), rs.genome_words(), rs.W, N, (int32_t)tile_begin, (int32_t)tile_end, units,     \
+		unit0, (int32_t)chunks, chunk_words, vall.get(), d_subst, d_homologs)
 			if (CT == 16 && tma)
 				PHY_LAUNCH_COMPARE(16, true);
 			else if (CT == 16)

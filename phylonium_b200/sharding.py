@@ -82,12 +82,27 @@ def tile_side(n_genomes: int) -> int:
     return 8 if n_genomes <= 24 else 16
 
 
+BAND = 12  # tile rows per band (CMP_BAND, csrc/tile_order.h)
+
+
+def tile_pairs(tile_begin: int, tile_end: int) -> List[tuple]:
+    """the tile pairs (ti <= tj, tile_begin <= tj < tile_end) in the order k_compare_tiles visits
+    them: bands of BAND tile rows, column by column inside a band — so that the blocks running at
+    the same time work on a compact patch of the matrix (csrc/tile_order.h)"""
+    out = []
+    for ti0 in range(0, tile_end, BAND):
+        for tj in range(max(tile_begin, ti0), tile_end):
+            for ti in range(ti0, min(ti0 + BAND, tj + 1)):
+                out.append((ti, tj))
+    return out
+
+
 def compare_units(n_genomes: int, words: int, world: int):
     """(tile pairs, chunks, chunk_words) of the all-pairs stage — the same arithmetic as
     compare_all_device (compare.cu); `words` = 32-bit words per row plane"""
     tile = tile_side(n_genomes)
     side = (n_genomes + tile - 1) // tile
-    pairs = [(ti, tj) for tj in range(side) for ti in range(tj + 1)]  # column by column, as k_compare_tiles
+    pairs = tile_pairs(0, side)
     want_blocks = NUM_SMS * 8 * world
     chunks = (want_blocks + len(pairs) - 1) // max(1, len(pairs))
     chunks = max(1, min(chunks, (words + 255) // 256))
@@ -98,11 +113,12 @@ def compare_units(n_genomes: int, words: int, world: int):
 
 
 def units_of_rank(n_genomes: int, words: int, rank: int, world: int) -> List[tuple]:
-    """the (ti, tj, chunk) work units rank `rank` computes: unit u = pair * chunks + chunk
-    belongs to rank u mod world — same enumeration as k_compare_tiles"""
+    """the (ti, tj, chunk) work units rank `rank` computes: unit u = pair * chunks + chunk; every
+    rank takes one contiguous range of ceil(units / world) — same as compare_all_device"""
     pairs, chunks, _ = compare_units(n_genomes, words, world)
     units = [(ti, tj, c) for (ti, tj) in pairs for c in range(chunks)]
-    return units[rank::world]
+    per_rank = (len(units) + world - 1) // world
+    return units[rank * per_rank:(rank + 1) * per_rank]
 
 
 class DeviceBuffer:

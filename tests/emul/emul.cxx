@@ -17,6 +17,7 @@
 #include "../../phylonium_b200/csrc/cld_search.h"
 #include "../../phylonium_b200/csrc/esa_search.h"
 #include "../../phylonium_b200/csrc/filter.h"
+#include "../../phylonium_b200/csrc/tile_order.h"
 #include "../../phylonium_b200/csrc/walk.h"
 
 using namespace phy;
@@ -100,6 +101,14 @@ int32_t scalar_first_mismatch(const uint8_t *q, const uint8_t *S, int64_t diag, 
 } // namespace
 
 extern "C" {
+
+// order of the tile pairs of the all-pairs stage (tile_order.h): pair p of a launch over the
+// tile columns [tile_begin, tile_end)
+void emul_unrank_pair(int64_t p, int32_t tile_begin, int32_t tile_end, int32_t *ti, int32_t *tj)
+{
+	phy::cmp_unrank_pair(p, tile_begin, tile_end, *ti, *tj);
+}
+
 
 // CLD from LCP through the min-pyramid closed form (cld_search.h)
 void emul_cld(const int64_t *LCP64, int32_t m, int64_t *CLD_out)

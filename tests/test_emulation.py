@@ -209,3 +209,22 @@ def test_filter_large_clusters_take_the_heap(emul, oracle):
         for variant in (None, 0, 1):
             got = _filter_via_emul(emul, pile, variant)
             assert np.array_equal(got, want), (trial, variant)
+
+
+def test_tile_pair_order_is_a_bijection_and_matches_the_python_mirror(emul):
+    """csrc/tile_order.h: every tile pair of a launch exactly once, in the band order that
+    sharding.tile_pairs spells out"""
+    from phylonium_b200 import sharding
+
+    emul.emul_unrank_pair.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    emul.emul_unrank_pair.restype = None
+    for tb, te in [(0, 1), (0, 2), (0, 11), (0, 12), (0, 13), (0, 63), (5, 30), (12, 13), (23, 25), (24, 64), (40, 41), (0, 200)]:
+        want = sharding.tile_pairs(tb, te)
+        assert len(want) == te * (te + 1) // 2 - tb * (tb + 1) // 2
+        assert len(set(want)) == len(want) and all(ti <= tj and tb <= tj < te for ti, tj in want)
+        ti, tj = C.c_int32(), C.c_int32()
+        got = []
+        for p in range(len(want)):
+            emul.emul_unrank_pair(p, tb, te, C.byref(ti), C.byref(tj))
+            got.append((ti.value, tj.value))
+        assert got == want, (tb, te)
