@@ -100,7 +100,10 @@ def main():
                 chunk=int(rng.choice([32, 64, 256, 2048])), cap=int(rng.choice([0, 64, 300])),
                 kmer_k=int(rng.choice([-1, 0, 1, 5, 9])), key_chars=int(rng.choice([0, 0, 2, 7, 16, 21])),
                 sort_path=int(rng.choice([0, 0, 1])), scan_mode=int(rng.choice([1, 1, 0])),
-                map_batch_bytes=int(rng.choice([1, 5000, 512 << 20])), table_direct=int(rng.choice([0, 2])), keep_raw=1,
+                map_batch_bytes=int(rng.choice([1, 5000, 512 << 20])), table_direct=int(rng.choice([0, 2])),
+                # (with keep_raw the rows of a batch are built after its lists are final; without,
+                # before the host has seen them — and again if they were not)
+                keep_raw=1 if rounds % 4 == 0 else 0, esa_graph=int(rng.choice([1, 1, 0])),
                 upload_raw=int(rng.choice([0, 0, 1, -1])), compare_path=int(rng.choice([0, 0, 1])),
                 esa_speculative=int(rng.choice([1, 1, 0])), stage_threads=int(rng.choice([0, 1, 3])),
             )
@@ -136,6 +139,16 @@ def main():
                             return 1
                         if not np.array_equal(ctx.homologies(k), oracle.sort_filter(raw)):
                             print("FILTERED HOMOLOGIES DIFFER:", k, recipe)
+                            return 1
+                if rounds % 3 == 1:
+                    # second pass on the resident sequences with another reference: the index build's
+                    # graph of the first pass is brought up to date or instantiated anew
+                    ref2 = int(rng.integers(0, len(genomes)))
+                    if len(genomes[ref2]):
+                        want2 = oracle.process(genomes, ref2, flags, threads=4)
+                        s2, h2 = ctx.process_again(ref2, flags)
+                        if not (np.array_equal(s2, want2["subst"]) and np.array_equal(h2, want2["homologs"])):
+                            print("COUNTS OF THE SECOND PASS DIFFER:", f"ref2={ref2}", recipe)
                             return 1
             rounds += 1
     except Exception:
