@@ -98,13 +98,17 @@ int phylo_set_stream(phylo_ctx *ctx, void *stream);
  *   "esa_speculative" 1 (default) = the index build makes no host round trip until its end and
  *               is redone step by step if what it took for granted (valid input, few separators,
  *               no repeats beyond the direct comparisons) turns out wrong; 0 = always step by step
+ *   "esa_graph" 1 (default) = the speculative build is submitted as one CUDA graph behind its
+ *               first radix pass (re-captured per call, the instantiated graph updated); 0 =
+ *               kernel by kernel
  *   "compare_path" how the all-pairs kernel brings the row tiles into shared memory: 0 = tensor
- *               copies (TMA) through a 3-stage transaction-barrier pipeline (default), 1 =
+ *               copies (TMA) through a 6-stage transaction-barrier pipeline (default), 1 =
  *               cp.async by all threads, double buffered (kept for comparison)
  *   "upload_raw" 0 (default) = pack on the host unless the input is pinned and under 128 MiB
  *               (then the plain asynchronous copies are hidden behind the index build anyway),
  *               1 = always send the bytes as they are, -1 = always pack
- *   "keep_raw" keep unsorted/unfiltered homology lists for phylo_get_homologies(raw=1)
+ *   "keep_raw" keep unsorted/unfiltered homology lists for phylo_get_homologies(raw=1) (the rows of
+ *               a batch are then built after its lists are final, not before the host has seen them)
  *   "timings"  record per-phase device times (adds synchronisation) */
 int phylo_set_option(phylo_ctx *ctx, const char *key, int64_t value);
 /* last recorded value of a named timing/statistic, e.g. "esa.sort_ms", "anchor.walk_ms",
@@ -130,7 +134,12 @@ int phylo_host_pack_2bit(const char *seq, uint64_t n, uint8_t *packed, uint32_t 
 
 /* esa::esa(const sequence &), src/esa.cxx:69-81: S = ref '#' revcomp(ref), suffix array
  * (replaces divsufsort64, :73-75), LCP (:305-347), CLD (:256-298), FVC (:239-250) and the
- * descent table (replaces init_cache, :90-228).  Result stays on the device. */
+ * descent table (replaces init_cache, :90-228).  Result stays on the device.
+ * The call returns as soon as the build is queued on the context's stream and the reference's
+ * alphabet has been checked (its first kernel's verdict): whatever is called next on the context
+ * is ordered behind the build, phylo_map_queries queues its kernels there without waiting.  Should
+ * the build's assumptions fail on the device (option "esa_speculative"), the next call that needs
+ * the index builds it again step by step first; a caller never sees that. */
 int phylo_esa_build(phylo_ctx *ctx, const char *ref, uint64_t n);
 /* esa::size(), src/esa.h:78-81: m = 2n + 1 */
 int phylo_esa_size(const phylo_ctx *ctx, uint64_t *m);
