@@ -27,6 +27,7 @@ struct phylo_ctx {
 	cudaStream_t own_stream = nullptr; // created with the context
 	cudaStream_t copy_stream = nullptr; // host-to-device copies that overlap the index build
 	cudaEvent_t ev_main = nullptr, ev_copy = nullptr;
+	cudaEvent_t ev_q_idle = nullptr; // recorded behind the last kernel of a mapping that reads the sequences
 	cudaEvent_t ev_mark[4] = {nullptr, nullptr, nullptr, nullptr}; // device timeline of process(): start, index, mapped, done
 	std::string err;
 
@@ -125,6 +126,8 @@ void trim_scratch_if_large(phylo_ctx *ctx)
 		cudaStreamSynchronize(ctx->stream);
 		g_block_cache.trim(ctx->device, ctx->stream);
 		if (ctx->stream != ctx->own_stream) g_block_cache.trim(ctx->device, ctx->own_stream);
+		cudaStreamSynchronize(ctx->copy_stream);
+		g_block_cache.trim(ctx->device, ctx->copy_stream); // (old sequence buffers)
 	}
 }
 
@@ -586,6 +589,8 @@ void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_
 		b0 = b1;
 	}
 	if (!c->peer_rows.empty()) join_pushes(c);
+	if (!c->ev_q_idle) CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_q_idle, cudaEventDisableTiming));
+	CUDA_CHECK(cudaEventRecord(c->ev_q_idle, s));
 	record_anchor_stats(c, sum);
 	c->stats["rows.ms"] = rows_ms;
 	c->stats["map.batches"] = (double)ends.size();
@@ -710,11 +715,13 @@ void phylo_ctx_destroy(phylo_ctx *c)
 		g_scan_states.drop(c->device, c->stream);
 		g_block_cache.trim(c->device, c->stream);
 	}
+	g_block_cache.trim(c->device, c->copy_stream);
 	cudaStreamDestroy(c->copy_stream);
 	cudaEventDestroy(c->ev_main);
 	cudaEventDestroy(c->ev_copy);
 	for (cudaEvent_t e : c->ev_mark)
 		if (e) cudaEventDestroy(e);
+	if (c->ev_q_idle) cudaEventDestroy(c->ev_q_idle);
 	cudaStreamDestroy(c->own_stream);
 	delete c;
 }
@@ -1232,8 +1239,18 @@ struct Uploader {
 		cudaStream_t s = c->stream;
 		CUDA_CHECK(cudaStreamSynchronize(c->copy_stream)); // nothing may still write into the old buffer
 		c->stager.drain();
-		c->q_own.alloc(total + 64, s);
-		c->q_own.zero();
+		// (a block of the copy stream's own cache: one freed on the main stream may still be written
+		// by work queued there — the scratch of a lazily built index)
+		c->q_own.alloc(total + 64, c->copy_stream);
+		// The buffer is cleared on the copy stream, behind whatever read the old one last (the row
+		// builder of the previous mapping) — NOT on the main stream: phylo_map_queries finds an
+		// index build queued there, and the sequences would start to cross the bus only after it
+		// (measured, 8 x 5 Mbp from host buffers through the stage calls: 2.2 ms, of which 0.7 ms
+		// were the uploads waiting behind the index).
+		if (c->ev_q_idle) CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_q_idle, 0));
+		CUDA_CHECK(cudaMemsetAsync(c->q_own.get(), 0, c->q_own.bytes(), c->copy_stream));
+		CUDA_CHECK(cudaEventRecord(c->ev_main, c->copy_stream));
+		CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_main, 0)); // (what the main stream does with the buffer comes after)
 		uint8_t *dq = c->q_own.get();
 		const uint64_t *offs = c->q_offs.data();
 		ends = plan_batches(lens, N);
@@ -1254,10 +1271,14 @@ struct Uploader {
 		// rate (measured: ~0.5 ms for 5 Mbp), so the workers take it first, in pieces small
 		// enough that each of them gets one.
 		ref_staged = packed && first < N && lens[first] && HostStager::is_pageable(seqs[first]);
-		if (first < N && lens[first] && !ref_staged)
+		cudaEvent_t after = c->ev_main; // what the uploads of the other sequences must not overtake
+		if (first < N && lens[first] && !ref_staged) {
+			// the reference first: everything waits for it
 			CUDA_CHECK(cudaMemcpyAsync(dq + offs[first], seqs[first], lens[first], cudaMemcpyHostToDevice, s));
-		CUDA_CHECK(cudaEventRecord(c->ev_main, s));
-		CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+			CUDA_CHECK(cudaEventRecord(c->ev_copy, s));
+			CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
+			after = c->ev_copy;
+		}
 		if (packed) {
 			// worker threads pack the pieces to 2 bits per base into pinned rings, a kernel unpacks
 			// them at their place (staging.h): a quarter of the bytes on the bus, pageable or pinned
@@ -1271,7 +1292,7 @@ struct Uploader {
 			for (size_t b = 0; b < ends.size(); b++)
 				for (; k < ends[b]; k++)
 					if (k != first && lens[k]) c->stager.add(dq + offs[k], seqs[k], lens[k], (int)b + shift);
-			if (!c->stager.empty()) c->stager.start(c->device, (int)ends.size() + shift, threads, c->ev_main);
+			if (!c->stager.empty()) c->stager.start(c->device, (int)ends.size() + shift, threads, after);
 			if (ref_staged) c->stager.wait_batch(0, s); // the index build is queued behind the reference's pieces
 		} else {
 			// option "upload_raw": the bytes as they are, plain asynchronous copies on the copy

@@ -19,7 +19,10 @@ def main():
     ap.add_argument("--length", type=int, default=5_000_000)
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--options", default="", help="k=v,k=v set on the context")
+    ap.add_argument("--staged", action="store_true")
     a = ap.parse_args()
+    if a.staged:
+        return staged(a)
 
     import numpy as np
     import torch
@@ -71,6 +74,47 @@ def main():
         print("graph: instantiated", ctx.stat("esa.graph_instantiated"), "updated", ctx.stat("esa.graph_updated"))
         print(name, "wall_ms %.3f" % (wall / a.reps), " ".join("%s %.3f" % (k.split(".")[1], v / a.reps) for k, v in acc.items()), flush=True)
         ctx.close()
+
+
+def staged(a):
+    """the calls a rank of a sharded run makes (bench.py: Pipeline.step_from_host), on one GPU, timed one by one"""
+    import numpy as np
+    import torch
+
+    import bench
+    import phylonium_b200 as pb
+    from phylonium_b200 import sharding, simgen
+
+    sys.argv = [sys.argv[0]]
+    args = bench.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    G, L = a.genomes, a.length
+    plan = sharding.make_plan(G, 1, 0)
+    specs = [bench.genome_spec(g) for g in plan.genomes()]
+    shard = bench.Shard(torch, simgen, dev, bench.SIMF_SEED, specs, L, 8)
+    pipe = bench.Pipeline((torch, None, pb, sharding), args, dev, 0, 0, 1, plan, shard, shard.host[:L], L, "replicate", "push")
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        pipe.step_from_host()
+    t = [0.0] * 5
+    for _ in range(a.reps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pipe._index(host=True)
+        t1 = time.perf_counter()
+        pipe.ctx.map_queries_ptrs(shard.ptrs, shard.lens, pipe.thr)
+        t2 = time.perf_counter()
+        pipe._matrix()
+        t3 = time.perf_counter()
+        torch.cuda.synchronize()
+        t4 = time.perf_counter()
+        for k, (x, y) in enumerate(((t0, t1), (t1, t2), (t2, t3), (t3, t4), (t0, t4))):
+            t[k] += 1e3 * (y - x) / a.reps
+    print("staged: index call %.3f  map call %.3f  matrix call %.3f  final sync %.3f  total %.3f ms" % tuple(t))
 
 
 if __name__ == "__main__":
