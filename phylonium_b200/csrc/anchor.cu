@@ -349,24 +349,28 @@ __global__ void k_continue(WalkParams P, const int32_t *__restrict__ stuck, int3
 
 // ------------------------------------------------------------------ events -> homologies
 
+// cap: entries out / out_q hold (the number of true events is only checked against it by the
+// host afterwards: nothing may be written past it meanwhile)
 __global__ void k_copy_events(WalkParams P, const uint8_t *__restrict__ reach, const int32_t *__restrict__ from,
-                              const uint32_t *__restrict__ offs, Event *__restrict__ out, int32_t *__restrict__ out_q)
+                              const uint32_t *__restrict__ offs, Event *__restrict__ out, int32_t *__restrict__ out_q,
+                              uint32_t cap)
 {
 	// one warp per chunk, lanes stride over its events
 	const int32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31;
+	if (P.skip && *P.skip) return;
 	if (g >= P.total_chunks || !reach[g]) return;
 	const ChunkRec &r = P.rec[g];
 	const int32_t qid = P.chunk_query[g];
 	const Event *ev = P.ev + (int64_t)g * P.cap_ev;
 	const int32_t f = from[g];
 	uint32_t w = offs[2 * (int64_t)g];
-	for (int32_t k = f + lane; k < r.n_events; k += 32) {
+	for (int32_t k = f + lane; k < r.n_events && w + (uint32_t)(k - f) < cap; k += 32) {
 		out[w + (k - f)] = ev[k];
 		out_q[w + (k - f)] = qid;
 	}
 	w = offs[2 * (int64_t)g + 1];
-	for (int32_t k = lane; k < r.n_bridge; k += 32) {
+	for (int32_t k = lane; k < r.n_bridge && w + (uint32_t)k < cap; k += 32) {
 		out[w + k] = r.bridge_ev[k];
 		out_q[w + k] = qid;
 	}
@@ -602,10 +606,9 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 		out.d_offs.zero();
 		out.d_begin.zero();
 		out.d_count.zero();
-		if (opt.input_flags) {
-			if (opt.input_flags_ready) CUDA_CHECK(cudaStreamWaitEvent(s, opt.input_flags_ready, 0));
-			ST.input_flags = d2h_scalar(opt.input_flags, s);
-		}
+		if (opt.input_flags && opt.input_flags_ready) CUDA_CHECK(cudaStreamWaitEvent(s, opt.input_flags_ready, 0));
+		if (opt.graph && opt.graph->capturing) opt.graph->launch();
+		if (opt.input_flags) ST.input_flags = d2h_scalar(opt.input_flags, s);
 		return;
 	}
 
@@ -620,9 +623,10 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	DevBuf<ChunkRec> rec(total_chunks, s);
 	// Everything the host reads back at its first stop, in one block (one copy to pinned memory):
 	// ctl[0] any_open, [1] error, [2] open chunks, [3] / [4] work counters of walk / bridge,
-	// [8] number of true events, [9] copy of *opt.input_flags, [10] number of raw homologies;
+	// [8] number of true events, [9] copy of *opt.input_flags, [10] number of raw homologies,
+	// [11] number of true events the buffers hold (= [8] unless something is wrong);
 	// from [CTL_INTS] on the path status of every query.
-	constexpr int CTL_INTS = 16, CTL_EVENTS = 8, CTL_INPUT = 9, CTL_RAW = 10;
+	constexpr int CTL_INTS = 16, CTL_EVENTS = 8, CTL_INPUT = 9, CTL_RAW = 10, CTL_NEFF = 11;
 	DevBuf<int> ctl((size_t)CTL_INTS + nq, s);
 	CUDA_CHECK(cudaMemsetAsync(ctl.get(), 0, CTL_INTS * sizeof(int), s));
 	int *const flags = ctl.get();
@@ -689,57 +693,147 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 	KERNEL_CHECK();
 	ST.bridge_ms = lap.lap();
 
-	// 4. true path, with exact continuation of give-ups that lie on it
+	// 4. true path; 5. true events, compacted, then homologies; per-query sort + filter.
+	// All of it is queued without the host in between: how many true events there are is only
+	// known on the device (ctl[CTL_NEFF]), the buffers hold what a true path can carry at most —
+	// an accepted anchor covers more than thr bases, a chunk adds its first event and its bridge's
+	// last —, the scans read their length on the device.  The host looks once, at the end.  A
+	// give-up that sits on a true path (rare) shows there as well: it is continued exactly and
+	// serially (k_continue), the path resolved again, and everything behind it run once more.
 	DevBuf<int32_t> jump_a(total_chunks, s), jump_b(total_chunks, s), from(total_chunks, s);
 	DevBuf<uint8_t> reach(total_chunks, s);
 	std::vector<DevBuf<Event>> overflow;
-	// number of true events per (walker, bridge), scanned right after every path resolution so
-	// that its total comes back with the same synchronisation as the path status
-	DevBuf<uint32_t> cnt((size_t)2 * total_chunks + 1, s);
-	uint32_t n_events = 0;
-	for (int iter = 0;; iter++) {
+	DevBuf<uint32_t> cnt((size_t)2 * total_chunks + 1, s); // true events per (walker, bridge), scanned
+	int64_t bases = 0;
+	for (const auto &q : qi)
+		bases += q.qlen;
+	const int64_t cap_true64 = bases / (thr + 1) + 2 * (int64_t)total_chunks + 64;
+	if (cap_true64 > 0x7fffffffll) throw std::invalid_argument("too many anchors possible in one batch: use smaller batches");
+	const uint32_t cap_true = (uint32_t)cap_true64;
+	DevBuf<Event> tev(cap_true, s);
+	DevBuf<int32_t> tevq(cap_true, s);
+	DevBuf<uint32_t> headcode(cap_true, s);
+	DevBuf<Hom> raw(cap_true, s);
+	DevBuf<int32_t> raw_q(cap_true, s);
+	DevBuf<Hom> fin(cap_true, s);
+	uint32_t *const d_n_eff = reinterpret_cast<uint32_t *>(ctl.get() + CTL_NEFF);
+	uint32_t *const d_n_raw = reinterpret_cast<uint32_t *>(ctl.get() + CTL_RAW);
+	// What the host wants to see of the filter sits in one block: raw_offs (nq + 1 int64), then
+	// as int32 the survivors per query, the per-query flags and the number of raw homologies.
+	DevBuf<int64_t> finrep((size_t)nq + 1 + ((size_t)2 * nq + 1 + 1) / 2, s);
+	int64_t *const d_raw_offs = finrep.get();
+	int32_t *const fin_count = reinterpret_cast<int32_t *>(finrep.get() + nq + 1);
+	int32_t *const fin_flags = fin_count + nq;
+	int64_t *const h_finrep = g_pinned.take<int64_t>(finrep.size());
+	CUDA_CHECK(cudaFuncSetAttribute(k_sort_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmem)));
+
+	auto resolve = [&](bool first) {
 		k_resolve_path<<<nq, 1024, 0, s>>>(P, jump_a.get(), jump_b.get(), reach.get(), from.get(), status);
 		KERNEL_CHECK();
-		if (opt.input_flags && opt.input_flags_ready && iter == 0) CUDA_CHECK(cudaStreamWaitEvent(s, opt.input_flags_ready, 0));
-		{
-			uint32_t *c = cnt.get();
-			const ChunkRec *rc = rec.get();
-			const uint8_t *rh = reach.get();
-			const int32_t *fr = from.get();
-			const int64_t n2 = 2 * (int64_t)total_chunks;
-			int *report = flags;
-			const int *input_flags = opt.input_flags;
-			device_scan<uint32_t>(
-				n2 + 1,
-				[rc, rh, fr, n2] __device__(int64_t i) -> uint32_t {
-					if (i >= n2) return 0u;
-					const int64_t g = i >> 1;
-					if (!rh[g]) return 0u;
-					return (i & 1) ? (uint32_t)rc[g].n_bridge : (uint32_t)(rc[g].n_events - fr[g]);
-				},
-				[c, n2, report, input_flags] __device__(int64_t i, uint32_t v) {
-					c[i] = v;
-					if (i == n2) { // the total, and the verdict of the input validation next to it
-						report[CTL_EVENTS] = (int)v;
-						report[CTL_INPUT] = input_flags ? *input_flags : 0;
-					}
-				},
-				OpSum(), 0u, false, s);
-		}
+		if (first && opt.input_flags && opt.input_flags_ready) CUDA_CHECK(cudaStreamWaitEvent(s, opt.input_flags_ready, 0));
+		uint32_t *c = cnt.get();
+		const ChunkRec *rc = rec.get();
+		const uint8_t *rh = reach.get();
+		const int32_t *fr = from.get();
+		const int64_t n2 = 2 * (int64_t)total_chunks;
+		int *report = flags;
+		const int *input_flags = opt.input_flags;
+		const int *skip = P.skip;
+		device_scan<uint32_t>(
+			n2 + 1,
+			[rc, rh, fr, n2, skip] __device__(int64_t i) -> uint32_t {
+				if (i >= n2 || (skip && *skip)) return 0u;
+				const int64_t g = i >> 1;
+				if (!rh[g]) return 0u;
+				return (i & 1) ? (uint32_t)rc[g].n_bridge : (uint32_t)(rc[g].n_events - fr[g]);
+			},
+			[c, n2, report, input_flags, cap_true] __device__(int64_t i, uint32_t v) {
+				c[i] = v;
+				if (i == n2) { // the total, and the verdict of the input validation next to it
+					report[CTL_EVENTS] = (int)v;
+					report[CTL_NEFF] = (int)(v < cap_true ? v : cap_true);
+					report[CTL_INPUT] = input_flags ? *input_flags : 0;
+					report[CTL_RAW] = 0;
+				}
+			},
+			OpSum(), 0u, false, s);
+	};
+	auto assemble_and_filter = [&] {
+		k_copy_events<<<div_up((int64_t)total_chunks * 32, 256), 256, 0, s>>>(P, reach.get(), from.get(), cnt.get(),
+		                                                                      tev.get(), tevq.get(), cap_true);
+		KERNEL_CHECK();
+		// run heads by inclusive max-scan: 2(t+1)+1 for a left anchor, 2(t+1) for a query's
+		// first event that extends the virtual anchor (0,0,0), 0 otherwise
+		const Event *E = tev.get();
+		const int32_t *EQ = tevq.get();
+		uint32_t *HC = headcode.get();
+		const int32_t border = esa.n;
+		device_scan_n<uint32_t>(
+			d_n_eff, cap_true,
+			[E, EQ, border] __device__(int64_t t) -> uint32_t {
+				const bool right = ev_is_right(E, EQ, t, border);
+				if (!right) return 2u * (uint32_t)(t + 1) + 1u;
+				return ev_first_of_query(EQ, t) ? 2u * (uint32_t)(t + 1) : 0u;
+			},
+			[HC] __device__(int64_t t, uint32_t v) { HC[t] = v; }, OpMax(), 0u, true, s);
+		// a run ends where the next event is a left anchor or belongs to another query
+		const uint32_t *NE = d_n_eff;
+		auto run_end_pushed = [E, EQ, HC, border, thr, NE] __device__(int64_t t, Hom *h) -> bool {
+			const bool last = (t + 1 == (int64_t)*NE) || EQ[t + 1] != EQ[t] || !ev_is_right(E, EQ, t + 1, border);
+			if (!last) return false;
+			const uint32_t code = HC[t];
+			const int64_t first = (int64_t)(code >> 1) - 1;
+			const Event *base = E + first; // run_homology indexes relative to the run's first real event
+			const int32_t a = (code & 1) ? 0 : -1;
+			const int32_t b = (int32_t)(t - first);
+			Hom tmp;
+			const bool ok = run_homology(base, a, b, thr, border, tmp);
+			if (ok && h) *h = tmp;
+			return ok;
+		};
+		// one pass: there are at most as many homologies as events
+		Hom *R = raw.get();
+		int32_t *RQ = raw_q.get();
+		device_select_n(
+			d_n_eff, cap_true, [run_end_pushed] __device__(int64_t t) { return run_end_pushed(t, nullptr); },
+			[run_end_pushed, R, RQ, EQ] __device__(int64_t t, uint32_t w) {
+				Hom h;
+				run_end_pushed(t, &h);
+				R[w] = h;
+				RQ[w] = EQ[t];
+			},
+			d_n_raw, s);
+		// per-query ranges of the raw lists, then the per-query sort + filter in shared memory
+		k_query_offsets<<<div_up(nq + 1, 128), 128, 0, s>>>(raw_q.get(), d_n_raw, nq, d_raw_offs, fin_flags + nq);
+		KERNEL_CHECK();
+		k_sort_filter<<<nq, FIN_THREADS, sizeof(FinSmem), s>>>(d_raw_offs, raw.get(), fin.get(), fin_count, fin_flags,
+		                                                       out.d_begin.get(), out.d_count.get());
+		KERNEL_CHECK();
 		CUDA_CHECK(cudaMemcpyAsync(h_ctl, ctl.get(), ((size_t)CTL_INTS + nq) * sizeof(int), cudaMemcpyDeviceToHost, s));
-		CUDA_CHECK(cudaStreamSynchronize(s));
-		if (iter == 0 && opt.index_verdict_host && *opt.index_verdict_host) throw IndexNotBuilt();
-		ST.input_flags = h_ctl[CTL_INPUT];
-		n_events = (uint32_t)h_ctl[CTL_EVENTS];
-		if (ST.input_flags) return; // the caller reports what is wrong with the input
-		if (h_ctl[1]) throw std::runtime_error("internal error: open match left unresolved");
-		ST.open_events += (iter == 0 && h_ctl[0]) ? 1 : 0;
+		CUDA_CHECK(cudaMemcpyAsync(h_finrep, finrep.get(), finrep.bytes(), cudaMemcpyDeviceToHost, s));
+	};
+
+	resolve(true);
+	ST.path_ms = lap.lap();
+	assemble_and_filter();
+	// the lists are final unless a query needs the general path or a bridge has to be continued
+	// (both rare): let the caller queue its next step behind them while the host waits for the verdict
+	if (opt.on_filtered && !opt.keep_raw) opt.on_filtered(fin.get(), out.d_begin.get(), out.d_count.get());
+	if (opt.graph && opt.graph->capturing) opt.graph->launch(); // everything queued so far, as one graph
+	CUDA_CHECK(cudaStreamSynchronize(s));
+	if (opt.index_verdict_host && *opt.index_verdict_host) throw IndexNotBuilt();
+	ST.input_flags = h_ctl[CTL_INPUT];
+	if (ST.input_flags) return; // the caller reports what is wrong with the input
+	if (h_ctl[1]) throw std::runtime_error("internal error: open match left unresolved");
+	ST.open_events += h_ctl[0] ? 1 : 0;
+	for (int iter = 0;; iter++) {
 		std::vector<int32_t> stuck;
 		for (int32_t q = 0; q < nq; q++)
 			if (h_ctl[CTL_INTS + q] >= 0) stuck.push_back(h_ctl[CTL_INTS + q]);
 		if (stuck.empty()) break;
 		if (iter > total_chunks + 2) throw std::runtime_error("internal error: path resolution does not terminate");
 		ST.unresolved += (int64_t)stuck.size();
+		ST.lists_redone = 1; // what was queued behind the lists so far worked on incomplete ones
 		std::vector<Event *> h_ptr;
 		std::vector<int64_t> h_cap;
 		for (int32_t g : stuck) {
@@ -758,92 +852,18 @@ void anchor_queries_device(const EsaDevice &esa, const uint8_t *d_Q, std::vector
 		k_continue<<<div_up((int64_t)stuck.size(), 32), 32, 0, s>>>(P, d_stuck.get(), (int32_t)stuck.size(), d_ptr.get(),
 		                                                            d_cap.get());
 		KERNEL_CHECK();
-		CUDA_CHECK(cudaStreamSynchronize(s)); // host vectors above go out of scope
+		resolve(false);
+		CUDA_CHECK(cudaMemcpyAsync(h_ctl, ctl.get(), ((size_t)CTL_INTS + nq) * sizeof(int), cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaStreamSynchronize(s)); // (also: the host vectors above go out of scope)
 	}
-	ST.path_ms = lap.lap();
-
-	// 5. true events, compacted; then homologies
-	ST.events = n_events;
-
-	DevBuf<Hom> raw;
-	DevBuf<int32_t> raw_q;
-	uint32_t *const d_n_raw = reinterpret_cast<uint32_t *>(ctl.get() + CTL_RAW); // zero so far
-	uint32_t n_raw = 0;
-	if (n_events) {
-		DevBuf<Event> tev(n_events, s);
-		DevBuf<int32_t> tevq(n_events, s);
-		k_copy_events<<<div_up((int64_t)total_chunks * 32, 256), 256, 0, s>>>(P, reach.get(), from.get(), cnt.get(),
-		                                                                      tev.get(), tevq.get());
-		KERNEL_CHECK();
-		// run heads by inclusive max-scan: 2(t+1)+1 for a left anchor, 2(t+1) for a query's
-		// first event that extends the virtual anchor (0,0,0), 0 otherwise
-		DevBuf<uint32_t> headcode(n_events, s);
-		const Event *E = tev.get();
-		const int32_t *EQ = tevq.get();
-		uint32_t *HC = headcode.get();
-		const int32_t border = esa.n;
-		device_scan<uint32_t>(
-			n_events,
-			[E, EQ, border] __device__(int64_t t) -> uint32_t {
-				const bool right = ev_is_right(E, EQ, t, border);
-				if (!right) return 2u * (uint32_t)(t + 1) + 1u;
-				return ev_first_of_query(EQ, t) ? 2u * (uint32_t)(t + 1) : 0u;
-			},
-			[HC] __device__(int64_t t, uint32_t v) { HC[t] = v; }, OpMax(), 0u, true, s);
-		// a run ends where the next event is a left anchor or belongs to another query
-		const int64_t ne = n_events;
-		auto run_end_pushed = [E, EQ, HC, border, thr, ne] __device__(int64_t t, Hom *h) -> bool {
-			const bool last = (t + 1 == ne) || EQ[t + 1] != EQ[t] || !ev_is_right(E, EQ, t + 1, border);
-			if (!last) return false;
-			const uint32_t code = HC[t];
-			const int64_t first = (int64_t)(code >> 1) - 1;
-			const Event *base = E + first; // run_homology indexes relative to the run's first real event
-			const int32_t a = (code & 1) ? 0 : -1;
-			const int32_t b = (int32_t)(t - first);
-			Hom tmp;
-			const bool ok = run_homology(base, a, b, thr, border, tmp);
-			if (ok && h) *h = tmp;
-			return ok;
-		};
-		// one pass: there are at most as many homologies as events
-		raw.alloc(n_events, s);
-		raw_q.alloc(n_events, s);
-		{
-			Hom *R = raw.get();
-			int32_t *RQ = raw_q.get();
-			device_select(
-				n_events, [run_end_pushed] __device__(int64_t t) { return run_end_pushed(t, nullptr); },
-				[run_end_pushed, R, RQ, EQ] __device__(int64_t t, uint32_t w) {
-					Hom h;
-					run_end_pushed(t, &h);
-					R[w] = h;
-					RQ[w] = EQ[t];
-				},
-				d_n_raw, s);
-		}
+	if (ST.lists_redone) {
+		assemble_and_filter();
+		CUDA_CHECK(cudaStreamSynchronize(s));
 	}
+	ST.events = (uint32_t)h_ctl[CTL_EVENTS];
+	if ((uint32_t)h_ctl[CTL_EVENTS] > cap_true) throw std::runtime_error("internal error: more true events than a path can carry");
 	ST.assemble_ms = lap.lap();
-
-	// per-query ranges of the raw lists, then the per-query sort + filter in shared memory.
-	// What the host wants to see of it sits in one block: raw_offs (nq + 1 int64), then as
-	// int32 the survivors per query, the per-query flags and the number of raw homologies.
-	DevBuf<int64_t> finrep((size_t)nq + 1 + ((size_t)2 * nq + 1 + 1) / 2, s);
-	int64_t *const d_raw_offs = finrep.get();
-	int32_t *const fin_count = reinterpret_cast<int32_t *>(finrep.get() + nq + 1);
-	int32_t *const fin_flags = fin_count + nq;
-	DevBuf<Hom> fin(n_events, s);
-	k_query_offsets<<<div_up(nq + 1, 128), 128, 0, s>>>(raw_q.get(), d_n_raw, nq, d_raw_offs, fin_flags + nq);
-	KERNEL_CHECK();
-	CUDA_CHECK(cudaFuncSetAttribute(k_sort_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmem)));
-	k_sort_filter<<<nq, FIN_THREADS, sizeof(FinSmem), s>>>(d_raw_offs, raw.get(), fin.get(), fin_count, fin_flags,
-	                                                       out.d_begin.get(), out.d_count.get());
-	KERNEL_CHECK();
-	int64_t *const h_finrep = g_pinned.take<int64_t>(finrep.size());
-	CUDA_CHECK(cudaMemcpyAsync(h_finrep, finrep.get(), finrep.bytes(), cudaMemcpyDeviceToHost, s));
-	// the lists are final unless a query needs the general path (rare): let the caller queue
-	// its next step behind them while the host waits for the verdict
-	if (opt.on_filtered && !opt.keep_raw) opt.on_filtered(fin.get(), out.d_begin.get(), out.d_count.get());
-	CUDA_CHECK(cudaStreamSynchronize(s));
+	uint32_t n_raw = 0;
 	const int32_t *const h_fin_count = reinterpret_cast<const int32_t *>(h_finrep + nq + 1);
 	const int32_t *const h_fin_flags = h_fin_count + nq;
 	std::copy(h_finrep, h_finrep + nq + 1, out.raw_offs.begin());

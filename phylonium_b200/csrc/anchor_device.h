@@ -20,6 +20,7 @@ struct AnchorStats {
 	int64_t unresolved = 0;    // bridges that gave up and were continued serially
 	int64_t tie_fallback = 0;  // batches whose sort went through std::sort on the host
 	int64_t general_path = 0;  // batches sorted/filtered by the global path (a list > 2048, or ties)
+	int lists_redone = 0;      // a bridge on a true path had to be continued: on_filtered saw lists that were not final
 	int input_flags = 0;       // copy of *AnchorOptions::input_flags; != 0: nothing was mapped
 	float walk_ms = 0, open_ms = 0, bridge_ms = 0, path_ms = 0, assemble_ms = 0, filter_ms = 0, total_ms = 0;
 };
@@ -46,6 +47,10 @@ struct AnchorOptions {
 	// need the general path (AnchorStats::general_path), the final ones replace them and the
 	// caller has to redo that work.
 	std::function<void(const Hom *, const int64_t *, const int64_t *)> on_filtered;
+	// If the caller is capturing the stream into this graph (GraphSegment, common.cuh): the
+	// mapping submits it right before its host stop — everything up to there, on_filtered's work
+	// included, is then one graph.
+	GraphSegment *graph = nullptr;
 };
 
 struct IndexNotBuilt : std::runtime_error {

@@ -124,7 +124,7 @@ constexpr unsigned long long SP_AGGREGATE = 1ull, SP_INCLUSIVE = 2ull;
 template <typename T, typename InF, typename OutF, typename Op>
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_single_pass_kernel(int64_t n, InF in, OutF out, Op op, T identity, bool inclusive, unsigned long long *status,
-                        uint32_t *tile_counter, uint32_t epoch)
+                        uint32_t *tile_counter, uint32_t epoch, const uint32_t *__restrict__ n_dev = nullptr)
 {
 	static_assert(sizeof(T) == 4, "status words carry 32-bit values");
 	__shared__ T smem[32];
@@ -136,6 +136,13 @@ scan_single_pass_kernel(int64_t n, InF in, OutF out, Op op, T identity, bool inc
 	}
 	__syncthreads();
 	const uint32_t tile = s_tile;
+	if (n_dev) {
+		// the length is only known on the device (the grid covers its upper bound n): tiles past
+		// the end leave at once — nobody looks back at them
+		const int64_t have = (int64_t)*n_dev;
+		if (have < n) n = have;
+		if ((int64_t)tile * SCAN_TILE >= n) return;
+	}
 	const unsigned long long tag_agg = ((unsigned long long)epoch << 2) | SP_AGGREGATE;
 	const unsigned long long tag_inc = ((unsigned long long)epoch << 2) | SP_INCLUSIVE;
 	const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
@@ -265,6 +272,20 @@ void device_scan(int64_t n, InF in, OutF out, Op op, T identity, bool inclusive,
 	KERNEL_CHECK();
 }
 
+// The same with a length that is only known on the device: *n_dev elements, at most n_max (what
+// the buffers hold and the grid covers).  Always the single-pass kernel.
+template <typename T, typename InF, typename OutF, typename Op>
+void device_scan_n(const uint32_t *n_dev, int64_t n_max, InF in, OutF out, Op op, T identity, bool inclusive, cudaStream_t s)
+{
+	if (n_max <= 0) return;
+	const int nblocks = div_up(n_max, SCAN_TILE);
+	uint32_t epoch = 0;
+	unsigned long long *status = g_scan_states.get(nblocks, s, &epoch);
+	scan_single_pass_kernel<T><<<nblocks, SCAN_THREADS, 0, s>>>(n_max, in, out, op, identity, inclusive, status + 1,
+	                                                            reinterpret_cast<uint32_t *>(status), epoch, n_dev);
+	KERNEL_CHECK();
+}
+
 struct OpSum {
 	template <typename T> __device__ __forceinline__ T operator()(T a, T b) const { return a + b; }
 };
@@ -307,6 +328,23 @@ void device_select(int64_t n, PredF pred, EmitF emit, uint32_t *d_count, cudaStr
 		[pred, emit, d_count, n] __device__(int64_t i, uint32_t before) {
 			const bool p = pred(i);
 			if (p) emit(i, before);
+			if (i == n - 1) *d_count = before + (p ? 1u : 0u);
+		},
+		OpSum(), 0u, false, s);
+}
+
+// device_select over *n_dev (<= n_max) elements.  *d_count must be zero beforehand (it stays
+// untouched when there is no element).
+template <typename PredF, typename EmitF>
+void device_select_n(const uint32_t *n_dev, int64_t n_max, PredF pred, EmitF emit, uint32_t *d_count, cudaStream_t s)
+{
+	if (n_max <= 0) return;
+	device_scan_n<uint32_t>(
+		n_dev, n_max, [pred] __device__(int64_t i) { return pred(i) ? 1u : 0u; },
+		[pred, emit, d_count, n_dev, n_max] __device__(int64_t i, uint32_t before) {
+			const bool p = pred(i);
+			if (p) emit(i, before);
+			const int64_t n = (int64_t)*n_dev < n_max ? (int64_t)*n_dev : n_max;
 			if (i == n - 1) *d_count = before + (p ? 1u : 0u);
 		},
 		OpSum(), 0u, false, s);

@@ -104,6 +104,7 @@ def main():
                 # (with keep_raw the rows of a batch are built after its lists are final; without,
                 # before the host has seen them — and again if they were not)
                 keep_raw=1 if rounds % 4 == 0 else 0, esa_graph=int(rng.choice([1, 1, 0])),
+                map_graph=int(rng.choice([0, 1, 2, 2])),
                 upload_raw=int(rng.choice([0, 0, 1, -1])), compare_path=int(rng.choice([0, 0, 1])),
                 esa_speculative=int(rng.choice([1, 1, 0])), stage_threads=int(rng.choice([0, 1, 3])),
             )

@@ -383,6 +383,22 @@ def test_equal_starts_take_the_host_sort(pb, oracle):
     assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
 
 
+@pytest.mark.parametrize("name", sorted(datasets.ALL_SETS))
+def test_process_with_the_mapping_as_one_graph(pb, oracle, name):
+    """map_graph = 2: validation, walk, path, lists, rows and comparison of every batch are
+    captured and submitted as one CUDA graph whatever the size; twice on one context, so that the
+    second call updates the instantiated graph of the first"""
+    genomes = datasets.ALL_SETS[name]()
+    want = oracle.process(genomes, 0, 0, threads=2)
+    with pb.Context(map_graph=2, map_batch_bytes=20000) as ctx:
+        for _ in range(2):
+            subst, homol = ctx.process(genomes, 0, 0)
+            assert np.array_equal(subst, want["subst"]) and np.array_equal(homol, want["homologs"])
+        again = ctx.process_again(len(genomes) - 1, 4)
+    want2 = oracle.process(genomes, len(genomes) - 1, 4, threads=2)
+    assert np.array_equal(again[0], want2["subst"]) and np.array_equal(again[1], want2["homologs"])
+
+
 def _general_path_genomes():
     """genome 2 and 3 carry more homologies than the per-query sort holds"""
     rng = np.random.default_rng(43)
@@ -394,14 +410,15 @@ def _general_path_genomes():
     return [r, datasets.mutate(rng, r, 0.02), q1, q2, datasets.mutate(rng, r, 0.01), datasets.mutate(rng, r, 0.03)]
 
 
+@pytest.mark.parametrize("map_graph", [1, 2])
 @pytest.mark.parametrize("batch_bytes", [0, 300_000, 700_000])
 @pytest.mark.parametrize("flags", [0, 4])
-def test_process_redoes_a_batch_whose_lists_were_not_final(pb, oracle, batch_bytes, flags):
+def test_process_redoes_a_batch_whose_lists_were_not_final(pb, oracle, batch_bytes, flags, map_graph):
     """phylo_process queues the rows (and the comparison) of a batch before the host has seen
     whether its filtered lists are final; a batch that needs the global sort after all is
     done again — in the first, a middle or the only batch"""
     genomes = _general_path_genomes()
-    with pb.Context() as ctx:
+    with pb.Context(map_graph=map_graph) as ctx:  # 2: also for batches this small, the mapping as one CUDA graph
         if batch_bytes:
             ctx.set_option("map_batch_bytes", batch_bytes)
         subst, homol = ctx.process(genomes, 0, flags)
@@ -413,8 +430,9 @@ def test_process_redoes_a_batch_whose_lists_were_not_final(pb, oracle, batch_byt
     assert np.array_equal(again[0], want["subst"]) and np.array_equal(again[1], want["homologs"])
 
 
+@pytest.mark.parametrize("map_graph", [1, 2])
 @pytest.mark.parametrize("kind", ["contigs", "repeats"])
-def test_process_on_an_index_the_speculative_build_gives_up_on(pb, oracle, kind):
+def test_process_on_an_index_the_speculative_build_gives_up_on(pb, oracle, kind, map_graph):
     """the mapping is queued behind the index build; when the build's assumptions fail (too
     many contigs for the packed sorter's list, repeats that need the doubling rounds) its kernels
     do nothing, the index is built again step by step and the batch is mapped again"""
@@ -425,7 +443,7 @@ def test_process_on_an_index_the_speculative_build_gives_up_on(pb, oracle, kind)
         unit = datasets.random_dna(rng, 700)
         r = unit * 6 + datasets.random_dna(rng, 3000) + unit * 3
     genomes = [r, datasets.mutate(rng, r, 0.02), datasets.mutate(rng, r, 0.05), datasets.random_dna(rng, 5000)]
-    with pb.Context() as ctx:
+    with pb.Context(map_graph=map_graph) as ctx:
         subst, homol = ctx.process(genomes, 0, 0)
         if kind == "contigs":
             assert ctx.stat("esa.packed") == 0
@@ -708,9 +726,10 @@ def test_sharded_plumbing_on_one_gpu(pb, oracle, flags):
             c.close()
 
 
+@pytest.mark.parametrize("map_graph", [1, 2])
 @pytest.mark.parametrize("flags", [0, 4])
 @pytest.mark.parametrize("world", [2, 3])
-def test_sharded_push_exchange_on_one_gpu(pb, oracle, world, flags):
+def test_sharded_push_exchange_on_one_gpu(pb, oracle, world, flags, map_graph):
     """rows pushed into the peers' stores while the next batch is mapped (phylo_rows_set_peers,
     the in-process form of the IPC exchange), genomes dealt round-robin to the ranks, the
     slot-ordered matrix brought back into genome order: counts equal to the oracle's"""
@@ -722,7 +741,9 @@ def test_sharded_push_exchange_on_one_gpu(pb, oracle, world, flags):
     total = len(genomes)
     want = oracle.process(genomes, 0, flags, threads=4)
     thr = pb.threshold_for(genomes[0])
-    ctxs = [pb.Context(map_batch_bytes=50000) for _ in range(world)]  # several batches per rank
+    # several batches per rank; map_graph = 2: the last batch of each (mapping, rows, the kernel
+    # that pushes them to the peers) goes out as one CUDA graph
+    ctxs = [pb.Context(map_batch_bytes=50000, map_graph=map_graph) for _ in range(world)]
     try:
         plans = [sharding.make_plan(total, world, k, "interleaved") for k in range(world)]
         _broadcast_stand_in(ctxs, genomes[0])
