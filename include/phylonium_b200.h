@@ -101,6 +101,10 @@ int phylo_set_stream(phylo_ctx *ctx, void *stream);
  *   "esa_graph" 1 (default) = the speculative build is submitted as one CUDA graph behind its
  *               first radix pass (re-captured per call, the instantiated graph updated); 0 =
  *               kernel by kernel
+ *   "map_graph" the mapping of a batch up to its one host stop (validation, walk, lists, rows,
+ *               comparison) submitted as one CUDA graph: 0 = never, 1 (default) = the first batch of
+ *               a call when it holds 4 Mbp or more (the host records it while the index is being
+ *               built), 2 = every batch (tests)
  *   "compare_path" how the all-pairs kernel brings the row tiles into shared memory: 0 = tensor
  *               copies (TMA) through a 6-stage transaction-barrier pipeline (default), 1 =
  *               cp.async by all threads, double buffered (kept for comparison)

@@ -501,14 +501,17 @@ void do_map(phylo_ctx *c, const uint8_t *dQ, const uint64_t *offs, const uint64_
 		std::vector<QueryInfo> qi(c->qi.begin() + (size_t)b0, c->qi.begin() + (size_t)b1);
 		// Everything from here to the host's one stop in the mapping — validation, walk, path,
 		// lists, rows, exchange, comparison — is recorded and submitted as one graph (GraphSegment,
-		// common.cuh): ~25 launches with 0.7 instead of 2.6 us between them.  Not when the rows of
-		// this batch go to the peers through the copy engines (their streams join the main one
-		// only after the last batch), and not for small batches (a new shape costs an instantiation).
+		// common.cuh): ~25 launches with 0.7 instead of 2.6 us between them.  Only for the first
+		// batch: while the host records it the GPU is busy with the index build; before a later
+		// batch it would sit idle for the whole recording (geometry, allocations, ~25 launches:
+		// measured at 1000 x 5 Mbp in 9 batches, +0.5 ms per batch).  Not when the rows of this
+		// batch go to the peers through the copy engines (their streams join the main one only
+		// after the last batch), and not for small batches (a new shape costs an instantiation).
 		const bool last_batch = b + 1 == ends.size();
 		uint64_t batch_bases = 0;
 		for (uint64_t k = b0; k < b1; k++)
 			batch_bases += lens[k];
-		const bool use_graph = !c->timings && !c->keep_raw && !c->last_general_path &&
+		const bool use_graph = (b == 0 || c->tuning.map_graph == 2) && !c->timings && !c->keep_raw && !c->last_general_path &&
 		                       (c->tuning.map_graph == 2 || (c->tuning.map_graph == 1 && batch_bases >= (4u << 20))) &&
 		                       (c->peer_rows.empty() || (last_batch && c->tuning.push_kernel && !c->pushed_async));
 		struct GraphGuard {
@@ -701,6 +704,21 @@ int phylo_ctx_create(int device, phylo_ctx **out)
 		return fail(nullptr, PHYLO_ERR_CUDA, "could not create the copy stream");
 	}
 	*out = c;
+	// PHYLO_B200_OPTIONS="key=value,key=value": options for every context of the process (A/B
+	// measurements through programs that do not pass them on); unknown keys are ignored here
+	if (const char *env = getenv("PHYLO_B200_OPTIONS")) {
+		std::string all(env);
+		size_t at = 0;
+		while (at < all.size()) {
+			size_t end = all.find(',', at);
+			if (end == std::string::npos) end = all.size();
+			const std::string kv = all.substr(at, end - at);
+			const size_t eq = kv.find('=');
+			if (eq != std::string::npos) phylo_set_option(c, kv.substr(0, eq).c_str(), atoll(kv.c_str() + eq + 1));
+			at = end + 1;
+		}
+		c->err.clear();
+	}
 	return PHYLO_OK;
 }
 

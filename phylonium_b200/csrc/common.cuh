@@ -56,7 +56,7 @@ struct Tuning {
 	int compare_path = 0;      // "compare_path": 0 = TMA + mbarrier pipeline, 1 = cp.async double buffering
 	int upload_raw = 0;        // "upload_raw": 1 = sequences cross PCIe as bytes instead of packed to 2 bits
 	int esa_graph = 1;         // "esa_graph": 1 = the speculative index build is replayed as a CUDA graph
-	int map_graph = 1;         // "map_graph": the mapping of a batch (+ rows, comparison) as one graph: 0 never, 1 from 4 Mbp per batch, 2 always
+	int map_graph = 1;         // "map_graph": the mapping of a batch (+ rows, comparison) as one graph: 0 never, 1 the first batch of a call if it has 4 Mbp or more, 2 every batch
 };
 inline thread_local Tuning g_tuning;
 
