@@ -134,6 +134,38 @@ k_make_keys(const uint8_t *__restrict__ S, int32_t m, int32_t padded, uint64_t *
 
 constexpr int32_t LCP_TIE = -2;
 
+// heads[] receives the first SA index of every tie group: the block's heads in one stretch, ONE
+// atomic per block of LCP_THREADS.  (One per warp was one atomic on a single address per 32
+// suffixes: at m = 5 * 10^8, where a tenth of the suffixes tie on 16 characters, 12 M of them —
+// most of the 15 ms this phase took.)  Called by all threads of the block.
+constexpr int LCP_THREADS = 1024;
+
+__device__ __forceinline__ void append_heads(bool head, int64_t j, int32_t *__restrict__ heads,
+                                             uint32_t *__restrict__ counters)
+{
+	__shared__ uint32_t warp_first[LCP_THREADS / 32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t bal = __ballot_sync(0xffffffffu, head);
+	if (lane == 0) warp_first[warp] = (uint32_t)__popc(bal);
+	__syncthreads();
+	if (warp == 0) {
+		const uint32_t c = lane < (int)(blockDim.x >> 5) ? warp_first[lane] : 0u;
+		uint32_t inc = c;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+			if (lane >= d) inc += o;
+		}
+		const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+		uint32_t base = 0;
+		if (lane == 0 && total) base = atomicAdd(&counters[0], total);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		warp_first[lane] = base + inc - c;
+	}
+	__syncthreads();
+	if (head) heads[warp_first[warp] + __popc(bal & ((1u << lane) - 1))] = (int32_t)j;
+}
+
 __global__ void k_keys_to_lcp(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ sa,
                               const uint8_t *__restrict__ S, int32_t m, int32_t *__restrict__ SA,
                               int32_t *__restrict__ LCP, uint8_t *__restrict__ FVC, int kc,
@@ -160,14 +192,7 @@ __global__ void k_keys_to_lcp(const uint64_t *__restrict__ keys, const uint32_t 
 		}
 		head = x != 0 && j + 1 < m && keys[j + 1] == key;
 	}
-	// heads[] receives the first SA index of every tie group; one atomic per warp
-	const uint32_t bal = __ballot_sync(0xffffffffu, head);
-	if (!bal) return;
-	const int lane = threadIdx.x & 31;
-	uint32_t base = 0;
-	if (lane == __ffs(bal) - 1) base = atomicAdd(&counters[0], (uint32_t)__popc(bal));
-	base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-	if (head) heads[base + __popc(bal & ((1u << lane) - 1))] = (int32_t)j;
+	append_heads(head, j, heads, counters);
 }
 
 // The same for the packed words of suffix_sort.cuh (2-bit codes in the top half, dirty flag,
@@ -209,13 +234,7 @@ __global__ void k_words_to_lcp(const uint64_t *__restrict__ words, const uint8_t
 		// dirty suffixes lead their key group and are final; a tie group is made of clean ones
 		head = first_of_key && !(low & PK_DIRTY) && j + 1 < m && (uint32_t)(words[j + 1] >> 32) == key;
 	}
-	const uint32_t bal = __ballot_sync(0xffffffffu, head);
-	if (!bal) return;
-	const int lane = threadIdx.x & 31;
-	uint32_t base = 0;
-	if (lane == __ffs(bal) - 1) base = atomicAdd(&counters[0], (uint32_t)__popc(bal));
-	base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-	if (head) heads[base + __popc(bal & ((1u << lane) - 1))] = (int32_t)j;
+	append_heads(head, j, heads, counters);
 }
 
 // ---------------------------------------------------------------- small tie groups
@@ -227,6 +246,10 @@ __global__ void k_words_to_lcp(const uint64_t *__restrict__ words, const uint8_t
 // harder (a real repeat) is left over.
 
 constexpr int SMALL_GROUP = 8;    // largest group handled by direct comparison
+// blocks of 128 threads per SM for k_small_groups: as many as its 40 registers per thread allow.
+// A thread chases dependent random loads; at m = 5 * 10^8 there are 27 M groups (16 characters
+// are few for that many suffixes) and the kernel is bound by how many threads wait at once.
+constexpr int SMALL_GROUP_BLOCKS = 12;
 constexpr int SMALL_COMPARE = 256; // characters beyond the key a comparison may look at
 
 // returns the number of equal characters beyond offset `from`, or -1 when the cap is hit;
@@ -1109,11 +1132,11 @@ bool esa_build_impl(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k,
 		DevBuf<int32_t> heads((size_t)m / 2 + 1, s);
 		uint32_t *const counters = reinterpret_cast<uint32_t *>(esa.report.get() + 10);
 		if (packed) {
-			k_words_to_lcp<<<div_up(m, 256), 256, 0, s>>>(K1, esa.S.get(), m, esa.SA.get(), esa.LCP.get(), esa.FVC.get(),
+			k_words_to_lcp<<<div_up(m, LCP_THREADS), LCP_THREADS, 0, s>>>(K1, esa.S.get(), m, esa.SA.get(), esa.LCP.get(), esa.FVC.get(),
 			                                              heads.get(), counters);
 		} else {
 			const uint32_t *V1 = K1 == keys.get() ? vals.get() : vals_alt.get();
-			k_keys_to_lcp<<<div_up(m, 256), 256, 0, s>>>(K1, V1, esa.S.get(), m, esa.SA.get(), esa.LCP.get(),
+			k_keys_to_lcp<<<div_up(m, LCP_THREADS), LCP_THREADS, 0, s>>>(K1, V1, esa.S.get(), m, esa.SA.get(), esa.LCP.get(),
 			                                             esa.FVC.get(), kc, heads.get(), counters);
 		}
 		KERNEL_CHECK();
@@ -1122,10 +1145,10 @@ bool esa_build_impl(EsaDevice &esa, const uint8_t *d_ref, int32_t n, int kmer_k,
 		uint32_t h_counters[2] = {0, 0};
 		{
 			if (packed)
-				k_small_groups<true><<<NUM_SMS_B200 * 4, 128, 0, s>>>(heads.get(), counters, K1, esa.S.get(), m,
+				k_small_groups<true><<<NUM_SMS_B200 * SMALL_GROUP_BLOCKS, 128, 0, s>>>(heads.get(), counters, K1, esa.S.get(), m,
 				                                                     esa.SA.get(), esa.LCP.get(), esa.FVC.get(), kc);
 			else
-				k_small_groups<false><<<NUM_SMS_B200 * 4, 128, 0, s>>>(heads.get(), counters, K1, esa.S.get(), m,
+				k_small_groups<false><<<NUM_SMS_B200 * SMALL_GROUP_BLOCKS, 128, 0, s>>>(heads.get(), counters, K1, esa.S.get(), m,
 				                                                      esa.SA.get(), esa.LCP.get(), esa.FVC.get(), kc);
 			KERNEL_CHECK();
 			if (spec) {
