@@ -135,10 +135,11 @@ k_make_keys(const uint8_t *__restrict__ S, int32_t m, int32_t padded, uint64_t *
 constexpr int32_t LCP_TIE = -2;
 
 // heads[] receives the first SA index of every tie group: the block's heads in one stretch, ONE
-// atomic per block of LCP_THREADS.  (One per warp was one atomic on a single address per 32
+// atomic per block.  (One per warp was one atomic on a single address per 32
 // suffixes: at m = 5 * 10^8, where a tenth of the suffixes tie on 16 characters, 12 M of them —
-// most of the 15 ms this phase took.)  Called by all threads of the block.
-constexpr int LCP_THREADS = 1024;
+// most of the 15 ms this phase took.)  Called by all threads of the block.  Blocks of 256: with
+// 1024 the two barriers cost the streaming part ~15 us at m = 10^7 (LCP phase 0.077 -> 0.098 ms).
+constexpr int LCP_THREADS = 256;
 
 __device__ __forceinline__ void append_heads(bool head, int64_t j, int32_t *__restrict__ heads,
                                              uint32_t *__restrict__ counters)
