@@ -115,6 +115,8 @@ int phylo_set_stream(phylo_ctx *ctx, void *stream);
  *               a batch are then built after its lists are final, not before the host has seen them)
  *   "timings"  record per-phase device times (adds synchronisation) */
 int phylo_set_option(phylo_ctx *ctx, const char *key, int64_t value);
+/* (The environment variable PHYLO_B200_OPTIONS="key=value,key=value" sets options on every
+ * context a process creates — for A/B measurements through programs that do not pass them on.) */
 /* last recorded value of a named timing/statistic, e.g. "esa.sort_ms", "anchor.walk_ms",
  * "compare.ms"; *out = -1 for unknown names */
 int phylo_get_stat(const phylo_ctx *ctx, const char *key, double *out);
